@@ -1,0 +1,147 @@
+// capi.cu -- extern "C" entry points declared in include/glass_b200.h.
+#include <new>
+
+#include "plan.h"
+
+namespace glb {
+const std::string& last_error();
+int plan_build(glb_plan* pl);
+void plan_free(glb_plan* pl);
+int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
+int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* d_map, const int* kind,
+                        const double* tparams, cudaStream_t st);
+
+static inline int group_size(int remaining, int max_batch) {
+  const int cap = max_batch >= 4 ? 4 : (max_batch >= 2 ? 2 : 1);
+  int g = remaining >= 4 ? 4 : (remaining >= 2 ? 2 : 1);
+  return g > cap ? cap : g;
+}
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" {
+
+const char* glb_version(void) { return "glass_b200 0.1 (sm_100a)"; }
+const char* glb_last_error(void) { return glb::last_error().c_str(); }
+
+const char* glb_status_string(int status) {
+  switch (status) {
+    case GLB_OK: return "ok";
+    case GLB_ERR_INVALID_ARG: return "invalid argument";
+    case GLB_ERR_UNSUPPORTED: return "unsupported size";
+    case GLB_ERR_CUDA: return "CUDA error";
+    case GLB_ERR_NOMEM: return "out of memory";
+    case GLB_ERR_NOT_POSDEF: return "covariance matrix is not positive definite";
+    case GLB_ERR_NEGATIVE_CL: return "negative values in cl";
+    default: return "unknown status";
+  }
+}
+
+int glb_plan_create(glb_plan** plan, int nside, int lmax, int max_batch, int device) {
+  GLB_REQUIRE(plan != nullptr, "plan pointer is null");
+  GLB_REQUIRE(nside >= 1, "nside must be >= 1");
+  GLB_REQUIRE(lmax >= 0, "lmax must be >= 0");
+  GLB_REQUIRE(max_batch >= 1, "max_batch must be >= 1");
+  glb_plan* pl = new (std::nothrow) glb_plan();
+  if (!pl) return GLB_ERR_NOMEM;
+  pl->nside = nside;
+  pl->lmax = lmax;
+  pl->max_batch = max_batch;
+  pl->device = device;
+  const int rc = plan_build(pl);
+  if (rc != GLB_OK) {
+    plan_free(pl);
+    delete pl;
+    return rc;
+  }
+  *plan = pl;
+  return GLB_OK;
+}
+
+int glb_plan_destroy(glb_plan* plan) {
+  if (!plan) return GLB_OK;
+  plan_free(plan);
+  delete plan;
+  return GLB_OK;
+}
+
+int glb_plan_info(const glb_plan* plan, int* nside, int* lmax, int64_t* npix, int64_t* nalm, int* max_batch,
+                  int64_t* workspace_bytes) {
+  GLB_REQUIRE(plan != nullptr, "plan is null");
+  if (nside) *nside = plan->nside;
+  if (lmax) *lmax = plan->lmax;
+  if (npix) *npix = plan->npix;
+  if (nalm) *nalm = plan->nalm;
+  if (max_batch) *max_batch = plan->max_batch;
+  if (workspace_bytes) *workspace_bytes = plan->workspace_bytes;
+  return GLB_OK;
+}
+
+int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, const int* h_transform,
+                const double* h_tparams, void* stream) {
+  GLB_REQUIRE(plan && d_alm && d_map, "null pointer");
+  GLB_REQUIRE(nmaps >= 1, "nmaps must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  int done = 0;
+  while (done < nmaps) {
+    const int g = group_size(nmaps - done, plan->max_batch);
+    int rc = sht_alm2phase_group(plan, reinterpret_cast<const double2*>(d_alm) + (int64_t)done * plan->nalm, g,
+                                 plan->d_phase, st);
+    if (rc != GLB_OK) return rc;
+    rc = sht_phase2map_group(plan, plan->d_phase, g, d_map + (int64_t)done * plan->npix,
+                             h_transform ? h_transform + done : nullptr, h_tparams ? h_tparams + 2 * done : nullptr,
+                             st);
+    if (rc != GLB_OK) return rc;
+    done += g;
+  }
+  return GLB_OK;
+}
+
+int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map, const int* h_transform,
+                     const double* h_tparams, void* stream) {
+  GLB_REQUIRE(plan && h_alm && h_map, "null pointer");
+  GLB_REQUIRE(nmaps >= 1 && nmaps <= plan->max_batch, "nmaps must be in [1, max_batch]");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const size_t alm_bytes = (size_t)plan->nalm * 2 * sizeof(double) * plan->max_batch;
+  const size_t map_bytes = (size_t)plan->npix * sizeof(double) * plan->max_batch;
+  if (!plan->d_stage_alm) GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_stage_alm, alm_bytes));
+  if (!plan->d_stage_map) GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_stage_map, map_bytes));
+  const size_t a_bytes = (size_t)plan->nalm * 2 * sizeof(double) * nmaps;
+  const size_t m_bytes = (size_t)plan->npix * sizeof(double) * nmaps;
+  GLB_CUDA_CHECK(cudaMemcpyAsync(plan->d_stage_alm, h_alm, a_bytes, cudaMemcpyHostToDevice, st));
+  const int rc = glb_alm2map(plan, plan->d_stage_alm, nmaps, plan->d_stage_map, h_transform, h_tparams, stream);
+  if (rc != GLB_OK) return rc;
+  GLB_CUDA_CHECK(cudaMemcpyAsync(h_map, plan->d_stage_map, m_bytes, cudaMemcpyDeviceToHost, st));
+  GLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return GLB_OK;
+}
+
+int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase, void* stream) {
+  GLB_REQUIRE(plan && d_alm && d_phase, "null pointer");
+  GLB_REQUIRE(nmaps == 1 || nmaps == 2 || nmaps == 4, "nmaps must be 1, 2 or 4");
+  GLB_REQUIRE(nmaps <= plan->max_batch, "nmaps exceeds max_batch");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  GLB_CUDA_CHECK(cudaMemsetAsync(d_phase, 0, (size_t)nmaps * plan->nring * (plan->mmax + 1) * sizeof(double2),
+                                 (cudaStream_t)stream));
+  return sht_alm2phase_group(plan, reinterpret_cast<const double2*>(d_alm), nmaps,
+                             reinterpret_cast<double2*>(d_phase), (cudaStream_t)stream);
+}
+
+int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double* d_map, void* stream) {
+  GLB_REQUIRE(plan && d_phase && d_map, "null pointer");
+  GLB_REQUIRE(nmaps >= 1 && nmaps <= 4, "nmaps must be in [1, 4]");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_phase), nmaps, d_map, nullptr, nullptr,
+                             (cudaStream_t)stream);
+}
+
+int glb_debug_mlim(const glb_plan* plan, int* h_mlim) {
+  GLB_REQUIRE(plan && h_mlim, "null pointer");
+  for (int r = 0; r < plan->npair; ++r) h_mlim[r] = plan->h_mlim[r];
+  return GLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// plan.h -- the opaque glb_plan: HEALPix ring geometry, Legendre work list, FFT tables
+// and workspace for one (nside, lmax, device).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace glb {
+
+// One Legendre work item: a fixed m and a tile of ring pairs.
+struct LegItem {
+  int m;
+  int tile;
+};
+
+// Per-ring descriptor for the ring-FFT stage.
+struct RingDesc {
+  int64_t start;   // first pixel
+  int nphi;        // pixels on the ring (multiple of 4)
+  int shifted;     // phi0 = pi/nphi if 1, else 0
+  int pair;        // ring-pair index (0 = polar ... 2*nside-1 = equator)
+  int L;           // Bluestein length (nphi/4) or 0 if nphi/2 is a power of two
+  int M;           // power-of-two convolution length (Bluestein) or nphi/2 (direct)
+  int64_t bf_off;  // offset (in double2) of the chirp spectrum in d_bf, -1 if direct
+};
+
+}  // namespace glb
+
+struct glb_plan {
+  int nside = 0, lmax = 0, mmax = 0, device = 0, max_batch = 1;
+  int nring = 0, npair = 0;
+  int64_t npix = 0, nalm = 0;
+
+  // ---- host copies ----
+  std::vector<double> h_z, h_sth;   // per ring pair (north ring / equator)
+  std::vector<int> h_mlim;          // per ring pair
+  std::vector<int> h_rmin;          // per m: first ring pair with mlim >= m
+  std::vector<glb::RingDesc> h_rings;
+
+  // ---- device tables ----
+  double* d_z = nullptr;            // [npair]
+  double* d_sth = nullptr;          // [npair]
+  int* d_mlim = nullptr;            // [npair]
+  double* d_cm_mant = nullptr;      // [mmax+1] mantissa of lambda_mm prefactor
+  int* d_cm_exp = nullptr;          // [mmax+1] binary exponent
+  int64_t* d_roff = nullptr;        // [mmax+2] record offsets (in l-pairs) per m
+  int64_t nrec = 0;                 // total l-pairs over all m
+
+  // Legendre work lists per (threads, R) configuration actually used
+  glb::LegItem* d_items = nullptr;
+  int nitems = 0;
+  int leg_threads = 256, leg_R = 4;  // tile = leg_threads * leg_R ring pairs
+
+  // ring FFT
+  glb::RingDesc* d_rings = nullptr;  // [nring]
+  int* d_ring_order[3] = {nullptr, nullptr, nullptr};  // ring index lists per size class
+  int n_ring_class[3] = {0, 0, 0};
+  double2* d_tw = nullptr;           // twiddles e^{-2 pi i t / TW_N}, t < TW_N/2
+  int tw_n = 0;
+  double2* d_bf = nullptr;           // concatenated chirp spectra (bit-reversed order, scaled 1/M)
+  int64_t bf_total = 0;
+
+  // workspace
+  double* d_rec = nullptr;           // Legendre records  [nrec * (2 + 4*B)]
+  double2* d_phase = nullptr;        // [max_batch][nring][mmax+1]
+  int64_t workspace_bytes = 0;
+
+  // pinned host staging for the host-buffer API
+  double* h_pin_in = nullptr;
+  double* h_pin_out = nullptr;
+  double* d_stage_alm = nullptr;
+  double* d_stage_map = nullptr;
+};

@@ -1,0 +1,436 @@
+// sht_legendre.cu -- Legendre stage of the scalar spherical-harmonic synthesis (K3).
+//
+// Replaces the Legendre part of healpy.alm2map -> libsharp2 (glass/healpix.py:71, called
+// from glass/fields.py:429 and glass/lensing.py:326):
+//     F_m(theta_r) = sum_{l=m..lmax} a_lm lambda_lm(cos theta_r)
+// for every ring r and every m <= mlim(r).
+//
+// Algorithm (B200-first; not a translation of libsharp):
+//  * x^2 recurrence.  From  x lam_l = e_{l+1} lam_{l+1} + e_l lam_{l-1},
+//    e_l = sqrt((l^2-m^2)/(4l^2-1)), the even-offset functions lam_{m+2k} obey a
+//    three-term recurrence in x^2.  Rescaling p_k = lam_{m+2k}/alpha_k makes it
+//        p_{k+1} = (a_k x^2 + b_k) p_k - p_{k-1}        (2 DFMA per TWO l values)
+//    and the odd-offset functions are x times a combination of the even ones, so
+//        F_m(+-x) = sum_k p_k(x^2) (Ae_k +- x Ao_k)
+//    with coefficients (Ae, Ao) obtained from a_lm by an O(lmax) pass per m
+//    (sht_prep_kernel).  North and south ring of a pair share everything but the sign.
+//  * one thread owns R adjacent ring pairs and walks l; a CTA owns (m, tile of ring
+//    pairs); the per-m record stream {a_k, b_k, Ae_k, Ao_k} is staged through shared
+//    memory by the TMA engine (cp.async.bulk + mbarrier, multi-stage), every thread
+//    reads it with broadcast LDS.128.  The inner loop is pure DFMA: (2 + 4B) per ring
+//    pair per l-pair for B maps batched on one recurrence.
+//  * dynamic range: lam_mm ~ sin^m(theta) underflows FP64; values carry an integer
+//    scale (true = v * 2^(512*scale)).  Per warp three phases: SKIP (recurrence only,
+//    nothing is significant yet), CHECK (accumulate with per-ring select + rescale
+//    test), FAST (all rings at scale 0: no tests).
+//  * rings with mlim(ring) < m are skipped entirely (mlim as in libsharp's
+//    sharp_get_mlim heuristic, shared with the FFT stage through the plan).
+#include "plan.h"
+
+namespace glb {
+
+constexpr int LEG_KT = 64;      // l-pairs per smem chunk
+constexpr int LEG_STAGES = 4;   // chunks in flight
+constexpr int SCALE_BITS = 512;
+constexpr int BEXP_BIG = 1023 + 256;  // rescale when |p| >= 2^256
+constexpr int BEXP_SIG = 1023 - 70;   // "significant" when scale==0 and |p| >= 2^-70
+
+__device__ __forceinline__ int bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
+
+__host__ __device__ __forceinline__ double eps_lm(int l, int m) {
+  // e_l = sqrt((l^2-m^2)/(4 l^2-1)); exact integer products in double
+  if (l <= m) return 0.0;  // also covers l == m (zero) and l < m
+  const double dl = (double)l, dm = (double)m;
+  return sqrt(((dl - dm) * (dl + dm)) / (4.0 * dl * dl - 1.0));
+}
+
+// -------------------------------------------------------------------------------------
+// prep: a_lm (m-major) -> per-m record stream {a_k, b_k, (Ae_re, Ae_im, Ao_re, Ao_im) x B}
+// one thread per m; sequential in k (alpha is a running product, Ao a backward recursion)
+// -------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(128) sht_prep_kernel(const double2* __restrict__ alm, int64_t alm_stride,
+                                                        int lmax, int mmax, const int64_t* __restrict__ roff,
+                                                        double* __restrict__ rec) {
+  constexpr int REC = 2 + 4 * B;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > mmax) return;
+  const int K = (lmax - m) / 2 + 1;
+  double* r = rec + roff[m] * REC;
+  const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;  // index of (l=0, m) (virtual)
+
+  // forward pass: alpha, a_k, b_k, Ae; stash s1 = alpha_k/e_{l+1}, s2 = e_{l+2}/e_{l+3}
+  double alpha_km1 = 0.0, alpha_k = 1.0;
+  double e_lm1 = 0.0;              // e_{l-1}
+  double e_l = 0.0;                // e_l   (l = m: zero)
+  double e_lp1 = eps_lm(m + 1, m);
+  double e_lp2 = eps_lm(m + 2, m);
+  for (int k = 0; k < K; ++k) {
+    const int l = m + 2 * k;
+    const double e_lp3 = eps_lm(l + 3, m);
+    const double e_lp4 = eps_lm(l + 4, m);
+    const double alpha_kp1 = (k == 0) ? 1.0 : alpha_km1 * ((e_l * e_lm1) / (e_lp1 * e_lp2));
+    const double a = alpha_k / (e_lp1 * e_lp2 * alpha_kp1);
+    const double b = -(e_lp1 * e_lp1 + e_l * e_l) * a;
+    double* rk = r + (int64_t)k * REC;
+    rk[0] = a;
+    rk[1] = b;
+#pragma unroll
+    for (int bb = 0; bb < B; ++bb) {
+      double2 v = alm[bb * alm_stride + base + l];
+      if (m == 0) v.y = 0.0;  // a_l0 is real (healpy ignores the imaginary part)
+      rk[2 + 4 * bb + 0] = v.x * alpha_k;
+      rk[2 + 4 * bb + 1] = v.y * alpha_k;
+    }
+    rk[2 + 2] = alpha_k / e_lp1;  // stash in map 0's Ao slot
+    rk[2 + 3] = e_lp2 / e_lp3;
+    alpha_km1 = alpha_k;
+    alpha_k = alpha_kp1;
+    e_lm1 = e_lp1;
+    e_l = e_lp2;
+    e_lp1 = e_lp3;
+    e_lp2 = e_lp4;
+  }
+  // backward pass: t_k = o_k - t_{k+1} * s2_k ; Ao_k = t_k * s1_k   (o_k = a_{m+2k+1,m})
+  double2 t[B];
+#pragma unroll
+  for (int bb = 0; bb < B; ++bb) t[bb] = make_double2(0.0, 0.0);
+  for (int k = K - 1; k >= 0; --k) {
+    const int l = m + 2 * k;
+    double* rk = r + (int64_t)k * REC;
+    const double s1 = rk[2 + 2], s2 = rk[2 + 3];
+#pragma unroll
+    for (int bb = B - 1; bb >= 0; --bb) {
+      double2 o = make_double2(0.0, 0.0);
+      if (l + 1 <= lmax) {
+        o = alm[bb * alm_stride + base + l + 1];
+        if (m == 0) o.y = 0.0;
+      }
+      t[bb].x = o.x - t[bb].x * s2;
+      t[bb].y = o.y - t[bb].y * s2;
+      rk[2 + 4 * bb + 2] = t[bb].x * s1;
+      rk[2 + 4 * bb + 3] = t[bb].y * s1;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// lambda_mm(theta) = (-1)^m c_m sin^m(theta) as (value, scale), true = value*2^(512*scale)
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ void lam_mm_scaled(int m, double sth, double cm_mant, int cm_exp, double& val,
+                                              int& scale) {
+  int e;
+  double bv = frexp(sth, &e);  // sth = bv * 2^e, bv in [0.5, 1)
+  int be = e;
+  double rv = 1.0;
+  int re = 0;
+  int mm = m;
+  while (mm) {
+    if (mm & 1) {
+      rv *= bv;
+      re += be;
+      if (rv < 0.5) {
+        rv *= 2.0;
+        re -= 1;
+      }
+    }
+    bv *= bv;
+    be *= 2;
+    if (bv < 0.5) {
+      bv *= 2.0;
+      be -= 1;
+    }
+    mm >>= 1;
+  }
+  double mant = rv * cm_mant;  // in [0.25, 1)
+  int E = re + cm_exp;
+  if (m & 1) mant = -mant;
+  if (E >= 0) {
+    scale = 0;
+    val = scalbn(mant, E);
+  } else {
+    const int s = (-E) / SCALE_BITS;  // truncation
+    scale = -s;
+    val = scalbn(mant, E + s * SCALE_BITS);  // exponent in (-512, 0]
+  }
+}
+
+struct LegParams {
+  const LegItem* items;
+  const double* rec;
+  const int64_t* roff;
+  const double* z;
+  const double* sth;
+  const int* mlim;
+  const double* cm_mant;
+  const int* cm_exp;
+  double2* phase;
+  int64_t phase_map_stride;  // in double2
+  int lmax, mmax, npair, nring;
+};
+
+template <int R, int B, int THREADS>
+__global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegParams p) {
+  constexpr int REC = 2 + 4 * B;
+  constexpr int CHUNK_DOUBLES = LEG_KT * REC;
+  constexpr int NWARPS = THREADS / 32;
+  __shared__ __align__(128) double s_rec[LEG_STAGES][CHUNK_DOUBLES];
+  __shared__ __align__(8) uint64_t s_full[LEG_STAGES];
+  __shared__ __align__(8) uint64_t s_empty[LEG_STAGES];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const LegItem item = p.items[blockIdx.x];
+  const int m = item.m;
+  const int K = (p.lmax - m) / 2 + 1;
+  const int nchunks = (K + LEG_KT - 1) / LEG_KT;
+  const double* rec_m = p.rec + p.roff[m] * REC;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < LEG_STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int c) {
+    const int s = c % LEG_STAGES;
+    const int kc = min(LEG_KT, K - c * LEG_KT);
+    const uint32_t bytes = (uint32_t)(kc * REC * sizeof(double));
+    mbar_arrive_expect_tx(&s_full[s], bytes);
+    bulk_g2s(&s_rec[s][0], rec_m + (int64_t)c * CHUNK_DOUBLES, bytes, &s_full[s]);
+  };
+  if (tid == 0) {
+    for (int c = 0; c < LEG_STAGES - 1 && c < nchunks; ++c) issue(c);
+  }
+
+  // ---- per-thread ring state ----
+  double p1[R], p2[R], x2[R], zz[R];
+  int sc[R];
+  bool live[R];
+  double acc[R][B][4];
+  const int pair0 = item.tile * (THREADS * R) + tid * R;
+  const double cm_mant = p.cm_mant[m];
+  const int cm_exp = p.cm_exp[m];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int r = pair0 + j;
+    live[j] = (r < p.npair) && (p.mlim[min(r, p.npair - 1)] >= m);
+    p1[j] = 0.0;
+    p2[j] = 0.0;
+    sc[j] = 0;
+    x2[j] = 0.0;
+    zz[j] = 0.0;
+    if (live[j]) {
+      zz[j] = p.z[r];
+      x2[j] = zz[j] * zz[j];
+      lam_mm_scaled(m, p.sth[r], cm_mant, cm_exp, p2[j], sc[j]);
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) acc[j][b][0] = acc[j][b][1] = acc[j][b][2] = acc[j][b][3] = 0.0;
+  }
+
+  const double SMALL = 7.458340731200207e-155;  // 2^-512
+  int phase = 0;  // 0 skip, 1 check, 2 fast (warp-uniform)
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % LEG_STAGES;
+    if (tid == 0) {
+      const int cn = c + LEG_STAGES - 1;
+      if (cn < nchunks) {
+        if (cn >= LEG_STAGES) mbar_wait(&s_empty[cn % LEG_STAGES], ((cn / LEG_STAGES) - 1) & 1);
+        issue(cn);
+      }
+    }
+    mbar_wait(&s_full[s], (c / LEG_STAGES) & 1);
+    const double* ck = &s_rec[s][0];
+    const int kc = min(LEG_KT, K - c * LEG_KT);
+    int k = 0;
+
+    if (phase == 0) {
+      while (k < kc) {
+        bool sig = false;
+#pragma unroll
+        for (int j = 0; j < R; ++j) sig |= (sc[j] == 0) && (bexp(p2[j]) >= BEXP_SIG);
+        if (__any_sync(0xffffffffu, sig)) {
+          phase = 1;
+          break;
+        }
+        const double2 ab = *reinterpret_cast<const double2*>(ck + k * REC);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double rr = fma(ab.x, x2[j], ab.y);
+          const double t = fma(rr, p2[j], -p1[j]);
+          p1[j] = p2[j];
+          p2[j] = t;
+          if (bexp(p2[j]) >= BEXP_BIG) {
+            p1[j] *= SMALL;
+            p2[j] *= SMALL;
+            sc[j] += 1;
+          }
+        }
+        ++k;
+      }
+    }
+    if (phase == 1) {
+      while (k < kc) {
+        bool allz = true;
+#pragma unroll
+        for (int j = 0; j < R; ++j) allz &= (sc[j] == 0);
+        if (__all_sync(0xffffffffu, allz)) {
+          phase = 2;
+          break;
+        }
+        const double* rk = ck + k * REC;
+        const double2 ab = *reinterpret_cast<const double2*>(rk);
+        double2 ce[B], co[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          ce[b] = *reinterpret_cast<const double2*>(rk + 2 + 4 * b);
+          co[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double pa = (sc[j] == 0) ? p2[j] : 0.0;
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            acc[j][b][0] = fma(pa, ce[b].x, acc[j][b][0]);
+            acc[j][b][1] = fma(pa, ce[b].y, acc[j][b][1]);
+            acc[j][b][2] = fma(pa, co[b].x, acc[j][b][2]);
+            acc[j][b][3] = fma(pa, co[b].y, acc[j][b][3]);
+          }
+          const double rr = fma(ab.x, x2[j], ab.y);
+          const double t = fma(rr, p2[j], -p1[j]);
+          p1[j] = p2[j];
+          p2[j] = t;
+          if (bexp(p2[j]) >= BEXP_BIG) {
+            p1[j] *= SMALL;
+            p2[j] *= SMALL;
+            sc[j] += 1;
+          }
+        }
+        ++k;
+      }
+    }
+    if (phase == 2) {
+#pragma unroll 2
+      for (; k < kc; ++k) {
+        const double* rk = ck + k * REC;
+        const double2 ab = *reinterpret_cast<const double2*>(rk);
+        double2 ce[B], co[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          ce[b] = *reinterpret_cast<const double2*>(rk + 2 + 4 * b);
+          co[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            acc[j][b][0] = fma(p2[j], ce[b].x, acc[j][b][0]);
+            acc[j][b][1] = fma(p2[j], ce[b].y, acc[j][b][1]);
+            acc[j][b][2] = fma(p2[j], co[b].x, acc[j][b][2]);
+            acc[j][b][3] = fma(p2[j], co[b].y, acc[j][b][3]);
+          }
+          const double rr = fma(ab.x, x2[j], ab.y);
+          const double t = fma(rr, p2[j], -p1[j]);
+          p1[j] = p2[j];
+          p2[j] = t;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+
+  // ---- write F_m for the north and south ring of every live pair ----
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (!live[j]) continue;
+    const int r = pair0 + j;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const double er = acc[j][b][0], ei = acc[j][b][1];
+      const double orr = acc[j][b][2] * zz[j], oi = acc[j][b][3] * zz[j];
+      double2* ph = p.phase + b * p.phase_map_stride;
+      ph[(int64_t)r * (p.mmax + 1) + m] = make_double2(er + orr, ei + oi);
+      if (r != p.npair - 1) ph[(int64_t)(p.nring - 1 - r) * (p.mmax + 1) + m] = make_double2(er - orr, ei - oi);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// host launchers
+// -------------------------------------------------------------------------------------
+template <int B>
+static int launch_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = (pl->mmax + 1 + threads - 1) / threads;
+  sht_prep_kernel<B><<<blocks, threads, 0, st>>>(d_alm, pl->nalm, pl->lmax, pl->mmax, pl->d_roff, pl->d_rec);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  return GLB_OK;
+}
+
+template <int B>
+static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
+  LegParams p;
+  p.items = pl->d_items;
+  p.rec = pl->d_rec;
+  p.roff = pl->d_roff;
+  p.z = pl->d_z;
+  p.sth = pl->d_sth;
+  p.mlim = pl->d_mlim;
+  p.cm_mant = pl->d_cm_mant;
+  p.cm_exp = pl->d_cm_exp;
+  p.phase = d_phase;
+  p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
+  p.lmax = pl->lmax;
+  p.mmax = pl->mmax;
+  p.npair = pl->npair;
+  p.nring = pl->nring;
+  constexpr int R = (B == 4) ? 2 : 4;
+  if (pl->leg_R != 4) {
+    set_last_error("internal: legendre tile configuration");
+    return GLB_ERR_INVALID_ARG;
+  }
+  // tile = leg_threads * 4 ring pairs; with R == 2 we use twice the threads per tile
+  const int threads = pl->leg_threads * 4 / R;
+  if (threads == 64)
+    sht_legendre_synth_kernel<R, B, 64><<<pl->nitems, 64, 0, st>>>(p);
+  else if (threads == 128)
+    sht_legendre_synth_kernel<R, B, 128><<<pl->nitems, 128, 0, st>>>(p);
+  else if (threads == 256)
+    sht_legendre_synth_kernel<R, B, 256><<<pl->nitems, 256, 0, st>>>(p);
+  else if (threads == 512)
+    sht_legendre_synth_kernel<R, B, 512><<<pl->nitems, 512, 0, st>>>(p);
+  else {
+    set_last_error("internal: legendre thread configuration");
+    return GLB_ERR_INVALID_ARG;
+  }
+  GLB_CUDA_CHECK(cudaGetLastError());
+  return GLB_OK;
+}
+
+// alm [nb][nalm] -> phase [nb][nring][mmax+1], nb in {1,2,4}
+int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
+  int rc;
+  switch (nb) {
+    case 1:
+      if ((rc = launch_prep<1>(pl, d_alm, st)) != GLB_OK) return rc;
+      return launch_legendre<1>(pl, d_phase, st);
+    case 2:
+      if ((rc = launch_prep<2>(pl, d_alm, st)) != GLB_OK) return rc;
+      return launch_legendre<2>(pl, d_phase, st);
+    case 4:
+      if ((rc = launch_prep<4>(pl, d_alm, st)) != GLB_OK) return rc;
+      return launch_legendre<4>(pl, d_phase, st);
+    default:
+      set_last_error("internal: batch group must be 1, 2 or 4");
+      return GLB_ERR_INVALID_ARG;
+  }
+}
+
+}  // namespace glb

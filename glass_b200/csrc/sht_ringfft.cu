@@ -1,0 +1,335 @@
+// sht_ringfft.cu -- phase shift + alias fold + per-ring complex-to-real FFT (K4) with the
+// pixel transform (K5: lognormal / squared-normal, glass/grf/_transformations.py:83-89,
+// :170) fused into the store.
+//
+// Replaces the Fourier part of healpy.alm2map (glass/healpix.py:71):
+//     f(theta_r, phi_j) = Re F_0 + 2 Re sum_{m>0} F_m e^{i m (phi0_r + 2 pi j / nphi_r)}
+//
+// One CTA per (ring, map).  Ring lengths are nphi = 4i (caps) and 4*nside (belt), so the
+// FFT length is arbitrary.  Per ring, with n = nphi, h = n/2:
+//   1. fold   G[k] = sum_{m = k (mod n)} t_m + sum_{m = -k (mod n)} conj(t_m),
+//             t_m = F_m e^{i m phi0}, m <= mlim(ring)               (k = 0..h)
+//   2. pack   Z[k] = (G[k] + conj G[h-k]) + i e^{2 pi i k/n} (G[k] - conj G[h-k])
+//             so that the length-h complex inverse DFT z of Z holds the real ring as
+//             x[2j] = Re z[j], x[2j+1] = Im z[j]
+//   3. DFT_h  h a power of two: radix-2 DIF in shared memory, output read bit-reversed.
+//             otherwise h = 2L: two length-L DFTs (even/odd k) by Bluestein's chirp-z
+//             with a power-of-two circular convolution of length M >= 2L-1
+//             (forward DIF -> multiply by the precomputed chirp spectrum, stored in the
+//             same bit-reversed order -> inverse DIT: no bit reversal anywhere), then
+//             one radix-2 butterfly.  Intermediate values live in registers so shared
+//             memory only ever holds one M-length buffer.
+//   4. store  coalesced 16-byte stores of (x[2j], x[2j+1]) with the transform applied.
+#include "plan.h"
+
+namespace glb {
+
+struct FftParams {
+  const RingDesc* rings;
+  const int* order;
+  const double2* phase;
+  int64_t phase_map_stride;  // double2 units
+  const int* mlim;           // per ring pair
+  const double2* tw;
+  const double2* bf;
+  double* map;
+  int64_t npix;
+  int mmax;
+  int tw_n;
+  int kind[4];
+  double p0[4];
+  double p1[4];
+};
+
+template <int THREADS>
+__device__ __forceinline__ void fft_dif(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
+  const int tid = threadIdx.x;
+  for (int s = M >> 1; s >= 1; s >>= 1) {
+    const int tstep = tw_n / (2 * s);
+    for (int b = tid; b < (M >> 1); b += THREADS) {
+      const int j = b & (s - 1);
+      const int i0 = ((b - j) << 1) + j;
+      const int i1 = i0 + s;
+      const double2 u = x[i0], v = x[i1];
+      double2 w = __ldg(&tw[j * tstep]);
+      if (inverse) w.y = -w.y;
+      x[i0] = cadd(u, v);
+      x[i1] = cmul(csub(u, v), w);
+    }
+    __syncthreads();
+  }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void fft_dit(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
+  const int tid = threadIdx.x;
+  for (int s = 1; s < M; s <<= 1) {
+    const int tstep = tw_n / (2 * s);
+    for (int b = tid; b < (M >> 1); b += THREADS) {
+      const int j = b & (s - 1);
+      const int i0 = ((b - j) << 1) + j;
+      const int i1 = i0 + s;
+      double2 w = __ldg(&tw[j * tstep]);
+      if (inverse) w.y = -w.y;
+      const double2 u = x[i0], v = cmul(x[i1], w);
+      x[i0] = cadd(u, v);
+      x[i1] = csub(u, v);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double apply_transform(double x, int kind, double p0, double p1) {
+  if (kind == GLB_T_LOGNORMAL) {
+    x = expm1(x - p0);
+    if (p1 != 1.0) x = p1 * x;
+  } else if (kind == GLB_T_SQUARED_NORMAL) {
+    const double d = x - p0;
+    x = d * d - 1.0;
+    if (p1 != 1.0) x = p1 * x;
+  }
+  return x;
+}
+
+// chirp c[q] = e^{i pi q^2 / L}
+__device__ __forceinline__ double2 chirp(int q, int L) {
+  const long long q2 = ((long long)q * q) % (2LL * L);
+  return cispi((double)q2 / (double)L);
+}
+
+// Z[k] from the folded bins
+__device__ __forceinline__ double2 pack_z(const double2* G, int k, int h, int n) {
+  const double2 g = G[k];
+  const double2 gr = cconj(G[h - k]);
+  const double2 s = cadd(g, gr);
+  const double2 d = csub(g, gr);
+  const double2 w = cispi(2.0 * (double)k / (double)n);
+  const double2 wd = cmul(w, d);  // i*wd = (-wd.y, wd.x)
+  return make_double2(s.x - wd.y, s.y + wd.x);
+}
+
+template <int THREADS, int NREG>
+__global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* buf = reinterpret_cast<double2*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int ring = p.order[blockIdx.x];
+  const int b = blockIdx.y;
+  const RingDesc d = p.rings[ring];
+  const int n = d.nphi, h = n >> 1;
+  const int mlim = min(p.mlim[d.pair], p.mmax);
+  const double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
+  double* __restrict__ out = p.map + (int64_t)b * p.npix + d.start;
+  const int kind = p.kind[b];
+  const double tp0 = p.p0[b], tp1 = p.p1[b];
+  const double inv_n = 1.0 / (double)n;
+
+  // ---- 1. fold with phase shift ----
+  for (int k = tid; k <= h; k += THREADS) {
+    double2 g = make_double2(0.0, 0.0);
+    for (int m = k; m <= mlim; m += n) {
+      double2 t = F[m];
+      if (m == 0) t.y = 0.0;
+      if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
+      g = cadd(g, t);
+    }
+    for (int m = n - k; m <= mlim; m += n) {
+      double2 t = F[m];
+      if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
+      g = cadd(g, cconj(t));
+    }
+    buf[k] = g;
+  }
+  __syncthreads();
+
+  double2 reg[NREG];
+  if (d.L == 0) {
+    // ---- direct power-of-two path ----
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int k = tid + t * THREADS;
+      if (k < h) reg[t] = pack_z(buf, k, h, n);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NREG; ++t) {
+      const int k = tid + t * THREADS;
+      if (k < h) buf[k] = reg[t];
+    }
+    __syncthreads();
+    fft_dif<THREADS>(buf, h, p.tw, p.tw_n, true);
+    const int lg = 31 - __clz(h);
+    for (int j = tid; j < h; j += THREADS) {
+      const int jr = (lg == 0) ? 0 : (int)(__brev((unsigned)j) >> (32 - lg));
+      const double2 zv = buf[jr];
+      double2 o;
+      o.x = apply_transform(zv.x, kind, tp0, tp1);
+      o.y = apply_transform(zv.y, kind, tp0, tp1);
+      *reinterpret_cast<double2*>(out + 2 * j) = o;
+    }
+    return;
+  }
+
+  // ---- Bluestein path: h = 2L ----
+  const int L = d.L, M = d.M;
+  constexpr int NQ = NREG / 2;
+  double2* ae = reg;
+  double2* ao = reg + NQ;
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) {
+    const int q = tid + t * THREADS;
+    if (q < L) {
+      const double2 c = chirp(q, L);
+      ae[t] = cmul(pack_z(buf, 2 * q, h, n), c);
+      ao[t] = cmul(pack_z(buf, 2 * q + 1, h, n), c);
+    }
+  }
+  __syncthreads();
+  const double2* __restrict__ bf = p.bf + d.bf_off;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    double2* a = pass ? ao : ae;
+    for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) buf[q] = a[t];
+    }
+    __syncthreads();
+    fft_dif<THREADS>(buf, M, p.tw, p.tw_n, false);
+    for (int i = tid; i < M; i += THREADS) buf[i] = cmul(buf[i], bf[i]);
+    __syncthreads();
+    fft_dit<THREADS>(buf, M, p.tw, p.tw_n, true);
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) a[t] = buf[q];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) {
+    const int q = tid + t * THREADS;
+    if (q < L) {
+      const double2 c = chirp(q, L);
+      const double2 E = cmul(ae[t], c);
+      const double2 O = cmul(cmul(ao[t], c), cispi(2.0 * (double)q / (double)h));
+      const double2 z0 = cadd(E, O), z1 = csub(E, O);
+      double2 o;
+      o.x = apply_transform(z0.x, kind, tp0, tp1);
+      o.y = apply_transform(z0.y, kind, tp0, tp1);
+      *reinterpret_cast<double2*>(out + 2 * q) = o;
+      o.x = apply_transform(z1.x, kind, tp0, tp1);
+      o.y = apply_transform(z1.y, kind, tp0, tp1);
+      *reinterpret_cast<double2*>(out + 2 * (q + L)) = o;
+    }
+  }
+}
+
+// chirp spectrum  Bf = DIF_M( b_wrapped ) / M,  b[d] = conj(c[d]) = e^{-i pi d^2 / L}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bluestein_spectrum_kernel(const int* Ls, const int* Ms, const int64_t* offs,
+                                                                     const double2* tw, int tw_n, double2* bf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* buf = reinterpret_cast<double2*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int L = Ls[blockIdx.x], M = Ms[blockIdx.x];
+  for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int q = tid; q < L; q += THREADS) {
+    const double2 c = cconj(chirp(q, L));
+    buf[q] = c;
+    if (q > 0) buf[M - q] = c;
+  }
+  __syncthreads();
+  fft_dif<THREADS>(buf, M, tw, tw_n, false);
+  const double inv = 1.0 / (double)M;
+  double2* o = bf + offs[blockIdx.x];
+  for (int i = tid; i < M; i += THREADS) o[i] = cscale(buf[i], inv);
+}
+
+// -------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------
+static const int kClassLB[3] = {512, 2048, 8192};
+
+int ringfft_class_of(int lbuf) {
+  for (int c = 0; c < 3; ++c)
+    if (lbuf <= kClassLB[c]) return c;
+  return -1;
+}
+
+int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::vector<int>& Ms,
+                          const std::vector<int64_t>& offs, cudaStream_t st) {
+  if (Ls.empty()) return GLB_OK;
+  int *dL = nullptr, *dM = nullptr;
+  int64_t* dO = nullptr;
+  const size_t n = Ls.size();
+  GLB_CUDA_CHECK(cudaMalloc(&dL, n * sizeof(int)));
+  GLB_CUDA_CHECK(cudaMalloc(&dM, n * sizeof(int)));
+  GLB_CUDA_CHECK(cudaMalloc(&dO, n * sizeof(int64_t)));
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dL, Ls.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dM, Ms.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dO, offs.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int maxM = 0;
+  for (int m : Ms) maxM = std::max(maxM, m);
+  const size_t smem = (size_t)maxM * sizeof(double2);
+  GLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_spectrum_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  bluestein_spectrum_kernel<512><<<(unsigned)n, 512, smem, st>>>(dL, dM, dO, pl->d_tw, pl->tw_n, pl->d_bf);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  GLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(dL);
+  cudaFree(dM);
+  cudaFree(dO);
+  return GLB_OK;
+}
+
+template <int THREADS, int NREG>
+static int launch_class(const FftParams& p, int nrings, int nb, int lb, cudaStream_t st) {
+  if (nrings == 0) return GLB_OK;
+  const size_t smem = (size_t)(lb + 2) * sizeof(double2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GLB_CUDA_CHECK(cudaFuncSetAttribute(sht_ringfft_synth_kernel<THREADS, NREG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nrings, (unsigned)nb);
+  sht_ringfft_synth_kernel<THREADS, NREG><<<grid, THREADS, smem, st>>>(p);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  return GLB_OK;
+}
+
+// phase [nb][nring][mmax+1] -> map [nb][npix]; nb <= 4
+int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* d_map, const int* kind,
+                        const double* tparams, cudaStream_t st) {
+  FftParams p;
+  p.rings = pl->d_rings;
+  p.phase = d_phase;
+  p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
+  p.mlim = pl->d_mlim;
+  p.tw = pl->d_tw;
+  p.bf = pl->d_bf;
+  p.map = d_map;
+  p.npix = pl->npix;
+  p.mmax = pl->mmax;
+  p.tw_n = pl->tw_n;
+  for (int b = 0; b < 4; ++b) {
+    p.kind[b] = (kind && b < nb) ? kind[b] : GLB_T_NORMAL;
+    p.p0[b] = (tparams && b < nb) ? tparams[2 * b] : 0.0;
+    p.p1[b] = (tparams && b < nb) ? tparams[2 * b + 1] : 1.0;
+  }
+  int rc;
+  // largest rings first (they take longest)
+  p.order = pl->d_ring_order[2];
+  if ((rc = launch_class<512, 16>(p, pl->n_ring_class[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
+  p.order = pl->d_ring_order[1];
+  if ((rc = launch_class<256, 8>(p, pl->n_ring_class[1], nb, kClassLB[1], st)) != GLB_OK) return rc;
+  p.order = pl->d_ring_order[0];
+  if ((rc = launch_class<64, 8>(p, pl->n_ring_class[0], nb, kClassLB[0], st)) != GLB_OK) return rc;
+  return GLB_OK;
+}
+
+}  // namespace glb

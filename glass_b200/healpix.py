@@ -1,0 +1,170 @@
+"""
+glass_b200.healpix -- B200-native mirror of the seam ``glass/healpix.py``.
+
+Same names and argument meaning as the reference wrappers, but instead of
+round-tripping through host NumPy into healpy / healpix (``@numpy_fallback``,
+glass/_array_api_utils.py:569) the work runs in the sm_100a kernels of
+libglassb200.so.  Array rule: NumPy in -> NumPy out (host buffers, copies inside
+the call); torch CUDA tensors in -> torch CUDA tensors out (no host traffic).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PLANS: dict[tuple[int, int, int, int], "Plan"] = {}
+
+
+def nside2npix(nside: int) -> int:
+    """glass/healpix.py:296."""
+    return 12 * int(nside) * int(nside)
+
+
+def npix2nside(npix: int) -> int:
+    """glass/healpix.py:279 (raises ValueError for an invalid pixel count)."""
+    nside = math.isqrt(int(npix) // 12)
+    if nside < 1 or 12 * nside * nside != int(npix):
+        raise ValueError(f"invalid npix: {npix}")
+    return nside
+
+
+def get_nside(m) -> int:
+    """glass/healpix.py:215."""
+    return npix2nside(m.shape[-1])
+
+
+def alm_getlmax(size: int) -> int:
+    lmax = (math.isqrt(8 * int(size) + 1) - 3) // 2
+    if (lmax + 1) * (lmax + 2) // 2 != int(size):
+        raise ValueError(f"invalid alm size: {size}")
+    return lmax
+
+
+def _device_index(device=None) -> int:
+    if not torch.cuda.is_available():
+        raise _lib.GlassB200Error("glass_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.cuda.current_device()
+    return torch.device(device).index or 0
+
+
+class Plan:
+    """Owner of a ``glb_plan`` (ring tables, twiddles, chirp spectra, workspace)."""
+
+    def __init__(self, nside: int, lmax: int, max_batch: int = 1, device=None):
+        self.lib = _lib.load()
+        self.nside, self.lmax, self.max_batch = int(nside), int(lmax), int(max_batch)
+        self.device = _device_index(device)
+        self.npix = nside2npix(nside)
+        self.nalm = (lmax + 1) * (lmax + 2) // 2
+        self.nring = 4 * self.nside - 1
+        h = C.c_void_p()
+        _lib.check(self.lib.glb_plan_create(C.byref(h), self.nside, self.lmax, self.max_batch, self.device), "glb_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.glb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.device)
+
+    def stream_ptr(self) -> int:
+        return torch.cuda.current_stream(self.torch_device).cuda_stream
+
+
+def get_plan(nside: int, lmax: int, max_batch: int = 1, device=None) -> Plan:
+    dev = _device_index(device)
+    key = (int(nside), int(lmax), dev)
+    for (ns, lm, d, mb), pl in _PLANS.items():
+        if (ns, lm, d) == key and mb >= max_batch:
+            return pl
+    pl = Plan(nside, lmax, max_batch, dev)
+    _PLANS[(int(nside), int(lmax), dev, int(max_batch))] = pl
+    return pl
+
+
+def clear_plans() -> None:
+    _PLANS.clear()
+
+
+def _as_cuda_c128(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.complex128).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.complex128)).to(device)
+
+
+def _transform_args(transforms):
+    """[(kind, p0, p1), ...] -> ctypes arrays (or NULLs)."""
+    if transforms is None:
+        return None, None, None
+    n = len(transforms)
+    kinds = (C.c_int * n)(*[int(t[0]) for t in transforms])
+    params = (C.c_double * (2 * n))(*[float(v) for t in transforms for v in (t[1], t[2])])
+    return kinds, params, (kinds, params)
+
+
+def alm2map_batch(alms: torch.Tensor, nside: int, lmax: int | None = None, transforms=None, out=None) -> torch.Tensor:
+    """
+    Batched scalar synthesis on device: alms [nmaps, nalm] complex128 CUDA ->
+    maps [nmaps, npix] float64 CUDA, optional fused per-map pixel transform
+    ``transforms = [(kind, p0, p1), ...]`` (see include/glass_b200.h).
+    """
+    if alms.dim() != 2 or not alms.is_cuda or alms.dtype != torch.complex128:
+        raise ValueError("alms must be a [nmaps, nalm] complex128 CUDA tensor")
+    alms = alms.contiguous()
+    nmaps = alms.shape[0]
+    lmax = alm_getlmax(alms.shape[1]) if lmax is None else int(lmax)
+    if (lmax + 1) * (lmax + 2) // 2 != alms.shape[1]:
+        raise ValueError("alm size does not match lmax (mmax == lmax is required)")
+    pl = get_plan(nside, lmax, max_batch=min(4, max(1, nmaps)), device=alms.device)
+    if out is None:
+        out = torch.empty((nmaps, pl.npix), dtype=torch.float64, device=alms.device)
+    kinds, params, _keep = _transform_args(transforms)
+    with torch.cuda.device(alms.device):
+        rc = pl.lib.glb_alm2map(pl.handle, alms.data_ptr(), nmaps, out.data_ptr(), kinds, params, pl.stream_ptr())
+    _lib.check(rc, "glb_alm2map")
+    return out
+
+
+def alm2map(
+    alms,
+    nside: int,
+    *,
+    inplace: bool = False,
+    lmax: int | None = None,
+    pixwin: bool = False,
+    pol: bool = True,
+):
+    """
+    Computes a HEALPix map given the alm (glass/healpix.py:38-78).
+
+    Scalar transforms only: a single alm array, or a sequence of alm arrays with
+    ``pol=False`` (each transformed independently, as healpy does).
+    """
+    if pixwin:
+        raise NotImplementedError("pixwin=True needs healpy's pixel-window data files (glass/healpix.py:351)")
+    single = not isinstance(alms, (list, tuple)) and getattr(alms, "ndim", 1) == 1
+    if not single and pol:
+        raise NotImplementedError("polarised (TEB) alm2map is outside the GLASS hot path; pass pol=False")
+    host = not isinstance(alms if single else alms[0], torch.Tensor)
+    dev = torch.device("cuda", _device_index()) if host else (alms if single else alms[0]).device
+    seq = [alms] if single else list(alms)
+    stack = torch.stack([_as_cuda_c128(a, dev) for a in seq])
+    maps = alm2map_batch(stack, nside, lmax)
+    if host:
+        res = maps.cpu().numpy()
+        return res[0] if single else [res[i] for i in range(len(seq))]
+    return maps[0] if single else [maps[i] for i in range(len(seq))]

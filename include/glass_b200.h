@@ -1,0 +1,109 @@
+/*
+ * glass_b200.h -- C ABI of libglassb200.so: the B200-native (sm_100a) kernels behind
+ * the GLASS per-shell field-generation hot path.
+ *
+ * This is the drop-in boundary.  The reference (glass-dev/glass) is pure Python and
+ * reaches native code only through the seam glass/healpix.py (healpy / healpix C
+ * extensions) and NumPy.  Every entry point below names the reference interface it
+ * replaces (file:line relative to the reference checkout).  INTEGRATION.md shows the
+ * ctypes stub a GLASS maintainer would add in glass/healpix.py to bind them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA types in signatures
+ *    (`stream` is a cudaStream_t passed as void*; NULL = default stream).
+ *  - `d_` pointers are DEVICE pointers on the plan's device, `h_` are HOST pointers.
+ *  - complex128 arrays are interleaved (re, im) doubles.
+ *  - maps are HEALPix RING order float64 of length 12*nside^2.
+ *  - alm are m-major ("HEALPix order", glass/fields.py:959-962):
+ *        index(l, m) = m*(2*lmax+1-m)/2 + l,  0 <= m <= l <= lmax  (mmax == lmax).
+ *  - all calls are asynchronous on `stream`, return 0 (GLB_OK) or a negative glb_status;
+ *    no call allocates caller-visible memory; a plan is not thread-safe (one per
+ *    host thread), distinct plans are independent.
+ */
+#ifndef GLASS_B200_H
+#define GLASS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum glb_status {
+  GLB_OK = 0,
+  GLB_ERR_INVALID_ARG = -1,   /* -> ValueError                                              */
+  GLB_ERR_UNSUPPORTED = -2,   /* size outside what the kernels handle (e.g. nside > 4096)   */
+  GLB_ERR_CUDA = -3,          /* a CUDA runtime call failed; see glb_last_error()           */
+  GLB_ERR_NOMEM = -4,
+  GLB_ERR_NOT_POSDEF = -10,   /* "covariance matrix is not positive definite" fields.py:181 */
+  GLB_ERR_NEGATIVE_CL = -11   /* "negative values in cl"                      fields.py:229 */
+} glb_status;
+
+/* pixel transform fused into the ring-FFT epilogue (glass/grf/_transformations.py) */
+typedef enum glb_transform {
+  GLB_T_NORMAL = 0,         /* Normal.__call__       :26   t(x) = x                            */
+  GLB_T_LOGNORMAL = 1,      /* Lognormal.__call__    :83   t(x) = lamda*expm1(x - var/2)       */
+  GLB_T_SQUARED_NORMAL = 2  /* SquaredNormal.__call__:170  t(x) = lamda*((x-a)^2 - 1)          */
+} glb_transform;
+
+typedef struct glb_plan glb_plan; /* opaque: ring tables, twiddles, chirp spectra, workspace */
+
+const char* glb_version(void);
+const char* glb_last_error(void);      /* thread-local description of the last failure */
+const char* glb_status_string(int status);
+
+/* ---- plan -------------------------------------------------------------------------- */
+/* One plan per (nside, lmax, device).  Replaces the implicit geometry set-up inside
+ * healpy.alm2map / map2alm (glass/healpix.py:71,270).  max_batch = how many maps one
+ * call may transform together (workspace is sized for it). */
+int glb_plan_create(glb_plan** plan, int nside, int lmax, int max_batch, int device);
+int glb_plan_destroy(glb_plan* plan);
+int glb_plan_info(const glb_plan* plan, int* nside, int* lmax, int64_t* npix, int64_t* nalm,
+                  int* max_batch, int64_t* workspace_bytes);
+
+/* ---- spherical-harmonic transforms (the seam glass/healpix.py) ---------------------- */
+/* healpy.alm2map(alm, nside, pol=False, pixwin=False)   glass/healpix.py:71
+ * (called from glass/fields.py:429, glass/lensing.py:326).
+ * nmaps alm sets [nmaps][nalm] complex128 -> nmaps maps [nmaps][npix] float64.
+ * transform/tparams (may be NULL): per-map glb_transform and 2 doubles (p0, p1):
+ *   LOGNORMAL: p0 = var/2, p1 = lamda;  SQUARED_NORMAL: p0 = a, p1 = lamda. */
+int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map,
+                const int* h_transform, const double* h_tparams, void* stream);
+
+/* healpy.alm2map_spin([alm1, alm2], nside, spin, lmax)   glass/healpix.py:107
+ * (called from glass/lensing.py:343,366,428).  d_alm2 may be NULL (B-modes zero, which
+ * is what GLASS always passes). */
+int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2, int spin,
+                     double* d_map1, double* d_map2, void* stream);
+
+/* healpy.map2alm(map, lmax, pol=False, use_pixel_weights=True)   glass/healpix.py:270
+ * (called from glass/lensing.py:306,408).  d_ring_weights: per-ring quadrature weights
+ * [4*nside-1] or NULL (uniform); niter Jacobi refinements (healpy default 3). */
+int glb_map2alm(glb_plan* plan, const double* d_map, const double* d_ring_weights, int niter,
+                double* d_alm, void* stream);
+
+/* healpy.almxfl(alm, fl)   glass/healpix.py:136 (called from glass/lensing.py:322,339,363,425)
+ * in place; fl has nfl entries, treated as zero beyond. */
+int glb_almxfl(glb_plan* plan, double* d_alm, const double* d_fl, int nfl, void* stream);
+
+/* host-buffer forms of the two transforms GLASS calls per shell: H2D, kernels, D2H on
+ * `stream`, synchronous on return.  These are what a ctypes binding inside
+ * glass/healpix.py would call with NumPy buffers. */
+int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map,
+                     const int* h_transform, const double* h_tparams, void* stream);
+
+/* ---- debug / test taps (stable, used by tests/ only) --------------------------------- */
+/* Legendre stage only: alm -> phase array F_m(ring), [nmaps][nring][lmax+1] complex128 */
+int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase,
+                        void* stream);
+/* ring-FFT stage only: phases -> map */
+int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double* d_map,
+                        void* stream);
+/* mlim[ring pair] table the two stages share (host copy), npair = 2*nside entries */
+int glb_debug_mlim(const glb_plan* plan, int* h_mlim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLASS_B200_H */

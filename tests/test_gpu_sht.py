@@ -1,0 +1,86 @@
+"""GPU parity: scalar synthesis (glb_alm2map and its two stages) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import healpix_ref as H
+
+pytestmark = pytest.mark.gpu
+
+# tolerance: maps from identical alm within 1e-10 relative (BASELINE.json north_star)
+RTOL = 1e-10
+
+
+def random_alm(lmax, seed, nmaps=1):
+    rng = np.random.default_rng(seed)
+    n = H.alm_size(lmax)
+    a = rng.standard_normal((nmaps, n)) + 1j * rng.standard_normal((nmaps, n))
+    a[:, : lmax + 1] = a[:, : lmax + 1].real
+    return a
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("nside,lmax", [(1, 2), (2, 5), (4, 11), (8, 23), (16, 40), (3, 7), (5, 14), (12, 30), (32, 95), (48, 100)])
+def test_stage_taps(cuda_device, nside, lmax):
+    from glass_b200 import _lib
+    from glass_b200.healpix import get_plan
+
+    alm = random_alm(lmax, 10 + nside)
+    pl = get_plan(nside, lmax, 1, cuda_device)
+    d_alm = torch.as_tensor(alm).to(cuda_device)
+    nring = 4 * nside - 1
+    d_phase = torch.zeros((1, nring, lmax + 1), dtype=torch.complex128, device=cuda_device)
+    _lib.check(pl.lib.glb_debug_alm2phase(pl.handle, d_alm.data_ptr(), 1, d_phase.data_ptr(), pl.stream_ptr()), "alm2phase")
+    torch.cuda.synchronize()
+    F = H.alm2phase(alm[0], nside, lmax)
+    mlim = (C.c_int * (2 * nside))()
+    _lib.check(pl.lib.glb_debug_mlim(pl.handle, mlim), "mlim")
+    mlim = np.array(mlim[:])
+    got = d_phase.cpu().numpy()[0]
+    # only m <= mlim(ring) is defined
+    for r in range(nring):
+        pr = r if r < 2 * nside else nring - 1 - r
+        ml = mlim[pr]
+        assert np.abs(got[r, : ml + 1] - F[r, : ml + 1]).max() <= 1e-12 * max(1.0, np.abs(F).max()), (r, ml)
+    # Fourier stage on the oracle phases
+    d_F = torch.as_tensor(F[None]).to(cuda_device).contiguous()
+    d_map = torch.empty((1, 12 * nside * nside), dtype=torch.float64, device=cuda_device)
+    _lib.check(pl.lib.glb_debug_phase2map(pl.handle, d_F.data_ptr(), 1, d_map.data_ptr(), pl.stream_ptr()), "phase2map")
+    torch.cuda.synchronize()
+    ref = H.phase2map(F, nside)
+    assert relerr(d_map.cpu().numpy()[0], ref) < 1e-12
+
+
+@pytest.mark.parametrize("nside,lmax,nmaps", [(4, 11, 1), (8, 16, 2), (16, 47, 4), (32, 64, 3), (64, 191, 1), (128, 383, 2), (20, 50, 5), (256, 300, 1)])
+def test_alm2map_vs_oracle(cuda_device, nside, lmax, nmaps):
+    from glass_b200.healpix import alm2map_batch
+
+    alm = random_alm(lmax, 100 + nside, nmaps)
+    maps = alm2map_batch(torch.as_tensor(alm).to(cuda_device), nside, lmax).cpu().numpy()
+    for b in range(nmaps):
+        ref = H.alm2map(alm[b], nside, lmax)
+        assert relerr(maps[b], ref) < RTOL, (b, relerr(maps[b], ref))
+
+
+def test_alm2map_numpy_in_numpy_out(cuda_device):
+    from glass_b200 import healpix as hp
+
+    alm = random_alm(23, 5)[0]
+    m = hp.alm2map(alm, 8, pol=False)
+    assert isinstance(m, np.ndarray) and m.shape == (768,)
+    assert relerr(m, H.alm2map(alm, 8, 23)) < RTOL
+    ms = hp.alm2map([alm, 2 * alm], 8, pol=False)
+    assert relerr(ms[1], 2 * m) < 1e-14
+
+
+def test_direct_sum_ground_truth(cuda_device):
+    from glass_b200.healpix import alm2map_batch
+
+    alm = random_alm(11, 7)
+    got = alm2map_batch(torch.as_tensor(alm).to(cuda_device), 4, 11).cpu().numpy()[0]
+    assert relerr(got, H.alm2map_direct(alm[0], 4, 11)) < 1e-12
