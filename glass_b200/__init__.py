@@ -1,0 +1,25 @@
+"""
+glass_b200 -- B200-native (sm_100a) implementation of the GLASS per-shell field-generation
+hot path behind GLASS's own API for that path (flat re-export like ``glass/__init__.py``).
+
+Only the hot path of SURVEY.md section 8 lives here; everything else (shells, n(z) models,
+spectra solvers, I/O) stays with upstream GLASS.  There is no CPU fallback: the kernels
+are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if it is
+missing.
+"""
+
+from . import fields, grf, harmonics, healpix, rng  # noqa: F401
+from .fields import (  # noqa: F401
+    cls2cov,
+    gaussian_fields,
+    generate,
+    generate_gaussian,
+    generate_lognormal,
+    getcl,
+    iternorm,
+    lognormal_fields,
+    nfields_from_nspectra,
+)
+from .harmonics import multalm  # noqa: F401
+
+__version__ = "0.1.0"

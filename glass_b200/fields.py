@@ -1,0 +1,352 @@
+"""
+glass_b200.fields -- B200-native mirror of the hot-path part of ``glass/fields.py``:
+``iternorm``, ``cls2cov``, ``getcl``, ``generate`` (+ the deprecated
+``generate_gaussian`` / ``generate_lognormal``), ``lognormal_fields``,
+``gaussian_fields``.
+
+Same signatures, argument meaning and error messages as the reference.  Per shell the
+reference does (glass/fields.py:404-429, 884-894): draw N_lm complex normals on one CPU
+thread, combine with the iternorm weights through full-size temporaries, re-order
+l-major -> m-major in a Python loop, call healpy.alm2map, then apply the transformation
+as one more pass.  Here: Philox normals are drawn directly in m-major order on the GPU
+(glb_alm_draw), combined in one fused kernel (glb_alm_combine), several shells are
+synthesised together so they share one Legendre recurrence (glb_alm2map with a batch),
+and the transformation is fused into the ring-FFT store.
+
+Array rule: if any ``gls`` entry is a CUDA tensor the maps are yielded as CUDA tensors,
+otherwise as NumPy arrays (device->host copies overlap the next shells' compute).
+"""
+
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import functools
+import math
+import warnings
+from typing import Callable, Iterable, Iterator, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, grf
+from . import healpix as hp
+from . import rng as _rng
+
+# how many shells share one Legendre recurrence (1, 2 or 4)
+SHT_BATCH = 4
+
+
+def deprecated(msg: str, /):
+    def decorator(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            warnings.warn(msg, category=DeprecationWarning, stacklevel=2)
+            return func(*args, **kwargs)
+
+        return wrapper
+
+    return decorator
+
+
+def _inv_triangle_number(triangle_number: int) -> int:
+    """glass/fields.py:69-80."""
+    n = math.floor(math.sqrt(2 * triangle_number))
+    if n * (n + 1) // 2 != triangle_number:
+        msg = f"not a triangle number: {triangle_number}"
+        raise ValueError(msg)
+    return n
+
+
+def nfields_from_nspectra(nspectra: int) -> int:
+    """glass/fields.py:83-98."""
+    try:
+        n = _inv_triangle_number(nspectra)
+    except ValueError:
+        msg = f"invalid number of spectra: {nspectra}"
+        raise ValueError(msg) from None
+    return n
+
+
+def _np(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+def iternorm(cov: Iterable) -> Iterator[np.ndarray]:
+    """
+    Scaling vectors for iterative normal sampling (glass/fields.py:101-188).
+
+    Host-side (NumPy float64): O(n k^2) per shell on tiny arrays.  Yields, per input
+    row of shape (..., k+1), the row ``[a, s]`` of the banded Cholesky factor.
+    """
+    for i, row in enumerate(cov):
+        row = _np(row)
+        k = row.shape[-1] - 1
+        if k < 0:
+            raise ValueError("empty covariance matrix")
+        if i == 0:
+            n = row.shape[:-1]
+            m = np.zeros((*n, k, k))
+            a = np.zeros((*n, k))
+            s = np.ones(n)
+        else:
+            if row.shape[:-1] != n:
+                raise ValueError("shape mismatch in covariance")
+            atm = a[..., None, :] @ m
+            m = np.concatenate([m, np.zeros((*n, m.shape[-2], 1), dtype=m.dtype)], axis=-1)
+            u = np.where(s > 0, np.ones(n, dtype=atm.dtype), np.zeros(n, dtype=atm.dtype))
+            r = np.concatenate([-atm, u[..., None, None]], axis=-1)
+            s = np.where(s > 0, s, np.ones(n, dtype=s.dtype))
+            r /= s[..., None, None]
+            m = np.concatenate([m, r], axis=-2)
+        m = m[..., m.shape[-2] - k :, m.shape[-1] - k :]
+        c = row[..., :0:-1]
+        a = (m @ c[..., None])[..., 0]
+        s = row[..., 0] - np.vecdot(a, a)
+        if np.any(s < 0):
+            raise ValueError("covariance matrix is not positive definite")
+        s = np.sqrt(s)
+        yield np.concatenate([a, s[..., None]], axis=-1)
+
+
+def cls2cov(cls, nl: int, nf: int, nc: int):
+    """
+    Cls as rows of a banded covariance for iterative sampling (glass/fields.py:191-236).
+    Like the reference (NumPy backend) the SAME buffer is mutated and re-yielded.
+    """
+    cov = np.zeros((nl, nc + 1))
+    end = 0
+    for j in range(nf):
+        begin, end = end, end + j + 1
+        for i, cl in enumerate(cls[begin:end][: nc + 1]):
+            cl = _np(cl)
+            if i == 0 and np.any(np.less(cl, 0)):
+                msg = "negative values in cl"
+                raise ValueError(msg)
+            n = cl.shape[0]
+            cov[:n, i] = cl
+            cov[n:, i] = 0.0
+        cov /= 2
+        yield cov
+
+
+def getcl(cls, i: int, j: int, lmax: int | None = None):
+    """glass/fields.py:525-560."""
+    if j > i:
+        i, j = j, i
+    cl = cls[i * (i + 1) // 2 + i - j]
+    if lmax is not None:
+        if cl.shape[0] > lmax + 1:
+            cl = cl[: lmax + 1]
+        elif isinstance(cl, torch.Tensor):
+            cl = torch.nn.functional.pad(cl, (0, lmax + 1 - cl.shape[0]))
+        else:
+            cl = np.pad(cl, (0, lmax + 1 - cl.shape[0]))
+    return cl
+
+
+def cltovar(cl) -> float:
+    """transformcl.cltovar as used at glass/fields.py:890: sum_l (2l+1)/(4 pi) C_l."""
+    cl = _np(cl)
+    ell = np.arange(cl.shape[0])
+    return float(np.sum((2 * ell + 1) / (4 * np.pi) * cl))
+
+
+def _glass_to_healpix_alm(alm):
+    """l-major -> m-major (glass/fields.py:943-962)."""
+    if isinstance(alm, torch.Tensor) and alm.is_cuda:
+        n = _inv_triangle_number(alm.numel())
+        a = alm.to(torch.complex128).contiguous()
+        out = torch.empty_like(a)
+        if n:
+            lib = _lib.load()
+            with torch.cuda.device(a.device):
+                st = torch.cuda.current_stream().cuda_stream
+                _lib.check(lib.glb_alm_glass_to_healpix(n - 1, a.data_ptr(), out.data_ptr(), st), "glb_alm_glass_to_healpix")
+        return out
+    alm = _np(alm)
+    n = _inv_triangle_number(alm.size)
+    ell = np.arange(n)
+    out = [alm[ell[m:] * (ell[m:] + 1) // 2 + m] for m in ell]
+    return np.concatenate(out) if out else alm
+
+
+# --------------------------------------------------------------------------------------
+# the generator chain
+# --------------------------------------------------------------------------------------
+
+
+class _ShellSampler:
+    """Device-side state of _generate_grf: z history, iternorm weights, alm batch."""
+
+    def __init__(self, gls, nside, ncorr, rng, device):
+        self.lib = _lib.load()
+        self.device = device
+        self.nside = nside
+        ngrf = nfields_from_nspectra(len(gls))
+        self.ngrf = ngrf
+        self.ncorr = ngrf - 1 if ncorr is None else ncorr
+        self.n = max((gl.shape[0] for gl in gls), default=0)
+        if self.n == 0:
+            raise ValueError("all gls are empty")
+        self.lmax = self.n - 1
+        self.nalm = self.n * (self.n + 1) // 2
+        self.deviates = rng if isinstance(rng, _rng.Deviates) else None
+        self.seed = _rng.seed_from(rng)
+        self.witer = iternorm(cls2cov(gls, self.n, ngrf, self.ncorr))
+        self.y: collections.deque = collections.deque()
+        self.shell = 0
+
+    def next_alm(self, out: torch.Tensor) -> bool:
+        """Fill ``out`` (nalm complex128, m-major) with the next shell's alm."""
+        try:
+            w = next(self.witer)
+        except StopIteration:
+            return False
+        lib, dev = self.lib, self.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        z = torch.empty(self.nalm, dtype=torch.complex128, device=dev)
+        if self.deviates is not None:
+            zg = torch.as_tensor(np.ascontiguousarray(self.deviates.next_normal_alm(), dtype=np.complex128)).to(dev)
+            _lib.check(lib.glb_alm_glass_to_healpix(self.lmax, zg.data_ptr(), z.data_ptr(), st), "glb_alm_glass_to_healpix")
+        else:
+            _lib.check(lib.glb_alm_draw(self.lmax, C.c_uint64(self.seed), C.c_uint32(self.shell), z.data_ptr(), st), "glb_alm_draw")
+        self.y.append(z)
+        while len(self.y) > w.shape[-1]:
+            self.y.popleft()
+        mis = w.shape[-1] - len(self.y)
+        nterms = len(self.y)
+        wd = torch.as_tensor(np.ascontiguousarray(w[:, mis:], dtype=np.float64)).to(dev)
+        zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in self.y])
+        _lib.check(
+            lib.glb_alm_combine(self.lmax, nterms, zptrs, wd.data_ptr(), nterms, out.data_ptr(), st),
+            "glb_alm_combine",
+        )
+        self._keep = (wd, zptrs)
+        self.shell += 1
+        return True
+
+
+def _generate_maps(gls, nside, ncorr, rng, transforms_for):
+    """
+    Core of _generate_grf / generate.  ``transforms_for(i)`` returns the fused
+    (kind, p0, p1) descriptor for shell i or None for "no fused transform".
+    Yields (i, map) with map a CUDA tensor or a NumPy array (array rule above).
+    """
+    on_device = any(isinstance(gl, torch.Tensor) and gl.is_cuda for gl in gls)
+    if on_device:
+        device = next(gl.device for gl in gls if isinstance(gl, torch.Tensor) and gl.is_cuda)
+    else:
+        device = torch.device("cuda", hp._device_index())
+    with torch.cuda.device(device):
+        sampler = _ShellSampler(gls, nside, ncorr, rng, device)
+        B = max(1, min(int(SHT_BATCH), 4))
+        npix = hp.nside2npix(nside)
+        copy_stream = None if on_device else torch.cuda.Stream(device)
+        i0 = 0
+        pending_error = None
+        while pending_error is None:
+            alms = torch.empty((B, sampler.nalm), dtype=torch.complex128, device=device)
+            nb = 0
+            while nb < B:
+                try:
+                    if not sampler.next_alm(alms[nb]):
+                        break
+                except ValueError as e:  # raise only once the earlier shells were yielded
+                    pending_error = e
+                    break
+                nb += 1
+            if nb == 0:
+                break
+            tr = [transforms_for(i0 + b) or (_lib.T_NORMAL, 0.0, 1.0) for b in range(nb)]
+            maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
+            if on_device:
+                for b in range(nb):
+                    yield i0 + b, maps[b]
+            else:
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(device))
+                host = []
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    for b in range(nb):
+                        h = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+                        h.copy_(maps[b], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        host.append((h, ev))
+                maps.record_stream(copy_stream)
+                for b, (h, ev) in enumerate(host):
+                    ev.synchronize()
+                    yield i0 + b, h.numpy()
+            i0 += nb
+            if nb < B:
+                break
+        if pending_error is not None:
+            raise pending_error
+
+
+def _generate_grf(gls, nside: int, *, ncorr: int | None = None, rng=None):
+    """Iteratively sample Gaussian random fields (glass/fields.py:334-429)."""
+    for _i, m in _generate_maps(gls, nside, ncorr, rng, lambda i: None):
+        yield m
+
+
+def generate(fields: Sequence, gls, nside: int, *, ncorr: int | None = None, rng=None) -> Iterator:
+    """
+    Sample random fields from Gaussian angular power spectra (glass/fields.py:839-894).
+    """
+    n = len(fields)
+    if len(gls) != n * (n + 1) // 2:
+        msg = "mismatch between number of fields and gls"
+        raise ValueError(msg)
+
+    variances: dict[int, float] = {}
+
+    def var_of(i: int) -> float:
+        if i not in variances:
+            variances[i] = cltovar(getcl(gls, i, i))
+        return variances[i]
+
+    def transforms_for(i: int):
+        if i >= n:
+            return None
+        return grf.fused_descriptor(fields[i], var_of(i))
+
+    for i, x in _generate_maps(gls, nside, ncorr, rng, transforms_for):
+        if i >= n:
+            break
+        t = fields[i]
+        if grf.fused_descriptor(t, 0.0) is None:
+            x = t(x, var_of(i))  # user-defined transformation: separate pass
+        yield x
+
+
+@deprecated("use glass.generate() instead")
+def generate_gaussian(gls, nside: int, *, ncorr: int | None = None, rng=None):
+    """glass/fields.py:432-483."""
+    n = nfields_from_nspectra(len(gls))
+    fields = [grf.Normal() for _ in range(n)]
+    yield from generate(fields, gls, nside, ncorr=ncorr, rng=rng)
+
+
+@deprecated("use glass.generate() instead")
+def generate_lognormal(gls, nside: int, shift: float = 1.0, *, ncorr: int | None = None, rng=None):
+    """glass/fields.py:485-522."""
+    n = nfields_from_nspectra(len(gls))
+    fields = [grf.Lognormal(shift) for _ in range(n)]
+    yield from generate(fields, gls, nside, ncorr=ncorr, rng=rng)
+
+
+def gaussian_fields(shells: Sequence) -> Sequence[grf.Normal]:
+    """glass/fields.py:697-713."""
+    return [grf.Normal() for _shell in shells]
+
+
+def lognormal_fields(shells: Sequence, shift: Callable[[float], float] | None = None) -> Sequence[grf.Lognormal]:
+    """glass/fields.py:716-740."""
+    if shift is None:
+        shift = lambda _z: 1.0  # noqa: E731
+    return [grf.Lognormal(shift(shell.zeff)) for shell in shells]

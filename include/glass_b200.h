@@ -85,7 +85,21 @@ int glb_map2alm(glb_plan* plan, const double* d_map, const double* d_ring_weight
 
 /* healpy.almxfl(alm, fl)   glass/healpix.py:136 (called from glass/lensing.py:322,339,363,425)
  * in place; fl has nfl entries, treated as zero beyond. */
-int glb_almxfl(glb_plan* plan, double* d_alm, const double* d_fl, int nfl, void* stream);
+int glb_almxfl(int lmax, double* d_alm, const double* d_fl, int nfl, void* stream);
+
+/* ---- correlated a_lm sampling across shells (glass/fields.py:404-425) ------------------ */
+/* z = rng.standard_normal((N_lm, 2)) @ [1, 1j]   fields.py:407.  Counter-based
+ * Philox4x32-10 + Box-Muller keyed by (seed, shell, GLASS index l(l+1)/2+m); the result is
+ * written in m-major order (so _glass_to_healpix_alm, fields.py:943-962, is folded in). */
+int glb_alm_draw(int lmax, uint64_t seed, uint32_t shell, double* d_z, void* stream);
+/* _glass_to_healpix_alm   fields.py:943-962: l-major -> m-major gather (for supplied z). */
+int glb_alm_glass_to_healpix(int lmax, const double* d_in, double* d_out, void* stream);
+/* alm = sum_i multalm(z_i, w[:, i])   fields.py:420 + harmonics.py:46-47, then the m = 0
+ * fix alm = Re + Im (fields.py:425).  h_zptrs: HOST array of nterms DEVICE pointers to
+ * m-major z arrays, oldest first; d_w: [lmax+1][w_stride] float64, column i scales z_i.
+ * Operation order and rounding match NumPy (no FMA contraction): bit-exact for given z. */
+int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const double* d_w, int w_stride,
+                    double* d_alm, void* stream);
 
 /* host-buffer forms of the two transforms GLASS calls per shell: H2D, kernels, D2H on
  * `stream`, synchronous on return.  These are what a ctypes binding inside
