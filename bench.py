@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""
+bench.py -- lognormal HEALPix shells/sec at nside=4096 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = every rank draws, combines and synthesises SHELLS_PER_STEP correlated
+lognormal matter shells (nside=4096, lmax=8191, ncorr=3; the shape of BASELINE.json
+configs[3], which fits one B200) through glass_b200.generate():
+iternorm (host) -> Philox a_lm draw + banded combine -> Legendre synthesis (FP64) ->
+ring FFT with fused lognormal.  Shells are sharded across ranks (rank r takes shells
+r, r+N, ...); the path has no exchange step, so there is no data-path collective and
+scaling is weak.
+
+Printed JSON line (rank 0): value = device-resident throughput (maps stay in HBM),
+e2e = same through the public API with HOST buffers (NumPy gls in, NumPy maps out; the
+device->host copy of every map is inside the timed region), roofline = the Legendre
+kernel against the FP64 DFMA peak measured in this run, cpu_baseline = the oracle's C
+port of the path timed on the host cores (N=1 only).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSIDE, LMAX, NCORR = 4096, 8191, 3
+SHELLS_PER_STEP = 4
+METRIC = "lognormal HEALPix shells/sec at nside=4096"
+UNIT = "shells/s"
+
+
+def synthetic_gls(nshell: int, lmax: int, ncorr: int):
+    """g_l = 1e-2 (l+1)^-1.5 (g_0 = 0), cross 0.5^|i-j| g_l within ncorr."""
+    l = np.arange(lmax + 1)
+    g = 1e-2 * (l + 1.0) ** -1.5
+    g[0] = 0.0
+    gls = []
+    for i in range(nshell):
+        for j in range(i, -1, -1):
+            gls.append(0.5 ** (i - j) * g if i - j <= ncorr else np.zeros(0))
+    return gls
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # the busiest samples are the ones under load
+        sm_load = sorted(sm)[len(sm) // 3 :] if sm else []
+        return {
+            "sm_mhz": float(np.median(sm_load)) if sm_load else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port): the reference path for one lognormal shell on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> float:
+    """One shell of the reference path on the CPU: NumPy normals + banded combine +
+    l-major->m-major (glass/fields.py:404-425), C-oracle alm2map standing in for healpy
+    (glass/healpix.py:71), NumPy expm1 (grf/_transformations.py:83-89)."""
+    from oracle import glass_ref as G
+    from oracle import sht_c
+
+    gls = synthetic_gls(NCORR + 1, lmax, NCORR)
+    rng = np.random.default_rng(42)
+    n = (lmax + 1) * (lmax + 2) // 2
+    zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR + 1)]
+    t0 = time.perf_counter()
+    # the (ncorr+1)-th shell has the full set of correlated terms, like every later shell
+    z_new = rng.standard_normal((n, 2)) @ np.array([1, 1j])
+    zs[-1] = z_new
+    alm = G.generate_alms(gls, NCORR, zs)[-1]
+    # only the last shell's combine+reorder is "this shell's" work; the loop above did
+    # NCORR+1 of them, so charge 1/(NCORR+1) of that part
+    t1 = time.perf_counter()
+    m = sht_c.alm2map(alm, nside, lmax, use_mlim=True, nthreads=nthreads)
+    var = G.cltovar(gls[0])
+    m = G.lognormal(m, var, 1.0)
+    t2 = time.perf_counter()
+    return (t1 - t0) / (NCORR + 1) + (t2 - t1)
+
+
+def cpu_baseline(budget_s: float = 25.0) -> dict:
+    from oracle import sht_c
+
+    cores = sht_c.max_threads()
+    # probe at nside=512 to choose the largest sample that fits the budget (cost ~ nside^3)
+    t512 = cpu_shell_seconds(512, 1023, cores)
+    ns = 4096
+    while ns > 512 and t512 * (ns / 512) ** 3 > budget_s:
+        ns //= 2
+    t = t512 if ns == 512 else cpu_shell_seconds(ns, 2 * ns - 1, cores)
+    scale = (NSIDE / ns) ** 3
+    sample = f"1 lognormal shell (alm draw+combine, alm2map, expm1) at nside={ns} lmax={2*ns-1}: {t:.2f} s on {cores} threads"
+    if ns != NSIDE:
+        sample += f"; extrapolated to nside={NSIDE} by (nside ratio)^3 = x{scale:.0f}"
+    return {
+        "value": 1.0 / (t * scale),
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": sample,
+        "note": "C/NumPy restatement of the reference path (healpy/libsharp2 unavailable offline); scalar double loops + OpenMP over m",
+    }
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import sht_c
+
+    cores = sht_c.max_threads()
+    t512 = cpu_shell_seconds(512, 1023, cores)
+    ns = 4096
+    per_step_budget = 15.0
+    while ns > 512 and t512 * (ns / 512) ** 3 > per_step_budget:
+        ns //= 2
+    for _ in range(args.warmup):
+        cpu_shell_seconds(ns, 2 * ns - 1, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_shell_seconds(ns, 2 * ns - 1, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    scale = (NSIDE / ns) ** 3
+    value = 1.0 / (dt * scale)
+    sample = f"each step = 1 lognormal shell at nside={ns} lmax={2*ns-1} ({dt:.2f} s on {cores} threads)"
+    if ns != NSIDE:
+        sample += f", extrapolated to nside={NSIDE} by x{scale:.0f} (cost ~ nside^3)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt * scale * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"lognormal shells nside={NSIDE} lmax={LMAX} ncorr={NCORR} (CPU arm: oracle port on host cores)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import glass_b200
+    from glass_b200 import _lib
+    from glass_b200.healpix import get_plan
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    nside, lmax = args.nside, args.lmax
+    K, W, S = args.steps, args.warmup, SHELLS_PER_STEP
+    nsteps = K + W
+    nshell_total = world * S * nsteps
+    gls = synthetic_gls(nshell_total, lmax, NCORR)
+    fields = [glass_b200.grf.Lognormal(1.0)] * nshell_total
+    mine = range(rank, nshell_total, world)
+    lib = _lib.load()
+    plan = get_plan(nside, lmax, max_batch=4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(gls_in, consume, stats=None):
+        """W warm-up steps, then exactly K timed steps; returns max-over-ranks seconds."""
+        gen = glass_b200.generate(fields, gls_in, nside, ncorr=NCORR, rng=42, shells=mine, stats=stats)
+        for _ in range(W * S):
+            consume(next(gen))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K * S):
+            consume(next(gen))
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) * 1e-3
+        barrier()
+        t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gen.close()
+        return float(t[0]), float(t[1])
+
+    # ---- FP64 peak (roofline denominator), measured live ----
+    import ctypes as C
+
+    peak_tf, peak_ms = C.c_double(), C.c_double()
+    _lib.check(lib.glb_measure_fp64_peak(local, C.byref(peak_tf), C.byref(peak_ms), None), "glb_measure_fp64_peak")
+
+    # ---- device-resident arm: gls on the device -> maps stay in HBM ----
+    gls_dev = [torch.as_tensor(g).to(dev) for g in gls]
+    checksum = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def consume_dev(m):
+        checksum.add_(m[::4097].sum())  # touch the result; negligible work
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.check(lib.glb_plan_timing_enable(plan.handle, 0), "timing")
+    launches0 = None
+
+    # warm-up happens inside timed_run; enable stage timing only for the timed region by
+    # wrapping consume: switch it on at the first timed shell
+    state = {"n": 0}
+
+    def consume_dev_timed(m):
+        nonlocal launches0
+        state["n"] += 1
+        if state["n"] == W * S:  # last warm-up shell consumed: the timed region starts next
+            torch.cuda.synchronize()
+            _lib.check(lib.glb_plan_timing_enable(plan.handle, 1), "timing")
+            launches0 = int(lib.glb_kernel_launch_count())
+        consume_dev(m)
+
+    if W == 0:
+        _lib.check(lib.glb_plan_timing_enable(plan.handle, 1), "timing")
+        launches0 = int(lib.glb_kernel_launch_count())
+    dev_s, _wall = timed_run(gls_dev, consume_dev_timed)
+    launches = int(lib.glb_kernel_launch_count()) - launches0
+    ms3 = (C.c_double * 3)()
+    l3 = (C.c_int64 * 3)()
+    nm = C.c_int64()
+    _lib.check(lib.glb_plan_timing_read(plan.handle, ms3, l3, C.byref(nm)), "timing")
+    _lib.check(lib.glb_plan_timing_enable(plan.handle, 0), "timing")
+    clk = clocks.stop() if rank == 0 else None
+    value = world * K * S / dev_s
+
+    # ---- end-to-end arm: NumPy gls in, NumPy maps out (D2H inside the timed region) ----
+    stats: dict = {}
+    sink = {"x": 0.0}
+
+    def consume_host(m):
+        assert isinstance(m, np.ndarray)
+        sink["x"] += float(m[0])
+
+    _e2e_dev_s, e2e_wall = timed_run(gls, consume_host, stats)
+    e2e_value = world * K * S / e2e_wall
+    npix = 12 * nside * nside
+    h2d = (lmax + 1) * (NCORR + 1) * 8 * S  # iternorm weights of S shells (the only per-step input)
+    d2h = npix * 8 * S
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (Legendre synthesis) ----
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    ntri = nalm * 2 * nside
+    leg_launches = max(int(l3[1]), 1)
+    leg_ms = ms3[1] / leg_launches
+    maps_per_launch = nm.value / leg_launches
+    # F = 4 N_tri (1 + 1/B) per map for B maps on one recurrence
+    alg_flop = 4.0 * ntri * (1.0 + 1.0 / maps_per_launch) * maps_per_launch
+    achieved = alg_flop / (leg_ms * 1e-3) / 1e12
+    fft_ms = ms3[2] / max(int(l3[2]), 1)
+    fft_bytes = (4 * nside - 1) * (lmax + 1) * 16 * maps_per_launch + npix * 8 * maps_per_launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    total_ms = dev_s * 1e3 / K
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": K,
+        "warmup": W,
+        "ms_per_step": total_ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{S} correlated lognormal shells per rank per step, nside={nside} lmax={lmax} ncorr={NCORR}, "
+            f"synthetic power-law C_l (BASELINE.json configs[3] shape, shell-sharded over {world} rank(s))",
+            "shells_per_step_per_rank": S,
+            "l2": "inputs larger than L2 (a_lm 0.54 GB, phases 2.1 GB, map 1.6 GB per shell)",
+            "parallelism": f"shell-sharded x{world}, no data-path collective",
+        },
+        "clocks": clk,
+        "e2e": {
+            "value": e2e_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h,
+            "note": "glass_b200.generate with NumPy gls -> NumPy maps; wall clock incl. device->host copies, max over ranks",
+        },
+        "gpu_launches": launches,
+        "roofline": {
+            "kernel": "sht_legendre_synth_kernel",
+            "bound": "fp64",
+            "achieved": achieved,
+            "peak": peak_tf.value,
+            "unit": "TFLOP/s",
+            "frac": achieved / peak_tf.value,
+            "traffic": None,
+            "peak_source": "measured live in this run: register-resident DFMA chains on all SMs "
+            "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+            "algorithmic_flop_per_launch": alg_flop,
+            "maps_per_launch": maps_per_launch,
+            "ms_per_launch": leg_ms,
+            "share_of_step": ms3[1] / (dev_s * 1e3),
+        },
+        "stages_ms_per_step": {
+            "prep": ms3[0] / K,
+            "legendre": ms3[1] / K,
+            "ringfft_lognormal": ms3[2] / K,
+            "other (draw, combine, host)": total_ms - (ms3[0] + ms3[1] + ms3[2]) / K,
+        },
+        "roofline_ringfft": {
+            "kernel": "sht_ringfft_synth_kernel (3 size classes per launch group)",
+            "bound": "hbm",
+            "achieved": fft_bytes / (fft_ms * 1e-3) / 1e9,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": fft_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
+            "traffic": None,
+        },
+    }
+    if world == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as e:  # the CPU arm must not take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nside", type=int, default=NSIDE, help="development override (the metric is quoted at 4096)")
+    ap.add_argument("--lmax", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.lmax is None:
+        args.lmax = 2 * args.nside - 1
+    if args.warmup < 3 and args.impl == "b200" and args.nside == NSIDE:
+        print("note: W >= 3 warm-up steps are required for a valid number", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

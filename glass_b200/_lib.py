@@ -41,6 +41,10 @@ SIGNATURES = {
     "glb_alm_glass_to_healpix": (_i, [_i, _dp, _dp, _vp]),
     "glb_alm_combine": (_i, [_i, _i, _vp, _dp, _i, _dp, _vp]),
     "glb_alm2map_host": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
+    "glb_plan_timing_enable": (_i, [_vp, _i]),
+    "glb_plan_timing_read": (_i, [_vp, _dp, _vp, _vp]),
+    "glb_kernel_launch_count": (C.c_uint64, []),
+    "glb_measure_fp64_peak": (_i, [_i, _dp, _dp, _vp]),
     "glb_debug_alm2phase": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_debug_phase2map": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_debug_mlim": (_i, [_vp, _ip]),

@@ -97,6 +97,7 @@ int glb_alm_draw(int lmax, uint64_t seed, uint32_t shell, double* d_z, void* str
   alm_draw_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(lmax, (uint32_t)seed, (uint32_t)(seed >> 32), shell,
                                                                    reinterpret_cast<double2*>(d_z));
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 
@@ -106,6 +107,7 @@ int glb_alm_glass_to_healpix(int lmax, const double* d_in, double* d_out, void* 
   alm_glass_to_healpix_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(
       lmax, reinterpret_cast<const double2*>(d_in), reinterpret_cast<double2*>(d_out));
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 
@@ -120,6 +122,7 @@ int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const do
   alm_combine_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(lmax, nterms, a, d_w, w_stride,
                                                                       reinterpret_cast<double2*>(d_alm));
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 
@@ -128,6 +131,7 @@ int glb_almxfl(int lmax, double* d_alm, const double* d_fl, int nfl, void* strea
   GLB_REQUIRE(d_alm && d_fl && nfl >= 0, "null pointer");
   almxfl_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(lmax, d_fl, nfl, reinterpret_cast<double2*>(d_alm));
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 

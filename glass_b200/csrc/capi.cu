@@ -8,6 +8,26 @@ const std::string& last_error();
 int plan_build(glb_plan* pl);
 void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
+int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st);
+unsigned long long launch_count();
+int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
+
+// fold finished event quadruples into the per-stage totals
+static int timing_collect(glb_plan* pl) {
+  for (size_t i = 0; i + 3 < pl->ev_pool.size(); i += 4) {
+    GLB_CUDA_CHECK(cudaEventSynchronize(pl->ev_pool[i + 3]));
+    for (int s = 0; s < 3; ++s) {
+      float ms = 0.f;
+      GLB_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_pool[i + s], pl->ev_pool[i + s + 1]));
+      pl->stage_ms[s] += ms;
+      pl->stage_launches[s] += 1;
+    }
+  }
+  for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
+  pl->ev_pool.clear();
+  return GLB_OK;
+}
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* d_map, const int* kind,
                         const double* tparams, cudaStream_t st);
 
@@ -87,13 +107,27 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
   int done = 0;
   while (done < nmaps) {
     const int g = group_size(nmaps - done, plan->max_batch);
-    int rc = sht_alm2phase_group(plan, reinterpret_cast<const double2*>(d_alm) + (int64_t)done * plan->nalm, g,
-                                 plan->d_phase, st);
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (plan->timing) {
+      for (int i = 0; i < 4; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
+      GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+    }
+    int rc = sht_prep_group(plan, reinterpret_cast<const double2*>(d_alm) + (int64_t)done * plan->nalm, g, st);
     if (rc != GLB_OK) return rc;
+    if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
+    rc = sht_legendre_group(plan, g, plan->d_phase, st);
+    if (rc != GLB_OK) return rc;
+    if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[2], st));
     rc = sht_phase2map_group(plan, plan->d_phase, g, d_map + (int64_t)done * plan->npix,
                              h_transform ? h_transform + done : nullptr, h_tparams ? h_tparams + 2 * done : nullptr,
                              st);
     if (rc != GLB_OK) return rc;
+    if (plan->timing) {
+      GLB_CUDA_CHECK(cudaEventRecord(ev[3], st));
+      for (int i = 0; i < 4; ++i) plan->ev_pool.push_back(ev[i]);
+      plan->stage_maps += g;
+      if (plan->ev_pool.size() > 4096) timing_collect(plan);
+    }
     done += g;
   }
   return GLB_OK;
@@ -136,6 +170,39 @@ int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double
   GLB_CUDA_CHECK(cudaSetDevice(plan->device));
   return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_phase), nmaps, d_map, nullptr, nullptr,
                              (cudaStream_t)stream);
+}
+
+int glb_plan_timing_enable(glb_plan* plan, int enable) {
+  GLB_REQUIRE(plan != nullptr, "plan is null");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  timing_collect(plan);
+  plan->timing = enable != 0;
+  for (int s = 0; s < 3; ++s) {
+    plan->stage_ms[s] = 0.0;
+    plan->stage_launches[s] = 0;
+  }
+  plan->stage_maps = 0;
+  return GLB_OK;
+}
+
+int glb_plan_timing_read(glb_plan* plan, double* ms3, int64_t* launches3, int64_t* nmaps) {
+  GLB_REQUIRE(plan && ms3 && launches3 && nmaps, "null pointer");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const int rc = timing_collect(plan);
+  if (rc != GLB_OK) return rc;
+  for (int s = 0; s < 3; ++s) {
+    ms3[s] = plan->stage_ms[s];
+    launches3[s] = plan->stage_launches[s];
+  }
+  *nmaps = plan->stage_maps;
+  return GLB_OK;
+}
+
+uint64_t glb_kernel_launch_count(void) { return (uint64_t)glb::launch_count(); }
+
+int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream) {
+  GLB_REQUIRE(tflops && ms, "null pointer");
+  return glb::measure_fp64_peak(device, tflops, ms, (cudaStream_t)stream);
 }
 
 int glb_debug_mlim(const glb_plan* plan, int* h_mlim) {

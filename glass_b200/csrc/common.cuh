@@ -10,6 +10,7 @@
 namespace glb {
 
 void set_last_error(const std::string& s);
+void count_launch(int n = 1);  // every kernel launch of this library is counted (glb_kernel_launch_count)
 
 #define GLB_CUDA_CHECK(expr)                                                              \
   do {                                                                                    \

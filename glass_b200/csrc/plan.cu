@@ -12,6 +12,9 @@ namespace glb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 const std::string& last_error() { return g_last_error; }
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ringfft_class_of(int lbuf);
 int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::vector<int>& Ms,
@@ -260,6 +263,8 @@ void plan_free(glb_plan* pl) {
   if (pl->h_pin_out) cudaFreeHost(pl->h_pin_out);
   cudaFree(pl->d_stage_alm);
   cudaFree(pl->d_stage_map);
+  for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
+  pl->ev_pool.clear();
 }
 
 }  // namespace glb

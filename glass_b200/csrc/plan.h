@@ -65,6 +65,13 @@ struct glb_plan {
   double2* d_phase = nullptr;        // [max_batch][nring][mmax+1]
   int64_t workspace_bytes = 0;
 
+  // optional per-stage timing (CUDA events on the launch stream): prep, legendre, ringfft
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;     // recorded quadruples e0..e3 per group
+  double stage_ms[3] = {0.0, 0.0, 0.0};
+  int64_t stage_launches[3] = {0, 0, 0};
+  int64_t stage_maps = 0;               // maps transformed while timing was on
+
   // pinned host staging for the host-buffer API
   double* h_pin_in = nullptr;
   double* h_pin_out = nullptr;

@@ -371,6 +371,7 @@ static int launch_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
   const int blocks = (pl->mmax + 1 + threads - 1) / threads;
   sht_prep_kernel<B><<<blocks, threads, 0, st>>>(d_alm, pl->nalm, pl->lmax, pl->mmax, pl->d_roff, pl->d_rec);
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 
@@ -411,26 +412,38 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
     return GLB_ERR_INVALID_ARG;
   }
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 
-// alm [nb][nalm] -> phase [nb][nring][mmax+1], nb in {1,2,4}
-int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
-  int rc;
+// alm [nb][nalm] -> Legendre records, nb in {1,2,4}
+int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st) {
   switch (nb) {
-    case 1:
-      if ((rc = launch_prep<1>(pl, d_alm, st)) != GLB_OK) return rc;
-      return launch_legendre<1>(pl, d_phase, st);
-    case 2:
-      if ((rc = launch_prep<2>(pl, d_alm, st)) != GLB_OK) return rc;
-      return launch_legendre<2>(pl, d_phase, st);
-    case 4:
-      if ((rc = launch_prep<4>(pl, d_alm, st)) != GLB_OK) return rc;
-      return launch_legendre<4>(pl, d_phase, st);
+    case 1: return launch_prep<1>(pl, d_alm, st);
+    case 2: return launch_prep<2>(pl, d_alm, st);
+    case 4: return launch_prep<4>(pl, d_alm, st);
     default:
       set_last_error("internal: batch group must be 1, 2 or 4");
       return GLB_ERR_INVALID_ARG;
   }
+}
+
+// records -> phase [nb][nring][mmax+1]
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st) {
+  switch (nb) {
+    case 1: return launch_legendre<1>(pl, d_phase, st);
+    case 2: return launch_legendre<2>(pl, d_phase, st);
+    case 4: return launch_legendre<4>(pl, d_phase, st);
+    default:
+      set_last_error("internal: batch group must be 1, 2 or 4");
+      return GLB_ERR_INVALID_ARG;
+  }
+}
+
+int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
+  const int rc = sht_prep_group(pl, d_alm, nb, st);
+  if (rc != GLB_OK) return rc;
+  return sht_legendre_group(pl, nb, d_phase, st);
 }
 
 }  // namespace glb

@@ -299,6 +299,7 @@ static int launch_class(const FftParams& p, int nrings, int nb, int lb, cudaStre
   dim3 grid((unsigned)nrings, (unsigned)nb);
   sht_ringfft_synth_kernel<THREADS, NREG><<<grid, THREADS, smem, st>>>(p);
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 

@@ -179,9 +179,16 @@ def _glass_to_healpix_alm(alm):
 
 
 class _ShellSampler:
-    """Device-side state of _generate_grf: z history, iternorm weights, alm batch."""
+    """Device-side state of _generate_grf: z history, iternorm weights, alm of each shell.
 
-    def __init__(self, gls, nside, ncorr, rng, device):
+    ``wanted`` (optional predicate on the shell index) implements shell sharding across
+    GPUs: the iternorm recursion (host, tiny) still walks every shell, but normals are
+    only drawn for the shells a wanted shell is correlated with -- they are a pure
+    function of (seed, shell, index), so every rank regenerates the neighbours it needs
+    and no data is exchanged.
+    """
+
+    def __init__(self, gls, nside, ncorr, rng, device, wanted=None):
         self.lib = _lib.load()
         self.device = device
         self.nside = nside
@@ -196,40 +203,58 @@ class _ShellSampler:
         self.deviates = rng if isinstance(rng, _rng.Deviates) else None
         self.seed = _rng.seed_from(rng)
         self.witer = iternorm(cls2cov(gls, self.n, ngrf, self.ncorr))
-        self.y: collections.deque = collections.deque()
+        self.wanted = wanted
+        self.zcache: dict[int, torch.Tensor] = {}
         self.shell = 0
+        self.h2d_bytes = 0
 
-    def next_alm(self, out: torch.Tensor) -> bool:
-        """Fill ``out`` (nalm complex128, m-major) with the next shell's alm."""
-        try:
-            w = next(self.witer)
-        except StopIteration:
-            return False
+    def _z(self, j: int) -> torch.Tensor:
+        z = self.zcache.get(j)
+        if z is None:
+            lib, dev = self.lib, self.device
+            st = torch.cuda.current_stream(dev).cuda_stream
+            z = torch.empty(self.nalm, dtype=torch.complex128, device=dev)
+            if self.deviates is not None:
+                zh = np.ascontiguousarray(self.deviates.normal_alm[j], dtype=np.complex128)
+                zg = torch.as_tensor(zh).to(dev)
+                self.h2d_bytes += zh.nbytes
+                _lib.check(lib.glb_alm_glass_to_healpix(self.lmax, zg.data_ptr(), z.data_ptr(), st), "glb_alm_glass_to_healpix")
+            else:
+                _lib.check(lib.glb_alm_draw(self.lmax, C.c_uint64(self.seed), C.c_uint32(j), z.data_ptr(), st), "glb_alm_draw")
+            self.zcache[j] = z
+        return z
+
+    def next_alm(self, out: torch.Tensor):
+        """Fill ``out`` (nalm complex128, m-major) with the next wanted shell's alm
+        (glass/fields.py:404-425); returns its shell index, or None when exhausted."""
+        while True:
+            try:
+                w = next(self.witer)
+            except StopIteration:
+                return None
+            j = self.shell
+            self.shell += 1
+            if self.wanted is None or self.wanted(j):
+                break
         lib, dev = self.lib, self.device
         st = torch.cuda.current_stream(dev).cuda_stream
-        z = torch.empty(self.nalm, dtype=torch.complex128, device=dev)
-        if self.deviates is not None:
-            zg = torch.as_tensor(np.ascontiguousarray(self.deviates.next_normal_alm(), dtype=np.complex128)).to(dev)
-            _lib.check(lib.glb_alm_glass_to_healpix(self.lmax, zg.data_ptr(), z.data_ptr(), st), "glb_alm_glass_to_healpix")
-        else:
-            _lib.check(lib.glb_alm_draw(self.lmax, C.c_uint64(self.seed), C.c_uint32(self.shell), z.data_ptr(), st), "glb_alm_draw")
-        self.y.append(z)
-        while len(self.y) > w.shape[-1]:
-            self.y.popleft()
-        mis = w.shape[-1] - len(self.y)
-        nterms = len(self.y)
-        wd = torch.as_tensor(np.ascontiguousarray(w[:, mis:], dtype=np.float64)).to(dev)
-        zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in self.y])
+        nterms = min(j + 1, w.shape[-1])  # len(y) after the deque trimming of fields.py:410-414
+        mis = w.shape[-1] - nterms
+        zs = [self._z(s) for s in range(j - nterms + 1, j + 1)]
+        for s in [s for s in self.zcache if s < j - self.ncorr]:
+            del self.zcache[s]
+        wh = np.ascontiguousarray(w[:, mis:], dtype=np.float64)
+        wd = torch.as_tensor(wh).to(dev)
+        self.h2d_bytes += wh.nbytes
+        zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in zs])
         _lib.check(
             lib.glb_alm_combine(self.lmax, nterms, zptrs, wd.data_ptr(), nterms, out.data_ptr(), st),
             "glb_alm_combine",
         )
-        self._keep = (wd, zptrs)
-        self.shell += 1
-        return True
+        return j
 
 
-def _generate_maps(gls, nside, ncorr, rng, transforms_for):
+def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=None):
     """
     Core of _generate_grf / generate.  ``transforms_for(i)`` returns the fused
     (kind, p0, p1) descriptor for shell i or None for "no fused transform".
@@ -240,35 +265,46 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for):
         device = next(gl.device for gl in gls if isinstance(gl, torch.Tensor) and gl.is_cuda)
     else:
         device = torch.device("cuda", hp._device_index())
+    wanted = None
+    if shells is not None:
+        wanted = shells if callable(shells) else (lambda j, _s=frozenset(int(i) for i in shells): j in _s)
     with torch.cuda.device(device):
-        sampler = _ShellSampler(gls, nside, ncorr, rng, device)
+        sampler = _ShellSampler(gls, nside, ncorr, rng, device, wanted)
         B = max(1, min(int(SHT_BATCH), 4))
         npix = hp.nside2npix(nside)
         copy_stream = None if on_device else torch.cuda.Stream(device)
-        i0 = 0
-        pending_error = None
-        while pending_error is None:
-            alms = torch.empty((B, sampler.nalm), dtype=torch.complex128, device=device)
-            nb = 0
-            while nb < B:
-                try:
-                    if not sampler.next_alm(alms[nb]):
+        state = {"error": None}
+
+        def batches():
+            """Launch one batch (<= B shells) per iteration: alm draw/combine, batched
+            synthesis with fused transforms and, in host mode, the async D2H copies."""
+            exhausted = False
+            while state["error"] is None and not exhausted:
+                alms = torch.empty((B, sampler.nalm), dtype=torch.complex128, device=device)
+                idx = []
+                while len(idx) < B:
+                    try:
+                        j = sampler.next_alm(alms[len(idx)])
+                    except ValueError as e:  # raise only once the earlier shells were yielded
+                        state["error"] = e
                         break
-                except ValueError as e:  # raise only once the earlier shells were yielded
-                    pending_error = e
+                    if j is None:
+                        exhausted = True
+                        break
+                    idx.append(j)
+                nb = len(idx)
+                if nb == 0:
                     break
-                nb += 1
-            if nb == 0:
-                break
-            tr = [transforms_for(i0 + b) or (_lib.T_NORMAL, 0.0, 1.0) for b in range(nb)]
-            maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
-            if on_device:
-                for b in range(nb):
-                    yield i0 + b, maps[b]
-            else:
+                tr = [transforms_for(j) or (_lib.T_NORMAL, 0.0, 1.0) for j in idx]
+                maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
+                if stats is not None:
+                    stats["h2d_bytes"] = sampler.h2d_bytes
+                if on_device:
+                    yield [(idx[b], maps[b], None) for b in range(nb)]
+                    continue
                 done = torch.cuda.Event()
                 done.record(torch.cuda.current_stream(device))
-                host = []
+                out = []
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(done)
                     for b in range(nb):
@@ -276,16 +312,35 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for):
                         h.copy_(maps[b], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
-                        host.append((h, ev))
+                        out.append((idx[b], h, ev))
                 maps.record_stream(copy_stream)
-                for b, (h, ev) in enumerate(host):
+                yield out
+
+        def drain(batch):
+            for j, m, ev in batch:
+                if ev is None:
+                    yield j, m
+                else:
                     ev.synchronize()
-                    yield i0 + b, h.numpy()
-            i0 += nb
-            if nb < B:
-                break
-        if pending_error is not None:
-            raise pending_error
+                    if stats is not None:
+                        stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + m.numel() * 8
+                    yield j, m.numpy()
+
+        if on_device:
+            for batch in batches():
+                yield from drain(batch)
+        else:
+            # one batch of look-ahead: the next batch's kernels are queued before the
+            # previous batch's device->host copies are waited for, so they overlap
+            prev = None
+            for batch in batches():
+                if prev is not None:
+                    yield from drain(prev)
+                prev = batch
+            if prev is not None:
+                yield from drain(prev)
+        if state["error"] is not None:
+            raise state["error"]
 
 
 def _generate_grf(gls, nside: int, *, ncorr: int | None = None, rng=None):
@@ -294,9 +349,14 @@ def _generate_grf(gls, nside: int, *, ncorr: int | None = None, rng=None):
         yield m
 
 
-def generate(fields: Sequence, gls, nside: int, *, ncorr: int | None = None, rng=None) -> Iterator:
+def generate(fields: Sequence, gls, nside: int, *, ncorr: int | None = None, rng=None, shells=None, stats=None) -> Iterator:
     """
     Sample random fields from Gaussian angular power spectra (glass/fields.py:839-894).
+
+    Extension over the reference signature (keyword-only, default = reference behaviour):
+    ``shells`` -- iterable of shell indices (or predicate) to produce; the others are
+    skipped.  This is the multi-GPU sharding of the path: rank r of W passes
+    ``shells=range(r, n, W)`` and no data is exchanged between ranks.
     """
     n = len(fields)
     if len(gls) != n * (n + 1) // 2:
@@ -315,7 +375,7 @@ def generate(fields: Sequence, gls, nside: int, *, ncorr: int | None = None, rng
             return None
         return grf.fused_descriptor(fields[i], var_of(i))
 
-    for i, x in _generate_maps(gls, nside, ncorr, rng, transforms_for):
+    for i, x in _generate_maps(gls, nside, ncorr, rng, transforms_for, shells, stats):
         if i >= n:
             break
         t = fields[i]

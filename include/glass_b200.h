@@ -107,6 +107,17 @@ int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const do
 int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map,
                      const int* h_transform, const double* h_tparams, void* stream);
 
+/* ---- measurement hooks (bench.py) --------------------------------------------------- */
+/* Per-stage device time of glb_alm2map, from CUDA events recorded on the launch stream:
+ * ms3 / launches3 = {prep, Legendre, ring FFT}; nmaps = maps transformed since enable. */
+int glb_plan_timing_enable(glb_plan* plan, int enable);
+int glb_plan_timing_read(glb_plan* plan, double* ms3, int64_t* launches3, int64_t* nmaps);
+/* number of kernels this library has launched in this process */
+uint64_t glb_kernel_launch_count(void);
+/* FP64 roofline denominator: register-resident DFMA chains on every SM, timed with CUDA
+ * events (MEASURED_PEAKS.json has no FP64 entry). */
+int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream);
+
 /* ---- debug / test taps (stable, used by tests/ only) --------------------------------- */
 /* Legendre stage only: alm -> phase array F_m(ring), [nmaps][nring][lmax+1] complex128 */
 int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase,

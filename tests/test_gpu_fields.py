@@ -48,10 +48,10 @@ def test_alm_bit_exact_with_supplied_z(cuda_device, nshell, lmax, ncorr, ragged)
     s = _ShellSampler(gls, 8, ncorr, Deviates(normal_alm=zs), cuda_device)
     for j in range(nshell):
         out = torch.empty(s.nalm, dtype=torch.complex128, device=cuda_device)
-        assert s.next_alm(out)
+        assert s.next_alm(out) == j
         got = out.cpu().numpy()
         assert np.array_equal(got, ref[j]), (j, np.abs(got - ref[j]).max())
-    assert not s.next_alm(out)
+    assert s.next_alm(out) is None
 
 
 @pytest.mark.parametrize("nside,lmax,nshell,ncorr", [(16, 32, 5, 2), (32, 64, 6, 3), (8, 23, 3, None)])
@@ -143,3 +143,19 @@ def test_philox_normals_statistics(cuda_device):
     assert stats.kstest(zz.real, "norm").pvalue > 1e-4
     assert stats.kstest(zz.imag, "norm").pvalue > 1e-4
     assert abs(np.corrcoef(zz.real, zz.imag)[0, 1]) < 5 / np.sqrt(n)
+
+
+def test_generate_shell_sharding(cuda_device):
+    """rank r of W produces shells r::W; the union equals the unsharded run exactly."""
+    import glass_b200
+
+    nside, lmax, nshell, ncorr = 16, 32, 7, 2
+    gls = synthetic_gls(nshell, lmax, ncorr)
+    fields = [glass_b200.grf.Lognormal()] * nshell
+    full = list(glass_b200.generate(fields, gls, nside, ncorr=ncorr, rng=11))
+    for world in (2, 3):
+        for rank in range(world):
+            mine = list(glass_b200.generate(fields, gls, nside, ncorr=ncorr, rng=11, shells=range(rank, nshell, world)))
+            assert len(mine) == len(range(rank, nshell, world))
+            for k, j in enumerate(range(rank, nshell, world)):
+                assert np.array_equal(mine[k], full[j])
