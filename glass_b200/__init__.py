@@ -8,7 +8,7 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import fields, grf, harmonics, healpix, rng  # noqa: F401
+from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, shells  # noqa: F401
 from .fields import (  # noqa: F401
     cls2cov,
     gaussian_fields,
@@ -20,6 +20,11 @@ from .fields import (  # noqa: F401
     lognormal_fields,
     nfields_from_nspectra,
 )
+from .galaxies import galaxy_shear, redshifts, redshifts_from_nz  # noqa: F401
 from .harmonics import multalm  # noqa: F401
+from .lensing import MultiPlaneConvergence, multi_plane_matrix, multi_plane_weights  # noqa: F401
+from .points import linear_bias, loglinear_bias, positions_from_delta  # noqa: F401
+from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
+from .shells import RadialWindow  # noqa: F401
 
 __version__ = "0.1.0"

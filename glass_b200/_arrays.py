@@ -1,0 +1,61 @@
+"""Array plumbing shared by the host-side mirrors: NumPy <-> CUDA tensor conversion and the
+leading-axes broadcasting rule of ``glass/arraytools.py:47-110``."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import healpix as hp
+
+
+def is_cuda(x) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def pick_device(*arrays) -> tuple[torch.device, bool]:
+    """(device, on_device): on_device is True when any input is a CUDA tensor."""
+    for a in arrays:
+        if is_cuda(a):
+            return a.device, True
+    return torch.device("cuda", hp._device_index()), False
+
+
+def to_dev(x, device, dtype=torch.float64) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
+
+
+def to_np(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def shape_of(x) -> tuple[int, ...]:
+    return tuple(x.shape) if hasattr(x, "shape") else ()
+
+
+def broadcast_leading_axes(*args):
+    """glass/arraytools.py:47-110: broadcast all but the last ``n`` axes of each input.
+    Returns (dims, *trailing shapes); the arrays themselves are indexed lazily with
+    :func:`take_leading` so nothing full-size is materialised."""
+    shapes, trails = [], []
+    for a, n in args:
+        s = shape_of(a)
+        i = len(s) - n
+        shapes.append(s[:i])
+        trails.append(s[i:])
+    dims = tuple(np.broadcast_shapes(*shapes))
+    return dims, shapes, trails
+
+
+def take_leading(a, lead_shape, dims, k):
+    """Element k (index tuple over ``dims``) of ``a`` whose leading axes ``lead_shape``
+    broadcast to ``dims``."""
+    if not lead_shape:
+        return a
+    off = len(dims) - len(lead_shape)
+    idx = tuple(0 if lead_shape[i] == 1 else k[off + i] for i in range(len(lead_shape)))
+    return a[idx]

@@ -40,6 +40,16 @@ SIGNATURES = {
     "glb_alm_draw": (_i, [_i, C.c_uint64, C.c_uint32, _dp, _vp]),
     "glb_alm_glass_to_healpix": (_i, [_i, _dp, _dp, _vp]),
     "glb_alm_combine": (_i, [_i, _i, _vp, _dp, _i, _dp, _vp]),
+    "glb_points_workspace_bytes": (C.c_size_t, [_i64]),
+    "glb_points_counts": (_i, [_i64, _dp, _dp, _i, C.c_double, C.c_double, _i, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp, _vp]),
+    "glb_points_fill": (_i, [_i64, _dp, _dp, _i64, _i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp]),
+    "glb_ring2ang_uv": (_i, [_i64, _dp, _dp, _dp, _i64, _i, _dp, _dp, _vp]),
+    "glb_randang": (_i, [_i64, _dp, _i64, C.c_uint64, C.c_uint32, _i, _dp, _dp, _vp]),
+    "glb_ang2pix": (_i, [_i64, _dp, _dp, _i64, _i, _dp, _vp]),
+    "glb_multiplane_update": (_i, [_dp, _dp, _dp, C.c_double, _i64, C.c_double, C.c_double, _vp]),
+    "glb_galaxy_shear": (_i, [_i64, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _i, _dp, _vp]),
+    "glb_ellipticity": (_i, [_i, C.c_double, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
+    "glb_redshifts_from_cdf": (_i, [_dp, _dp, _i, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_alm2map_host": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_plan_timing_enable": (_i, [_vp, _i]),
     "glb_plan_timing_read": (_i, [_vp, _dp, _vp, _vp]),

@@ -1,0 +1,118 @@
+"""
+glass_b200.galaxies -- B200-native mirror of the hot-path part of ``glass/galaxies.py``:
+``galaxy_shear``, ``redshifts`` / ``redshifts_from_nz``.
+
+``galaxy_shear`` replaces the Python loop over 10 000-galaxy chunks (glass/galaxies.py:330-335)
+by one kernel doing the pixel lookup, the three map gathers and the reduced-shear formula.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import warnings
+
+import numpy as np
+import torch
+
+from . import _arrays as A
+from . import _lib
+from . import healpix as hp
+from . import rng as _rng
+
+_CALLS = itertools.count()  # distinct Philox stream per call, in call order
+
+
+def _cumulative_trapezoid(f, x):
+    """glass/arraytools.py:197-226."""
+    f = np.asarray(f, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    return np.concatenate([np.zeros(f.shape[:-1] + (1,)), np.cumsum((f[..., 1:] + f[..., :-1]) * 0.5 * np.diff(x), axis=-1)], axis=-1)
+
+
+def redshifts(n, w, *, rng=None):
+    """Sample redshifts from a radial window function (glass/galaxies.py:92-119)."""
+    return redshifts_from_nz(n, w.za, w.wa, rng=rng, warn=False)
+
+
+def redshifts_from_nz(count, z, nz, *, rng=None, warn: bool = True):
+    """
+    Generate galaxy redshifts from a source distribution (glass/galaxies.py:188-268):
+    inverse-CDF sampling ``interp(U, cdf, z)`` per population (glass/galaxies.py:77-89).
+    Returns a CUDA tensor when ``z``/``nz`` are CUDA tensors, else a NumPy array.
+    """
+    if warn:
+        warnings.warn(
+            "when sampling galaxies, redshifts_from_nz() is often not the function you"
+            " want. Try redshifts() instead. Use warn=False to suppress this warning.",
+            stacklevel=2,
+        )
+    device, on_device = A.pick_device(z, nz, count)
+    deviates = rng if isinstance(rng, _rng.Deviates) else None
+    seed = _rng.seed_from(rng)
+    zh, nzh, ch = A.to_np(z), A.to_np(nz), A.to_np(count)
+    dims = np.broadcast_shapes(ch.shape, zh.shape[:-1], nzh.shape[:-1])
+    count_out = np.broadcast_to(ch, dims)
+    z_out = np.broadcast_to(zh, dims + zh.shape[-1:])
+    nz_out = np.broadcast_to(nzh, dims + nzh.shape[-1:])
+    total = int(np.sum(count_out))
+    out = torch.empty(total, dtype=torch.float64, device=device)
+    lib = _lib.load()
+    call = next(_CALLS)
+    pos = 0
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        for k in np.ndindex(*dims):
+            n_k = int(count_out[k])
+            if n_k == 0:
+                continue
+            cdf = _cumulative_trapezoid(nz_out[k], z_out[k])
+            cdf /= cdf[-1]
+            d_cdf = A.to_dev(cdf, device)
+            d_z = A.to_dev(z_out[k], device)
+            u = None
+            if deviates is not None and deviates.uniform is not None:
+                u = A.to_dev(deviates.uniform(n_k) if callable(deviates.uniform) else deviates.uniform[pos : pos + n_k], device)
+            _lib.check(
+                lib.glb_redshifts_from_cdf(
+                    d_cdf.data_ptr(), d_z.data_ptr(), int(cdf.shape[0]), None if u is None else u.data_ptr(), n_k,
+                    C.c_uint64(seed), C.c_uint32(call & 0xFFFFFFFF), C.c_uint64(pos), out[pos:].data_ptr(), st,
+                ),
+                "glb_redshifts_from_cdf",
+            )
+            pos += n_k
+    return out if on_device else out.cpu().numpy()
+
+
+def galaxy_shear(lon, lat, eps, kappa, gamma1, gamma2, *, reduced_shear: bool = True, ipix=None):
+    """
+    Observed galaxy shears from weak lensing (glass/galaxies.py:271-347).
+
+    ``ipix`` (extension, optional): ring pixel index of every galaxy if already known
+    (e.g. from the position sampler); skips the ang2pix lookup.
+    """
+    device, on_device = A.pick_device(lon, lat, eps, kappa, gamma1, gamma2)
+    k = A.to_dev(kappa, device)
+    g1 = A.to_dev(gamma1, device)
+    g2 = A.to_dev(gamma2, device)
+    npix = max(k.shape[-1], g1.shape[-1], g2.shape[-1])
+    nside = hp.npix2nside(npix)
+    k, g1, g2 = (t.expand(npix).contiguous() if t.numel() != npix else t.reshape(npix) for t in (k, g1, g2))
+    lon_d, lat_d = A.to_dev(lon, device), A.to_dev(lat, device)
+    eps_d = A.to_dev(eps, device, torch.complex128)
+    lon_d, lat_d, eps_d = torch.broadcast_tensors(lon_d, lat_d, eps_d)
+    lon_d, lat_d, eps_d = lon_d.contiguous().reshape(-1), lat_d.contiguous().reshape(-1), eps_d.contiguous().reshape(-1)
+    n = eps_d.numel()
+    out = torch.empty(n, dtype=torch.complex128, device=device)
+    ip = None if ipix is None else A.to_dev(ipix, device, torch.int64)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(
+            lib.glb_galaxy_shear(
+                nside, lon_d.data_ptr(), lat_d.data_ptr(), None if ip is None else ip.data_ptr(), eps_d.data_ptr(), n,
+                k.data_ptr(), g1.data_ptr(), g2.data_ptr(), int(bool(reduced_shear)), out.data_ptr(), st,
+            ),
+            "glb_galaxy_shear",
+        )
+    return out if on_device else out.cpu().numpy()

@@ -168,3 +168,98 @@ def alm2map(
         res = maps.cpu().numpy()
         return res[0] if single else [res[i] for i in range(len(seq))]
     return maps[0] if single else [maps[i] for i in range(len(seq))]
+
+
+# --------------------------------------------------------------------------------------
+# pixel <-> angle, alm scaling
+# --------------------------------------------------------------------------------------
+
+
+def _dev_and_kind(*arrays):
+    for a in arrays:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device, True
+    return torch.device("cuda", _device_index()), False
+
+
+def _to(x, device, dtype):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
+
+
+def _out(t, on_device):
+    return t if on_device else t.cpu().numpy()
+
+
+def ring2ang_uv(nside: int, ipix, u, v, *, lonlat: bool = False):
+    """Position inside ring pixel ``ipix`` at in-pixel offsets (u, v) in [0,1)^2: the
+    kernel behind ``healpix.randang`` (glass/healpix.py:426-431), (u, v) = (1/2, 1/2) is
+    the pixel centre."""
+    dev, on_device = _dev_and_kind(ipix, u, v)
+    ip = _to(ipix, dev, torch.int64)
+    shape = ip.shape
+    ip = ip.reshape(-1)
+    uu = _to(u, dev, torch.float64).expand(shape).contiguous().reshape(-1)
+    vv = _to(v, dev, torch.float64).expand(shape).contiguous().reshape(-1)
+    o1 = torch.empty(ip.numel(), dtype=torch.float64, device=dev)
+    o2 = torch.empty_like(o1)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.glb_ring2ang_uv(int(nside), ip.data_ptr(), uu.data_ptr(), vv.data_ptr(), ip.numel(), int(lonlat), o1.data_ptr(), o2.data_ptr(), st), "glb_ring2ang_uv")
+    return _out(o1.reshape(shape), on_device), _out(o2.reshape(shape), on_device)
+
+
+def randang(nside: int, ipix, *, lonlat: bool = False):
+    """Sample random spherical coordinates from the given HEALPix pixels
+    (glass/healpix.py:398-432).  Like the reference, every call uses the same seed-42
+    stream (glass/healpix.py:430)."""
+    dev, on_device = _dev_and_kind(ipix)
+    ip = _to(ipix, dev, torch.int64)
+    shape = ip.shape
+    ip = ip.reshape(-1)
+    o1 = torch.empty(ip.numel(), dtype=torch.float64, device=dev)
+    o2 = torch.empty_like(o1)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.glb_randang(int(nside), ip.data_ptr(), ip.numel(), C.c_uint64(42), C.c_uint32(0), int(lonlat), o1.data_ptr(), o2.data_ptr(), st), "glb_randang")
+    return _out(o1.reshape(shape), on_device), _out(o2.reshape(shape), on_device)
+
+
+def ang2pix(nside: int, theta, phi, *, lonlat: bool = False):
+    """Angles to RING pixel indices (glass/healpix.py:144-178)."""
+    dev, on_device = _dev_and_kind(theta, phi)
+    a = _to(theta, dev, torch.float64)
+    b = _to(phi, dev, torch.float64)
+    a, b = torch.broadcast_tensors(a, b)
+    shape = a.shape
+    a, b = a.contiguous().reshape(-1), b.contiguous().reshape(-1)
+    out = torch.empty(a.numel(), dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.glb_ang2pix(int(nside), a.data_ptr(), b.data_ptr(), a.numel(), int(lonlat), out.data_ptr(), st), "glb_ang2pix")
+    return _out(out.reshape(shape), on_device)
+
+
+def almxfl(alm, fl, *, inplace: bool = False):
+    """Multiply alm by a function of l, zero where not defined (glass/healpix.py:111-140)."""
+    dev, on_device = _dev_and_kind(alm)
+    a = _to(alm, dev, torch.complex128)
+    if not (inplace and on_device and a.data_ptr() == alm.data_ptr()):
+        a = a.clone()
+    f = _to(fl, dev, torch.float64)
+    lmax = alm_getlmax(a.numel())
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.glb_almxfl(lmax, a.data_ptr(), f.data_ptr(), f.numel(), st), "glb_almxfl")
+    if on_device:
+        return a
+    res = a.cpu().numpy()
+    if inplace and isinstance(alm, np.ndarray):
+        alm[...] = res
+        return alm
+    return res

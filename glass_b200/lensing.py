@@ -1,0 +1,149 @@
+"""
+glass_b200.lensing -- B200-native mirror of the hot-path part of ``glass/lensing.py``:
+``MultiPlaneConvergence``, ``from_convergence``, ``shear_from_convergence``,
+``multi_plane_matrix`` and ``multi_plane_weights``.
+
+The multi-plane recurrence (glass/lensing.py:584-586) is one fused kernel instead of three
+full-map NumPy passes; the kappa -> (psi, alpha, gamma) conversions run the forward and
+spin-weighted transforms of libglassb200 instead of healpy (glass/healpix.py:107,270).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _arrays as A
+from . import _lib
+from . import healpix as hp
+
+
+class MultiPlaneConvergence:
+    """Compute convergence fields iteratively from multiple matter planes
+    (glass/lensing.py:431-606).  Same state machine, properties and error behaviour; the
+    convergence planes live on the GPU and ``kappa`` is returned in the array kind of the
+    ``delta`` that was added (CUDA tensor -> the internal buffer, which like the
+    reference's is recycled two calls later; NumPy -> a host copy)."""
+
+    def __init__(self, cosmo) -> None:
+        self.cosmo = cosmo
+        self.z2 = 0.0
+        self.z3 = 0.0
+        self.x3 = 0.0
+        self.w3 = 0.0
+        self.r23 = 1.0
+        self.delta3 = None
+        self.kappa2 = None
+        self.kappa3 = None
+        self._host = False
+
+    def add_window(self, delta, w) -> None:
+        """Add a mass plane from a window function (glass/lensing.py:489-509)."""
+        zsrc = w.zeff
+        za, wa = A.to_np(w.za), A.to_np(w.wa)
+        lens_weight = float(np.trapezoid(wa, za) / np.interp(zsrc, za, wa))
+        self.add_plane(delta, zsrc, lens_weight)
+
+    def add_plane(self, delta, zsrc, wlens: float = 1.0) -> None:
+        """Add a mass plane at redshift ``zsrc`` (glass/lensing.py:511-586)."""
+        if zsrc <= self.z3:
+            msg = "source redshift must be increasing"
+            raise ValueError(msg)
+        device, on_device = A.pick_device(delta)
+        self._host = not on_device
+        delta_d = A.to_dev(delta, device)
+
+        # cycle mass plane, redshifts and weights (lensing.py:544-549)
+        delta2, self.delta3 = self.delta3, delta_d
+        z1, self.z2, self.z3 = self.z2, self.z3, zsrc
+        w2, self.w3 = self.w3, wlens
+
+        # extrapolation law (lensing.py:551-563): five scalar cosmology calls on the host
+        x2, self.x3 = (
+            self.x3,
+            self.cosmo.transverse_comoving_distance(self.z3) / self.cosmo.hubble_distance,
+        )
+        r12 = self.r23
+        r13, self.r23 = np.asarray(
+            self.cosmo.transverse_comoving_distance([z1, self.z2], self.z3)
+        ) / (self.cosmo.hubble_distance * self.x3)
+        t = r13 / r12
+
+        # lensing weight of mass plane to be added (lensing.py:565-569)
+        f = 3 * self.cosmo.Omega_m0 / 2
+        f *= x2 * self.r23
+        f *= (1 + self.z2) / self.cosmo.H_over_H0(self.z2)
+        f *= w2
+
+        if self.kappa2 is None:
+            self.kappa2 = torch.zeros_like(delta_d)
+            self.kappa3 = torch.zeros_like(delta_d)
+
+        # cycle convergence planes and update in place of the oldest (lensing.py:580-586)
+        self.kappa2, self.kappa3 = self.kappa3, self.kappa2
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(
+                lib.glb_multiplane_update(
+                    self.kappa3.data_ptr(),
+                    self.kappa2.data_ptr(),
+                    None if delta2 is None else delta2.data_ptr(),
+                    0.0,
+                    self.kappa3.numel(),
+                    float(t),
+                    float(f),
+                    st,
+                ),
+                "glb_multiplane_update",
+            )
+
+    @property
+    def zsrc(self):
+        """The redshift of the current convergence plane."""
+        return self.z3
+
+    @property
+    def kappa(self):
+        """The current convergence plane."""
+        if self.kappa3 is None:
+            return None
+        return self.kappa3.cpu().numpy() if self._host else self.kappa3
+
+    @property
+    def delta(self):
+        """The current matter plane."""
+        if self.delta3 is None:
+            return None
+        return self.delta3.cpu().numpy() if self._host else self.delta3
+
+    @property
+    def wlens(self) -> float:
+        """The weight of the current matter plane."""
+        return self.w3
+
+
+def multi_plane_matrix(shells, cosmo):
+    """Compute the matrix of lensing contributions from each shell
+    (glass/lensing.py:609-635): row i = kappa after adding shells 0..i, for unit deltas."""
+    mpc = MultiPlaneConvergence(cosmo)
+    n = len(shells)
+    device = torch.device("cuda", hp._device_index())
+    wmat = torch.eye(n, dtype=torch.float64, device=device)
+    rows = []
+    for i, w in enumerate(shells):
+        mpc.add_window(wmat[i].clone(), w)
+        rows.append(mpc.kappa.clone())
+    return torch.stack(rows).cpu().numpy()
+
+
+def multi_plane_weights(weights, shells, cosmo):
+    """Compute effective weights for multi-plane convergence (glass/lensing.py:638-684)."""
+    weights = A.to_np(weights)
+    shape = weights.shape
+    if not shape or shape[0] != len(shells):
+        msg = "shape mismatch between weights and shells"
+        raise ValueError(msg)
+    weights = weights / np.sum(weights, axis=0)
+    mat = multi_plane_matrix(shells, cosmo)
+    return np.matmul(mat.T, weights)

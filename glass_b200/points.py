@@ -1,0 +1,210 @@
+"""
+glass_b200.points -- B200-native mirror of the hot-path part of ``glass/points.py``:
+``positions_from_delta`` with its helpers and the two built-in bias models.
+
+The reference walks the map in 1000-pixel steps in a Python loop, repeats pixel indices
+with ``np.repeat`` and calls ``healpix.randang`` per batch (glass/points.py:389-440).  Here
+one fused kernel makes the per-pixel Poisson counts, a scan turns them into offsets, and one
+kernel writes every galaxy's position; the generator then hands out slices that follow the
+reference's batch-cut rule exactly (greedy pixel-aligned batches of at most ``batch``
+points, "first pixel alone" rule, points.py:409-424).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from typing import Callable
+
+import numpy as np
+import torch
+
+from . import _arrays as A
+from . import _lib
+from . import healpix as hp
+from . import rng as _rng
+
+ARCMIN2_SPHERE = 60**6 // 100 / math.pi  # glass/points.py:72
+
+
+def linear_bias(delta, b):
+    r"""Linear bias model :math:`\delta_g = b \, \delta` (glass/points.py:115-134)."""
+    return b * delta
+
+
+def loglinear_bias(delta, b):
+    r"""Log-linear bias model :math:`\ln(1+\delta_g) = b \ln(1+\delta)` (glass/points.py:137-160)."""
+    if isinstance(delta, torch.Tensor):
+        return torch.expm1(torch.log1p(delta) * b)
+    delta_g = np.log1p(delta)
+    delta_g *= b
+    return np.expm1(delta_g)
+
+
+_BIAS_NONE, _BIAS_LINEAR, _BIAS_LOGLINEAR = 0, 1, 2
+
+
+def _bias_code(bias, bias_model):
+    """(kernel code, needs_prepass): built-in models are fused; any other callable is
+    applied as a separate pass on the device tensor (glass/points.py:243-249)."""
+    if bias is None:
+        return _BIAS_NONE, False
+    name = getattr(bias_model, "__name__", "")
+    mod = getattr(bias_model, "__module__", "") or ""
+    if bias_model is linear_bias or (name == "linear_bias" and mod.startswith("glass")):
+        return _BIAS_LINEAR, False
+    if bias_model is loglinear_bias or (name == "loglinear_bias" and mod.startswith("glass")):
+        return _BIAS_LOGLINEAR, False
+    return _BIAS_NONE, True
+
+
+class _Population:
+    """Counts, offsets and positions of one population on the device."""
+
+    def __init__(self, delta_k, vis_k, ngal_k, bias_k, bias_model, remove_monopole, seed, stream_id, counts_in, device, want_nbar=False):
+        lib = _lib.load()
+        self.lib, self.device = lib, device
+        code, prepass = _bias_code(bias_k, bias_model)
+        d = A.to_dev(delta_k, device)
+        if prepass:
+            d = A.to_dev(bias_model(d, bias_k), device)
+        self.npix = d.numel()
+        self.nside = hp.npix2nside(self.npix)
+        v = None if vis_k is None else A.to_dev(vis_k, device)
+        scale = ARCMIN2_SPHERE / self.npix * float(ngal_k)  # same order as points.py:287
+        self.counts = torch.empty(self.npix, dtype=torch.int64, device=device)
+        self.off = torch.empty(self.npix + 1, dtype=torch.int64, device=device)
+        self.nbar = torch.empty(self.npix, dtype=torch.float64, device=device) if want_nbar else None
+        ws = torch.empty(int(lib.glb_points_workspace_bytes(self.npix)), dtype=torch.uint8, device=device)
+        cin = None if counts_in is None else A.to_dev(counts_in, device, torch.int64)
+        st = torch.cuda.current_stream(device).cuda_stream
+        self.seed, self.stream_id = seed, stream_id
+        _lib.check(
+            lib.glb_points_counts(
+                self.npix,
+                d.data_ptr(),
+                None if v is None else v.data_ptr(),
+                code,
+                float(bias_k) if (bias_k is not None and not prepass) else 0.0,
+                scale,
+                int(bool(remove_monopole)),
+                None if cin is None else cin.data_ptr(),
+                C.c_uint64(seed),
+                C.c_uint32(stream_id),
+                None if self.nbar is None else self.nbar.data_ptr(),
+                self.counts.data_ptr(),
+                self.off.data_ptr(),
+                ws.data_ptr(),
+                st,
+            ),
+            "glb_points_counts",
+        )
+        self.total = int(self.off[-1].item())
+
+    def cuts(self, batch: int):
+        """Pixel ranges (start, stop, npoints) of glass/points.py:409-437."""
+        start, remaining = 0, self.total
+        off = self.off
+        while remaining > 0:
+            base = int(off[start].item())
+            # largest stop with off[stop] - base <= batch
+            stop = int(torch.searchsorted(off, torch.tensor(base + batch, device=off.device), right=True).item()) - 1
+            stop = min(stop, self.npix)
+            if stop <= start:
+                stop = start + 1  # the first pixel alone is too much: use it anyway
+            n = int(off[stop].item()) - base
+            if n > 0:
+                yield start, stop, n
+            start = stop
+            remaining -= n
+
+    def fill(self, start: int, stop: int, n: int, uv=None, want_ipix=False):
+        lon = torch.empty(n, dtype=torch.float64, device=self.device)
+        lat = torch.empty(n, dtype=torch.float64, device=self.device)
+        ipix = torch.empty(n, dtype=torch.int64, device=self.device) if want_ipix else None
+        u = v = None
+        if uv is not None:
+            uu, vv = uv(n) if callable(uv) else uv
+            u, v = A.to_dev(uu, self.device), A.to_dev(vv, self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(
+            self.lib.glb_points_fill(
+                self.nside,
+                self.counts.data_ptr(),
+                self.off.data_ptr(),
+                start,
+                stop,
+                None if u is None else u.data_ptr(),
+                None if v is None else v.data_ptr(),
+                C.c_uint64(self.seed),
+                C.c_uint32(self.stream_id),
+                lon.data_ptr(),
+                lat.data_ptr(),
+                None if ipix is None else ipix.data_ptr(),
+                st,
+            ),
+            "glb_points_fill",
+        )
+        return lon, lat, ipix
+
+
+def positions_from_delta(  # noqa: PLR0913
+    ngal,
+    delta,
+    bias=None,
+    vis=None,
+    *,
+    bias_model: Callable = linear_bias,
+    remove_monopole: bool = False,
+    batch: int = 1_000_000,
+    rng=None,
+):
+    """
+    Generate positions tracing a density contrast (glass/points.py:443-540).
+
+    Yields ``(lon, lat, count)`` batches: longitudes/latitudes in degrees and the number
+    of points (an int, or an int64 array of shape ``dims`` with the count in the
+    population's slot when the inputs have leading "population" axes).  Arrays are CUDA
+    tensors when ``delta`` (or ``vis``) is a CUDA tensor, NumPy arrays otherwise.
+    """
+    if not callable(bias_model):
+        raise TypeError("bias_model must be callable")
+
+    device, on_device = A.pick_device(delta, vis, ngal, bias)
+    deviates = rng if isinstance(rng, _rng.Deviates) else None
+    seed = _rng.seed_from(rng)
+
+    inputs = [(ngal, 0), (delta, 1)]
+    if bias is not None:
+        inputs.append((bias, 0))
+    if vis is not None:
+        inputs.append((vis, 1))
+    dims, leads, _trails = A.broadcast_leading_axes(*inputs)
+    lead = dict(zip(["ngal", "delta"] + (["bias"] if bias is not None else []) + (["vis"] if vis is not None else []), leads))
+
+    with torch.cuda.device(device):
+        for ipop, k in enumerate(itertools.product(*map(range, dims))):
+            delta_k = A.take_leading(delta, lead["delta"], dims, k)
+            ngal_k = A.take_leading(ngal, lead["ngal"], dims, k) if lead["ngal"] else ngal
+            bias_k = None if bias is None else (A.take_leading(bias, lead["bias"], dims, k) if lead["bias"] else bias)
+            vis_k = None if vis is None else A.take_leading(vis, lead["vis"], dims, k)
+            counts_in = deviates.next_poisson() if (deviates is not None and deviates.poisson is not None) else None
+            pop = _Population(
+                delta_k, vis_k, float(A.to_np(ngal_k)), None if bias_k is None else float(A.to_np(bias_k)),
+                bias_model, remove_monopole, seed, ipop, counts_in, device,
+            )
+            if pop.total == 0:
+                continue
+            if dims:
+                cmask = np.zeros(dims, dtype=np.int64)
+                cmask[k] = 1
+            else:
+                cmask = 1
+            uv = deviates.uv if deviates is not None else None
+            for start, stop, n in pop.cuts(batch):
+                lon, lat, _ = pop.fill(start, stop, n, uv)
+                if on_device:
+                    yield lon, lat, n * cmask
+                else:
+                    yield lon.cpu().numpy(), lat.cpu().numpy(), n * cmask

@@ -101,6 +101,64 @@ int glb_alm_glass_to_healpix(int lmax, const double* d_in, double* d_out, void* 
 int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const double* d_w, int w_stride,
                     double* d_alm, void* stream);
 
+/* ---- galaxy counts and positions (glass/points.py:520-540) --------------------------- */
+/* bytes of scratch glb_points_counts needs for a map of npix pixels */
+size_t glb_points_workspace_bytes(int64_t npix);
+/* One population: biased density -> expected count -> Poisson count per pixel, plus the
+ * exclusive prefix sum of the counts.  Replaces _compute_density_contrast (points.py:243-249;
+ * bias_model 0 = none/copy, 1 = linear_bias :134, 2 = loglinear_bias :157-160),
+ * _compute_expected_count (:279-288; scale = ARCMIN2_SPHERE/npix*ngal computed by the caller,
+ * remove_monopole subtracts the map mean), _apply_visibility (:314-316; d_vis may be NULL) and
+ * _sample_number_galaxies (:340-348; Philox Poisson keyed by (seed, stream_id, pixel), or, in
+ * parity mode, d_counts_in supplies the deviates).  Outputs: d_counts [npix] int64,
+ * d_off [npix+1] int64 (d_off[p] = galaxies before pixel p, d_off[npix] = total) and,
+ * if not NULL, d_nbar_out [npix] = expected counts before clipping. */
+int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, int bias_model, double bias,
+                      double scale, int remove_monopole, const int64_t* d_counts_in, uint64_t seed,
+                      uint32_t stream_id, double* d_nbar_out, int64_t* d_counts, int64_t* d_off,
+                      void* d_workspace, void* stream);
+/* Positions of every galaxy in ring pixels [pix0, pix1): ipix = repeat(arange, n) (points.py:426)
+ * and healpix.randang(nside, ipix, lonlat=True) (points.py:427 -> glass/healpix.py:426-431),
+ * written at index d_off[p] - d_off[pix0] + i.  (u, v) in-pixel offsets: Philox keyed by
+ * (seed, stream_id, global galaxy index) or supplied arrays (parity mode).  d_ipix optional. */
+int glb_points_fill(int64_t nside, const int64_t* d_counts, const int64_t* d_off, int64_t pix0, int64_t pix1,
+                    const double* d_u, const double* d_v, uint64_t seed, uint32_t stream_id, double* d_lon,
+                    double* d_lat, int64_t* d_ipix, void* stream);
+/* healpix `_chp.ring2ang_uv` behind healpix.randang (glass/healpix.py:426-431): lonlat=1 ->
+ * (lon, lat) degrees, else (theta, phi) radians. */
+int glb_ring2ang_uv(int64_t nside, const int64_t* d_ipix, const double* d_u, const double* d_v, int64_t n,
+                    int lonlat, double* d_out1, double* d_out2, void* stream);
+/* healpix.randang(nside, ipix, lonlat) as called at glass/healpix.py:426-431: in-pixel
+ * offsets from Philox keyed by (seed, stream_id, element index) -- the same sequence on every
+ * call with the same seed, like the reference's fresh default_rng(42) per call. */
+int glb_randang(int64_t nside, const int64_t* d_ipix, int64_t n, uint64_t seed, uint32_t stream_id, int lonlat,
+                double* d_out1, double* d_out2, void* stream);
+/* healpix.ang2pix(nside, theta|lon, phi|lat, lonlat)   glass/healpix.py:172 (RING scheme). */
+int glb_ang2pix(int64_t nside, const double* d_a, const double* d_b, int64_t n, int lonlat, int64_t* d_ipix,
+                void* stream);
+
+/* ---- lensing in pixel / galaxy space -------------------------------------------------- */
+/* MultiPlaneConvergence.add_plane update (glass/lensing.py:584-586), one fused pass:
+ * kappa3 = ((kappa3*(1-t)) + t*kappa2) + f*delta2, rounded like NumPy's three passes.
+ * d_delta2 NULL -> the scalar delta2_scalar is used (first plane: delta is 0-d, :486). */
+int glb_multiplane_update(double* d_kappa3, const double* d_kappa2, const double* d_delta2, double delta2_scalar,
+                          int64_t npix, double t, double f, void* stream);
+/* galaxy_shear (glass/galaxies.py:311-347): pixel lookup via ang2pix(lon, lat, lonlat=True)
+ * -- or d_ipix if the caller already knows it -- gather kappa, gamma1, gamma2, then
+ * g = gamma/(1-kappa); (eps+g)/(1+conj(g) eps)  [reduced_shear]  or  gamma + eps.
+ * d_eps, d_out complex128 [n]. */
+int glb_galaxy_shear(int64_t nside, const double* d_lon, const double* d_lat, const int64_t* d_ipix,
+                     const double* d_eps, int64_t n, const double* d_kappa, const double* d_gamma1,
+                     const double* d_gamma2, int reduced_shear, double* d_out, void* stream);
+/* ellipticity_intnorm (glass/shapes.py:323-362; mode 0, sigma = sigma_eta computed by the
+ * caller) / ellipticity_gaussian (shapes.py:255-285; mode 1, redraw while |e| > 1).
+ * d_normals (mode 0 only, may be NULL): supplied complex standard normals. */
+int glb_ellipticity(int mode, double sigma, const double* d_normals, int64_t n, uint64_t seed, uint32_t stream_id,
+                    uint64_t index0, double* d_out, void* stream);
+/* _draw_nz (glass/galaxies.py:77-89): z = interp(U[0,1), cdf, zgrid); d_u may be NULL. */
+int glb_redshifts_from_cdf(const double* d_cdf, const double* d_z, int nz, const double* d_u, int64_t n,
+                           uint64_t seed, uint32_t stream_id, uint64_t index0, double* d_out, void* stream);
+
 /* host-buffer forms of the two transforms GLASS calls per shell: H2D, kernels, D2H on
  * `stream`, synchronous on return.  These are what a ctypes binding inside
  * glass/healpix.py would call with NumPy buffers. */

@@ -1,0 +1,132 @@
+"""GPU parity: multi-plane convergence, galaxy_shear, ellipticities, redshifts."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import MockCosmology, triangular_shells
+from oracle import glass_ref as G
+from oracle import healpix_ref as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_multi_plane_bit_exact(cuda_device):
+    import glass_b200
+
+    cosmo = MockCosmology()
+    shells = triangular_shells(5)
+    rng = np.random.default_rng(42)
+    deltas = rng.random((5, 12 * 4**2))
+    a = glass_b200.MultiPlaneConvergence(cosmo)
+    b = G.MultiPlaneConvergence(cosmo)
+    for i, w in enumerate(shells):
+        a.add_window(deltas[i], w)
+        b.add_window(deltas[i].copy(), w.za, w.wa, w.zeff)
+        assert np.array_equal(a.kappa, b.kappa), i  # same roundings as NumPy's three passes
+        assert a.zsrc == w.zeff
+    with pytest.raises(ValueError, match="source redshift must be increasing"):
+        a.add_plane(deltas[0], 1.0)
+    # device tensors stay on the device
+    c = glass_b200.MultiPlaneConvergence(cosmo)
+    for i, w in enumerate(shells):
+        c.add_window(torch.as_tensor(deltas[i]).to(cuda_device), w)
+    assert c.kappa.is_cuda and np.array_equal(c.kappa.cpu().numpy(), b.kappa)
+
+
+def test_multi_plane_matrix_and_weights(cuda_device):
+    """Port of tests/core/test_lensing.py:64-117."""
+    import glass_b200
+
+    cosmo = MockCosmology()
+    shells = triangular_shells(5)
+    mat = glass_b200.multi_plane_matrix(shells, cosmo)
+    assert np.array_equal(mat, np.tril(mat)) and np.all(np.triu(mat, 1) == 0)
+    conv = glass_b200.MultiPlaneConvergence(cosmo)
+    rng = np.random.default_rng(42)
+    deltas = rng.random((5, 10))
+    kappas = []
+    for i in range(5):
+        conv.add_window(deltas[i], shells[i])
+        kappas.append(np.array(conv.kappa, copy=True))
+    np.testing.assert_allclose(mat @ deltas, np.stack(kappas), rtol=1e-12, atol=1e-14)
+    w_out = glass_b200.multi_plane_weights(np.eye(5), shells, cosmo)
+    assert np.array_equal(w_out, np.triu(w_out, 1))
+    weights = rng.random((5, 3))
+    conv = glass_b200.MultiPlaneConvergence(cosmo)
+    kappa = 0
+    for i in range(5):
+        conv.add_window(deltas[i], shells[i])
+        kappa = kappa + weights[i][..., None] * conv.kappa
+    kappa /= weights.sum(axis=0)[..., None]
+    wmat = glass_b200.multi_plane_weights(weights, shells, cosmo)
+    np.testing.assert_allclose(np.einsum("ij,ik", wmat, deltas), kappa, rtol=1e-12)
+    with pytest.raises(ValueError, match="shape mismatch between weights and shells"):
+        glass_b200.multi_plane_weights(np.ones((4, 2)), shells, cosmo)
+
+
+@pytest.mark.parametrize("reduced", [True, False])
+def test_galaxy_shear_vs_oracle(cuda_device, reduced):
+    import glass_b200
+
+    nside = 16
+    npix = 12 * nside**2
+    rng = np.random.default_rng(1)
+    kappa, g1, g2 = 0.1 * rng.standard_normal((3, npix))
+    n = 5000
+    ipix = rng.integers(0, npix, n)
+    lon, lat = H.ring2ang_uv(nside, ipix, rng.random(n), rng.random(n), lonlat=True)
+    eps = 0.3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    got = glass_b200.galaxy_shear(lon, lat, eps, kappa, g1, g2, reduced_shear=reduced)
+    ref = G.galaxy_shear(lon, lat, eps, kappa, g1, g2, reduced_shear=reduced)
+    assert got.dtype == np.complex128 and got.shape == (n,)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-15)
+    got2 = glass_b200.galaxy_shear(lon, lat, eps, kappa, g1, g2, reduced_shear=reduced, ipix=ipix)
+    assert np.array_equal(got, got2)
+    # shapes-only cases of tests/core/test_galaxies.py:175-232
+    k12 = np.zeros(12)
+    assert glass_b200.galaxy_shear(np.zeros(0), np.zeros(0), np.zeros(0, dtype=complex), k12, k12, k12).shape == (0,)
+    assert glass_b200.galaxy_shear(np.zeros(5), np.zeros(5), np.zeros(5, dtype=complex), k12, k12, k12).shape == (5,)
+
+
+def test_ellipticities(cuda_device):
+    """Supplied normals -> oracle formula; Philox draws -> the reference's statistical
+    checks (tests/core/test_shapes.py:130-252)."""
+    import glass_b200
+    from glass_b200.rng import Deviates
+
+    rng = np.random.default_rng(2)
+    nrm = rng.standard_normal(1000) + 1j * rng.standard_normal(1000)
+    got = glass_b200.ellipticity_intnorm(1000, 0.256, rng=Deviates(normal=nrm))
+    np.testing.assert_allclose(got, G.ellipticity_intnorm_from_normals(0.256, nrm), rtol=1e-14, atol=1e-16)
+    n = 1_000_000
+    for fn in (glass_b200.ellipticity_intnorm, glass_b200.ellipticity_gaussian):
+        eps = fn(n, 0.256, rng=3)
+        assert eps.shape == (n,) and np.all(np.abs(eps) < 1)
+        assert abs(np.std(eps.real) - 0.256) < 1e-3 and abs(np.std(eps.imag) - 0.256) < 1e-3
+    eps = glass_b200.ellipticity_intnorm([n, n], [0.128, 0.256], rng=4)
+    assert eps.shape == (2 * n,)
+    assert abs(np.std(eps.real[:n]) - 0.128) < 1e-3 and abs(np.std(eps.real[n:]) - 0.256) < 1e-3
+    with pytest.raises(ValueError, match="sigma must be between 0 and sqrt\\(0.5\\)"):
+        glass_b200.ellipticity_intnorm(1, 0.71)
+
+
+def test_redshifts(cuda_device):
+    import glass_b200
+    from glass_b200.rng import Deviates
+    from scipy import stats
+
+    z = np.linspace(0.0, 2.0, 201)
+    nz = z**2 * np.exp(-((z / 0.5) ** 1.5))
+    u = np.random.default_rng(0).random(10_000)
+    w = glass_b200.RadialWindow(z, nz, 1.0)
+    got = glass_b200.redshifts(u.size, w, rng=Deviates(uniform=u))
+    np.testing.assert_allclose(got, G.redshifts_from_nz_uniform(z, nz, u), rtol=1e-13, atol=1e-15)
+    zs = glass_b200.redshifts(200_000, w, rng=5)
+    cdf = G.redshifts_from_nz_uniform  # noqa: F841
+    cd = np.concatenate([[0], np.cumsum((nz[1:] + nz[:-1]) * 0.5 * np.diff(z))])
+    cd /= cd[-1]
+    assert stats.kstest(zs, lambda x: np.interp(x, z, cd)).pvalue > 1e-4
+    with pytest.warns(UserWarning):
+        glass_b200.redshifts_from_nz(10, z, nz, rng=1)
+    out = glass_b200.redshifts_from_nz(np.array([3, 4]), z, np.stack([nz, nz[::-1]]), rng=1, warn=False)
+    assert out.shape == (7,)

@@ -1,0 +1,155 @@
+"""GPU parity: galaxy counts / positions / pixel functions against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import glass_ref as G
+from oracle import healpix_ref as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nside", [1, 2, 4, 16, 3, 48, 128])
+def test_ring2ang_uv_and_ang2pix(cuda_device, nside):
+    from glass_b200 import healpix as hp
+
+    rng = np.random.default_rng(nside)
+    npix = 12 * nside * nside
+    ipix = np.arange(npix) if npix <= 4096 else rng.integers(0, npix, 4096)
+    u, v = rng.random(ipix.size), rng.random(ipix.size)
+    for lonlat in (False, True):
+        a, b = hp.ring2ang_uv(nside, ipix, u, v, lonlat=lonlat)
+        ra, rb = H.ring2ang_uv(nside, ipix, u, v, lonlat=lonlat)
+        np.testing.assert_allclose(a, ra, rtol=0, atol=1e-12 * (57.3 if lonlat else 1.0))
+        np.testing.assert_allclose(b, rb, rtol=0, atol=1e-12 * (57.3 if lonlat else 1.0))
+        # pixel indexing bit-exact, and identical to the oracle's on the same angles
+        p = hp.ang2pix(nside, ra, rb, lonlat=lonlat)
+        assert p.dtype == np.int64
+        assert np.array_equal(p, H.ang2pix(nside, ra, rb, lonlat=lonlat))
+    # pixel centres map back to their pixel
+    th, ph = hp.ring2ang_uv(nside, ipix, 0.5, 0.5)
+    assert np.array_equal(hp.ang2pix(nside, th, ph), ipix)
+    lon, lat = hp.randang(nside, ipix, lonlat=True)
+    assert lon.min() >= 0 and lon.max() < 360 and lat.min() >= -90 and lat.max() <= 90
+    assert np.array_equal(hp.ang2pix(nside, lon, lat, lonlat=True), ipix)
+    lon2, _ = hp.randang(nside, ipix, lonlat=True)  # same seed-42 stream on every call
+    assert np.array_equal(lon, lon2)
+
+
+def _nbar(delta, ngal, bias, vis, model, remove_monopole, cuda_device):
+    from glass_b200.points import _Population, linear_bias, loglinear_bias
+
+    bm = {"linear": linear_bias, "loglinear": loglinear_bias}[model]
+    pop = _Population(delta, vis, ngal, bias, bm, remove_monopole, 42, 0, np.zeros(delta.size, dtype=np.int64), cuda_device, want_nbar=True)
+    return pop.nbar.cpu().numpy()
+
+
+@pytest.mark.parametrize("bias,vis,model,rm", [(None, False, "linear", False), (0.8, True, "linear", False), (1.3, False, "loglinear", False), (0.8, True, "linear", True)])
+def test_expected_count_vs_oracle(cuda_device, bias, vis, model, rm):
+    nside = 16
+    rng = np.random.default_rng(3)
+    delta = np.expm1(0.5 * rng.standard_normal(12 * nside**2) - 0.125)
+    v = rng.random(delta.size) if vis else None
+    got = _nbar(delta, 1e-3, bias, v, model, rm, cuda_device)
+    ref = G.expected_count(delta, 1e-3, bias, v, model, rm)
+    if model == "linear" and not rm:
+        assert np.array_equal(got, ref)  # same roundings as NumPy: bit-identical
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("batch", [1_000_000, 500, 37, 1])
+def test_positions_supplied_deviates(cuda_device, batch):
+    """Counts, pixel indices and batch cuts bit-exact given supplied Poisson/uniform deviates."""
+    import glass_b200
+    from glass_b200.rng import Deviates
+
+    nside = 8
+    npix = 12 * nside**2
+    rng = np.random.default_rng(5)
+    delta = rng.random(npix) - 0.5
+    counts = rng.poisson(3.0 * (1 + delta))
+    counts[10:40] = 0
+    counts[100] = 60  # a pixel larger than the small batches
+    uv = lambda n: (np.random.default_rng(42).random(n), np.random.default_rng(43).random(n))  # noqa: E731
+    ref = G.positions_from_counts(counts, nside, batch, uv)
+    got = list(glass_b200.positions_from_delta(1e-3, delta, rng=Deviates(poisson=[counts], uv=uv), batch=batch))
+    assert len(got) == len(ref)
+    for (lon, lat, n), (rlon, rlat, rn) in zip(got, ref):
+        assert n == rn and lon.shape == (rn,)
+        np.testing.assert_allclose(lon, rlon, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(lat, rlat, rtol=0, atol=1e-10)
+        assert np.array_equal(H.ang2pix(nside, lon, lat, lonlat=True), H.ang2pix(nside, rlon, rlat, lonlat=True))
+    assert sum(g[2] for g in got) == counts.sum()
+
+
+def test_positions_from_delta_structure(cuda_device):
+    """Port of the reference's structural tests (tests/core/test_points.py:235-384)."""
+    import glass_b200
+
+    nside = 32
+    npix = 12 * nside**2
+    # zero delta, no bias: expected total = ngal * ARCMIN2_SPHERE
+    ngal = 1e-3
+    tot = 0
+    for lon, lat, cnt in glass_b200.positions_from_delta(ngal, np.zeros(npix), rng=7):
+        assert isinstance(cnt, int) and lon.shape == lat.shape == (cnt,)
+        assert lon.min() >= 0 and lon.max() < 360 and lat.min() >= -90 and lat.max() <= 90
+        tot += cnt
+    mean = ngal * glass_b200.points.ARCMIN2_SPHERE
+    assert abs(tot - mean) < 6 * np.sqrt(mean)
+    # populations: ngal (2,), delta (3,1,npix) -> dims (3,2); count is one-hot * n
+    delta = np.zeros((3, 1, npix))
+    ngal2 = np.array([1e-3, 2e-3])
+    vis = np.ones(npix)
+    vis[: npix // 2] = 0.0
+    seen = np.zeros((3, 2), dtype=np.int64)
+    for lon, lat, cnt in glass_b200.positions_from_delta(ngal2, delta, 0.8, vis, rng=8):
+        assert cnt.shape == (3, 2) and np.count_nonzero(cnt) == 1
+        assert lat.max() < 1.0  # southern half only (vis zero in the north)
+        seen += cnt
+    assert np.all(seen > 0) and abs(seen[:, 1].sum() / seen[:, 0].sum() - 2) < 0.1
+    # all-zero visibility: nothing is yielded
+    assert list(glass_b200.positions_from_delta(ngal, np.zeros(npix), None, np.zeros(npix))) == []
+    with pytest.raises(TypeError, match="bias_model must be callable"):
+        next(glass_b200.positions_from_delta(ngal, np.zeros(npix), bias_model=0))
+    # device in -> device out, custom callable bias model
+    d = torch.zeros(npix, dtype=torch.float64, device=cuda_device)
+    out = list(glass_b200.positions_from_delta(ngal, d, 1.0, bias_model=lambda dd, b: b * dd * 0.5, rng=9))
+    assert out and out[0][0].is_cuda
+
+
+def test_poisson_and_position_statistics(cuda_device):
+    """Random draws validated statistically (north_star): KS/moment tests on counts and
+    uniformity of in-pixel positions."""
+    from scipy import stats
+
+    from glass_b200.points import _Population, linear_bias
+
+    nside = 64
+    npix = 12 * nside**2
+    for lam in (0.08, 3.0, 9.5, 25.0, 400.0):
+        ngal = lam / (G.ARCMIN2_SPHERE / npix)
+        pop = _Population(np.zeros(npix), None, ngal, None, linear_bias, False, 123, 0, None, cuda_device)
+        c = pop.counts.cpu().numpy()
+        assert abs(c.mean() - lam) < 6 * np.sqrt(lam / npix)
+        assert abs(c.var() - lam) < 6 * lam * np.sqrt(2.0 / npix) + 6 * np.sqrt(lam / npix)
+        # chi-square of the histogram against the Poisson pmf
+        kmax = int(lam + 6 * np.sqrt(lam) + 6)
+        obs = np.bincount(np.minimum(c, kmax), minlength=kmax + 1).astype(float)
+        pmf = stats.poisson.pmf(np.arange(kmax + 1), lam)
+        pmf[-1] += stats.poisson.sf(kmax, lam)
+        keep = pmf * npix > 5
+        chi2 = ((obs[keep] - pmf[keep] * npix) ** 2 / (pmf[keep] * npix)).sum()
+        assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-5, (lam, chi2)
+        assert pop.off[-1].item() == c.sum() and np.array_equal(pop.off.cpu().numpy()[:-1], np.cumsum(c) - c)
+    # in-pixel (u, v) uniformity: invert positions of a single big pixel population
+    pop = _Population(np.zeros(npix), None, 200.0 / (G.ARCMIN2_SPHERE / npix), None, linear_bias, False, 5, 0, None, cuda_device)
+    lon, lat, ipix = pop.fill(0, npix, pop.total, None, want_ipix=True)
+    ip = ipix.cpu().numpy()
+    assert np.array_equal(H.ang2pix(nside, lon.cpu().numpy(), lat.cpu().numpy(), lonlat=True), ip)
+    assert np.all(np.diff(ip) >= 0)  # sorted by ring pixel index (points.py:426)
+    # z = sin(lat) is uniform over the sphere for uniform-in-pixel sampling on an equal-area grid
+    z = np.sin(np.radians(lat.cpu().numpy()))
+    assert stats.kstest(z, "uniform", args=(-1, 2)).pvalue > 1e-4
+    assert stats.kstest(lon.cpu().numpy(), "uniform", args=(0, 360)).pvalue > 1e-4
