@@ -104,18 +104,32 @@ class _Population:
 
     def cuts(self, batch: int):
         """Pixel ranges (start, stop, npoints) of glass/points.py:409-437."""
+        # Closed form of the reference's 1000-pixel stepping loop: a batch is the longest
+        # run of pixels from ``start`` whose total is <= batch (so it may be EMPTY when
+        # zero-count pixels precede a pixel that alone exceeds ``batch`` -- the reference
+        # yields that empty batch too); a pixel that alone exceeds ``batch`` is taken by
+        # itself; and on an exact fit the reference stops at the end of the 1000-pixel
+        # group (counted from ``start``) in which the fit completes.
         start, remaining = 0, self.total
         off = self.off
+
+        def search(value, right):
+            v = torch.tensor(value, device=off.device)
+            return int(torch.searchsorted(off, v, right=right).item())
+
         while remaining > 0:
             base = int(off[start].item())
-            # largest stop with off[stop] - base <= batch
-            stop = int(torch.searchsorted(off, torch.tensor(base + batch, device=off.device), right=True).item()) - 1
-            stop = min(stop, self.npix)
-            if stop <= start:
+            target = base + batch
+            p = min(search(target, True) - 1, self.npix)  # largest p with off[p] <= target
+            if p <= start:
                 stop = start + 1  # the first pixel alone is too much: use it anyway
+            else:
+                stop = p
+                if int(off[p].item()) == target and p < self.npix:
+                    qstar = search(target, False) - 1  # pixel that completes the exact fit
+                    stop = min(start + 1000 * ((qstar - start) // 1000 + 1), p)
             n = int(off[stop].item()) - base
-            if n > 0:
-                yield start, stop, n
+            yield start, stop, n
             start = stop
             remaining -= n
 
@@ -123,6 +137,8 @@ class _Population:
         lon = torch.empty(n, dtype=torch.float64, device=self.device)
         lat = torch.empty(n, dtype=torch.float64, device=self.device)
         ipix = torch.empty(n, dtype=torch.int64, device=self.device) if want_ipix else None
+        if n == 0:
+            return lon, lat, ipix
         u = v = None
         if uv is not None:
             uu, vv = uv(n) if callable(uv) else uv

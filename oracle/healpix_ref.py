@@ -82,7 +82,7 @@ def ring_info(nside: int):
     tcap = fi * fi / (3.0 * n * n)
     zeq = (2.0 * n - i) * 2.0 / (3.0 * n)
     z = np.where(cap, np.where(south, -zcap, zcap), zeq)
-    sth = np.where(cap, np.sqrt(tcap * (2.0 - tcap)), np.sqrt(np.maximum((1.0 - zeq) * (1.0 + zeq), 0.0)))
+    sth = np.where(cap, np.sqrt(np.maximum(tcap * (2.0 - tcap), 0.0)), np.sqrt(np.maximum((1.0 - zeq) * (1.0 + zeq), 0.0)))
     shifted = np.where(cap, True, ((i - n) % 2) == 0)
     phi0 = np.where(shifted, np.pi / nphi, 0.0)
     start_n = 2 * ip * (ip - 1)

@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""
+Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCE (/root/reference/glass)
+in the build container.  Nothing of the reference is copied into this repo: the package is
+imported from where it lies, on top of small shim modules standing in for its third-party
+dependencies that are not installed here (array_api_compat, array_api_extra, transformcl,
+healpy, healpix).  The shims for healpy/healpix only *record* what the GLASS code passes to
+the seam (alm, ipix, ...) or delegate to the oracle; the vectors therefore pin the GLASS-side
+NumPy code, not healpy.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+
+The GPU box has no /root/reference: tests only read the committed .npz files.
+"""
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import healpix_ref as H  # noqa: E402
+
+REF = "/root/reference"
+
+
+def install_shims():
+    # ---- array_api_compat -------------------------------------------------
+    aac = types.ModuleType("array_api_compat")
+
+    def array_namespace(*xs, use_compat=None, api_version=None):
+        return np
+
+    aac.array_namespace = array_namespace
+    aac.is_jax_array = lambda x: False
+    aac.is_numpy_array = lambda x: isinstance(x, np.ndarray)
+    aac.is_array_api_obj = lambda x: isinstance(x, np.ndarray)
+    aac.is_numpy_namespace = lambda xp: xp is np
+    aac.is_jax_namespace = lambda xp: False
+    aac.is_array_api_strict_namespace = lambda xp: False
+    aac.size = lambda x: x.size
+    aac.device = lambda x: "cpu"
+    sys.modules["array_api_compat"] = aac
+    # numpy lacks a few array-API spellings used by the reference
+    if not hasattr(np, "concat"):
+        np.concat = np.concatenate
+
+    # ---- array_api_extra ---------------------------------------------------
+    xpx = types.ModuleType("array_api_extra")
+
+    class _At:
+        def __init__(self, x, idx=None):
+            self.x, self.idx = x, idx
+
+        def __getitem__(self, idx):
+            return _At(self.x, idx)
+
+        def set(self, v, copy=None):
+            self.x[self.idx] = v
+            return self.x
+
+        def add(self, v, copy=None):
+            self.x[self.idx] += v
+            return self.x
+
+        def multiply(self, v, copy=None):
+            self.x[self.idx] *= v
+            return self.x
+
+    xpx.at = lambda x, idx=None: _At(x, idx)
+    xpx.pad = lambda x, pad_width, mode="constant", constant_values=0, xp=None: np.pad(x, pad_width, constant_values=constant_values)
+
+    def apply_where(cond, args, f1, f2=None, /, *, fill_value=None, xp=None):
+        args = args if isinstance(args, tuple) else (args,)
+        out = np.full(np.shape(cond), fill_value if fill_value is not None else 0.0, dtype=np.result_type(*args, float))
+        with np.errstate(all="ignore"):
+            out[cond] = f1(*[a[cond] for a in args])
+            if f2 is not None:
+                out[~cond] = f2(*[a[~cond] for a in args])
+        return out
+
+    xpx.apply_where = apply_where
+    sys.modules["array_api_extra"] = xpx
+
+    # ---- transformcl --------------------------------------------------------
+    tcl = types.ModuleType("transformcl")
+
+    def cltovar(cl):
+        cl = np.asarray(cl)
+        ell = np.arange(cl.shape[0])
+        return np.sum((2 * ell + 1) / (4 * np.pi) * cl)
+
+    tcl.cltovar = cltovar
+    tcl.cltocorr = tcl.corrtocl = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+    sys.modules["transformcl"] = tcl
+
+    # ---- healpy / healpix: record + oracle ----------------------------------
+    hpy = types.ModuleType("healpy")
+    REC = {"alm": [], "ipix": []}
+    hpy._rec = REC
+
+    def alm2map(alms, nside, inplace=False, lmax=None, pixwin=False, pol=True, **kw):
+        REC["alm"].append(np.array(alms, copy=True))
+        return np.array(alms, copy=True)  # the GLASS code just yields it on
+
+    hpy.alm2map = alm2map
+    hpy.npix2nside = H.npix2nside
+    hpy.nside2npix = H.nside2npix
+    hpy.Rotator = object
+    sys.modules["healpy"] = hpy
+
+    hpx = types.ModuleType("healpix")
+    hpx.npix2nside = H.npix2nside
+    hpx.nside2npix = H.nside2npix
+
+    def randang(nside, ipix, lonlat=False, rng=None):
+        REC["ipix"].append(np.array(ipix, copy=True))
+        n = np.asarray(ipix).size
+        return H.ring2ang_uv(nside, ipix, np.full(n, 0.5), np.full(n, 0.5), lonlat=lonlat)
+
+    hpx.randang = randang
+    hpx.ang2pix = lambda nside, a, b, nest=False, lonlat=False: H.ang2pix(nside, a, b, lonlat=lonlat)
+    sys.modules["healpix"] = hpx
+    return REC
+
+
+def synthetic_gls(nshell, lmax, ncorr, ragged=False):
+    l = np.arange(lmax + 1)
+    g = 1e-2 * (l + 1.0) ** -1.5
+    g[0] = 0.0
+    gls = []
+    for i in range(nshell):
+        for j in range(i, -1, -1):
+            d = i - j
+            if d <= ncorr:
+                gl = 0.5**d * g
+                if ragged and d == 1:
+                    gl = gl[: lmax // 2]
+                gls.append(gl)
+            else:
+                gls.append(np.zeros(0))
+    return gls
+
+
+class MockCosmology:  # tests/fixtures/domain.py:36-97
+    Omega_m0 = 0.3
+    hubble_distance = 4.4e3
+
+    def H_over_H0(self, z):  # noqa: N802
+        return (self.Omega_m0 * (1 + z) ** 3 + 1 - self.Omega_m0) ** 0.5
+
+    def transverse_comoving_distance(self, z, z2=None):
+        if z2 is None:
+            return self.hubble_distance * np.asarray(z) * 1_000
+        return self.hubble_distance * (np.asarray(z2) - np.asarray(z)) * 1_000
+
+
+def main():
+    REC = install_shims()
+    sys.path.insert(0, REF)
+    import glass  # the reference itself
+    import glass.fields
+    import glass.points
+
+    out = {}
+
+    # ---- fields: iternorm / cls2cov / alm of _generate_grf with seed-42 NumPy normals ----
+    cov = np.array([[1.0, 0.2, 0.1], [0.2, 0.5, 0.2], [0.1, 0.2, 0.3]])
+    for k in (0, 1, 2):
+        rows = [cov[i, i::-1][: min(i, k) + 1] for i in range(3)]
+        # iternorm needs a fixed row width
+        rows = [np.pad(r, (0, k + 1 - r.size)) for r in rows]
+        out[f"iternorm_k{k}"] = np.stack(list(glass.iternorm(rows)))
+    for name, (nshell, lmax, ncorr, ragged) in {"a": (4, 12, 2, False), "b": (5, 9, None, False), "c": (4, 10, 1, True)}.items():
+        nc = nshell - 1 if ncorr is None else ncorr
+        gls = synthetic_gls(nshell, lmax, nc, ragged)
+        out[f"cls2cov_{name}"] = np.stack([c.copy() for c in glass.cls2cov(gls, lmax + 1, nshell, nc)])
+        out[f"iternorm_{name}"] = np.stack(list(glass.iternorm(glass.cls2cov(gls, lmax + 1, nshell, nc))))
+        REC["alm"].clear()
+        maps = list(glass.fields._generate_grf(gls, 4, ncorr=ncorr, rng=np.random.default_rng(42)))
+        out[f"grf_alm_{name}"] = np.stack(REC["alm"])
+        # lognormal transform through generate (alm passthrough "map" -> use real part)
+    x = np.linspace(-2, 2, 41)
+    out["lognormal_x"] = x
+    out["lognormal_y"] = glass.grf.Lognormal(0.7)(x.copy(), 0.35)
+    out["lognormal_y1"] = glass.grf.Lognormal()(x.copy(), 0.35)
+    out["sqnormal_y"] = glass.grf.SquaredNormal(0.3, 1.5)(x.copy(), 0.35)
+    alm = np.arange(10) + 1j * np.arange(10)[::-1]
+    out["g2h_in"] = alm
+    out["g2h_out"] = glass.fields._glass_to_healpix_alm(alm)
+    out["multalm_out"] = glass.harmonics.multalm(alm[:6], np.array([2.0, 0.5, 1.0]))
+
+    # ---- points: expected counts and batch cuts ----
+    rng = np.random.default_rng(3)
+    nside = 8
+    npix = 12 * nside**2
+    delta = np.expm1(0.5 * rng.standard_normal(npix) - 0.125)
+    vis = rng.random(npix)
+    out["pt_delta"], out["pt_vis"] = delta, vis
+    ngal = np.asarray(1e-3)
+    for tag, (bias, v, model, rm) in {
+        "none": (None, None, glass.linear_bias, False),
+        "lin_vis": (np.asarray(0.8), vis, glass.linear_bias, False),
+        "loglin": (np.asarray(1.3), None, glass.loglinear_bias, False),
+        "lin_vis_rm": (np.asarray(0.8), vis, glass.linear_bias, True),
+    }.items():
+        n = glass.points._compute_density_contrast(bias, model, delta, ())
+        n = glass.points._compute_expected_count((), n, ngal, remove_monopole=rm)
+        n = glass.points._apply_visibility((), n, v)
+        out[f"pt_nbar_{tag}"] = n
+    counts = rng.poisson(3.0 * (1 + np.clip(delta, -1, 3)))
+    counts[10:40] = 0
+    counts[100] = 60
+    out["pt_counts"] = counts
+    for batch in (1_000_000, 500, 37, 1):
+        REC["ipix"].clear()
+        sizes = [int(c) for _lo, _la, c in glass.points._sample_galaxies_per_pixel(batch, (), (), counts)]
+        out[f"pt_batches_{batch}"] = np.array(sizes)
+        out[f"pt_ipix_{batch}"] = np.concatenate(REC["ipix"]) if REC["ipix"] else np.zeros(0, dtype=np.int64)
+    out["ARCMIN2_SPHERE"] = np.asarray(glass.points.ARCMIN2_SPHERE)
+
+    # ---- lensing: multi-plane convergence with MockCosmology ----
+    cosmo = MockCosmology()
+    shells = [glass.RadialWindow(np.array([i, i + 1.0, i + 2.0]), np.array([0.0, 1.0, 0.0]), i + 1.0) for i in range(5)]
+    deltas = np.random.default_rng(42).random((5, 48))
+    mpc = glass.MultiPlaneConvergence(cosmo)
+    kap = []
+    for i, w in enumerate(shells):
+        mpc.add_window(deltas[i].copy(), w)
+        kap.append(np.array(mpc.kappa, copy=True))
+    out["mpc_deltas"], out["mpc_kappas"] = deltas, np.stack(kap)
+    out["mpc_matrix"] = glass.multi_plane_matrix(shells, cosmo)
+
+    # ---- galaxies / shapes ----
+    nside = 4
+    npix = 12 * nside**2
+    r = np.random.default_rng(1)
+    kappa, g1, g2 = 0.1 * r.standard_normal((3, npix))
+    n = 300
+    ipix = r.integers(0, npix, n)
+    lon, lat = H.ring2ang_uv(nside, ipix, r.random(n), r.random(n), lonlat=True)
+    eps = 0.3 * (r.standard_normal(n) + 1j * r.standard_normal(n))
+    out["gs_kappa"], out["gs_g1"], out["gs_g2"], out["gs_lon"], out["gs_lat"], out["gs_eps"] = kappa, g1, g2, lon, lat, eps
+    out["gs_reduced"] = glass.galaxy_shear(lon, lat, eps, kappa, g1, g2, reduced_shear=True)
+    out["gs_plain"] = glass.galaxy_shear(lon, lat, eps, kappa, g1, g2, reduced_shear=False)
+    rr = np.random.default_rng(7)
+    out["eps_intnorm"] = glass.ellipticity_intnorm(500, 0.256, rng=rr, xp=np)
+    rr = np.random.default_rng(7)
+    out["eps_normals"] = rr.standard_normal(500) + 1j * rr.standard_normal(500)
+    z = np.linspace(0.0, 2.0, 101)
+    nz = z**2 * np.exp(-((z / 0.5) ** 1.5))
+    rr = np.random.default_rng(9)
+    out["z_grid"], out["z_nz"] = z, nz
+    out["z_samples"] = glass.redshifts_from_nz(400, z, nz, rng=rr, warn=False)
+    out["z_uniform"] = np.random.default_rng(9).uniform(0.0, 1.0, size=400)
+
+    np.savez_compressed(os.path.join(HERE, "glass_reference_vectors.npz"), **out)
+    print("wrote", len(out), "arrays,", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

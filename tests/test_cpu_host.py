@@ -1,0 +1,156 @@
+"""CPU tests (-m "not gpu"): host-side logic of glass_b200 (no kernel launches) and the C ABI."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import synthetic_gls
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/glass_b200.h is the contract: every glb_* function it declares must be
+    exported by libglassb200.so and bound in glass_b200._lib.SIGNATURES."""
+    from glass_b200 import _lib, build
+
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "glass_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(glb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.fspath(_lib.lib_path()))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib2 = _lib.load()
+    assert lib2.glb_version().startswith(b"glass_b200")
+    assert lib2.glb_status_string(-10) == b"covariance matrix is not positive definite"
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, not compute on the CPU."""
+    import torch
+
+    import glass_b200
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception, match="CUDA device"):
+        next(glass_b200.generate([glass_b200.grf.Normal()], [np.ones(4)], 4))
+    with pytest.raises(Exception, match="CUDA device"):
+        glass_b200.healpix.alm2map(np.zeros(6, dtype=complex), 2, pol=False)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "glass_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_iternorm_cls2cov_host_mirror():
+    import glass_b200
+
+    cov = np.array([[1.0, 0.2, 0.1], [0.2, 0.5, 0.2], [0.1, 0.2, 0.3]])
+    for k in (0, 1, 2):
+        rows = [np.pad(cov[i, i::-1][: min(i, k) + 1], (0, k + 1 - min(i + 1, k + 1))) for i in range(3)]
+        assert np.array_equal(np.stack(list(glass_b200.iternorm(rows))), GOLD[f"iternorm_k{k}"])
+    for name, (nshell, lmax, ncorr, ragged) in {"a": (4, 12, 2, False), "b": (5, 9, None, False), "c": (4, 10, 1, True)}.items():
+        nc = nshell - 1 if ncorr is None else ncorr
+        gls = synthetic_gls(nshell, lmax, nc, ragged)
+        got = np.stack([c.copy() for c in glass_b200.cls2cov(gls, lmax + 1, nshell, nc)])
+        assert np.array_equal(got, GOLD[f"cls2cov_{name}"])
+        assert np.array_equal(np.stack(list(glass_b200.iternorm(glass_b200.cls2cov(gls, lmax + 1, nshell, nc)))), GOLD[f"iternorm_{name}"])
+    # the same buffer is re-yielded (tests/core/test_fields.py:239-242)
+    gen = glass_b200.cls2cov([np.array(a) for a in ([1.0, 0.5, 0.3], [0.8, 0.4, 0.2], [0.7, 0.6, 0.1], [0.9, 0.5, 0.3], [0.6, 0.3, 0.2], [0.8, 0.7, 0.4])], 3, 3, 2)
+    c1 = next(gen)
+    c1_copy = c1.copy()
+    c2 = next(gen)
+    assert c1 is c2 and np.array_equal(c1_copy[:, 0], [0.5, 0.25, 0.15]) and np.array_equal(c1[:, 0], [0.4, 0.2, 0.1])
+    with pytest.raises(ValueError, match="negative values in cl"):
+        next(glass_b200.cls2cov([np.array([-1.0, 0.5, 0.3])], 3, 1, 0))
+    with pytest.raises(ValueError, match="empty covariance"):
+        list(glass_b200.iternorm([np.ones(0)]))
+    with pytest.raises(ValueError, match="shape mismatch"):
+        list(glass_b200.iternorm([np.ones(1), np.ones((5, 2))]))
+    with pytest.raises(ValueError, match="not positive definite"):
+        list(glass_b200.iternorm([np.array([1.0]), np.array([0.1, 1.0])]))
+
+
+def test_getcl_multalm_misc():
+    """tests/core/test_fields.py:441-465, 649-655; tests/core/test_harmonics.py:15-52."""
+    import glass_b200
+    from glass_b200.fields import _glass_to_healpix_alm, _inv_triangle_number
+
+    cls = [np.array([i, j], dtype=float) for i in range(10) for j in range(i, -1, -1)]
+    for i in range(10):
+        for j in range(10):
+            assert np.array_equal(np.sort(glass_b200.getcl(cls, i, j)), [min(i, j), max(i, j)])
+            assert np.array_equal(glass_b200.getcl(cls, i, j, lmax=0), [max(i, j)])
+            r = glass_b200.getcl(cls, i, j, lmax=50)
+            assert r.shape[0] == 51 and np.all(r[2:] == 0)
+    assert np.array_equal(glass_b200.multalm(np.arange(1.0, 7.0), np.array([2.0, 0.5, 1.0])), [2.0, 1.0, 1.5, 4.0, 5.0, 6.0])
+    assert glass_b200.multalm(np.array([]), np.array([])).size == 0
+    inp = np.array([0, 10, 11, 20, 21, 22, 30, 31, 32, 33], dtype=complex)
+    assert np.array_equal(_glass_to_healpix_alm(inp), np.array([0, 10, 20, 30, 11, 21, 31, 22, 32, 33], dtype=complex))
+    for n in range(2000):
+        assert _inv_triangle_number(n * (n + 1) // 2) == n
+    for t in [2, 4, 5, 7, 8, 9, 11, 12, 13, 14, 16, 17, 18, 19, 20]:
+        with pytest.raises(ValueError, match="not a triangle number"):
+            _inv_triangle_number(t)
+    with pytest.raises(ValueError, match="invalid number of spectra: 4"):
+        glass_b200.nfields_from_nspectra(4)
+    x = GOLD["lognormal_x"]
+    assert np.array_equal(glass_b200.grf.Lognormal(0.7)(x.copy(), 0.35), GOLD["lognormal_y"])
+    assert np.array_equal(glass_b200.grf.SquaredNormal(0.3, 1.5)(x.copy(), 0.35), GOLD["sqnormal_y"])
+    assert glass_b200.points.ARCMIN2_SPHERE == float(GOLD["ARCMIN2_SPHERE"])
+    shells = [glass_b200.RadialWindow(np.zeros(2), np.zeros(2), z) for z in (0.5, 1.0)]
+    lf = glass_b200.lognormal_fields(shells, lambda z: 2 * z)
+    assert [f.lamda for f in lf] == [1.0, 2.0] and len(glass_b200.gaussian_fields(shells)) == 2
+
+
+def _gloo_worker(rank, world, port, nshell, ncorr, q):
+    import torch.distributed as dist
+
+    from glass_b200.sharding import max_over_ranks, neighbours_needed, shard_shells
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = list(shard_shells(nshell, rank, world))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    tmax = max_over_ranks(1.0 + rank)
+    need = sorted(neighbours_needed(mine, ncorr))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, gathered, tmax, need))
+
+
+def test_shell_sharding_world2_gloo():
+    """N>1 host logic on CPU: ranks partition the shells, timing is the max over ranks."""
+    import torch.multiprocessing as mp
+
+    world, nshell, ncorr = 2, 11, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, nshell, ncorr, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, gathered, tmax, need in res:
+        allsh = sorted(s for g in gathered for s in g)
+        assert allsh == list(range(nshell))  # a partition: every shell exactly once
+        assert set(gathered[0]).isdisjoint(gathered[1])
+        assert tmax == 2.0  # max over ranks
+        mine = gathered[rank]
+        assert set(mine) <= set(need) and all(0 <= s < nshell for s in need)
+        assert all(any(0 <= j - s <= ncorr for j in mine) for s in need)

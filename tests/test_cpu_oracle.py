@@ -1,0 +1,211 @@
+"""CPU tests (-m "not gpu"): the oracle against the golden vectors produced by executing the
+reference's own source (tests/golden/make_golden.py), the reference's dependency-free
+known-answer tests, and the mathematical ground truth for the SHT restatements."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import MockCosmology, synthetic_gls
+from oracle import glass_ref as G
+from oracle import healpix_ref as H
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_golden_iternorm_cls2cov():
+    cov = np.array([[1.0, 0.2, 0.1], [0.2, 0.5, 0.2], [0.1, 0.2, 0.3]])
+    for k in (0, 1, 2):
+        rows = [np.pad(cov[i, i::-1][: min(i, k) + 1], (0, k + 1 - min(i + 1, k + 1))) for i in range(3)]
+        assert np.array_equal(np.stack(G.iternorm(rows)), GOLD[f"iternorm_k{k}"])
+    for name, (nshell, lmax, ncorr, ragged) in {"a": (4, 12, 2, False), "b": (5, 9, None, False), "c": (4, 10, 1, True)}.items():
+        nc = nshell - 1 if ncorr is None else ncorr
+        gls = synthetic_gls(nshell, lmax, nc, ragged)
+        rows = G.cls2cov_rows(gls, lmax + 1, nshell, nc)
+        assert np.array_equal(np.stack(rows), GOLD[f"cls2cov_{name}"])
+        assert np.array_equal(np.stack(G.iternorm(rows)), GOLD[f"iternorm_{name}"])
+
+
+def test_golden_generate_alm():
+    """alm of _generate_grf with the seed-42 NumPy normals the reference draws."""
+    for name, (nshell, lmax, ncorr, ragged) in {"a": (4, 12, 2, False), "b": (5, 9, None, False), "c": (4, 10, 1, True)}.items():
+        nc = nshell - 1 if ncorr is None else ncorr
+        gls = synthetic_gls(nshell, lmax, nc, ragged)
+        rng = np.random.default_rng(42)
+        n = (lmax + 1) * (lmax + 2) // 2
+        zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(nshell)]
+        alms = G.generate_alms(gls, ncorr, zs)
+        assert np.array_equal(np.stack(alms), GOLD[f"grf_alm_{name}"])
+
+
+def test_golden_transformations_and_reorder():
+    x = GOLD["lognormal_x"]
+    assert np.array_equal(G.lognormal(x, 0.35, 0.7), GOLD["lognormal_y"])
+    assert np.array_equal(G.lognormal(x, 0.35, 1.0), GOLD["lognormal_y1"])
+    assert np.array_equal(G.squared_normal(x, 0.3, 1.5), GOLD["sqnormal_y"])
+    assert np.array_equal(G.glass_to_healpix_alm(GOLD["g2h_in"]), GOLD["g2h_out"])
+    assert np.array_equal(G.multalm(GOLD["g2h_in"][:6], np.array([2.0, 0.5, 1.0])), GOLD["multalm_out"])
+
+
+def test_golden_points():
+    delta, vis = GOLD["pt_delta"], GOLD["pt_vis"]
+    assert float(GOLD["ARCMIN2_SPHERE"]) == G.ARCMIN2_SPHERE
+    for tag, (bias, v, model, rm) in {
+        "none": (None, None, "linear", False),
+        "lin_vis": (0.8, vis, "linear", False),
+        "loglin": (1.3, None, "loglinear", False),
+        "lin_vis_rm": (0.8, vis, "linear", True),
+    }.items():
+        assert np.array_equal(G.expected_count(delta, 1e-3, bias, v, model, rm), GOLD[f"pt_nbar_{tag}"]), tag
+    counts = GOLD["pt_counts"]
+    for batch in (1_000_000, 500, 37, 1):
+        cuts = G.batch_cuts(counts, batch)
+        assert [c[2] for c in cuts] == list(GOLD[f"pt_batches_{batch}"])
+        ipix = np.concatenate([np.repeat(np.arange(a, b), counts[a:b]) for a, b, _ in cuts])
+        assert np.array_equal(ipix, GOLD[f"pt_ipix_{batch}"])
+
+
+def test_golden_lensing_galaxies_shapes():
+    cosmo = MockCosmology()
+    deltas = GOLD["mpc_deltas"]
+    mpc = G.MultiPlaneConvergence(cosmo)
+    for i in range(5):
+        mpc.add_window(deltas[i].copy(), np.array([i, i + 1.0, i + 2.0]), np.array([0.0, 1.0, 0.0]), i + 1.0)
+        assert np.array_equal(mpc.kappa, GOLD["mpc_kappas"][i])
+    for red, key in ((True, "gs_reduced"), (False, "gs_plain")):
+        got = G.galaxy_shear(GOLD["gs_lon"], GOLD["gs_lat"], GOLD["gs_eps"], GOLD["gs_kappa"], GOLD["gs_g1"], GOLD["gs_g2"], red)
+        np.testing.assert_allclose(got, GOLD[key], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(G.ellipticity_intnorm_from_normals(0.256, GOLD["eps_normals"]), GOLD["eps_intnorm"], rtol=1e-15)
+    np.testing.assert_allclose(G.redshifts_from_nz_uniform(GOLD["z_grid"], GOLD["z_nz"], GOLD["z_uniform"]), GOLD["z_samples"], rtol=1e-15)
+
+
+# ------------------------------------------------------------------ reference known-answer tests, ported
+@pytest.mark.parametrize("k", [0, 1, 2])
+@pytest.mark.parametrize("nd", [False, True])
+def test_iternorm_against_explicit(k, nd):
+    """tests/core/test_fields.py:31-104."""
+    cov = np.array([[1.0, 0.2, 0.1], [0.2, 0.5, 0.2], [0.1, 0.2, 0.3]])
+    if nd:
+        cov = np.stack([cov, np.array([[1.4, 0.4, 0.5], [0.4, 1.5, 0.8], [0.5, 0.8, 1.3]])])
+    rows = [cov[..., i, i::-1][..., : min(i, k) + 1] for i in range(3)]
+    rows = [np.concatenate([r, np.zeros(r.shape[:-1] + (k + 1 - r.shape[-1],))], axis=-1) for r in rows]
+    for n, w in enumerate(G.iternorm(rows)):
+        Sn = cov[..., :n, :n].copy()
+        cn = cov[..., :n, n].copy()
+        vn = cov[..., n, n]
+        if n > k:
+            Sn *= np.abs(np.arange(n)[:, None] - np.arange(n)) <= k
+            cn *= np.arange(n) >= n - k
+        Sninv = np.linalg.pinv(Sn)
+        An = np.swapaxes(np.linalg.cholesky(Sninv + 1e-100 * np.eye(n)), -1, -2) if n else np.zeros(Sn.shape)
+        an = (An @ cn[..., None])[..., 0]
+        sn = np.sqrt(vn - np.vecdot(an, an))
+        a, s = w[..., :-1], w[..., -1]
+        np.testing.assert_allclose(np.vecdot(a, a), np.vecdot(an, an), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(s, sn, rtol=1e-12)
+
+
+def test_iternorm_errors():
+    """tests/core/test_fields.py:107-119."""
+    with pytest.raises(ValueError, match="empty covariance"):
+        G.iternorm([np.ones(0)])
+    with pytest.raises(ValueError, match="shape mismatch"):
+        G.iternorm([np.ones(1), np.ones((5, 2))])
+    with pytest.raises(ValueError, match="not positive definite"):
+        G.iternorm([np.array([1.0]), np.array([0.1, 1.0])])
+
+
+def test_multi_plane_matrix_relation():
+    """tests/core/test_lensing.py:64-86 on the oracle: kappa_i = sum_j M_ij delta_j."""
+    mat = GOLD["mpc_matrix"]
+    assert np.array_equal(mat, np.tril(mat))
+    np.testing.assert_allclose(mat @ GOLD["mpc_deltas"], GOLD["mpc_kappas"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------ SHT restatement vs ground truth
+def _alm(lmax, seed):
+    rng = np.random.default_rng(seed)
+    n = H.alm_size(lmax)
+    a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    a[: lmax + 1] = a[: lmax + 1].real
+    return a
+
+
+@pytest.mark.parametrize("nside,lmax", [(1, 3), (2, 6), (4, 11), (3, 8)])
+def test_alm2map_vs_direct_sum(nside, lmax):
+    alm = _alm(lmax, nside)
+    d = H.alm2map_direct(alm, nside, lmax)
+    assert np.abs(H.alm2map(alm, nside, lmax) - d).max() < 1e-12 * np.abs(d).max()
+
+
+def test_analytic_maps():
+    nside, lmax = 8, 4
+    th, _ = H.pix2ang_centers(nside)
+    alm = np.zeros(H.alm_size(lmax), dtype=complex)
+    alm[H.alm_index(lmax, 0, 0)] = 2.0
+    np.testing.assert_allclose(H.alm2map(alm, nside, lmax), 2.0 / np.sqrt(4 * np.pi), rtol=1e-14)
+    alm[:] = 0
+    alm[H.alm_index(lmax, 1, 0)] = 1.5
+    np.testing.assert_allclose(H.alm2map(alm, nside, lmax), np.sqrt(3 / (4 * np.pi)) * 1.5 * np.cos(th), atol=1e-14)
+
+
+@pytest.mark.parametrize("spin", [1, 2])
+def test_alm2map_spin_vs_direct_sum(spin):
+    nside, lmax = 4, 9
+    e, b = _alm(lmax, 20 + spin), _alm(lmax, 30 + spin)
+    for l in range(spin):
+        for m in range(l + 1):
+            e[H.alm_index(lmax, l, m)] = b[H.alm_index(lmax, l, m)] = 0
+    d1, d2 = H.alm2map_spin_direct(e, b, nside, spin, lmax)
+    r1, r2 = H.alm2map_spin(e, b, nside, spin, lmax)
+    assert max(np.abs(r1 - d1).max(), np.abs(r2 - d2).max()) < 1e-12 * np.abs(d1).max()
+
+
+def test_spin0_goldberg_equals_scipy():
+    from scipy.special import sph_harm_y
+
+    th, ph = np.linspace(0.1, 3.0, 9), np.linspace(0.0, 6.0, 9)
+    for l, m in [(3, 2), (5, -3), (4, 0), (7, 7)]:
+        assert np.abs(H.sYlm_goldberg(0, l, m, th, ph) - sph_harm_y(l, m, th, ph)).max() < 1e-14
+
+
+def test_map2alm_roundtrip():
+    nside, lmax = 8, 10
+    alm = _alm(lmax, 5)
+    mp = H.alm2map(alm, nside, lmax)
+    e0 = np.abs(H.map2alm(mp, lmax, niter=0) - alm).max()
+    e3 = np.abs(H.map2alm(mp, lmax, niter=3) - alm).max()
+    assert e3 < 1e-3 * e0 and e3 < 1e-4
+
+
+def test_pixel_functions():
+    rng = np.random.default_rng(0)
+    for nside in (1, 2, 4, 16, 3, 48):
+        npix = 12 * nside**2
+        p = np.arange(npix)
+        th, ph = H.pix2ang_centers(nside)
+        t2, p2 = H.ring2ang_uv(nside, p, 0.5, 0.5)
+        assert np.allclose(th, t2, atol=1e-14) and np.allclose(np.mod(ph, 2 * np.pi), p2, atol=1e-13)
+        u, v = rng.random(npix), rng.random(npix)
+        assert np.array_equal(H.ang2pix(nside, *H.ring2ang_uv(nside, p, u, v)), p)
+        lon, lat = H.ring2ang_uv(nside, p, u, v, lonlat=True)
+        assert lon.min() >= 0 and lon.max() < 360 and lat.min() >= -90 and lat.max() <= 90
+    with pytest.raises(ValueError):
+        H.npix2nside(13)
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import sht_c
+
+    for nside, lmax in [(4, 11), (3, 7), (16, 47), (48, 100)]:
+        alm = _alm(lmax, nside)
+        ref = H.alm2map(alm, nside, lmax)
+        for ld in (False, True):
+            got = sht_c.alm2map(alm, nside, lmax, long_double=ld)
+            assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
+    # the mlim cut-off (shared with the CUDA kernels) does not change the result
+    alm = _alm(300, 1)
+    a = sht_c.alm2map(alm, 128, 300)
+    b = sht_c.alm2map(alm, 128, 300, use_mlim=True)
+    assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()

@@ -106,7 +106,7 @@ def test_positions_from_delta_structure(cuda_device):
     seen = np.zeros((3, 2), dtype=np.int64)
     for lon, lat, cnt in glass_b200.positions_from_delta(ngal2, delta, 0.8, vis, rng=8):
         assert cnt.shape == (3, 2) and np.count_nonzero(cnt) == 1
-        assert lat.max() < 1.0  # southern half only (vis zero in the north)
+        assert lat.max() < 2.0  # southern half only (vis zero in the north; boundary pixels straddle the equator)
         seen += cnt
     assert np.all(seen > 0) and abs(seen[:, 1].sum() / seen[:, 0].sum() - 2) < 0.1
     # all-zero visibility: nothing is yielded
@@ -153,3 +153,30 @@ def test_poisson_and_position_statistics(cuda_device):
     z = np.sin(np.radians(lat.cpu().numpy()))
     assert stats.kstest(z, "uniform", args=(-1, 2)).pvalue > 1e-4
     assert stats.kstest(lon.cpu().numpy(), "uniform", args=(0, 360)).pvalue > 1e-4
+
+
+def test_batch_cut_corner_cases(cuda_device):
+    """Exact fit ending at a 1000-pixel group boundary, empty batches before an oversize
+    pixel, trailing zeros: the cut sequence equals the reference loop's (points.py:409-437)."""
+    import glass_b200
+    from glass_b200.rng import Deviates
+
+    nside = 16
+    npix = 12 * nside**2
+    uv = lambda n: (np.full(n, 0.5), np.full(n, 0.5))  # noqa: E731
+    cases = []
+    c = np.zeros(npix, dtype=np.int64)
+    c[0], c[1500], c[1501], c[2999] = 5, 9, 1, 2
+    cases.append((c, 5))
+    c = np.zeros(npix, dtype=np.int64)
+    c[999], c[1000], c[2500] = 3, 2, 4
+    cases.append((c, 3))
+    c = np.random.default_rng(0).poisson(0.01, npix)
+    cases.append((c, 2))
+    c = np.random.default_rng(1).poisson(2.0, npix)
+    cases.append((c, 1000))
+    for counts, batch in cases:
+        ref = G.batch_cuts(counts, batch)
+        got = list(glass_b200.positions_from_delta(1e-3, np.zeros(npix), rng=Deviates(poisson=[counts], uv=uv), batch=batch))
+        assert [g[2] for g in got] == [r[2] for r in ref], batch
+        assert sum(g[2] for g in got) == counts.sum()
