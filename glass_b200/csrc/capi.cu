@@ -28,8 +28,11 @@ static int timing_collect(glb_plan* pl) {
   pl->ev_pool.clear();
   return GLB_OK;
 }
-int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* d_map, const int* kind,
-                        const double* tparams, cudaStream_t st);
+int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
+                        const double* tparams, const int* d_mlim, cudaStream_t st);
+int sht_spin_alm2phase(glb_plan* pl, const double2* d_alm1, const double2* d_alm2, int spin, double2* d_phase,
+                       cudaStream_t st);
+int plan_ensure_spin(glb_plan* pl, int spin);
 
 static inline int group_size(int remaining, int max_batch) {
   const int cap = max_batch >= 4 ? 4 : (max_batch >= 2 ? 2 : 1);
@@ -118,9 +121,10 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
     rc = sht_legendre_group(plan, g, plan->d_phase, st);
     if (rc != GLB_OK) return rc;
     if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[2], st));
-    rc = sht_phase2map_group(plan, plan->d_phase, g, d_map + (int64_t)done * plan->npix,
-                             h_transform ? h_transform + done : nullptr, h_tparams ? h_tparams + 2 * done : nullptr,
-                             st);
+    double* outs[4];
+    for (int b = 0; b < g; ++b) outs[b] = d_map + (int64_t)(done + b) * plan->npix;
+    rc = sht_phase2map_group(plan, plan->d_phase, g, outs, h_transform ? h_transform + done : nullptr,
+                             h_tparams ? h_tparams + 2 * done : nullptr, nullptr, st);
     if (rc != GLB_OK) return rc;
     if (plan->timing) {
       GLB_CUDA_CHECK(cudaEventRecord(ev[3], st));
@@ -131,6 +135,22 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
     done += g;
   }
   return GLB_OK;
+}
+
+int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2, int spin, double* d_map1,
+                     double* d_map2, void* stream) {
+  GLB_REQUIRE(plan && d_alm1 && d_map1 && d_map2, "null pointer");
+  GLB_REQUIRE(spin >= 1 && spin <= 3, "spin must be 1, 2 or 3");
+  GLB_REQUIRE(spin <= plan->lmax, "spin exceeds lmax");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  int rc = plan_ensure_spin(plan, spin);
+  if (rc != GLB_OK) return rc;
+  rc = sht_spin_alm2phase(plan, reinterpret_cast<const double2*>(d_alm1), reinterpret_cast<const double2*>(d_alm2), spin,
+                          plan->d_phase, st);
+  if (rc != GLB_OK) return rc;
+  double* outs[4] = {d_map1, d_map2, nullptr, nullptr};
+  return sht_phase2map_group(plan, plan->d_phase, 2, outs, nullptr, nullptr, plan->d_mlim_spin, st);
 }
 
 int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map, const int* h_transform,
@@ -168,7 +188,9 @@ int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double
   GLB_REQUIRE(plan && d_phase && d_map, "null pointer");
   GLB_REQUIRE(nmaps >= 1 && nmaps <= 4, "nmaps must be in [1, 4]");
   GLB_CUDA_CHECK(cudaSetDevice(plan->device));
-  return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_phase), nmaps, d_map, nullptr, nullptr,
+  double* outs[4];
+  for (int b = 0; b < nmaps; ++b) outs[b] = d_map + (int64_t)b * plan->npix;
+  return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_phase), nmaps, outs, nullptr, nullptr, nullptr,
                              (cudaStream_t)stream);
 }
 

@@ -236,8 +236,10 @@ int plan_build(glb_plan* pl) {
   // ---- workspace ----
   const int gb = std::min(pl->max_batch, 4);
   const int gmax = gb >= 4 ? 4 : (gb >= 2 ? 2 : 1);
-  const size_t rec_bytes = (size_t)pl->nrec * (2 + 4 * gmax) * sizeof(double);
-  const size_t phase_bytes = (size_t)gmax * pl->nring * (pl->mmax + 1) * sizeof(double2);
+  // records: scalar synthesis needs nrec*(2+4B) doubles, the spin transform (E and B) 6 per (l,m)
+  pl->rec_capacity = std::max<int64_t>(pl->nrec * (2 + 4 * gmax), pl->nalm * 6);
+  const size_t rec_bytes = (size_t)pl->rec_capacity * sizeof(double);
+  const size_t phase_bytes = (size_t)std::max(gmax, 2) * pl->nring * (pl->mmax + 1) * sizeof(double2);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_rec, rec_bytes));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_phase, phase_bytes));
   pl->workspace_bytes = (int64_t)(rec_bytes + phase_bytes + bf_total * sizeof(double2));
@@ -259,6 +261,13 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_bf);
   cudaFree(pl->d_rec);
   cudaFree(pl->d_phase);
+  cudaFree(pl->d_ch);
+  cudaFree(pl->d_sh);
+  cudaFree(pl->d_mlim_spin);
+  cudaFree(pl->d_sn_mant);
+  cudaFree(pl->d_sn_exp);
+  cudaFree(pl->d_soff);
+  cudaFree(pl->d_items_spin);
   if (pl->h_pin_in) cudaFreeHost(pl->h_pin_in);
   if (pl->h_pin_out) cudaFreeHost(pl->h_pin_out);
   cudaFree(pl->d_stage_alm);

@@ -51,6 +51,20 @@ struct glb_plan {
   int nitems = 0;
   int leg_threads = 256, leg_R = 4;  // tile = leg_threads * leg_R ring pairs
 
+  // spin-weighted synthesis (built lazily by plan_ensure_spin for one spin at a time)
+  int spin_ready = 0;                // spin the tables below were built for (0 = none)
+  double* d_ch = nullptr;            // [npair] cos(theta/2)
+  double* d_sh = nullptr;            // [npair] sin(theta/2)
+  int* d_mlim_spin = nullptr;        // [npair]
+  std::vector<int> h_mlim_spin;
+  double* d_sn_mant = nullptr;       // [mmax+1] seed norm N_j*sqrt((2j)!/((j+q)!(j-q)!)), mantissa
+  int* d_sn_exp = nullptr;           // [mmax+1] ... binary exponent
+  int64_t* d_soff = nullptr;         // [mmax+2] spin record offsets (one record per l >= max(m,s))
+  int64_t nrec_spin = 0;
+  glb::LegItem* d_items_spin = nullptr;
+  int nitems_spin = 0;
+  int64_t rec_capacity = 0;          // doubles available in d_rec
+
   // ring FFT
   glb::RingDesc* d_rings = nullptr;  // [nring]
   int* d_ring_order[3] = {nullptr, nullptr, nullptr};  // ring index lists per size class

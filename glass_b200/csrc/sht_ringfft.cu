@@ -32,8 +32,7 @@ struct FftParams {
   const int* mlim;           // per ring pair
   const double2* tw;
   const double2* bf;
-  double* map;
-  int64_t npix;
+  double* maps[4];   // output map of each batch entry
   int mmax;
   int tw_n;
   int kind[4];
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   const int n = d.nphi, h = n >> 1;
   const int mlim = min(p.mlim[d.pair], p.mmax);
   const double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
-  double* __restrict__ out = p.map + (int64_t)b * p.npix + d.start;
+  double* __restrict__ out = p.maps[b] + d.start;
   const int kind = p.kind[b];
   const double tp0 = p.p0[b], tp1 = p.p1[b];
   const double inv_n = 1.0 / (double)n;
@@ -304,17 +303,16 @@ static int launch_class(const FftParams& p, int nrings, int nb, int lb, cudaStre
 }
 
 // phase [nb][nring][mmax+1] -> map [nb][npix]; nb <= 4
-int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* d_map, const int* kind,
-                        const double* tparams, cudaStream_t st) {
+int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
+                        const double* tparams, const int* d_mlim, cudaStream_t st) {
   FftParams p;
   p.rings = pl->d_rings;
   p.phase = d_phase;
   p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
-  p.mlim = pl->d_mlim;
+  p.mlim = d_mlim ? d_mlim : pl->d_mlim;
   p.tw = pl->d_tw;
   p.bf = pl->d_bf;
-  p.map = d_map;
-  p.npix = pl->npix;
+  for (int b = 0; b < 4; ++b) p.maps[b] = (b < nb) ? d_maps[b] : nullptr;
   p.mmax = pl->mmax;
   p.tw_n = pl->tw_n;
   for (int b = 0; b < 4; ++b) {

@@ -263,3 +263,29 @@ def almxfl(alm, fl, *, inplace: bool = False):
         alm[...] = res
         return alm
     return res
+
+
+def alm2map_spin(alms: Sequence, nside: int, spin: int, lmax: int):
+    """
+    Computes maps from a set of 2 spinned alm (glass/healpix.py:81-108):
+    ``map1 + i map2 = sum -(alm1 + i alm2)_lm  sY_lm``.  ``alms[1]`` may be ``None`` or all
+    zeros (what GLASS always passes, glass/lensing.py:334,411) for the E-only fast path.
+    Returns a list of the 2 maps in RING scheme.
+    """
+    a1, a2 = alms[0], alms[1]
+    dev, on_device = _dev_and_kind(a1, a2)
+    d1 = _to(a1, dev, torch.complex128)
+    d2 = None
+    if a2 is not None:
+        d2 = _to(a2, dev, torch.complex128)
+        if not bool(torch.any(d2 != 0)):
+            d2 = None
+    if (lmax + 1) * (lmax + 2) // 2 != d1.numel():
+        raise ValueError("alm size does not match lmax (mmax == lmax is required)")
+    pl = get_plan(nside, lmax, max_batch=1, device=dev)
+    m1 = torch.empty(pl.npix, dtype=torch.float64, device=dev)
+    m2 = torch.empty(pl.npix, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = pl.lib.glb_alm2map_spin(pl.handle, d1.data_ptr(), None if d2 is None else d2.data_ptr(), int(spin), m1.data_ptr(), m2.data_ptr(), pl.stream_ptr())
+    _lib.check(rc, "glb_alm2map_spin")
+    return [_out(m1, on_device), _out(m2, on_device)]
