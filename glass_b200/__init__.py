@@ -22,7 +22,13 @@ from .fields import (  # noqa: F401
 )
 from .galaxies import galaxy_shear, redshifts, redshifts_from_nz  # noqa: F401
 from .harmonics import multalm  # noqa: F401
-from .lensing import MultiPlaneConvergence, multi_plane_matrix, multi_plane_weights  # noqa: F401
+from .lensing import (  # noqa: F401
+    MultiPlaneConvergence,
+    from_convergence,
+    multi_plane_matrix,
+    multi_plane_weights,
+    shear_from_convergence,
+)
 from .points import linear_bias, loglinear_bias, positions_from_delta  # noqa: F401
 from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
 from .shells import RadialWindow  # noqa: F401

@@ -33,6 +33,10 @@ int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* co
 int sht_spin_alm2phase(glb_plan* pl, const double2* d_alm1, const double2* d_alm2, int spin, double2* d_phase,
                        cudaStream_t st);
 int plan_ensure_spin(glb_plan* pl, int spin);
+int plan_ensure_analysis(glb_plan* pl);
+int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w, int accumulate, double2* d_alm,
+                      cudaStream_t st);
+int sht_residual(const double* a, const double* b, int64_t n, double* out, cudaStream_t st);
 
 static inline int group_size(int remaining, int max_batch) {
   const int cap = max_batch >= 4 ? 4 : (max_batch >= 2 ? 2 : 1);
@@ -151,6 +155,29 @@ int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2,
   if (rc != GLB_OK) return rc;
   double* outs[4] = {d_map1, d_map2, nullptr, nullptr};
   return sht_phase2map_group(plan, plan->d_phase, 2, outs, nullptr, nullptr, plan->d_mlim_spin, st);
+}
+
+int glb_map2alm(glb_plan* plan, const double* d_map, const double* d_ring_weights, int niter, double* d_alm,
+                void* stream) {
+  GLB_REQUIRE(plan && d_map && d_alm, "null pointer");
+  GLB_REQUIRE(niter >= 0 && niter <= 100, "niter must be in [0, 100]");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  int rc = plan_ensure_analysis(plan);
+  if (rc != GLB_OK) return rc;
+  double2* alm = reinterpret_cast<double2*>(d_alm);
+  if ((rc = sht_analysis_pass(plan, d_map, d_ring_weights, 0, alm, st)) != GLB_OK) return rc;
+  for (int it = 0; it < niter; ++it) {
+    // alm += A(map - S(alm))
+    double* synth = plan->d_tmpmap;
+    double* resid = plan->d_tmpmap + plan->npix;
+    if ((rc = sht_alm2phase_group(plan, alm, 1, plan->d_phase, st)) != GLB_OK) return rc;
+    double* outs[4] = {synth, nullptr, nullptr, nullptr};
+    if ((rc = sht_phase2map_group(plan, plan->d_phase, 1, outs, nullptr, nullptr, nullptr, st)) != GLB_OK) return rc;
+    if ((rc = sht_residual(d_map, synth, plan->npix, resid, st)) != GLB_OK) return rc;
+    if ((rc = sht_analysis_pass(plan, resid, d_ring_weights, 1, alm, st)) != GLB_OK) return rc;
+  }
+  return GLB_OK;
 }
 
 int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map, const int* h_transform,

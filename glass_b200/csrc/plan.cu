@@ -268,6 +268,8 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_sn_exp);
   cudaFree(pl->d_soff);
   cudaFree(pl->d_items_spin);
+  cudaFree(pl->d_partial);
+  cudaFree(pl->d_tmpmap);
   if (pl->h_pin_in) cudaFreeHost(pl->h_pin_in);
   if (pl->h_pin_out) cudaFreeHost(pl->h_pin_out);
   cudaFree(pl->d_stage_alm);

@@ -65,6 +65,11 @@ struct glb_plan {
   int nitems_spin = 0;
   int64_t rec_capacity = 0;          // doubles available in d_rec
 
+  // analysis (map2alm): per-tile partial sums and a scratch map pair, built lazily
+  double* d_partial = nullptr;       // [ana_ntile][nrec][4]
+  double* d_tmpmap = nullptr;        // [2][npix]
+  int ana_ntile = 0;
+
   // ring FFT
   glb::RingDesc* d_rings = nullptr;  // [nring]
   int* d_ring_order[3] = {nullptr, nullptr, nullptr};  // ring index lists per size class

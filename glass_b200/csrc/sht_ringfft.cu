@@ -226,6 +226,124 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   }
 }
 
+// -------------------------------------------------------------------------------------
+// analysis direction (first stage of map2alm, glass/healpix.py:270): one CTA per (ring, map)
+//   real ring x[0..n) -> z[j] = x[2j] + i x[2j+1] -> forward DFT_h (same machinery, run as
+//   conj(IDFT(conj .))) -> X[k] = sum_t x_t e^{-2 pi i tk/n} -> G_m = X[m mod n] e^{-i m phi0}
+//   scaled by the ring's quadrature weight * 4 pi / npix, for m <= mlim(ring).
+// -------------------------------------------------------------------------------------
+struct FftAnaParams {
+  const RingDesc* rings;
+  const int* order;
+  double2* phase;
+  int64_t phase_map_stride;
+  const int* mlim;
+  const double2* tw;
+  const double2* bf;
+  const double* maps[4];
+  const double* ring_w;   // [nring] or null
+  double norm;            // 4 pi / npix
+  int mmax;
+  int tw_n;
+};
+
+template <int THREADS, int NREG>
+__global__ void __launch_bounds__(THREADS) sht_ringfft_analysis_kernel(const FftAnaParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* buf = reinterpret_cast<double2*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int ring = p.order[blockIdx.x];
+  const int b = blockIdx.y;
+  const RingDesc d = p.rings[ring];
+  const int n = d.nphi, h = n >> 1;
+  const int mlim = min(p.mlim[d.pair], p.mmax);
+  const double* __restrict__ in = p.maps[b] + d.start;
+  double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
+  const double wscale = p.norm * (p.ring_w ? p.ring_w[ring] : 1.0);
+  const int lg = 31 - __clz(h);
+  bool bitrev_out;
+
+  if (d.L == 0) {
+    for (int j = tid; j < h; j += THREADS) buf[j] = *reinterpret_cast<const double2*>(in + 2 * j);
+    __syncthreads();
+    fft_dif<THREADS>(buf, h, p.tw, p.tw_n, false);
+    bitrev_out = true;
+  } else {
+    const int L = d.L, M = d.M;
+    constexpr int NQ = NREG / 2;
+    double2 reg[NREG];
+    double2* ae = reg;
+    double2* ao = reg + NQ;
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) {
+        const double2 c = chirp(q, L);
+        const double2 ze = *reinterpret_cast<const double2*>(in + 4 * q);
+        const double2 zo = *reinterpret_cast<const double2*>(in + 4 * q + 2);
+        ae[t] = cmul(cconj(ze), c);  // forward DFT as conj(IDFT(conj .))
+        ao[t] = cmul(cconj(zo), c);
+      }
+    }
+    const double2* __restrict__ bf = p.bf + d.bf_off;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      double2* a = pass ? ao : ae;
+      for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) {
+        const int q = tid + t * THREADS;
+        if (q < L) buf[q] = a[t];
+      }
+      __syncthreads();
+      fft_dif<THREADS>(buf, M, p.tw, p.tw_n, false);
+      for (int i = tid; i < M; i += THREADS) buf[i] = cmul(buf[i], bf[i]);
+      __syncthreads();
+      fft_dit<THREADS>(buf, M, p.tw, p.tw_n, true);
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) {
+        const int q = tid + t * THREADS;
+        if (q < L) a[t] = buf[q];
+      }
+      __syncthreads();
+    }
+    // Zf[k] = E[k] + w^k O[k], Zf[k+L] = E[k] - w^k O[k], w = e^{-2 pi i / h}; natural order in buf
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) {
+        const double2 c = chirp(q, L);
+        const double2 E = cconj(cmul(ae[t], c));
+        const double2 O = cmul(cconj(cmul(ao[t], c)), cispi(-2.0 * (double)q / (double)h));
+        buf[q] = cadd(E, O);
+        buf[q + L] = csub(E, O);
+      }
+    }
+    __syncthreads();
+    bitrev_out = false;
+  }
+
+  const double inv_n = 1.0 / (double)n;
+  for (int m = tid; m <= mlim; m += THREADS) {
+    const int k = m % n;
+    const int kk = (k <= h) ? k : n - k;
+    int i0 = kk % h, i1 = (h - kk) % h;
+    if (bitrev_out && lg > 0) {
+      i0 = (int)(__brev((unsigned)i0) >> (32 - lg));
+      i1 = (int)(__brev((unsigned)i1) >> (32 - lg));
+    }
+    const double2 zk = buf[i0];
+    const double2 zr = cconj(buf[i1]);
+    const double2 sum = cadd(zk, zr), dif = csub(zk, zr);
+    const double2 wd = cmul(cispi(-2.0 * (double)kk * inv_n), dif);  // -i*wd = (wd.y, -wd.x)
+    double2 X = make_double2(0.5 * (sum.x + wd.y), 0.5 * (sum.y - wd.x));
+    if (k > h) X = cconj(X);
+    if (d.shifted) X = cmul(X, cispi(-(double)(m % (2 * n)) * inv_n));
+    F[m] = cscale(X, wscale);
+  }
+}
+
 // chirp spectrum  Bf = DIF_M( b_wrapped ) / M,  b[d] = conj(c[d]) = e^{-i pi d^2 / L}
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bluestein_spectrum_kernel(const int* Ls, const int* Ms, const int64_t* offs,
@@ -328,6 +446,48 @@ int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* co
   if ((rc = launch_class<256, 8>(p, pl->n_ring_class[1], nb, kClassLB[1], st)) != GLB_OK) return rc;
   p.order = pl->d_ring_order[0];
   if ((rc = launch_class<64, 8>(p, pl->n_ring_class[0], nb, kClassLB[0], st)) != GLB_OK) return rc;
+  return GLB_OK;
+}
+
+template <int THREADS, int NREG>
+static int launch_class_ana(const FftAnaParams& p, int nrings, int nb, int lb, cudaStream_t st) {
+  if (nrings == 0) return GLB_OK;
+  const size_t smem = (size_t)(lb + 2) * sizeof(double2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GLB_CUDA_CHECK(cudaFuncSetAttribute(sht_ringfft_analysis_kernel<THREADS, NREG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nrings, (unsigned)nb);
+  sht_ringfft_analysis_kernel<THREADS, NREG><<<grid, THREADS, smem, st>>>(p);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+// maps [nb] -> weighted phases [nb][nring][mmax+1]
+int sht_map2phase_group(glb_plan* pl, const double* const* d_maps, int nb, const double* d_ring_w, double2* d_phase,
+                        cudaStream_t st) {
+  FftAnaParams p;
+  p.rings = pl->d_rings;
+  p.phase = d_phase;
+  p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
+  p.mlim = pl->d_mlim;
+  p.tw = pl->d_tw;
+  p.bf = pl->d_bf;
+  for (int b = 0; b < 4; ++b) p.maps[b] = (b < nb) ? d_maps[b] : nullptr;
+  p.ring_w = d_ring_w;
+  p.norm = 4.0 * 3.14159265358979323846 / (double)pl->npix;
+  p.mmax = pl->mmax;
+  p.tw_n = pl->tw_n;
+  int rc;
+  p.order = pl->d_ring_order[2];
+  if ((rc = launch_class_ana<512, 16>(p, pl->n_ring_class[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
+  p.order = pl->d_ring_order[1];
+  if ((rc = launch_class_ana<256, 8>(p, pl->n_ring_class[1], nb, kClassLB[1], st)) != GLB_OK) return rc;
+  p.order = pl->d_ring_order[0];
+  if ((rc = launch_class_ana<64, 8>(p, pl->n_ring_class[0], nb, kClassLB[0], st)) != GLB_OK) return rc;
   return GLB_OK;
 }
 

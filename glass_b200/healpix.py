@@ -289,3 +289,33 @@ def alm2map_spin(alms: Sequence, nside: int, spin: int, lmax: int):
         rc = pl.lib.glb_alm2map_spin(pl.handle, d1.data_ptr(), None if d2 is None else d2.data_ptr(), int(spin), m1.data_ptr(), m2.data_ptr(), pl.stream_ptr())
     _lib.check(rc, "glb_alm2map_spin")
     return [_out(m1, on_device), _out(m2, on_device)]
+
+
+def map2alm(maps, *, lmax: int | None = None, pol: bool = True, use_pixel_weights: bool = False, niter: int = 3, ring_weights=None):
+    """
+    Computes the alm of a HEALPix map in RING ordering (glass/healpix.py:232-276; GLASS calls
+    it with ``pol=False, use_pixel_weights=True``, glass/lensing.py:306,408).
+
+    healpy's pixel-weight tables are data files that cannot be obtained offline, so
+    ``use_pixel_weights`` is accepted for signature compatibility and quadrature weights are
+    passed explicitly instead: ``ring_weights`` ([4*nside-1], default uniform) and ``niter``
+    Jacobi refinements ``alm += A(map - S(alm))`` (healpy's default ``iter=3``).
+    """
+    single = not isinstance(maps, (list, tuple)) and getattr(maps, "ndim", 1) == 1
+    if not single:
+        if pol:
+            raise NotImplementedError("polarised (TQU) map2alm is outside the GLASS hot path; pass pol=False")
+        return [map2alm(m, lmax=lmax, pol=False, use_pixel_weights=use_pixel_weights, niter=niter, ring_weights=ring_weights) for m in maps]
+    dev, on_device = _dev_and_kind(maps)
+    m = _to(maps, dev, torch.float64)
+    nside = npix2nside(m.numel())
+    lmax = 3 * nside - 1 if lmax is None else int(lmax)
+    pl = get_plan(nside, lmax, max_batch=1, device=dev)
+    alm = torch.empty(pl.nalm, dtype=torch.complex128, device=dev)
+    w = None if ring_weights is None else _to(ring_weights, dev, torch.float64)
+    if w is not None and w.numel() != 4 * nside - 1:
+        raise ValueError("ring_weights must have 4*nside-1 entries")
+    with torch.cuda.device(dev):
+        rc = pl.lib.glb_map2alm(pl.handle, m.data_ptr(), None if w is None else w.data_ptr(), int(niter), alm.data_ptr(), pl.stream_ptr())
+    _lib.check(rc, "glb_map2alm")
+    return _out(alm, on_device)

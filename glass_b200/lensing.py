@@ -147,3 +147,102 @@ def multi_plane_weights(weights, shells, cosmo):
     weights = weights / np.sum(weights, axis=0)
     mat = multi_plane_matrix(shells, cosmo)
     return np.matmul(mat.T, weights)
+
+
+def _kappa_alm(kappa, lmax, niter, ring_weights):
+    device, on_device = A.pick_device(kappa)
+    k = A.to_dev(kappa, device)
+    nside = hp.get_nside(k)
+    if lmax is None:
+        lmax = 3 * nside - 1
+    alm = hp.map2alm(k, lmax=lmax, pol=False, use_pixel_weights=True, niter=niter, ring_weights=ring_weights)
+    return alm, nside, lmax, device, on_device
+
+
+def _pixwin_ratio(nside, lmax, pixwin):
+    """pw2/pw0 of glass/lensing.py:361-362,421-422.  healpy.pixwin reads data files shipped
+    with healpy (glass/healpix.py:351) that are not available offline: the two window
+    functions are therefore an input here (``pixwin=(pw0, pw2)``)."""
+    if pixwin is None:
+        raise NotImplementedError(
+            "discretized=True needs the HEALPix pixel window functions (healpy data files, "
+            "glass/healpix.py:313-356): pass pixwin=(pw0, pw2) or use discretized=False"
+        )
+    pw0, pw2 = (A.to_np(p)[: lmax + 1] for p in pixwin)
+    return pw2 / pw0
+
+
+def from_convergence(  # noqa: PLR0913
+    kappa,
+    lmax: int | None = None,
+    *,
+    potential: bool = False,
+    deflection: bool = False,
+    shear: bool = False,
+    discretized: bool = True,
+    pixwin=None,
+    niter: int = 3,
+    ring_weights=None,
+):
+    r"""
+    Compute other weak lensing maps from the convergence (glass/lensing.py:185-371).
+
+    Returns the requested maps in the order potential, deflection, shear; deflection and
+    shear are complex128 maps.  Extensions over the reference signature: ``pixwin`` (see
+    :func:`_pixwin_ratio`), ``niter`` and ``ring_weights`` (see
+    :func:`glass_b200.healpix.map2alm`).
+    """
+    if not (potential or deflection or shear):
+        return ()
+    alm, nside, lmax, device, on_device = _kappa_alm(kappa, lmax, niter, ring_weights)
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    results = ()
+
+    def out(t):
+        return t if on_device else t.cpu().numpy()
+
+    # convert convergence to potential (lensing.py:316-322)
+    fl = np.zeros(lmax + 1)
+    fl[1:] = -2.0 / (ell[1:] * (ell[1:] + 1))
+    alm = hp.almxfl(alm, fl, inplace=True)
+    if potential:
+        psi = hp.alm2map_batch(alm[None], nside, lmax)[0]
+        results += (out(psi),)
+    if not (deflection or shear):
+        return results
+    # deflection alms (lensing.py:337-339)
+    fl = np.sqrt(ell * (ell + 1))
+    alm = hp.almxfl(alm, fl, inplace=True)
+    if deflection:
+        a1, a2 = hp.alm2map_spin([alm, None], nside, 1, lmax)
+        results += (out(torch.complex(a1, a2)),)
+    if not shear:
+        return results
+    # shear alms (lensing.py:353-363)
+    fl = np.zeros(lmax + 1)
+    fl[1:] = np.sqrt((ell[1:] - 1) * (ell[1:] + 2))
+    fl /= 2
+    if discretized:
+        fl *= _pixwin_ratio(nside, lmax, pixwin)
+    alm = hp.almxfl(alm, fl, inplace=True)
+    g1, g2 = hp.alm2map_spin([alm, None], nside, 2, lmax)
+    results += (out(torch.complex(g1, g2)),)
+    return results
+
+
+def shear_from_convergence(kappa, lmax: int | None = None, *, discretized: bool = True, pixwin=None, niter: int = 3, ring_weights=None):
+    r"""
+    Weak lensing shear from convergence (glass/lensing.py:374-428; deprecated in the
+    reference in favour of :func:`from_convergence`, but what every example calls).
+    Returns ``[gamma1, gamma2]``.
+    """
+    alm, nside, lmax, device, on_device = _kappa_alm(kappa, lmax, niter, ring_weights)
+    ell = np.arange(lmax + 1)
+    fl = np.sqrt((ell + 2) * (ell + 1) * ell * (ell - 1))
+    fl /= np.clip(ell * (ell + 1), 1, None)
+    fl *= -1
+    if discretized:
+        fl *= _pixwin_ratio(nside, lmax, pixwin)
+    alm = hp.almxfl(alm, fl, inplace=True)
+    g1, g2 = hp.alm2map_spin([alm, None], nside, 2, lmax)
+    return [g1, g2] if on_device else [g1.cpu().numpy(), g2.cpu().numpy()]

@@ -130,3 +130,31 @@ def test_redshifts(cuda_device):
         glass_b200.redshifts_from_nz(10, z, nz, rng=1)
     out = glass_b200.redshifts_from_nz(np.array([3, 4]), z, np.stack([nz, nz[::-1]]), rng=1, warn=False)
     assert out.shape == (7,)
+
+
+@pytest.mark.parametrize("nside,lmax", [(8, 16), (16, None)])
+def test_from_convergence_vs_oracle(cuda_device, nside, lmax):
+    import glass_b200
+
+    rng = np.random.default_rng(nside)
+    kappa = 0.05 * rng.standard_normal(12 * nside**2)
+    got = glass_b200.from_convergence(kappa, lmax, potential=True, deflection=True, shear=True, discretized=False)
+    ref = G.from_convergence(kappa, lmax, potential=True, deflection=True, shear=True)
+    assert len(got) == 3 and got[1].dtype == np.complex128 and got[2].dtype == np.complex128
+    for g, r in zip(got, ref):
+        assert np.abs(g - r).max() < 1e-10 * np.abs(r).max()
+    # tuple lengths for the 8 flag combinations (tests/core/test_lensing.py:21-56)
+    for p in (False, True):
+        for d in (False, True):
+            for s in (False, True):
+                res = glass_b200.from_convergence(kappa, lmax, potential=p, deflection=d, shear=s, discretized=False, niter=0)
+                assert len(res) == p + d + s
+    g1, g2 = glass_b200.shear_from_convergence(kappa, lmax, discretized=False)
+    r1, r2 = G.shear_from_convergence(kappa, lmax)
+    assert np.abs(g1 - r1).max() < 1e-10 * np.abs(r1).max() and np.abs(g2 - r2).max() < 1e-10 * np.abs(r1).max()
+    np.testing.assert_allclose(g1 + 1j * g2, got[2], rtol=0, atol=1e-12 * np.abs(got[2]).max())
+    with pytest.raises(NotImplementedError, match="pixel window"):
+        glass_b200.shear_from_convergence(kappa, lmax)
+    pw = (np.ones(3 * nside), np.linspace(1.0, 0.9, 3 * nside))
+    gd = glass_b200.shear_from_convergence(kappa, lmax, discretized=True, pixwin=pw)
+    assert gd[0].shape == kappa.shape

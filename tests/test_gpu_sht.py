@@ -132,3 +132,33 @@ def test_alm2map_vs_long_double_oracle(cuda_device, nside, lmax):
     ref = sht_c.alm2map(alm[0], nside, lmax, long_double=True)
     err = relerr(got, ref)
     assert err < 1e-11, err
+
+
+@pytest.mark.parametrize("nside,lmax,niter", [(4, 8, 0), (8, 16, 0), (8, 23, 3), (3, 6, 2), (16, 40, 1), (32, 64, 3), (64, 150, 0)])
+def test_map2alm_vs_oracle(cuda_device, nside, lmax, niter):
+    from glass_b200 import healpix as hp
+
+    rng = np.random.default_rng(nside + lmax)
+    mp = rng.standard_normal(12 * nside**2)
+    got = hp.map2alm(mp, lmax=lmax, pol=False, niter=niter)
+    ref = H.map2alm(mp, lmax=lmax, niter=niter)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < RTOL * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+    w = 1.0 + 0.1 * rng.random(4 * nside - 1)
+    got = hp.map2alm(mp, lmax=lmax, pol=False, niter=0, ring_weights=w)
+    ref = H.map2alm(mp, lmax=lmax, niter=0, ring_w=w)
+    assert np.abs(got - ref).max() < RTOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nside,lmax", [(64, 64), (256, 300), (1024, 1100)])
+def test_roundtrip_band_limited(cuda_device, nside, lmax):
+    """Size-independent property: S(A(S(alm))) == S(alm) for band-limited input, and the
+    iterations drive alm itself back."""
+    from glass_b200.healpix import alm2map_batch, map2alm
+
+    alm = torch.as_tensor(random_alm(lmax, 3)).to(cuda_device)
+    m1 = alm2map_batch(alm, nside, lmax)[0]
+    a2 = map2alm(m1, lmax=lmax, pol=False, niter=3)
+    assert (a2 - alm[0]).abs().max().item() < 1e-6 * alm.abs().max().item()
+    m2 = alm2map_batch(a2[None], nside, lmax)[0]
+    assert (m2 - m1).abs().max().item() < 1e-6 * m1.abs().max().item()
