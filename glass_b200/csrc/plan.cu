@@ -3,6 +3,7 @@
 // spectra, and the workspace.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 
 #include "plan.h"
@@ -17,6 +18,7 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ringfft_class_of(int lbuf);
+int sht_build_prep_tables(glb_plan* pl, cudaStream_t st);
 int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::vector<int>& Ms,
                           const std::vector<int64_t>& offs, cudaStream_t st);
 
@@ -122,10 +124,16 @@ int plan_build(glb_plan* pl) {
     if ((rc = upload(&pl->d_roff, roff)) != GLB_OK) return rc;
   }
 
+  if ((rc = sht_build_prep_tables(pl, 0)) != GLB_OK) return rc;
+
   // ---- Legendre work list, most expensive first ----
   {
     pl->leg_R = 4;
     pl->leg_threads = (pl->npair >= 1024) ? 256 : (pl->npair >= 512 ? 128 : 64);
+    if (const char* env = getenv("GLB_LEG_TILE")) {  // tuning knob: ring pairs per CTA tile (256/512/1024)
+      const int t = atoi(env);
+      if (t == 256 || t == 512 || t == 1024) pl->leg_threads = t / 4;
+    }
     const int T = pl->leg_threads * pl->leg_R;
     const int ntile = (pl->npair + T - 1) / T;
     struct Tmp {
@@ -242,7 +250,7 @@ int plan_build(glb_plan* pl) {
   const size_t phase_bytes = (size_t)std::max(gmax, 2) * pl->nring * (pl->mmax + 1) * sizeof(double2);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_rec, rec_bytes));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_phase, phase_bytes));
-  pl->workspace_bytes = (int64_t)(rec_bytes + phase_bytes + bf_total * sizeof(double2));
+  pl->workspace_bytes = (int64_t)(rec_bytes + phase_bytes + bf_total * sizeof(double2) + (size_t)pl->nrec * 5 * sizeof(double));
   return GLB_OK;
 }
 
@@ -254,6 +262,7 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_cm_mant);
   cudaFree(pl->d_cm_exp);
   cudaFree(pl->d_roff);
+  cudaFree(pl->d_prep_tab);
   cudaFree(pl->d_items);
   cudaFree(pl->d_rings);
   for (int c = 0; c < 3; ++c) cudaFree(pl->d_ring_order[c]);

@@ -45,6 +45,7 @@ struct glb_plan {
   int* d_cm_exp = nullptr;          // [mmax+1] binary exponent
   int64_t* d_roff = nullptr;        // [mmax+2] record offsets (in l-pairs) per m
   int64_t nrec = 0;                 // total l-pairs over all m
+  double* d_prep_tab = nullptr;     // [nrec][5] static recurrence / rescaling tables
 
   // Legendre work lists per (threads, R) configuration actually used
   glb::LegItem* d_items = nullptr;

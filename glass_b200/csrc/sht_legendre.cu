@@ -45,21 +45,17 @@ __host__ __device__ __forceinline__ double eps_lm(int l, int m) {
 }
 
 // -------------------------------------------------------------------------------------
-// prep: a_lm (m-major) -> per-m record stream {a_k, b_k, (Ae_re, Ae_im, Ao_re, Ao_im) x B}
-// one thread per m; sequential in k (alpha is a running product, Ao a backward recursion)
+// static per-plan tables (depend on l, m only), one thread per m, run once at plan creation:
+//   tab[roff[m]+k] = {a_k, b_k, alpha_k, s1_k = alpha_k/e_{l+1}, c_k = e_{l+2}/e_{l+3}},  l = m+2k
 // -------------------------------------------------------------------------------------
-template <int B>
-__global__ void __launch_bounds__(128) sht_prep_kernel(const double2* __restrict__ alm, int64_t alm_stride,
-                                                        int lmax, int mmax, const int64_t* __restrict__ roff,
-                                                        double* __restrict__ rec) {
-  constexpr int REC = 2 + 4 * B;
+constexpr int PREP_TAB = 5;
+
+__global__ void __launch_bounds__(128) sht_prep_tables_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
+                                                              double* __restrict__ tab) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m > mmax) return;
   const int K = (lmax - m) / 2 + 1;
-  double* r = rec + roff[m] * REC;
-  const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;  // index of (l=0, m) (virtual)
-
-  // forward pass: alpha, a_k, b_k, Ae; stash s1 = alpha_k/e_{l+1}, s2 = e_{l+2}/e_{l+3}
+  double* t = tab + roff[m] * PREP_TAB;
   double alpha_km1 = 0.0, alpha_k = 1.0;
   double e_lm1 = 0.0;              // e_{l-1}
   double e_l = 0.0;                // e_l   (l = m: zero)
@@ -71,19 +67,12 @@ __global__ void __launch_bounds__(128) sht_prep_kernel(const double2* __restrict
     const double e_lp4 = eps_lm(l + 4, m);
     const double alpha_kp1 = (k == 0) ? 1.0 : alpha_km1 * ((e_l * e_lm1) / (e_lp1 * e_lp2));
     const double a = alpha_k / (e_lp1 * e_lp2 * alpha_kp1);
-    const double b = -(e_lp1 * e_lp1 + e_l * e_l) * a;
-    double* rk = r + (int64_t)k * REC;
-    rk[0] = a;
-    rk[1] = b;
-#pragma unroll
-    for (int bb = 0; bb < B; ++bb) {
-      double2 v = alm[bb * alm_stride + base + l];
-      if (m == 0) v.y = 0.0;  // a_l0 is real (healpy ignores the imaginary part)
-      rk[2 + 4 * bb + 0] = v.x * alpha_k;
-      rk[2 + 4 * bb + 1] = v.y * alpha_k;
-    }
-    rk[2 + 2] = alpha_k / e_lp1;  // stash in map 0's Ao slot
-    rk[2 + 3] = e_lp2 / e_lp3;
+    double* tk = t + (int64_t)k * PREP_TAB;
+    tk[0] = a;
+    tk[1] = -(e_lp1 * e_lp1 + e_l * e_l) * a;
+    tk[2] = alpha_k;
+    tk[3] = alpha_k / e_lp1;
+    tk[4] = e_lp2 / e_lp3;
     alpha_km1 = alpha_k;
     alpha_k = alpha_kp1;
     e_lm1 = e_lp1;
@@ -91,26 +80,82 @@ __global__ void __launch_bounds__(128) sht_prep_kernel(const double2* __restrict
     e_lp1 = e_lp3;
     e_lp2 = e_lp4;
   }
-  // backward pass: t_k = o_k - t_{k+1} * s2_k ; Ao_k = t_k * s1_k   (o_k = a_{m+2k+1,m})
-  double2 t[B];
+}
+
+// -------------------------------------------------------------------------------------
+// prep: a_lm (m-major) -> per-m record stream {a_k, b_k, (Ae_re, Ae_im, Ao_re, Ao_im) x B}
+//   Ae_k = alpha_k a_{m+2k};  Ao_k = s1_k t_k,  t_k = a_{m+2k+1} - c_k t_{k+1}  (backward in k)
+// One CTA per m.  Chunks of PREP_CH l-pairs, from the top: coalesced loads into shared memory,
+// the short sequential recursion by 2B threads (one per map and re/im), coalesced record
+// writes by all threads.
+// -------------------------------------------------------------------------------------
+constexpr int PREP_CH = 512;
+constexpr int PREP_THREADS = 128;
+
+template <int B>
+__global__ void __launch_bounds__(PREP_THREADS) sht_prep_kernel(const double2* __restrict__ alm, int64_t alm_stride,
+                                                                 int lmax, int mmax, const int64_t* __restrict__ roff,
+                                                                 const double* __restrict__ tab, double* __restrict__ rec) {
+  constexpr int REC = 2 + 4 * B;
+  __shared__ double s_t[2 * B][PREP_CH + 1];  // odd-coefficient stream, then t_k in place (+1: no bank conflicts)
+  __shared__ double s_c[PREP_CH];
+  __shared__ double s_carry[2 * B];
+  const int m = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int K = (lmax - m) / 2 + 1;
+  const double* t = tab + roff[m] * PREP_TAB;
+  double* r = rec + roff[m] * REC;
+  const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;  // index of (l=0, m) (virtual)
+  if (tid < 2 * B) s_carry[tid] = 0.0;
+  __syncthreads();
+  for (int khi = K; khi > 0; khi -= PREP_CH) {
+    const int klo = max(khi - PREP_CH, 0);
+    const int n = khi - klo;
+    // load o_k = a_{m+2k+1} (zero beyond lmax; m = 0: imaginary part ignored) and c_k
+    for (int i = tid; i < n; i += PREP_THREADS) {
+      const int k = klo + i;
+      const int l = m + 2 * k;
+      s_c[i] = t[(int64_t)k * PREP_TAB + 4];
 #pragma unroll
-  for (int bb = 0; bb < B; ++bb) t[bb] = make_double2(0.0, 0.0);
-  for (int k = K - 1; k >= 0; --k) {
-    const int l = m + 2 * k;
-    double* rk = r + (int64_t)k * REC;
-    const double s1 = rk[2 + 2], s2 = rk[2 + 3];
-#pragma unroll
-    for (int bb = B - 1; bb >= 0; --bb) {
-      double2 o = make_double2(0.0, 0.0);
-      if (l + 1 <= lmax) {
-        o = alm[bb * alm_stride + base + l + 1];
-        if (m == 0) o.y = 0.0;
+      for (int bb = 0; bb < B; ++bb) {
+        double2 o = make_double2(0.0, 0.0);
+        if (l + 1 <= lmax) {
+          o = alm[bb * alm_stride + base + l + 1];
+          if (m == 0) o.y = 0.0;
+        }
+        s_t[2 * bb][i] = o.x;
+        s_t[2 * bb + 1][i] = o.y;
       }
-      t[bb].x = o.x - t[bb].x * s2;
-      t[bb].y = o.y - t[bb].y * s2;
-      rk[2 + 4 * bb + 2] = t[bb].x * s1;
-      rk[2 + 4 * bb + 3] = t[bb].y * s1;
     }
+    __syncthreads();
+    if (tid < 2 * B) {
+      double tv = s_carry[tid];
+      for (int i = n - 1; i >= 0; --i) {
+        tv = s_t[tid][i] - tv * s_c[i];
+        s_t[tid][i] = tv;
+      }
+      s_carry[tid] = tv;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += PREP_THREADS) {
+      const int k = klo + i;
+      const int l = m + 2 * k;
+      const double* tk = t + (int64_t)k * PREP_TAB;
+      const double alpha = tk[2], s1 = tk[3];
+      double* rk = r + (int64_t)k * REC;
+      rk[0] = tk[0];
+      rk[1] = tk[1];
+#pragma unroll
+      for (int bb = 0; bb < B; ++bb) {
+        double2 v = alm[bb * alm_stride + base + l];
+        if (m == 0) v.y = 0.0;  // a_l0 is real (healpy ignores the imaginary part)
+        rk[2 + 4 * bb + 0] = v.x * alpha;
+        rk[2 + 4 * bb + 1] = v.y * alpha;
+        rk[2 + 4 * bb + 2] = s_t[2 * bb][i] * s1;
+        rk[2 + 4 * bb + 3] = s_t[2 * bb + 1][i] * s1;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -367,9 +412,8 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
 // -------------------------------------------------------------------------------------
 template <int B>
 static int launch_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
-  const int threads = 128;
-  const int blocks = (pl->mmax + 1 + threads - 1) / threads;
-  sht_prep_kernel<B><<<blocks, threads, 0, st>>>(d_alm, pl->nalm, pl->lmax, pl->mmax, pl->d_roff, pl->d_rec);
+  sht_prep_kernel<B><<<pl->mmax + 1, PREP_THREADS, 0, st>>>(d_alm, pl->nalm, pl->lmax, pl->mmax, pl->d_roff,
+                                                             pl->d_prep_tab, pl->d_rec);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;
@@ -412,6 +456,18 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
     return GLB_ERR_INVALID_ARG;
   }
   GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+// static tables of the prep stage (once per plan)
+int sht_build_prep_tables(glb_plan* pl, cudaStream_t st) {
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_prep_tab, (size_t)pl->nrec * PREP_TAB * sizeof(double)));
+  const int threads = 128;
+  sht_prep_tables_kernel<<<(pl->mmax + threads) / threads, threads, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff,
+                                                                             pl->d_prep_tab);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  GLB_CUDA_CHECK(cudaStreamSynchronize(st));
   count_launch();
   return GLB_OK;
 }

@@ -24,6 +24,7 @@ import ctypes as C
 import functools
 import math
 import warnings
+import weakref
 from typing import Callable, Iterable, Iterator, Sequence
 
 import numpy as np
@@ -35,6 +36,44 @@ from . import rng as _rng
 
 # how many shells share one Legendre recurrence (1, 2 or 4)
 SHT_BATCH = 4
+
+
+class _PinnedPool:
+    """Page-locked host buffers for the NumPy-out path.
+
+    cudaHostAlloc of a 1.6 GB map costs 0.2-0.9 s, far more than computing the map, so
+    buffers are recycled: a buffer is handed out again only when the NumPy array that was
+    yielded from it (and every view of it) has been garbage collected -- the caller owns
+    what it was given for as long as it keeps it."""
+
+    def __init__(self):
+        self._bufs: dict[int, list] = {}
+
+    def take(self, n: int) -> torch.Tensor:
+        for ent in self._bufs.setdefault(n, []):
+            if ent[1] is None or ent[1]() is None:
+                ent[1] = _BUSY
+                return ent[0]
+        t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        self._bufs[n].append([t, _BUSY])
+        return t
+
+    def lend(self, t: torch.Tensor) -> np.ndarray:
+        arr = t.numpy()
+        for ent in self._bufs.get(t.numel(), []):
+            if ent[0] is t:
+                ent[1] = weakref.ref(arr)
+        return arr
+
+    def clear(self):
+        self._bufs.clear()
+
+
+def _BUSY():  # sentinel "weakref" that is always alive
+    return True
+
+
+_PINNED = _PinnedPool()
 
 
 def deprecated(msg: str, /):
@@ -244,7 +283,8 @@ class _ShellSampler:
         for s in [s for s in self.zcache if s < j - self.ncorr]:
             del self.zcache[s]
         wh = np.ascontiguousarray(w[:, mis:], dtype=np.float64)
-        wd = torch.as_tensor(wh).to(dev)
+        # pinned staging + async copy: a pageable H2D would block the host until the stream drains
+        wd = torch.from_numpy(wh).pin_memory().to(dev, non_blocking=True)
         self.h2d_bytes += wh.nbytes
         zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in zs])
         _lib.check(
@@ -308,7 +348,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(done)
                     for b in range(nb):
-                        h = torch.empty(npix, dtype=torch.float64, pin_memory=True)
+                        h = _PINNED.take(npix)
                         h.copy_(maps[b], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
@@ -324,7 +364,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                     ev.synchronize()
                     if stats is not None:
                         stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + m.numel() * 8
-                    yield j, m.numpy()
+                    yield j, _PINNED.lend(m)
 
         if on_device:
             for batch in batches():
