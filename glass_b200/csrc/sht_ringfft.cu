@@ -40,42 +40,131 @@ struct FftParams {
   double p1[4];
 };
 
+// ---- shared-memory power-of-two FFTs, radix-8 passes (three butterfly levels per pass held in
+// registers: 5 passes instead of 13 for 8192 points, one table twiddle per thread and pass --
+// the others follow by squaring and by constant 8th roots of unity).
+// DIF: natural in -> bit-reversed out.  DIT: bit-reversed in -> natural out.
+// sign: inverse == false -> e^{-2 pi i jk/M}, inverse == true -> e^{+2 pi i jk/M}.
+__device__ __forceinline__ double2 csq(double2 a) { return make_double2(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
+// multiply by e^{-i pi a/4} (forward) or its conjugate (inverse), a = 0..3
+template <int A>
+__device__ __forceinline__ double2 mul_root8(double2 v, bool inverse) {
+  const double h = 0.70710678118654752440;
+  if (A == 0) return v;
+  if (A == 2) return inverse ? make_double2(-v.y, v.x) : make_double2(v.y, -v.x);            // -+ i
+  if (A == 1) return inverse ? make_double2(h * (v.x - v.y), h * (v.x + v.y))                  // (1+i)/sqrt2
+                             : make_double2(h * (v.x + v.y), h * (v.y - v.x));                 // (1-i)/sqrt2
+  return inverse ? make_double2(-h * (v.x + v.y), h * (v.x - v.y))                            // (-1+i)/sqrt2
+                 : make_double2(h * (v.y - v.x), -h * (v.x + v.y));                            // (-1-i)/sqrt2
+}
+
+// one DIF pass fusing K levels with half-spans s, s/2, ..., s/2^(K-1)
+template <int THREADS, int K>
+__device__ __forceinline__ void dif_pass(double2* x, int M, int s, const double2* __restrict__ tw, int tw_n, bool inverse) {
+  constexpr int R = 1 << K;
+  const int q = s >> (K - 1);
+  const int lq = 31 - __clz(q);
+  const int tstep = tw_n / (2 * s);
+  for (int g = threadIdx.x; g < (M >> K); g += THREADS) {
+    const int lo = g & (q - 1);
+    const int base = ((g >> lq) << (lq + K)) + lo;
+    double2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = x[base + t * q];
+    double2 w = __ldg(&tw[lo * tstep]);  // e^{-2 pi i lo/(2s)}
+    if (inverse) w.y = -w.y;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int hs = R >> (j + 1);
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        if ((t & hs) == 0) {
+          const double2 u = v[t], z = v[t + hs];
+          v[t] = cadd(u, z);
+          double2 d = cmul(csub(u, z), w);
+          const int a = (t & (hs - 1)) * (4 / hs);  // (t mod hs)/(2hs) turns, in units of 1/8
+          if (a == 1) d = mul_root8<1>(d, inverse);
+          else if (a == 2) d = mul_root8<2>(d, inverse);
+          else if (a == 3) d = mul_root8<3>(d, inverse);
+          v[t + hs] = d;
+        }
+      }
+      w = csq(w);
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[base + t * q] = v[t];
+  }
+  __syncthreads();
+}
+
+// one DIT pass fusing K levels with half-spans s, 2s, ..., s*2^(K-1)
+template <int THREADS, int K>
+__device__ __forceinline__ void dit_pass(double2* x, int M, int s, const double2* __restrict__ tw, int tw_n, bool inverse) {
+  constexpr int R = 1 << K;
+  const int q = s;
+  const int lq = 31 - __clz(q);
+  const int tstep = tw_n / (q * R);  // top level: span q*R
+  for (int g = threadIdx.x; g < (M >> K); g += THREADS) {
+    const int lo = g & (q - 1);
+    const int base = ((g >> lq) << (lq + K)) + lo;
+    double2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = x[base + t * q];
+    // lo-dependent twiddle of each level: wl[K-1] = e^{-2 pi i lo/(q R)}, wl[j] = wl[j+1]^2
+    double2 wl[K];
+    wl[K - 1] = __ldg(&tw[lo * tstep]);
+    if (inverse) wl[K - 1].y = -wl[K - 1].y;
+#pragma unroll
+    for (int j = K - 2; j >= 0; --j) wl[j] = csq(wl[j + 1]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int hs = 1 << j;
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        if ((t & hs) == 0) {
+          double2 z = cmul(v[t + hs], wl[j]);
+          const int a = (t & (hs - 1)) * (4 / hs);
+          if (a == 1) z = mul_root8<1>(z, inverse);
+          else if (a == 2) z = mul_root8<2>(z, inverse);
+          else if (a == 3) z = mul_root8<3>(z, inverse);
+          const double2 u = v[t];
+          v[t] = cadd(u, z);
+          v[t + hs] = csub(u, z);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) x[base + t * q] = v[t];
+  }
+  __syncthreads();
+}
+
 template <int THREADS>
 __device__ __forceinline__ void fft_dif(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  const int tid = threadIdx.x;
-  for (int s = M >> 1; s >= 1; s >>= 1) {
-    const int tstep = tw_n / (2 * s);
-    for (int b = tid; b < (M >> 1); b += THREADS) {
-      const int j = b & (s - 1);
-      const int i0 = ((b - j) << 1) + j;
-      const int i1 = i0 + s;
-      const double2 u = x[i0], v = x[i1];
-      double2 w = __ldg(&tw[j * tstep]);
-      if (inverse) w.y = -w.y;
-      x[i0] = cadd(u, v);
-      x[i1] = cmul(csub(u, v), w);
-    }
-    __syncthreads();
+  int s = M >> 1;
+  while (s >= 4) {
+    dif_pass<THREADS, 3>(x, M, s, tw, tw_n, inverse);
+    s >>= 3;
   }
+  if (s == 2)
+    dif_pass<THREADS, 2>(x, M, s, tw, tw_n, inverse);
+  else if (s == 1)
+    dif_pass<THREADS, 1>(x, M, s, tw, tw_n, inverse);
 }
 
 template <int THREADS>
 __device__ __forceinline__ void fft_dit(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  const int tid = threadIdx.x;
-  for (int s = 1; s < M; s <<= 1) {
-    const int tstep = tw_n / (2 * s);
-    for (int b = tid; b < (M >> 1); b += THREADS) {
-      const int j = b & (s - 1);
-      const int i0 = ((b - j) << 1) + j;
-      const int i1 = i0 + s;
-      double2 w = __ldg(&tw[j * tstep]);
-      if (inverse) w.y = -w.y;
-      const double2 u = x[i0], v = cmul(x[i1], w);
-      x[i0] = cadd(u, v);
-      x[i1] = csub(u, v);
-    }
-    __syncthreads();
+  int s = 1;
+  while (s * 8 <= M) {
+    dit_pass<THREADS, 3>(x, M, s, tw, tw_n, inverse);
+    s <<= 3;
   }
+  if (s * 4 == M)
+    dit_pass<THREADS, 2>(x, M, s, tw, tw_n, inverse);
+  else if (s * 2 == M)
+    dit_pass<THREADS, 1>(x, M, s, tw, tw_n, inverse);
 }
 
 __device__ __forceinline__ double apply_transform(double x, int kind, double p0, double p1) {
