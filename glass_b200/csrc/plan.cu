@@ -254,7 +254,41 @@ int plan_build(glb_plan* pl) {
   return GLB_OK;
 }
 
+// scalar (m, ring tile) work list for an arbitrary tile size, most expensive first
+int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems) {
+  auto it = pl->item_lists.find(tile);
+  if (it == pl->item_lists.end()) {
+    const int ntile = (pl->npair + tile - 1) / tile;
+    struct Tmp {
+      LegItem it;
+      double cost;
+    };
+    std::vector<Tmp> tmp;
+    for (int m = 0; m <= pl->mmax; ++m) {
+      const int K = (pl->lmax - m) / 2 + 1;
+      for (int t = 0; t < ntile; ++t) {
+        const int lo = std::max(t * tile, pl->h_rmin[m]);
+        const int hi = std::min((t + 1) * tile, pl->npair);
+        if (hi <= lo) continue;
+        tmp.push_back({{m, t}, (double)K * (hi - lo)});
+      }
+    }
+    std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& b) { return a.cost > b.cost; });
+    std::vector<LegItem> items(tmp.size());
+    for (size_t i = 0; i < tmp.size(); ++i) items[i] = tmp[i].it;
+    LegItem* d = nullptr;
+    const int rc = upload(&d, items);
+    if (rc != GLB_OK) return rc;
+    it = pl->item_lists.emplace(tile, std::make_pair(d, (int)items.size())).first;
+  }
+  *d_items = it->second.first;
+  *nitems = it->second.second;
+  return GLB_OK;
+}
+
 void plan_free(glb_plan* pl) {
+  for (auto& kv : pl->item_lists) cudaFree(kv.second.first);
+  pl->item_lists.clear();
   cudaSetDevice(pl->device);
   cudaFree(pl->d_z);
   cudaFree(pl->d_sth);

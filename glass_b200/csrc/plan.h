@@ -1,6 +1,8 @@
 // plan.h -- the opaque glb_plan: HEALPix ring geometry, Legendre work list, FFT tables
 // and workspace for one (nside, lmax, device).
 #pragma once
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -51,6 +53,8 @@ struct glb_plan {
   glb::LegItem* d_items = nullptr;
   int nitems = 0;
   int leg_threads = 256, leg_R = 4;  // tile = leg_threads * leg_R ring pairs
+  // extra scalar work lists keyed by tile size (ring pairs per CTA), built on demand
+  std::map<int, std::pair<glb::LegItem*, int>> item_lists;
 
   // spin-weighted synthesis (built lazily by plan_ensure_spin for one spin at a time)
   int spin_ready = 0;                // spin the tables below were built for (0 = none)

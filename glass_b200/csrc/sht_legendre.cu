@@ -25,6 +25,9 @@
 //    test), FAST (all rings at scale 0: no tests).
 //  * rings with mlim(ring) < m are skipped entirely (mlim as in libsharp's
 //    sharp_get_mlim heuristic, shared with the FFT stage through the plan).
+#include <cstdio>
+#include <cstdlib>
+
 #include "plan.h"
 
 namespace glb {
@@ -199,6 +202,8 @@ __device__ __forceinline__ void lam_mm_scaled(int m, double sth, double cm_mant,
     val = scalbn(mant, E + s * SCALE_BITS);  // exponent in (-512, 0]
   }
 }
+
+int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems);
 
 struct LegParams {
   const LegItem* items;
@@ -436,23 +441,46 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
   p.mmax = pl->mmax;
   p.npair = pl->npair;
   p.nring = pl->nring;
-  constexpr int R = (B == 4) ? 2 : 4;
-  if (pl->leg_R != 4) {
-    set_last_error("internal: legendre tile configuration");
-    return GLB_ERR_INVALID_ARG;
+  // (R ring pairs per thread, THREADS) per batch size.  Shared-memory wavefronts per DFMA scale
+  // as 2/R (every broadcast LDS.128 costs two), registers as 8*R*B for the accumulators.
+  int R = 4, threads = pl->leg_threads;
+  if (B == 4 && pl->npair >= 1024) {
+    R = 4;
+    threads = 256;
+    if (const char* env = getenv("GLB_LEG_CFG4")) {  // tuning knob "R,THREADS"
+      int r = 0, t = 0;
+      if (sscanf(env, "%d,%d", &r, &t) == 2) {
+        R = r;
+        threads = t;
+      }
+    }
   }
-  // tile = leg_threads * 4 ring pairs; with R == 2 we use twice the threads per tile
-  const int threads = pl->leg_threads * 4 / R;
-  if (threads == 64)
-    sht_legendre_synth_kernel<R, B, 64><<<pl->nitems, 64, 0, st>>>(p);
-  else if (threads == 128)
-    sht_legendre_synth_kernel<R, B, 128><<<pl->nitems, 128, 0, st>>>(p);
-  else if (threads == 256)
-    sht_legendre_synth_kernel<R, B, 256><<<pl->nitems, 256, 0, st>>>(p);
-  else if (threads == 512)
-    sht_legendre_synth_kernel<R, B, 512><<<pl->nitems, 512, 0, st>>>(p);
-  else {
-    set_last_error("internal: legendre thread configuration");
+  LegItem* items = nullptr;
+  int nitems = 0;
+  int rc = plan_items(pl, R * threads, &items, &nitems);
+  if (rc != GLB_OK) return rc;
+  p.items = items;
+#define GLB_LEG_LAUNCH(RR, TT)                                                   \
+  if (R == RR && threads == TT) {                                                \
+    sht_legendre_synth_kernel<RR, B, TT><<<nitems, TT, 0, st>>>(p);              \
+    launched = true;                                                             \
+  }
+  bool launched = false;
+  GLB_LEG_LAUNCH(4, 64)
+  GLB_LEG_LAUNCH(4, 128)
+  GLB_LEG_LAUNCH(4, 256)
+  if (B == 4) {
+    GLB_LEG_LAUNCH(2, 512)
+    GLB_LEG_LAUNCH(2, 256)
+    GLB_LEG_LAUNCH(3, 384)
+    GLB_LEG_LAUNCH(3, 256)
+    GLB_LEG_LAUNCH(3, 320)
+    GLB_LEG_LAUNCH(4, 192)
+    GLB_LEG_LAUNCH(4, 320)
+  }
+#undef GLB_LEG_LAUNCH
+  if (!launched) {
+    set_last_error("internal: legendre (R, threads) configuration not instantiated");
     return GLB_ERR_INVALID_ARG;
   }
   GLB_CUDA_CHECK(cudaGetLastError());
