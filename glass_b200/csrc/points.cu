@@ -70,22 +70,9 @@ __global__ void __launch_bounds__(1024) final_sum_kernel(const double* __restric
 }
 
 // ---- Poisson from Philox --------------------------------------------------------------
-__device__ __forceinline__ int64_t poisson_philox(double lam, uint32_t k0, uint32_t k1, uint64_t idx, uint32_t stream) {
-  if (!(lam > 0.0)) return 0;
-  if (lam < 10.0) {
-    // inversion by sequential search, one uniform
-    const Philox4 r = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), stream, RNG_TAG_POISSON, k0, k1);
-    const double u = u01_closed_open(r.v[0], r.v[1]);
-    double p = exp(-lam), F = p;
-    int64_t x = 0;
-    while (u > F && x < 256) {
-      ++x;
-      p *= lam / (double)x;
-      F += p;
-    }
-    return x;
-  }
-  // PTRS, Hoermann 1993 (the algorithm NumPy uses for lam >= 10)
+// PTRS, Hoermann 1993 (the algorithm NumPy uses for lam >= 10); kept out of line so that its
+// registers (log, lgamma) do not limit the occupancy of the common small-lambda path
+__device__ __noinline__ int64_t poisson_ptrs(double lam, uint32_t k0, uint32_t k1, uint64_t idx, uint32_t stream) {
   const double slam = sqrt(lam), loglam = log(lam);
   const double b = 0.931 + 2.53 * slam;
   const double a = -0.059 + 0.02483 * b;
@@ -104,6 +91,25 @@ __device__ __forceinline__ int64_t poisson_philox(double lam, uint32_t k0, uint3
   return (int64_t)floor(lam);
 }
 
+// u: the pixel's own uniform (one Philox call serves the two pixels of a pair)
+__device__ __forceinline__ int64_t poisson_from_uniform(double lam, double u, uint32_t k0, uint32_t k1, uint64_t pix,
+                                                        uint32_t stream) {
+  if (!(lam > 0.0)) return 0;
+  if (lam < 10.0) {
+    // inversion by sequential search
+    if (u < 1.0 - lam) return 0;  // u < 1 - lam <= e^{-lam}: zero galaxies without evaluating exp
+    double p = exp(-lam), F = p;
+    int64_t x = 0;
+    while (u > F && x < 256) {
+      ++x;
+      p *= lam / (double)x;
+      F += p;
+    }
+    return x;
+  }
+  return poisson_ptrs(lam, k0, k1, pix, stream);
+}
+
 struct CountParams {
   const double* delta;
   const double* vis;        // may be null
@@ -120,29 +126,51 @@ struct CountParams {
   uint32_t k0, k1, stream;
 };
 
-__global__ void __launch_bounds__(PT_THREADS) points_count_kernel(const CountParams p) {
+__global__ void __launch_bounds__(PT_THREADS, 4) points_count_kernel(const CountParams p) {
   __shared__ int64_t sh[PT_THREADS / 32];
   const int64_t base = (int64_t)blockIdx.x * PT_TILE;
   const double mean = p.mean ? p.mean[0] : 0.0;
   int64_t s = 0;
+  constexpr int NP = PT_ITEMS / 2;  // pixel pairs per thread (npix = 12 nside^2 is even)
+  // issue all loads of the tile first (memory-level parallelism), then do the arithmetic
+  double2 dv[NP], vv[NP];
+  longlong2 cin[NP];
 #pragma unroll
-  for (int i = 0; i < PT_ITEMS; ++i) {
-    const int64_t pix = base + threadIdx.x + (int64_t)i * PT_THREADS;
+  for (int i = 0; i < NP; ++i) {
+    const int64_t pix = base + 2 * (threadIdx.x + (int64_t)i * PT_THREADS);
+    const bool ok = pix < p.npix;
+    dv[i] = ok ? *reinterpret_cast<const double2*>(p.delta + pix) : make_double2(0.0, 0.0);
+    vv[i] = (ok && p.vis) ? *reinterpret_cast<const double2*>(p.vis + pix) : make_double2(1.0, 1.0);
+    cin[i] = (ok && !p.sample) ? *reinterpret_cast<const longlong2*>(p.counts_in + pix) : make_longlong2(0, 0);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int64_t pix = base + 2 * (threadIdx.x + (int64_t)i * PT_THREADS);
     if (pix >= p.npix) continue;
-    double n = biased(p.delta[pix], p.model, p.bias);
-    if (p.mean) n = __dsub_rn(n, mean);
-    n = __dadd_rn(n, 1.0);
-    n = __dmul_rn(n, p.scale);
-    if (p.vis) n = __dmul_rn(n, p.vis[pix]);
-    if (p.nbar_out) p.nbar_out[pix] = n;
-    int64_t c;
-    if (p.sample) {
-      c = poisson_philox(fmax(n, 0.0), p.k0, p.k1, (uint64_t)pix, p.stream);
-    } else {
-      c = p.counts_in[pix];
+    double n0 = biased(dv[i].x, p.model, p.bias), n1 = biased(dv[i].y, p.model, p.bias);
+    if (p.mean) {
+      n0 = __dsub_rn(n0, mean);
+      n1 = __dsub_rn(n1, mean);
     }
-    p.counts[pix] = c;
-    s += c;
+    n0 = __dmul_rn(__dadd_rn(n0, 1.0), p.scale);
+    n1 = __dmul_rn(__dadd_rn(n1, 1.0), p.scale);
+    if (p.vis) {
+      n0 = __dmul_rn(n0, vv[i].x);
+      n1 = __dmul_rn(n1, vv[i].y);
+    }
+    if (p.nbar_out) *reinterpret_cast<double2*>(p.nbar_out + pix) = make_double2(n0, n1);
+    longlong2 c;
+    if (p.sample) {
+      // one Philox call per pixel pair: words (0,1) -> even pixel, (2,3) -> odd pixel
+      const uint64_t pr = (uint64_t)pix >> 1;
+      const Philox4 r = philox4x32_10((uint32_t)pr, (uint32_t)(pr >> 32), p.stream, RNG_TAG_POISSON, p.k0, p.k1);
+      c.x = poisson_from_uniform(fmax(n0, 0.0), u01_closed_open(r.v[0], r.v[1]), p.k0, p.k1, (uint64_t)pix, p.stream);
+      c.y = poisson_from_uniform(fmax(n1, 0.0), u01_closed_open(r.v[2], r.v[3]), p.k0, p.k1, (uint64_t)pix + 1, p.stream);
+    } else {
+      c = cin[i];
+    }
+    *reinterpret_cast<longlong2*>(p.counts + pix) = c;
+    s += c.x + c.y;
   }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -184,33 +212,53 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(const int64_t* __
 __global__ void __launch_bounds__(PT_THREADS) points_offsets_kernel(const int64_t* __restrict__ counts, int64_t npix,
                                                                     const int64_t* __restrict__ block_off, int nblocks,
                                                                     int64_t* __restrict__ off) {
-  __shared__ int64_t sh[PT_THREADS];
+  __shared__ int64_t s_c[PT_TILE];      // counts, then offsets, of the tile
+  __shared__ int64_t sh[PT_THREADS / 32];
   const int64_t base = (int64_t)blockIdx.x * PT_TILE;
+  const int tid = threadIdx.x;
+  // coalesced load into shared memory
+#pragma unroll
+  for (int i = 0; i < PT_ITEMS; ++i) {
+    const int k = tid + i * PT_THREADS;
+    s_c[k] = (base + k < npix) ? counts[base + k] : 0;
+  }
+  __syncthreads();
   // thread t owns PT_ITEMS consecutive pixels
   int64_t c[PT_ITEMS];
   int64_t s = 0;
 #pragma unroll
   for (int i = 0; i < PT_ITEMS; ++i) {
-    const int64_t pix = base + (int64_t)threadIdx.x * PT_ITEMS + i;
-    c[i] = (pix < npix) ? counts[pix] : 0;
+    c[i] = s_c[tid * PT_ITEMS + i];
     s += c[i];
   }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < PT_THREADS; o <<= 1) {
-    const int64_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += t;
-    __syncthreads();
+  // block scan of the per-thread sums: warp shuffles, then the warp totals
+  int64_t incl = s;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  int64_t run = block_off[blockIdx.x] + sh[threadIdx.x] - s;
+  if (lane == 31) sh[warp] = incl;
+  __syncthreads();
+  int64_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < PT_THREADS / 32; ++w)
+    if (w < warp) woff += sh[w];
+  int64_t run = block_off[blockIdx.x] + woff + incl - s;
 #pragma unroll
   for (int i = 0; i < PT_ITEMS; ++i) {
-    const int64_t pix = base + (int64_t)threadIdx.x * PT_ITEMS + i;
-    if (pix < npix) off[pix] = run;
+    s_c[tid * PT_ITEMS + i] = run;
     run += c[i];
   }
-  if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) off[npix] = block_off[nblocks];
+  __syncthreads();
+  // coalesced store
+#pragma unroll
+  for (int i = 0; i < PT_ITEMS; ++i) {
+    const int k = tid + i * PT_THREADS;
+    if (base + k < npix) off[base + k] = s_c[k];
+  }
+  if (blockIdx.x == nblocks - 1 && tid == 0) off[npix] = block_off[nblocks];
 }
 
 struct FillParams {
@@ -226,32 +274,83 @@ struct FillParams {
   uint32_t k0, k1, stream;
 };
 
-__global__ void __launch_bounds__(256) points_fill_kernel(const FillParams p) {
-  const int64_t pix = p.p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= p.p1) return;
-  const int64_t n = p.counts[pix];
-  if (n == 0) return;
-  const int64_t g0 = p.off[pix];
-  const int64_t o0 = g0 - p.off[p.p0];
-  int x, y, f;
-  ring2xyf(p.nside, pix, x, y, f);
+// One CTA per tile of FILL_TILE pixels: the tile's counts are expanded in shared memory
+// (block scan -> local offsets), then threads walk GALAXIES, not pixels, so the expensive
+// pixel->angle arithmetic runs on dense warps and the (lon, lat) stores are coalesced.
+constexpr int FILL_TILE = 2048;
+constexpr int FILL_THREADS = 256;
+constexpr int FILL_ITEMS = FILL_TILE / FILL_THREADS;
+
+__global__ void __launch_bounds__(FILL_THREADS) points_fill_kernel(const FillParams p) {
+  __shared__ int s_off[FILL_TILE + 1];
+  __shared__ int s_tsum[FILL_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t tile0 = p.p0 + (int64_t)blockIdx.x * FILL_TILE;
+  const int npx = (int)min((int64_t)FILL_TILE, p.p1 - tile0);
+  // coalesced load of the counts
+#pragma unroll
+  for (int i = 0; i < FILL_ITEMS; ++i) {
+    const int k = tid + i * FILL_THREADS;
+    s_off[k] = (k < npx) ? (int)p.counts[tile0 + k] : 0;
+  }
+  __syncthreads();
+  // blocked exclusive scan: thread t owns entries [t*ITEMS, (t+1)*ITEMS)
+  int c[FILL_ITEMS];
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < FILL_ITEMS; ++i) {
+    c[i] = s_off[tid * FILL_ITEMS + i];
+    sum += c[i];
+  }
+  s_tsum[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < FILL_THREADS; o <<= 1) {
+    const int t = (tid >= o) ? s_tsum[tid - o] : 0;
+    __syncthreads();
+    s_tsum[tid] += t;
+    __syncthreads();
+  }
+  int run = s_tsum[tid] - sum;
+#pragma unroll
+  for (int i = 0; i < FILL_ITEMS; ++i) {
+    s_off[tid * FILL_ITEMS + i] = run;
+    run += c[i];
+  }
+  if (tid == FILL_THREADS - 1) s_off[FILL_TILE] = run;
+  __syncthreads();
+  const int total = s_off[FILL_TILE];
+  if (total == 0) return;
+  const int64_t g0 = p.off[tile0];          // global index of the tile's first galaxy
+  const int64_t o0 = g0 - p.off[p.p0];      // its position in this call's output
   const double rad2deg = 57.295779513082320877;  // 180/pi, as np.degrees
-  for (int64_t i = 0; i < n; ++i) {
+  for (int g = tid; g < total; g += FILL_THREADS) {
+    // largest i with s_off[i] <= g
+    int lo = 0, hi = FILL_TILE;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= g)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const int64_t pix = tile0 + lo;
     double u, v;
     if (p.u) {
-      u = p.u[o0 + i];
-      v = p.v[o0 + i];
+      u = p.u[o0 + g];
+      v = p.v[o0 + g];
     } else {
-      const uint64_t g = (uint64_t)(g0 + i);
-      const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), p.stream, RNG_TAG_POS, p.k0, p.k1);
+      const uint64_t gi = (uint64_t)(g0 + g);
+      const Philox4 r = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.stream, RNG_TAG_POS, p.k0, p.k1);
       u = u01_closed_open(r.v[0], r.v[1]);
       v = u01_closed_open(r.v[2], r.v[3]);
     }
+    int x, y, f;
+    ring2xyf(p.nside, pix, x, y, f);
     double z, sth, phi;
     hpc2loc((double)p.nside, x, y, f, u, v, z, sth, phi);
-    p.lon[o0 + i] = phi * rad2deg;
-    p.lat[o0 + i] = 90.0 - atan2(sth, z) * rad2deg;
-    if (p.ipix) p.ipix[o0 + i] = pix;
+    p.lon[o0 + g] = phi * rad2deg;
+    p.lat[o0 + g] = 90.0 - atan2(sth, z) * rad2deg;
+    if (p.ipix) p.ipix[o0 + g] = pix;
   }
 }
 
@@ -391,7 +490,7 @@ int glb_points_fill(int64_t nside, const int64_t* d_counts, const int64_t* d_off
   p.k1 = (uint32_t)(seed >> 32);
   p.stream = stream_id;
   const int64_t n = pix1 - pix0;
-  points_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  points_fill_kernel<<<(unsigned)((n + FILL_TILE - 1) / FILL_TILE), FILL_THREADS, 0, (cudaStream_t)stream>>>(p);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;
