@@ -53,6 +53,9 @@ SIGNATURES = {
     "glb_ellipticity": (_i, [_i, C.c_double, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_redshifts_from_cdf": (_i, [_dp, _dp, _i, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_alm2map_host": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
+    "glb_dist_setup": (_i, [_vp, _i, _i, _ip, _ip, _i]),
+    "glb_dist_alm2phase": (_i, [_vp, _dp, _i, _dp, _vp]),
+    "glb_dist_phase2map": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_plan_timing_enable": (_i, [_vp, _i]),
     "glb_plan_timing_read": (_i, [_vp, _dp, _vp, _vp]),
     "glb_kernel_launch_count": (C.c_uint64, []),

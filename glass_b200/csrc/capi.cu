@@ -9,7 +9,7 @@ int plan_build(glb_plan* pl);
 void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
-int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st);
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false);
 unsigned long long launch_count();
 int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
 
@@ -29,7 +29,8 @@ static int timing_collect(glb_plan* pl) {
   return GLB_OK;
 }
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
-                        const double* tparams, const int* d_mlim, cudaStream_t st);
+                        const double* tparams, const int* d_mlim, cudaStream_t st, bool dist = false);
+int plan_dist_setup(glb_plan* pl, int world, int rank, const int* h_rowmap, const int* h_my_rings, int n_my);
 int sht_spin_alm2phase(glb_plan* pl, const double2* d_alm1, const double2* d_alm2, int spin, double2* d_phase,
                        cudaStream_t st);
 int plan_ensure_spin(glb_plan* pl, int spin);
@@ -219,6 +220,37 @@ int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double
   for (int b = 0; b < nmaps; ++b) outs[b] = d_map + (int64_t)b * plan->npix;
   return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_phase), nmaps, outs, nullptr, nullptr, nullptr,
                              (cudaStream_t)stream);
+}
+
+int glb_dist_setup(glb_plan* plan, int world, int rank, const int* h_rowmap, const int* h_my_rings, int n_my_rings) {
+  GLB_REQUIRE(plan && h_rowmap && h_my_rings, "null pointer");
+  GLB_REQUIRE(world >= 1 && rank >= 0 && rank < world && n_my_rings >= 0, "bad world/rank");
+  return plan_dist_setup(plan, world, rank, h_rowmap, h_my_rings, n_my_rings);
+}
+
+int glb_dist_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_send, void* stream) {
+  GLB_REQUIRE(plan && d_alm && d_send, "null pointer");
+  GLB_REQUIRE(nmaps == 1 || nmaps == 2 || nmaps == 4, "nmaps must be 1, 2 or 4");
+  GLB_REQUIRE(nmaps <= plan->max_batch, "nmaps exceeds max_batch");
+  GLB_REQUIRE(plan->dist_W > 0, "glb_dist_setup has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  GLB_CUDA_CHECK(cudaMemsetAsync(d_send, 0, (size_t)nmaps * plan->nring * plan->dist_W * sizeof(double2), st));
+  int rc = sht_prep_group(plan, reinterpret_cast<const double2*>(d_alm), nmaps, st);
+  if (rc != GLB_OK) return rc;
+  return sht_legendre_group(plan, nmaps, reinterpret_cast<double2*>(d_send), st, true);
+}
+
+int glb_dist_phase2map(glb_plan* plan, const double* d_recv, int nmaps, double* d_map, const int* h_transform,
+                       const double* h_tparams, void* stream) {
+  GLB_REQUIRE(plan && d_recv && d_map, "null pointer");
+  GLB_REQUIRE(nmaps >= 1 && nmaps <= 4, "nmaps must be in [1, 4]");
+  GLB_REQUIRE(plan->dist_W > 0, "glb_dist_setup has not been called");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  double* outs[4];
+  for (int b = 0; b < nmaps; ++b) outs[b] = d_map + (int64_t)b * plan->npix;
+  return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_recv), nmaps, outs, h_transform, h_tparams,
+                             nullptr, (cudaStream_t)stream, true);
 }
 
 int glb_plan_timing_enable(glb_plan* plan, int enable) {

@@ -255,8 +255,9 @@ int plan_build(glb_plan* pl) {
 }
 
 // scalar (m, ring tile) work list for an arbitrary tile size, most expensive first
-int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems) {
-  auto it = pl->item_lists.find(tile);
+int plan_items(glb_plan* pl, int tile, int G, int rank, LegItem** d_items, int* nitems) {
+  const int64_t key = (int64_t)tile | ((int64_t)G << 24) | ((int64_t)rank << 36);
+  auto it = pl->item_lists.find(key);
   if (it == pl->item_lists.end()) {
     const int ntile = (pl->npair + tile - 1) / tile;
     struct Tmp {
@@ -265,6 +266,7 @@ int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems) {
     };
     std::vector<Tmp> tmp;
     for (int m = 0; m <= pl->mmax; ++m) {
+      if (m % G != rank) continue;  // m-split: this rank's share of the m values
       const int K = (pl->lmax - m) / 2 + 1;
       for (int t = 0; t < ntile; ++t) {
         const int lo = std::max(t * tile, pl->h_rmin[m]);
@@ -279,10 +281,45 @@ int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems) {
     LegItem* d = nullptr;
     const int rc = upload(&d, items);
     if (rc != GLB_OK) return rc;
-    it = pl->item_lists.emplace(tile, std::make_pair(d, (int)items.size())).first;
+    it = pl->item_lists.emplace(key, std::make_pair(d, (int)items.size())).first;
   }
   *d_items = it->second.first;
   *nitems = it->second.second;
+  return GLB_OK;
+}
+
+// m-split set-up: rowmap[ring] = row in the permuted send layout, my_rings = rings this rank owns
+int plan_dist_setup(glb_plan* pl, int world, int rank, const int* h_rowmap, const int* h_my_rings, int n_my) {
+  GLB_CUDA_CHECK(cudaSetDevice(pl->device));
+  pl->dist_world = world;
+  pl->dist_rank = rank;
+  pl->dist_W = (pl->mmax + 1 + world - 1) / world;
+  pl->dist_rows_local = n_my;
+  std::vector<int> rowmap(h_rowmap, h_rowmap + pl->nring), rowidx(pl->nring, -1);
+  for (int i = 0; i < n_my; ++i) {
+    if (h_my_rings[i] < 0 || h_my_rings[i] >= pl->nring) {
+      set_last_error("glb_dist_setup: ring index out of range");
+      return GLB_ERR_INVALID_ARG;
+    }
+    rowidx[h_my_rings[i]] = i;
+  }
+  cudaFree(pl->d_dist_rowmap);
+  cudaFree(pl->d_dist_rowidx);
+  pl->d_dist_rowmap = pl->d_dist_rowidx = nullptr;
+  int rc;
+  if ((rc = upload(&pl->d_dist_rowmap, rowmap)) != GLB_OK) return rc;
+  if ((rc = upload(&pl->d_dist_rowidx, rowidx)) != GLB_OK) return rc;
+  // ring lists per FFT size class, largest first (same order as the single-GPU lists)
+  std::vector<int> mine(h_my_rings, h_my_rings + n_my);
+  std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) { return pl->h_rings[a].M > pl->h_rings[b].M; });
+  std::vector<int> order[3];
+  for (int r : mine) order[ringfft_class_of(pl->h_rings[r].M)].push_back(r);
+  for (int c = 0; c < 3; ++c) {
+    cudaFree(pl->d_dist_ring_order[c]);
+    pl->d_dist_ring_order[c] = nullptr;
+    pl->n_dist_ring_class[c] = (int)order[c].size();
+    if ((rc = upload(&pl->d_dist_ring_order[c], order[c])) != GLB_OK) return rc;
+  }
   return GLB_OK;
 }
 
@@ -311,6 +348,9 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_sn_exp);
   cudaFree(pl->d_soff);
   cudaFree(pl->d_items_spin);
+  cudaFree(pl->d_dist_rowmap);
+  cudaFree(pl->d_dist_rowidx);
+  for (int c = 0; c < 3; ++c) cudaFree(pl->d_dist_ring_order[c]);
   cudaFree(pl->d_partial);
   cudaFree(pl->d_tmpmap);
   if (pl->h_pin_in) cudaFreeHost(pl->h_pin_in);

@@ -54,7 +54,7 @@ struct glb_plan {
   int nitems = 0;
   int leg_threads = 256, leg_R = 4;  // tile = leg_threads * leg_R ring pairs
   // extra scalar work lists keyed by tile size (ring pairs per CTA), built on demand
-  std::map<int, std::pair<glb::LegItem*, int>> item_lists;
+  std::map<int64_t, std::pair<glb::LegItem*, int>> item_lists;
 
   // spin-weighted synthesis (built lazily by plan_ensure_spin for one spin at a time)
   int spin_ready = 0;                // spin the tables below were built for (0 = none)
@@ -74,6 +74,16 @@ struct glb_plan {
   double* d_partial = nullptr;       // [ana_ntile][nrec][4]
   double* d_tmpmap = nullptr;        // [2][npix]
   int ana_ntile = 0;
+
+  // m-split distribution over GPUs (glb_dist_setup): this rank computes the Legendre stage for
+  // m = rank (mod world) and the Fourier stage for its own ring bands
+  int dist_world = 1, dist_rank = 0;
+  int dist_W = 0;                    // m slots per rank = ceil((mmax+1)/world)
+  int dist_rows_local = 0;           // rings owned by this rank
+  int* d_dist_rowmap = nullptr;      // [nring] row of each ring in the permuted send layout
+  int* d_dist_rowidx = nullptr;      // [nring] local row of each owned ring (-1 otherwise)
+  int* d_dist_ring_order[3] = {nullptr, nullptr, nullptr};
+  int n_dist_ring_class[3] = {0, 0, 0};
 
   // ring FFT
   glb::RingDesc* d_rings = nullptr;  // [nring]

@@ -203,7 +203,7 @@ __device__ __forceinline__ void lam_mm_scaled(int m, double sth, double cm_mant,
   }
 }
 
-int plan_items(glb_plan* pl, int tile, LegItem** d_items, int* nitems);
+int plan_items(glb_plan* pl, int tile, int G, int rank, LegItem** d_items, int* nitems);
 
 struct LegParams {
   const LegItem* items;
@@ -217,6 +217,9 @@ struct LegParams {
   double2* phase;
   int64_t phase_map_stride;  // in double2
   int lmax, mmax, npair, nring;
+  // phase layout: row(ring) * W + m / G.  Single GPU: G = 1, W = mmax+1, rowmap = null (identity).
+  int G, W;
+  const int* rowmap;
 };
 
 template <int R, int B, int THREADS>
@@ -406,8 +409,14 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
       const double er = acc[j][b][0], ei = acc[j][b][1];
       const double orr = acc[j][b][2] * zz[j], oi = acc[j][b][3] * zz[j];
       double2* ph = p.phase + b * p.phase_map_stride;
-      ph[(int64_t)r * (p.mmax + 1) + m] = make_double2(er + orr, ei + oi);
-      if (r != p.npair - 1) ph[(int64_t)(p.nring - 1 - r) * (p.mmax + 1) + m] = make_double2(er - orr, ei - oi);
+      const int slot = m / p.G;
+      const int rs = p.nring - 1 - r;
+      const int row_n = p.rowmap ? p.rowmap[r] : r;
+      ph[(int64_t)row_n * p.W + slot] = make_double2(er + orr, ei + oi);
+      if (r != p.npair - 1) {
+        const int row_s = p.rowmap ? p.rowmap[rs] : rs;
+        ph[(int64_t)row_s * p.W + slot] = make_double2(er - orr, ei - oi);
+      }
     }
   }
 }
@@ -425,7 +434,7 @@ static int launch_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
 }
 
 template <int B>
-static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
+static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, bool dist = false) {
   LegParams p;
   p.items = pl->d_items;
   p.rec = pl->d_rec;
@@ -436,11 +445,14 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
   p.cm_mant = pl->d_cm_mant;
   p.cm_exp = pl->d_cm_exp;
   p.phase = d_phase;
-  p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
   p.lmax = pl->lmax;
   p.mmax = pl->mmax;
   p.npair = pl->npair;
   p.nring = pl->nring;
+  p.G = dist ? pl->dist_world : 1;
+  p.W = dist ? pl->dist_W : pl->mmax + 1;
+  p.rowmap = dist ? pl->d_dist_rowmap : nullptr;
+  p.phase_map_stride = (int64_t)pl->nring * p.W;
   // (R ring pairs per thread, THREADS) per batch size.  Shared-memory wavefronts per DFMA scale
   // as 2/R (every broadcast LDS.128 costs two), registers as 8*R*B for the accumulators.
   int R = 4, threads = pl->leg_threads;
@@ -457,7 +469,7 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
   }
   LegItem* items = nullptr;
   int nitems = 0;
-  int rc = plan_items(pl, R * threads, &items, &nitems);
+  int rc = plan_items(pl, R * threads, p.G, dist ? pl->dist_rank : 0, &items, &nitems);
   if (rc != GLB_OK) return rc;
   p.items = items;
 #define GLB_LEG_LAUNCH(RR, TT)                                                   \
@@ -479,6 +491,7 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
     GLB_LEG_LAUNCH(4, 320)
   }
 #undef GLB_LEG_LAUNCH
+  if (nitems == 0) launched = true;  // nothing to do for this rank
   if (!launched) {
     set_last_error("internal: legendre (R, threads) configuration not instantiated");
     return GLB_ERR_INVALID_ARG;
@@ -512,12 +525,12 @@ int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st) 
   }
 }
 
-// records -> phase [nb][nring][mmax+1]
-int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st) {
+// records -> phase [nb][nring][mmax+1]  (dist: [nb][nring (permuted rows)][W], this rank's m only)
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist) {
   switch (nb) {
-    case 1: return launch_legendre<1>(pl, d_phase, st);
-    case 2: return launch_legendre<2>(pl, d_phase, st);
-    case 4: return launch_legendre<4>(pl, d_phase, st);
+    case 1: return launch_legendre<1>(pl, d_phase, st, dist);
+    case 2: return launch_legendre<2>(pl, d_phase, st, dist);
+    case 4: return launch_legendre<4>(pl, d_phase, st, dist);
     default:
       set_last_error("internal: batch group must be 1, 2 or 4");
       return GLB_ERR_INVALID_ARG;
@@ -527,7 +540,7 @@ int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st) 
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
   const int rc = sht_prep_group(pl, d_alm, nb, st);
   if (rc != GLB_OK) return rc;
-  return sht_legendre_group(pl, nb, d_phase, st);
+  return sht_legendre_group(pl, nb, d_phase, st, false);
 }
 
 }  // namespace glb

@@ -33,6 +33,11 @@ struct FftParams {
   const double2* tw;
   const double2* bf;
   double* maps[4];   // output map of each batch entry
+  // phase addressing: F(m) = base + rowidx(ring)*W + (m % G)*blk + m / G
+  // single GPU: G = 1, W = mmax+1, blk = 0, rowidx = null (identity)
+  int G, W;
+  int64_t blk;
+  const int* rowidx;
   int mmax;
   int tw_n;
   int kind[4];
@@ -206,7 +211,9 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   const RingDesc d = p.rings[ring];
   const int n = d.nphi, h = n >> 1;
   const int mlim = min(p.mlim[d.pair], p.mmax);
-  const double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
+  const int row = p.rowidx ? p.rowidx[ring] : ring;
+  const double2* __restrict__ Fb = p.phase + b * p.phase_map_stride + (int64_t)row * p.W;
+  auto F = [&](int m) -> double2 { return Fb[(int64_t)(m % p.G) * p.blk + m / p.G]; };
   double* __restrict__ out = p.maps[b] + d.start;
   const int kind = p.kind[b];
   const double tp0 = p.p0[b], tp1 = p.p1[b];
@@ -216,13 +223,13 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   for (int k = tid; k <= h; k += THREADS) {
     double2 g = make_double2(0.0, 0.0);
     for (int m = k; m <= mlim; m += n) {
-      double2 t = F[m];
+      double2 t = F(m);
       if (m == 0) t.y = 0.0;
       if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
       g = cadd(g, t);
     }
     for (int m = n - k; m <= mlim; m += n) {
-      double2 t = F[m];
+      double2 t = F(m);
       if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
       g = cadd(g, cconj(t));
     }
@@ -511,11 +518,23 @@ static int launch_class(const FftParams& p, int nrings, int nb, int lb, cudaStre
 
 // phase [nb][nring][mmax+1] -> map [nb][npix]; nb <= 4
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
-                        const double* tparams, const int* d_mlim, cudaStream_t st) {
+                        const double* tparams, const int* d_mlim, cudaStream_t st, bool dist) {
   FftParams p;
   p.rings = pl->d_rings;
   p.phase = d_phase;
-  p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
+  if (dist) {
+    p.G = pl->dist_world;
+    p.W = pl->dist_W;
+    p.blk = (int64_t)pl->dist_rows_local * pl->dist_W;
+    p.rowidx = pl->d_dist_rowidx;
+    p.phase_map_stride = (int64_t)pl->dist_world * p.blk;
+  } else {
+    p.G = 1;
+    p.W = pl->mmax + 1;
+    p.blk = 0;
+    p.rowidx = nullptr;
+    p.phase_map_stride = (int64_t)pl->nring * (pl->mmax + 1);
+  }
   p.mlim = d_mlim ? d_mlim : pl->d_mlim;
   p.tw = pl->d_tw;
   p.bf = pl->d_bf;
@@ -528,13 +547,15 @@ int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* co
     p.p1[b] = (tparams && b < nb) ? tparams[2 * b + 1] : 1.0;
   }
   int rc;
+  int* const* order = dist ? pl->d_dist_ring_order : pl->d_ring_order;
+  const int* count = dist ? pl->n_dist_ring_class : pl->n_ring_class;
   // largest rings first (they take longest)
-  p.order = pl->d_ring_order[2];
-  if ((rc = launch_class<512, 16>(p, pl->n_ring_class[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
-  p.order = pl->d_ring_order[1];
-  if ((rc = launch_class<256, 8>(p, pl->n_ring_class[1], nb, kClassLB[1], st)) != GLB_OK) return rc;
-  p.order = pl->d_ring_order[0];
-  if ((rc = launch_class<64, 8>(p, pl->n_ring_class[0], nb, kClassLB[0], st)) != GLB_OK) return rc;
+  p.order = order[2];
+  if ((rc = launch_class<512, 16>(p, count[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
+  p.order = order[1];
+  if ((rc = launch_class<256, 8>(p, count[1], nb, kClassLB[1], st)) != GLB_OK) return rc;
+  p.order = order[0];
+  if ((rc = launch_class<64, 8>(p, count[0], nb, kClassLB[0], st)) != GLB_OK) return rc;
   return GLB_OK;
 }
 

@@ -165,6 +165,19 @@ int glb_redshifts_from_cdf(const double* d_cdf, const double* d_z, int nz, const
 int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map,
                      const int* h_transform, const double* h_tparams, void* stream);
 
+/* ---- m-split of ONE transform over the GPUs of a box (axis 2) ----------------
+ * Legendre stage m-sharded (rank r owns m = r mod world), Fourier stage ring-sharded; between
+ * them the caller does ONE all-to-all of the phase array over NVLink (torch.distributed /
+ * ncclAllToAll).  Layouts are chosen so that both sides of the all-to-all are contiguous:
+ *   send  [map][row][W]           row = h_rowmap[ring]: rings grouped by owning rank
+ *   recv  [map][src rank][local row][W]      W = ceil((lmax+1)/world) m slots, slot = m / world
+ * h_my_rings lists the rings this rank owns, in local-row order (see glass_b200/sharding.py). */
+int glb_dist_setup(glb_plan* plan, int world, int rank, const int* h_rowmap, const int* h_my_rings,
+                   int n_my_rings);
+int glb_dist_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_send, void* stream);
+int glb_dist_phase2map(glb_plan* plan, const double* d_recv, int nmaps, double* d_map,
+                       const int* h_transform, const double* h_tparams, void* stream);
+
 /* ---- measurement hooks (bench.py) --------------------------------------------------- */
 /* Per-stage device time of glb_alm2map, from CUDA events recorded on the launch stream:
  * ms3 / launches3 = {prep, Legendre, ring FFT}; nmaps = maps transformed since enable. */

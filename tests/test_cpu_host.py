@@ -154,3 +154,66 @@ def test_shell_sharding_world2_gloo():
         mine = gathered[rank]
         assert set(mine) <= set(need) and all(0 <= s < nshell for s in need)
         assert all(any(0 <= j - s <= ncorr for j in mine) for s in need)
+
+
+def _msplit_worker(rank, world, port, nside, lmax, q):
+    import torch
+    import torch.distributed as dist
+
+    from glass_b200.sharding import msplit_layout
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lay = msplit_layout(nside, lmax, world)
+    nring, W = 4 * nside - 1, lay["W"]
+    # what the Legendre stage of this rank writes: value(ring, m) at [rowmap[ring], m // world]
+    send = torch.full((nring, W), -1.0, dtype=torch.float64)
+    for ring in range(nring):
+        for m in range(rank, lmax + 1, world):
+            send[int(lay["rowmap"][ring]), m // world] = ring * 10000.0 + m
+    rows_me = lay["rows"][rank]
+    recv = torch.empty((world, rows_me, W), dtype=torch.float64)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), output_split_sizes=[rows_me * W] * world,
+                           input_split_sizes=[r * W for r in lay["rows"]])
+    # what the Fourier stage of this rank reads: F(ring, m) = recv[m % world, local row, m // world]
+    ok = True
+    for row, ring in enumerate(lay["rings"][rank]):
+        for m in range(lmax + 1):
+            ok &= recv[m % world, row, m // world].item() == ring * 10000.0 + m
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_msplit_alltoall_layout_world2_gloo():
+    """m -> ring transpose: after the all-to-all every rank holds all m of its own rings."""
+    import torch.multiprocessing as mp
+
+    world, nside, lmax = 2, 4, 9
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_msplit_worker, args=(r, world, port, nside, lmax, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _r, ok in res)
+
+
+def test_msplit_layout_partitions():
+    from glass_b200.sharding import msplit_layout, owned_pixel_ranges
+
+    for nside, world in [(4, 2), (8, 3), (64, 8), (48, 5), (2, 2), (4096, 8)]:
+        lay = msplit_layout(nside, 2 * nside - 1, world)
+        nring = 4 * nside - 1
+        assert sorted(r for rs in lay["rings"] for r in rs) == list(range(nring))
+        assert sorted(lay["rowmap"]) == list(range(nring))
+        segs = sorted(s for d in range(world) for s in owned_pixel_ranges(nside, lay, d))
+        assert segs[0][0] == 0 and segs[-1][1] == 12 * nside**2
+        assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        # north/south mirrors stay on the same rank
+        for rs in lay["rings"]:
+            s = set(rs)
+            assert all((nring - 1 - r) in s for r in rs)
