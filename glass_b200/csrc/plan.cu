@@ -348,11 +348,13 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_sn_exp);
   cudaFree(pl->d_soff);
   cudaFree(pl->d_items_spin);
+  cudaFree(pl->d_spin_tab);
   cudaFree(pl->d_dist_rowmap);
   cudaFree(pl->d_dist_rowidx);
   for (int c = 0; c < 3; ++c) cudaFree(pl->d_dist_ring_order[c]);
   cudaFree(pl->d_partial);
   cudaFree(pl->d_tmpmap);
+  cudaFree(pl->d_ab_tab);
   if (pl->h_pin_in) cudaFreeHost(pl->h_pin_in);
   if (pl->h_pin_out) cudaFreeHost(pl->h_pin_out);
   cudaFree(pl->d_stage_alm);

@@ -66,6 +66,7 @@ struct glb_plan {
   int* d_sn_exp = nullptr;           // [mmax+1] ... binary exponent
   int64_t* d_soff = nullptr;         // [mmax+2] spin record offsets (one record per l >= max(m,s))
   int64_t nrec_spin = 0;
+  double* d_spin_tab = nullptr;      // [nrec_spin][3] {A'_l, B'_l, sigma_l}
   glb::LegItem* d_items_spin = nullptr;
   int nitems_spin = 0;
   int64_t rec_capacity = 0;          // doubles available in d_rec
@@ -73,6 +74,7 @@ struct glb_plan {
   // analysis (map2alm): per-tile partial sums and a scratch map pair, built lazily
   double* d_partial = nullptr;       // [ana_ntile][nrec][4]
   double* d_tmpmap = nullptr;        // [2][npix]
+  double* d_ab_tab = nullptr;        // [nrec] {a_k, b_k} recurrence coefficients (TMA-streamed by the analysis kernel)
   int ana_ntile = 0;
 
   // m-split distribution over GPUs (glb_dist_setup): this rank computes the Legendre stage for

@@ -21,8 +21,9 @@
 
 namespace glb {
 
-constexpr int AN_KT = 256;     // l-pairs per smem chunk (multiple of AN_KB)
-constexpr int AN_KB = 8;       // l-pairs per reduction round
+constexpr int AN_KT = 256;     // l-pairs per smem chunk (multiple of AN_SK)
+constexpr int AN_KB = 4;       // l-pairs per warp-level reduction round (4 or 8)
+constexpr int AN_SK = 64;      // l-pairs between cross-warp reductions (one CTA-wide sync each)
 constexpr int AN_STAGES = 3;
 constexpr int AN_BEXP_BIG = 1023 + 256;
 
@@ -110,12 +111,12 @@ struct AnaParams {
 };
 
 template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS) legendre_analysis_kernel(const AnaParams p) {
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) legendre_analysis_kernel(const AnaParams p) {
   constexpr int NWARPS = THREADS / 32;
   __shared__ __align__(128) double2 s_rec[AN_STAGES][AN_KT];
   __shared__ __align__(8) uint64_t s_full[AN_STAGES];
   __shared__ __align__(8) uint64_t s_empty[AN_STAGES];
-  __shared__ double s_wsum[2][NWARPS][32];
+  __shared__ double s_wsum[2][NWARPS][AN_SK * 4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const LegItem item = p.items[blockIdx.x];
@@ -184,39 +185,61 @@ __global__ void __launch_bounds__(THREADS) legendre_analysis_kernel(const AnaPar
     const double2* ck = &s_rec[s][0];
     const int kc = min(AN_KT, K - c * AN_KT);
 
-    for (int k0 = 0; k0 < kc; k0 += AN_KB) {
-      double part[AN_KB * 4];
-#pragma unroll
-      for (int i = 0; i < AN_KB * 4; ++i) part[i] = 0.0;
+    for (int ks = 0; ks < kc; ks += AN_SK) {
       bool contrib = false;
 #pragma unroll
       for (int j = 0; j < R; ++j) contrib |= (sc[j] == 0) && (p2[j] != 0.0);
+      for (int k0 = ks; k0 < min(ks + AN_SK, kc); k0 += AN_KB) {
+        double part[AN_KB * 4];
 #pragma unroll
-      for (int kk = 0; kk < AN_KB; ++kk) {
-        if (k0 + kk < kc) {
-          const double2 ab = ck[k0 + kk];
+        for (int i = 0; i < AN_KB * 4; ++i) part[i] = 0.0;
+        // FAST when every ring of the warp is at scale 0 (no select, no rescale test) and the
+        // round is complete; otherwise the CHECKED form
+        bool allz = (k0 + AN_KB <= kc);
 #pragma unroll
-          for (int j = 0; j < R; ++j) {
-            const double pa = (sc[j] == 0) ? p2[j] : 0.0;
-            part[kk * 4 + 0] = fma(pa, ge_r[j], part[kk * 4 + 0]);
-            part[kk * 4 + 1] = fma(pa, ge_i[j], part[kk * 4 + 1]);
-            part[kk * 4 + 2] = fma(pa, go_r[j], part[kk * 4 + 2]);
-            part[kk * 4 + 3] = fma(pa, go_i[j], part[kk * 4 + 3]);
-            const double rr = fma(ab.x, x2[j], ab.y);
-            const double t = fma(rr, p2[j], -p1[j]);
-            p1[j] = p2[j];
-            p2[j] = t;
-            if (an_bexp(p2[j]) >= AN_BEXP_BIG) {
-              p1[j] *= SMALL;
-              p2[j] *= SMALL;
-              sc[j] += 1;
+        for (int j = 0; j < R; ++j) allz &= (sc[j] == 0);
+        if (__all_sync(0xffffffffu, allz)) {
+#pragma unroll
+          for (int kk = 0; kk < AN_KB; ++kk) {
+            const double2 ab = ck[k0 + kk];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              part[kk * 4 + 0] = fma(p2[j], ge_r[j], part[kk * 4 + 0]);
+              part[kk * 4 + 1] = fma(p2[j], ge_i[j], part[kk * 4 + 1]);
+              part[kk * 4 + 2] = fma(p2[j], go_r[j], part[kk * 4 + 2]);
+              part[kk * 4 + 3] = fma(p2[j], go_i[j], part[kk * 4 + 3]);
+              const double rr = fma(ab.x, x2[j], ab.y);
+              const double t = fma(rr, p2[j], -p1[j]);
+              p1[j] = p2[j];
+              p2[j] = t;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < AN_KB; ++kk) {
+            if (k0 + kk < kc) {
+              const double2 ab = ck[k0 + kk];
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                const double pa = (sc[j] == 0) ? p2[j] : 0.0;
+                part[kk * 4 + 0] = fma(pa, ge_r[j], part[kk * 4 + 0]);
+                part[kk * 4 + 1] = fma(pa, ge_i[j], part[kk * 4 + 1]);
+                part[kk * 4 + 2] = fma(pa, go_r[j], part[kk * 4 + 2]);
+                part[kk * 4 + 3] = fma(pa, go_i[j], part[kk * 4 + 3]);
+                const double rr = fma(ab.x, x2[j], ab.y);
+                const double t = fma(rr, p2[j], -p1[j]);
+                p1[j] = p2[j];
+                p2[j] = t;
+                if (an_bexp(p2[j]) >= AN_BEXP_BIG) {
+                  p1[j] *= SMALL;
+                  p2[j] *= SMALL;
+                  sc[j] += 1;
+                }
+              }
             }
           }
         }
-      }
-#pragma unroll
-      for (int j = 0; j < R; ++j) contrib |= (sc[j] == 0) && (p2[j] != 0.0);
-      // warp transpose-reduce: 32 values per lane -> lane i holds the warp total of value i
+        // warp transpose-reduce of the AN_KB*4 values: lane i ends with the warp total of value i
 #define GLB_TR_STEP(O, NH)                                                   \
   {                                                                          \
     const bool up = (lane & (O)) != 0;                                       \
@@ -226,20 +249,35 @@ __global__ void __launch_bounds__(THREADS) legendre_analysis_kernel(const AnaPar
       part[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));              \
     }                                                                        \
   }
-      GLB_TR_STEP(16, 16)
-      GLB_TR_STEP(8, 8)
-      GLB_TR_STEP(4, 4)
-      GLB_TR_STEP(2, 2)
-      GLB_TR_STEP(1, 1)
+        if (AN_KB == 8) {
+          GLB_TR_STEP(16, 16)
+          GLB_TR_STEP(8, 8)
+          GLB_TR_STEP(4, 4)
+          GLB_TR_STEP(2, 2)
+          GLB_TR_STEP(1, 1)
+          s_wsum[wbuf][warp][(k0 - ks) * 4 + lane] = part[0];
+        } else {  // AN_KB == 4: 16 values over 32 lanes
+          GLB_TR_STEP(8, 8)
+          GLB_TR_STEP(4, 4)
+          GLB_TR_STEP(2, 2)
+          GLB_TR_STEP(1, 1)
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], 16);
+          if (lane < 16) s_wsum[wbuf][warp][(k0 - ks) * 4 + lane] = part[0];
+        }
 #undef GLB_TR_STEP
-      s_wsum[wbuf][warp][lane] = part[0];
-      const int any = __syncthreads_or(contrib ? 1 : 0);
-      if (any && warp == 0) {
-        double tot = 0.0;
+      }
 #pragma unroll
-        for (int w = 0; w < NWARPS; ++w) tot += s_wsum[wbuf][w][lane];
-        const int kidx = c * AN_KT + k0 + (lane >> 2);
-        if (kidx < K) out_m[(int64_t)kidx * 4 + (lane & 3)] = tot;
+      for (int j = 0; j < R; ++j) contrib |= (sc[j] == 0) && (p2[j] != 0.0);
+      const int any = __syncthreads_or(contrib ? 1 : 0);
+      if (any) {
+        // cross-warp sum of the AN_SK*4 staged values, coalesced store to this tile's partials
+        const int nval = (min(ks + AN_SK, kc) - ks) * 4;
+        for (int i = tid; i < nval; i += THREADS) {
+          double tot = 0.0;
+#pragma unroll
+          for (int w = 0; w < NWARPS; ++w) tot += s_wsum[wbuf][w][i];
+          out_m[((int64_t)c * AN_KT + ks) * 4 + i] = tot;
+        }
       }
       wbuf ^= 1;
     }
@@ -248,57 +286,82 @@ __global__ void __launch_bounds__(THREADS) legendre_analysis_kernel(const AnaPar
   }
 }
 
-// per m: add the tiles in order, a_{m+2k} = alpha_k ce_k, odd coefficients by the forward
-// recursion; accumulate != 0 adds to alm (Jacobi refinement)
-__global__ void __launch_bounds__(128) analysis_finalize_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
-                                                                const double* __restrict__ partial, int ntile,
-                                                                int64_t nrec, int accumulate, double2* __restrict__ alm) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m > mmax) return;
+// rec[i] = {a_k, b_k} gathered from the static prep table (once per plan)
+__global__ void __launch_bounds__(256) analysis_ab_gather_kernel(const double* __restrict__ tab, int64_t nrec,
+                                                                 double2* __restrict__ ab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrec) ab[i] = make_double2(tab[i * 5], tab[i * 5 + 1]);
+}
+
+// One CTA per m: add the tiles in fixed order (coalesced, deterministic), a_{m+2k} = alpha_k ce_k,
+// odd coefficients by the forward recursion v_k = s1_k y_k - c_{k-1} v_{k-1} run by two threads
+// (re, im) on shared memory; accumulate != 0 adds to alm (Jacobi refinement).
+constexpr int FIN_CH = 512;
+constexpr int FIN_THREADS = 128;
+
+__global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
+                                                                        const double* __restrict__ tab,
+                                                                        const double* __restrict__ partial, int ntile,
+                                                                        int64_t nrec, int accumulate,
+                                                                        double2* __restrict__ alm) {
+  __shared__ double s_y[2][FIN_CH + 1];   // s1_k * y_k (re, im), then v_k in place
+  __shared__ double s_c[FIN_CH];          // c_{k-1}
+  __shared__ double s_carry[2];
+  const int m = blockIdx.x, tid = threadIdx.x;
   const int K = (lmax - m) / 2 + 1;
   const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;
-  double alpha_km1 = 0.0, alpha_k = 1.0;
-  double e_lm1 = 0.0, e_l = 0.0, e_lp1 = an_eps(m + 1, m), e_lp2 = an_eps(m + 2, m);
-  double vr = 0.0, vi = 0.0, c_prev = 0.0;
-  for (int k = 0; k < K; ++k) {
-    const int l = m + 2 * k;
-    const double e_lp3 = an_eps(l + 3, m), e_lp4 = an_eps(l + 4, m);
-    const double alpha_kp1 = (k == 0) ? 1.0 : alpha_km1 * ((e_l * e_lm1) / (e_lp1 * e_lp2));
-    double s0 = 0.0, s1v = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int t = 0; t < ntile; ++t) {
-      const double* q = partial + ((int64_t)t * nrec + roff[m] + k) * 4;
-      s0 += q[0];
-      s1v += q[1];
-      s2 += q[2];
-      s3 += q[3];
-    }
-    double2 ev = make_double2(alpha_k * s0, alpha_k * s1v);
-    const double s1 = alpha_k / e_lp1;
-    vr = s1 * s2 - c_prev * vr;
-    vi = s1 * s3 - c_prev * vi;
-    c_prev = e_lp2 / e_lp3;
-    if (m == 0) ev.y = 0.0;
-    if (accumulate) {
-      const double2 o = alm[base + l];
-      ev.x += o.x;
-      ev.y += o.y;
-    }
-    alm[base + l] = ev;
-    if (l + 1 <= lmax) {
-      double2 ov = make_double2(vr, (m == 0) ? 0.0 : vi);
-      if (accumulate) {
-        const double2 o = alm[base + l + 1];
-        ov.x += o.x;
-        ov.y += o.y;
+  const double* t = tab + roff[m] * 5;
+  if (tid < 2) s_carry[tid] = 0.0;
+  __syncthreads();
+  for (int klo = 0; klo < K; klo += FIN_CH) {
+    const int n = min(FIN_CH, K - klo);
+    for (int i = tid; i < n; i += FIN_THREADS) {
+      const int k = klo + i;
+      const int l = m + 2 * k;
+      double s0 = 0.0, s1v = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int tl = 0; tl < ntile; ++tl) {
+        const double4 q = *reinterpret_cast<const double4*>(partial + ((int64_t)tl * nrec + roff[m] + k) * 4);
+        s0 += q.x;
+        s1v += q.y;
+        s2 += q.z;
+        s3 += q.w;
       }
-      alm[base + l + 1] = ov;
+      const double* tk = t + (int64_t)k * 5;
+      const double alpha = tk[2], s1 = tk[3];
+      double2 ev = make_double2(alpha * s0, (m == 0) ? 0.0 : alpha * s1v);
+      if (accumulate) {
+        const double2 o = alm[base + l];
+        ev.x += o.x;
+        ev.y += o.y;
+      }
+      alm[base + l] = ev;
+      s_y[0][i] = s1 * s2;
+      s_y[1][i] = s1 * s3;
+      s_c[i] = (k > 0) ? t[(int64_t)(k - 1) * 5 + 4] : 0.0;
     }
-    alpha_km1 = alpha_k;
-    alpha_k = alpha_kp1;
-    e_lm1 = e_lp1;
-    e_l = e_lp2;
-    e_lp1 = e_lp3;
-    e_lp2 = e_lp4;
+    __syncthreads();
+    if (tid < 2) {
+      double v = s_carry[tid];
+      for (int i = 0; i < n; ++i) {
+        v = s_y[tid][i] - s_c[i] * v;
+        s_y[tid][i] = v;
+      }
+      s_carry[tid] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += FIN_THREADS) {
+      const int l = m + 2 * (klo + i);
+      if (l + 1 <= lmax) {
+        double2 ov = make_double2(s_y[0][i], (m == 0) ? 0.0 : s_y[1][i]);
+        if (accumulate) {
+          const double2 o = alm[base + l + 1];
+          ov.x += o.x;
+          ov.y += o.y;
+        }
+        alm[base + l + 1] = ov;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -318,6 +381,12 @@ int plan_ensure_analysis(glb_plan* pl) {
   const size_t bytes = (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_partial, bytes));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_tmpmap, (size_t)pl->npix * sizeof(double) * 2));
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_ab_tab, (size_t)pl->nrec * sizeof(double2)));
+  analysis_ab_gather_kernel<<<(unsigned)((pl->nrec + 255) / 256), 256>>>(pl->d_prep_tab, pl->nrec,
+                                                                        reinterpret_cast<double2*>(pl->d_ab_tab));
+  GLB_CUDA_CHECK(cudaGetLastError());
+  GLB_CUDA_CHECK(cudaDeviceSynchronize());
+  count_launch();
   pl->workspace_bytes += (int64_t)bytes + pl->npix * 16;
   return GLB_OK;
 }
@@ -329,11 +398,9 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
   const double* maps[1] = {d_map};
   if ((rc = sht_map2phase_group(pl, maps, 1, d_ring_w, pl->d_phase, st)) != GLB_OK) return rc;
   GLB_CUDA_CHECK(cudaMemsetAsync(pl->d_partial, 0, (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double), st));
-  const int threads = 128, blocks = (pl->mmax + threads) / threads;
-  analysis_coef_kernel<<<blocks, threads, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff, reinterpret_cast<double2*>(pl->d_rec));
   AnaParams p;
   p.items = pl->d_items;
-  p.rec = reinterpret_cast<const double2*>(pl->d_rec);
+  p.rec = reinterpret_cast<const double2*>(pl->d_ab_tab);
   p.roff = pl->d_roff;
   p.z = pl->d_z;
   p.sth = pl->d_sth;
@@ -354,10 +421,11 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
     legendre_analysis_kernel<R, 128><<<pl->nitems, 128, 0, st>>>(p);
   else
     legendre_analysis_kernel<R, 256><<<pl->nitems, 256, 0, st>>>(p);
-  analysis_finalize_kernel<<<blocks, threads, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff, pl->d_partial, pl->ana_ntile,
-                                                       pl->nrec, accumulate, d_alm);
+  analysis_finalize_kernel<<<pl->mmax + 1, FIN_THREADS, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff, pl->d_prep_tab,
+                                                                 pl->d_partial, pl->ana_ntile, pl->nrec, accumulate,
+                                                                 d_alm);
   GLB_CUDA_CHECK(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
   return GLB_OK;
 }
 

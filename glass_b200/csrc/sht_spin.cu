@@ -31,18 +31,14 @@ constexpr int SP_BEXP_SIG = 1023 - 70;
 
 __device__ __forceinline__ int sp_bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
-// ---- prep: per m tables A'_l, B'_l and E'_l = E_l sigma_l (NB maps) ---------------------
-template <int NB>
-__global__ void __launch_bounds__(128) spin_prep_kernel(const double2* __restrict__ alm1, const double2* __restrict__ alm2,
-                                                         int lmax, int mmax, int spin, const int64_t* __restrict__ soff,
-                                                         double* __restrict__ rec) {
-  constexpr int REC = 2 + 2 * NB;
+// ---- static tables (once per plan and spin): tab[soff[m] + (l-l0)] = {A'_l, B'_l, sigma_l} ----
+__global__ void __launch_bounds__(128) spin_tables_kernel(int lmax, int mmax, int spin, const int64_t* __restrict__ soff,
+                                                          double* __restrict__ tab) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m > mmax) return;
   const int l0 = max(m, spin);
   if (l0 > lmax) return;
-  double* r = rec + soff[m] * REC;
-  const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;
+  double* r = tab + soff[m] * 3;
   const double dm = (double)m, ds = (double)spin;
   auto Rfun = [&](int l) {
     const double dl = (double)l;
@@ -63,24 +59,43 @@ __global__ void __launch_bounds__(128) spin_prep_kernel(const double2* __restric
       sig_lp1 = Cl * sig_lm1;
     }
     const double ratio = sig_l / sig_lp1;
-    double* rk = r + (int64_t)(l - l0) * REC;
+    double* rk = r + (int64_t)(l - l0) * 3;
     rk[0] = Al * ratio;
     rk[1] = Bl * ratio;
-    {
-      double2 e = alm1[base + l];
-      if (m == 0) e.y = 0.0;
-      rk[2] = e.x * sig_l;
-      rk[3] = e.y * sig_l;
-    }
-    if (NB == 2) {
-      double2 b = alm2[base + l];
-      if (m == 0) b.y = 0.0;
-      rk[4] = b.x * sig_l;
-      rk[5] = b.y * sig_l;
-    }
+    rk[2] = sig_l;
     sig_lm1 = sig_l;
     sig_l = sig_lp1;
     R_l = R_lp1;
+  }
+}
+
+// ---- prep (per call, fully parallel): records {A'_l, B'_l, E_l sigma_l [, B_l sigma_l]} ----
+// grid: (ceil((lmax+1)/256), mmax+1): blockIdx.y = m, threads over l
+template <int NB>
+__global__ void __launch_bounds__(256) spin_prep_kernel(const double2* __restrict__ alm1, const double2* __restrict__ alm2,
+                                                         int lmax, int spin, const int64_t* __restrict__ soff,
+                                                         const double* __restrict__ tab, double* __restrict__ rec) {
+  constexpr int REC = 2 + 2 * NB;
+  const int m = blockIdx.y;
+  const int l0 = max(m, spin);
+  const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > lmax) return;
+  const int64_t i = soff[m] + (l - l0);
+  const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;
+  const double* tk = tab + i * 3;
+  const double sig = tk[2];
+  double* rk = rec + i * REC;
+  rk[0] = tk[0];
+  rk[1] = tk[1];
+  double2 e = alm1[base + l];
+  if (m == 0) e.y = 0.0;
+  rk[2] = e.x * sig;
+  rk[3] = e.y * sig;
+  if (NB == 2) {
+    double2 b = alm2[base + l];
+    if (m == 0) b.y = 0.0;
+    rk[4] = b.x * sig;
+    rk[5] = b.y * sig;
   }
 }
 
@@ -128,7 +143,7 @@ struct SpinParams {
 };
 
 template <int R, int NB, int THREADS>
-__global__ void __launch_bounds__(THREADS) spin_legendre_synth_kernel(const SpinParams p) {
+__global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256) ? 512 / THREADS : 1) spin_legendre_synth_kernel(const SpinParams p) {
   constexpr int REC = 2 + 2 * NB;
   constexpr int CHUNK_DOUBLES = SP_KT * REC;
   constexpr int NWARPS = THREADS / 32;
@@ -511,15 +526,22 @@ int plan_ensure_spin(glb_plan* pl, int spin) {
     pl->nitems_spin = (int)items.size();
     if ((rc = upload_vec(&pl->d_items_spin, items)) != GLB_OK) return rc;
   }
+  // static recurrence tables for this spin
+  cudaFree(pl->d_spin_tab);
+  pl->d_spin_tab = nullptr;
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_spin_tab, std::max<int64_t>(pl->nrec_spin, 1) * 3 * sizeof(double)));
+  spin_tables_kernel<<<(pl->mmax + 128) / 128, 128>>>(lmax, pl->mmax, spin, pl->d_soff, pl->d_spin_tab);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  GLB_CUDA_CHECK(cudaDeviceSynchronize());
+  count_launch();
   pl->spin_ready = spin;
   return GLB_OK;
 }
 
 template <int NB>
 static int launch_spin(glb_plan* pl, const double2* a1, const double2* a2, int spin, double2* d_phase, cudaStream_t st) {
-  const int threads = 128;
-  spin_prep_kernel<NB><<<(pl->mmax + threads) / threads, threads, 0, st>>>(a1, a2, pl->lmax, pl->mmax, spin, pl->d_soff,
-                                                                           pl->d_rec);
+  dim3 pgrid((unsigned)((pl->lmax + 1 + 255) / 256), (unsigned)(pl->mmax + 1));
+  spin_prep_kernel<NB><<<pgrid, 256, 0, st>>>(a1, a2, pl->lmax, spin, pl->d_soff, pl->d_spin_tab, pl->d_rec);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   // phases of rings beyond mlim are never written nor read; zero the rest for m < spin rows etc.
@@ -542,9 +564,13 @@ static int launch_spin(glb_plan* pl, const double2* a1, const double2* a2, int s
   p.npair = pl->npair;
   p.nring = pl->nring;
   p.spin = spin;
-  constexpr int R = 2;
+  // E-only: 4 ring pairs per thread (fewer shared-memory wavefronts per DFMA, 2 CTAs per SM);
+  // E+B: 2 ring pairs per thread (twice the accumulators)
+  constexpr int R = (NB == 1) ? 4 : 2;
   const int th = pl->leg_threads * pl->leg_R / R;  // same ring tile as the scalar work list
-  if (th == 128)
+  if (th == 64)
+    spin_legendre_synth_kernel<R, NB, 64><<<pl->nitems_spin, 64, 0, st>>>(p);
+  else if (th == 128)
     spin_legendre_synth_kernel<R, NB, 128><<<pl->nitems_spin, 128, 0, st>>>(p);
   else if (th == 256)
     spin_legendre_synth_kernel<R, NB, 256><<<pl->nitems_spin, 256, 0, st>>>(p);

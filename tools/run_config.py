@@ -1,0 +1,108 @@
+"""
+End-to-end run of the BASELINE.json configurations through the glass_b200 API (the user loop
+of examples/2-advanced/stage_4_galaxies.ipynb cell 13), device-resident:
+
+    matter = generate(lognormal_fields(shells), gls, nside, ncorr=3)
+    for delta_i in matter:
+        convergence.add_window(delta_i, shell_i); kappa_i = convergence.kappa
+        gamma1, gamma2 = shear_from_convergence(kappa_i, lmax, discretized=False)
+        for lon, lat, count in positions_from_delta(ngal_i, delta_i, bias):
+            z = redshifts(count, shell_i); eps = ellipticity_intnorm(count, sigma_e)
+            she = galaxy_shear(lon, lat, eps, kappa_i, gamma1, gamma2)
+
+    python tools/run_config.py 1|2|3 [--shells S] [--niter K]
+Prints per-stage device times (CUDA events) and totals as one JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import glass_b200  # noqa: E402
+from bench import synthetic_gls  # noqa: E402
+
+CONFIGS = {1: (10, 128, 383, False), 2: (20, 1024, 2047, False), 3: (40, 2048, 4095, True), 4: (60, 4096, 8191, False)}
+
+
+class MockCosmology:  # reference tests/fixtures/domain.py:36-97
+    Omega_m0 = 0.3
+    hubble_distance = 4.4e3
+
+    def H_over_H0(self, z):  # noqa: N802
+        return (self.Omega_m0 * (1 + z) ** 3 + 1 - self.Omega_m0) ** 0.5
+
+    def transverse_comoving_distance(self, z, z2=None):
+        if z2 is None:
+            return self.hubble_distance * np.asarray(z) * 1_000
+        return self.hubble_distance * (np.asarray(z2) - np.asarray(z)) * 1_000
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", type=int, choices=[1, 2, 3, 4])
+    ap.add_argument("--shells", type=int, default=None)
+    ap.add_argument("--niter", type=int, default=3)
+    ap.add_argument("--ngal", type=float, default=None, help="galaxies per arcmin^2 per shell")
+    ap.add_argument("--lensing", action="store_true")
+    args = ap.parse_args()
+    S, nside, lmax, lensing = CONFIGS[args.config]
+    S = args.shells or S
+    lensing = lensing or args.lensing
+    dev = torch.device("cuda", 0)
+    npix = 12 * nside * nside
+    dz = 1.0 / (S + 1)
+    shells = [glass_b200.RadialWindow(np.array([i, i + 1.0, i + 2.0]) * dz, np.array([0.0, 1.0, 0.0]), (i + 1.0) * dz) for i in range(S)]
+    gls = [torch.as_tensor(g).to(dev) for g in synthetic_gls(S, lmax, 3)]
+    ngal = args.ngal if args.ngal is not None else 0.083 * npix / glass_b200.points.ARCMIN2_SPHERE * (4096 / nside) ** 2 * 0 + 6.7335 / 60
+    stages = {k: 0.0 for k in ("generate", "multiplane", "shear_from_convergence", "positions", "redshifts", "ellipticity", "galaxy_shear")}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        pend.append((name, a, b))
+        return r
+
+    pend = []
+    conv = glass_b200.MultiPlaneConvergence(MockCosmology())
+    matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=3, rng=42)
+    ngal_tot = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(S):
+        delta = timed("generate", lambda: next(matter))
+        if lensing:
+            timed("multiplane", lambda: conv.add_window(delta, shells[i]))
+            kappa = conv.kappa
+            g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
+        it = glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
+        while True:
+            try:
+                lon, lat, cnt = timed("positions", lambda: next(it))
+            except StopIteration:
+                break
+            ngal_tot += cnt
+            z = timed("redshifts", lambda: glass_b200.redshifts(torch.as_tensor(cnt), glass_b200.RadialWindow(torch.as_tensor(shells[i].za, device=dev), torch.as_tensor(shells[i].wa, device=dev), shells[i].zeff), rng=i))
+            if lensing:
+                eps = timed("ellipticity", lambda: glass_b200.ellipticity_intnorm(cnt, 0.27, rng=i, xp=torch))
+                she = timed("galaxy_shear", lambda: glass_b200.galaxy_shear(lon, lat, eps, kappa, g1, g2))
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    for name, a, b in pend:
+        stages[name] += a.elapsed_time(b)
+    out = {
+        "config": args.config, "shells": S, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
+        "galaxies": int(ngal_tot), "wall_s": wall, "shells_per_s": S / wall, "galaxies_per_s": ngal_tot / wall,
+        "stage_ms_total": {k: round(v, 2) for k, v in stages.items()},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
