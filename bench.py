@@ -163,6 +163,89 @@ def cpu_baseline(budget_s: float = 25.0) -> dict:
     }
 
 
+def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
+    """Secondary measurements (N=1 only, a few seconds): the HBM-bound sampling / lensing
+    kernels at nside=4096 and the other two FP64 transforms at nside=2048, each timed with CUDA
+    events on the launching stream, against the algorithmic bytes / flops of SURVEY.md 8(d)."""
+    import ctypes as C
+
+    import torch
+
+    import glass_b200
+    from glass_b200 import _lib
+    from glass_b200 import healpix as hp
+    from glass_b200.points import ARCMIN2_SPHERE
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def ev(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    out = {}
+    nside = 4096
+    npix = 12 * nside * nside
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    delta = torch.expm1(0.5 * torch.randn(npix, dtype=torch.float64, device=dev, generator=g) - 0.125)
+    counts = torch.empty(npix, dtype=torch.int64, device=dev)
+    off = torch.empty(npix + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.glb_points_workspace_bytes(npix)), dtype=torch.uint8, device=dev)
+    scale = 0.083  # expected galaxies per pixel (1e9 galaxies over 60 shells at nside 4096)
+
+    def k67():
+        _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, 1.2, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
+                                         counts.data_ptr(), off.data_ptr(), ws.data_ptr(), st))
+
+    t = ev(k67)
+    out["points_counts+offsets (K6+K7)"] = {"ms": t, "GB/s": npix * 32 / t / 1e6, "frac_hbm": npix * 32 / t / 1e6 / hbm_peak, "algorithmic_bytes": npix * 32}
+    tot = int(off[-1].item())
+    lon = torch.empty(tot, dtype=torch.float64, device=dev)
+    lat = torch.empty(tot, dtype=torch.float64, device=dev)
+
+    def k8():
+        _lib.check(lib.glb_points_fill(nside, counts.data_ptr(), off.data_ptr(), 0, npix, None, None, C.c_uint64(42), C.c_uint32(0),
+                                       lon.data_ptr(), lat.data_ptr(), None, st))
+
+    t = ev(k8)
+    by = npix * 8 + tot * 16
+    out["points_fill (K8)"] = {"ms": t, "GB/s": by / t / 1e6, "frac_hbm": by / t / 1e6 / hbm_peak, "galaxies": tot, "algorithmic_bytes": by}
+    k3 = torch.zeros(npix, dtype=torch.float64, device=dev)
+    k2 = torch.rand(npix, dtype=torch.float64, device=dev, generator=g)
+    t = ev(lambda: _lib.check(lib.glb_multiplane_update(k3.data_ptr(), k2.data_ptr(), delta.data_ptr(), 0.0, npix, 0.3, 0.01, st)))
+    out["multiplane_update (K9)"] = {"ms": t, "GB/s": npix * 32 / t / 1e6, "frac_hbm": npix * 32 / t / 1e6 / hbm_peak, "algorithmic_bytes": npix * 32}
+    eps = glass_b200.ellipticity_intnorm(tot, 0.27, rng=1, xp=torch)
+    res = torch.empty(tot, dtype=torch.complex128, device=dev)
+    t = ev(lambda: _lib.check(lib.glb_galaxy_shear(nside, lon.data_ptr(), lat.data_ptr(), None, eps.data_ptr(), tot, k2.data_ptr(),
+                                                   k2.data_ptr(), k2.data_ptr(), 1, res.data_ptr(), st)))
+    out["galaxy_shear (K12)"] = {"ms": t, "GB/s": tot * 72 / t / 1e6, "frac_hbm": tot * 72 / t / 1e6 / hbm_peak, "algorithmic_bytes": tot * 72}
+    del delta, counts, off, lon, lat, k3, k2, eps, res
+    torch.cuda.empty_cache()
+    # FP64 transforms of the lensing stage at nside 2048 (BASELINE.json configs[2])
+    nside, lmax = 2048, 4095
+    ntri = (lmax + 1) * (lmax + 2) // 2 * 2 * nside
+    kap = 0.01 * torch.randn(12 * nside * nside, dtype=torch.float64, device=dev, generator=g)
+    t = ev(lambda: hp.map2alm(kap, lmax=lmax, pol=False, niter=0), n=3, warm=1)
+    out["map2alm niter=0 (K10)"] = {"ms": t, "TFLOP/s": 8 * ntri / t / 1e9, "frac_fp64": 8 * ntri / t / 1e9 / fp64_peak, "algorithmic_flop": 8 * ntri}
+    alm = hp.map2alm(kap, lmax=lmax, pol=False, niter=0)
+    t = ev(lambda: hp.alm2map_spin([alm, None], nside, 2, lmax), n=3, warm=1)
+    out["alm2map_spin s=2 E-only (K11)"] = {"ms": t, "TFLOP/s": 16 * ntri / t / 1e9, "frac_fp64": 16 * ntri / t / 1e9 / fp64_peak, "algorithmic_flop": 16 * ntri}
+    hp.clear_plans()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -408,6 +491,11 @@ def run_b200(args) -> None:
             "traffic": None,
         },
     }
+    if world == 1 and not args.no_extra:
+        try:
+            line["other_stages"] = extra_stage_rooflines(dev, hbm_peak, peak_tf.value)
+        except Exception as e:  # secondary numbers must not take the headline down
+            line["other_stages"] = {"failed": str(e)}
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_baseline()
@@ -427,6 +515,7 @@ def main():
     ap.add_argument("--nside", type=int, default=NSIDE, help="development override (the metric is quoted at 4096)")
     ap.add_argument("--lmax", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary per-stage measurements")
     args = ap.parse_args()
     if args.lmax is None:
         args.lmax = 2 * args.nside - 1

@@ -283,44 +283,19 @@ constexpr int FILL_ITEMS = FILL_TILE / FILL_THREADS;
 
 __global__ void __launch_bounds__(FILL_THREADS) points_fill_kernel(const FillParams p) {
   __shared__ int s_off[FILL_TILE + 1];
-  __shared__ int s_tsum[FILL_THREADS];
   const int tid = threadIdx.x;
   const int64_t tile0 = p.p0 + (int64_t)blockIdx.x * FILL_TILE;
   const int npx = (int)min((int64_t)FILL_TILE, p.p1 - tile0);
-  // coalesced load of the counts
+  const int64_t g0 = p.off[tile0];          // global index of the tile's first galaxy
+  // local offsets straight from the global exclusive scan (coalesced load, no block scan)
 #pragma unroll
-  for (int i = 0; i < FILL_ITEMS; ++i) {
+  for (int i = 0; i <= FILL_ITEMS; ++i) {
     const int k = tid + i * FILL_THREADS;
-    s_off[k] = (k < npx) ? (int)p.counts[tile0 + k] : 0;
+    if (k <= FILL_TILE) s_off[k] = (int)(p.off[tile0 + min(k, npx)] - g0);
   }
-  __syncthreads();
-  // blocked exclusive scan: thread t owns entries [t*ITEMS, (t+1)*ITEMS)
-  int c[FILL_ITEMS];
-  int sum = 0;
-#pragma unroll
-  for (int i = 0; i < FILL_ITEMS; ++i) {
-    c[i] = s_off[tid * FILL_ITEMS + i];
-    sum += c[i];
-  }
-  s_tsum[tid] = sum;
-  __syncthreads();
-  for (int o = 1; o < FILL_THREADS; o <<= 1) {
-    const int t = (tid >= o) ? s_tsum[tid - o] : 0;
-    __syncthreads();
-    s_tsum[tid] += t;
-    __syncthreads();
-  }
-  int run = s_tsum[tid] - sum;
-#pragma unroll
-  for (int i = 0; i < FILL_ITEMS; ++i) {
-    s_off[tid * FILL_ITEMS + i] = run;
-    run += c[i];
-  }
-  if (tid == FILL_THREADS - 1) s_off[FILL_TILE] = run;
   __syncthreads();
   const int total = s_off[FILL_TILE];
   if (total == 0) return;
-  const int64_t g0 = p.off[tile0];          // global index of the tile's first galaxy
   const int64_t o0 = g0 - p.off[p.p0];      // its position in this call's output
   const double rad2deg = 57.295779513082320877;  // 180/pi, as np.degrees
   for (int g = tid; g < total; g += FILL_THREADS) {
