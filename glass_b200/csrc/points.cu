@@ -8,13 +8,15 @@
 //   ipix = repeat(arange(start, stop), n[start:stop])          points.py:426
 //   lon, lat = randang(nside, ipix, lonlat=True)               points.py:427 -> healpix.py:426-431
 //
-// K6 fuses bias, normalisation, visibility, clip and the Poisson draw into one pass that
-// also emits per-block count sums; K7 turns them into exclusive pixel offsets (the batch
-// cuts of points.py:409-424 are then a searchsorted on that array); K8 walks pixels and
+// K6 fuses bias, normalisation, visibility, clip and the Poisson draw, and K7 (exclusive pixel
+// offsets; the batch cuts of points.py:409-424 are then a searchsorted on that array) rides in
+// the same pass as a chained scan with decoupled look-back; K8 walks pixels and
 // writes every galaxy's (lon, lat) at its offset, galaxies ordered by ring pixel index as
 // in the reference.  All arithmetic that the reference does in NumPy is rounded the same
 // way (separate multiplies/adds, no FMA contraction) so that the expected-count map is
 // bit-identical for the linear / no-bias models.
+#include <algorithm>
+
 #include "common.cuh"
 #include "healpix_geom.cuh"
 #include "rng.cuh"
@@ -91,13 +93,12 @@ __device__ __noinline__ int64_t poisson_ptrs(double lam, uint32_t k0, uint32_t k
   return (int64_t)floor(lam);
 }
 
-// u: the pixel's own uniform (one Philox call serves the two pixels of a pair)
-__device__ __forceinline__ int64_t poisson_from_uniform(double lam, double u, uint32_t k0, uint32_t k1, uint64_t pix,
-                                                        uint32_t stream) {
-  if (!(lam > 0.0)) return 0;
+// slow path of the small-lambda inversion / PTRS: only pixels that did not resolve to zero
+// galaxies by the cheap test get here, compacted to dense warps by the caller
+__device__ __forceinline__ int64_t poisson_slow(double lam, double u, uint32_t k0, uint32_t k1, uint64_t pix,
+                                                uint32_t stream) {
   if (lam < 10.0) {
     // inversion by sequential search
-    if (u < 1.0 - lam) return 0;  // u < 1 - lam <= e^{-lam}: zero galaxies without evaluating exp
     double p = exp(-lam), F = p;
     int64_t x = 0;
     while (u > F && x < 256) {
@@ -116,9 +117,12 @@ struct CountParams {
   const double* mean;       // may be null (device scalar to subtract: remove_monopole)
   const int64_t* counts_in; // parity mode: supplied counts (may be null)
   double* nbar_out;         // may be null
-  int64_t* counts;          // out
-  int64_t* block_sums;      // out [nblocks]
+  int64_t* counts;          // out [npix]
+  int64_t* off;             // out [npix+1]
+  unsigned long long* status;  // [ntiles] decoupled look-back words, zeroed before the launch
+  unsigned int* ticket;        // tile ticket counter, zeroed before the launch
   int64_t npix;
+  int ntiles;
   double scale;             // ARCMIN2_SPHERE / npix * ngal   (computed on the host like points.py:287)
   double bias;
   int model;
@@ -126,139 +130,228 @@ struct CountParams {
   uint32_t k0, k1, stream;
 };
 
-__global__ void __launch_bounds__(PT_THREADS, 4) points_count_kernel(const CountParams p) {
-  __shared__ int64_t sh[PT_THREADS / 32];
-  const int64_t base = (int64_t)blockIdx.x * PT_TILE;
+constexpr int PT_WARPS = PT_THREADS / 32;     // worker warps; one more warp does the look-back
+constexpr int PT_WSEG = PT_TILE / PT_WARPS;   // pixels per worker warp (contiguous)
+constexpr int PT_QUADS = PT_WSEG / 128;       // 4-pixel groups per lane
+constexpr int PT_QCAP = PT_WSEG;              // slow-pixel queue entries per warp (worst case: every pixel)
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_VAL = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// named barriers: bar.sync blocks, bar.arrive only signals (producer side)
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K6 + K7 in ONE pass over the map: expected count -> Poisson count -> exclusive offsets.
+//  * a CTA takes a tile of 2048 pixels by atomic ticket; a worker warp owns 256 contiguous
+//    pixels, a lane two groups of 4 (coalesced 16-byte loads);
+//  * one Philox call gives the four pixels of a group 32 random bits each.  A pixel whose bits
+//    already prove u < 1 - lam <= e^{-lam} has zero galaxies (at 0.08 galaxies per pixel: 11 of
+//    12).  The others are queued in shared memory, get the remaining 21 bits of their uniform
+//    from a second Philox call and are drawn by DENSE warps, so the exp / division / PTRS code
+//    runs once per 32 queued pixels instead of once per group of 32 mostly idle lanes;
+//  * the tile's counts are scanned with shuffles and chained to the preceding tiles by a
+//    decoupled look-back on one 64-bit status word per tile (flag | value).  A ninth warp does
+//    the look-back WHILE the workers draw, and the counts are stored before the workers wait
+//    for it, so the offsets cost no second pass: 8 B read + 16 B written per pixel.
+//  (Measured alternatives, nside 4096, 0.083 galaxies/pixel: three kernels count / scan /
+//  offsets 2.57 ms; look-back by warp 0 after the draw 2.04 ms; this version 1.73 ms; a
+//  persistent variant that defers the offsets of a tile by one tile 1.99 ms; 128-wide
+//  look-back windows 2.51 ms.)
+template <bool VIS, bool SAMPLE, bool LOGLIN>
+__global__ void __launch_bounds__(PT_THREADS + 32, 4) points_count_scan_kernel(const CountParams p) {
+  // SAMPLE only: per-pixel counts of the tile and the per-warp queue of pixels that need the slow draw
+  __shared__ __align__(16) int s_cnt[SAMPLE ? PT_TILE : 4];
+  __shared__ double s_qlam[SAMPLE ? PT_WARPS : 1][SAMPLE ? PT_QCAP : 1];
+  __shared__ unsigned s_qbits[SAMPLE ? PT_WARPS : 1][SAMPLE ? PT_QCAP : 1];
+  __shared__ unsigned short s_qidx[SAMPLE ? PT_WARPS : 1][SAMPLE ? PT_QCAP : 1];
+  __shared__ int64_t s_wtot[PT_WARPS];
+  __shared__ int64_t s_excl;
+  __shared__ unsigned s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  constexpr int NALL = PT_THREADS + 32;
+  // named barriers: 1 warp totals ready (workers arrive, look-back warp syncs), 2 tile prefix
+  // ready (look-back warp arrives, workers sync), 3 workers only
+  if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+
+  if (warp == PT_WARPS) {
+    // ---- look-back warp: exclusive prefix of this tile from its predecessors' status words ----
+    int64_t excl = 0;
+    if (tile > 0) {
+      int64_t look = (int64_t)tile - 1;
+      for (;;) {
+        const int64_t t = look - lane;
+        unsigned long long w = ST_INCL;  // before the first tile: inclusive prefix 0
+        do {
+          if (t >= 0) w = ld_relaxed_u64(p.status + t);
+        } while (__any_sync(full, (w >> 62) == 0));
+        const unsigned inc = __ballot_sync(full, (w >> 62) == 2);
+        const int64_t v = (int64_t)(w & ST_VAL);
+        if (inc) {
+          const int first = __ffs(inc) - 1;  // nearest predecessor holding an inclusive prefix
+          excl += warp_sum_i64(lane <= first ? v : 0);
+          break;
+        }
+        excl += warp_sum_i64(v);
+        look -= 32;
+      }
+    }
+    if (lane == 0) s_excl = excl;
+    named_sync(1, NALL);
+    if (lane == 0) {
+      int64_t agg = 0;
+#pragma unroll
+      for (int w = 0; w < PT_WARPS; ++w) agg += s_wtot[w];
+      // max: never replace an inclusive word by the aggregate the workers publish
+      atomicMax(p.status + tile, ST_INCL | (unsigned long long)(excl + agg));
+      if ((int)tile == p.ntiles - 1) p.off[p.npix] = excl + agg;
+    }
+    named_arrive(2, NALL);
+    return;
+  }
+
+  const int64_t wbase = (int64_t)tile * PT_TILE + warp * PT_WSEG;
   const double mean = p.mean ? p.mean[0] : 0.0;
-  int64_t s = 0;
-  constexpr int NP = PT_ITEMS / 2;  // pixel pairs per thread (npix = 12 nside^2 is even)
+
   // issue all loads of the tile first (memory-level parallelism), then do the arithmetic
-  double2 dv[NP], vv[NP];
-  longlong2 cin[NP];
+  double2 dv[PT_QUADS][2], vv[PT_QUADS][2];
+  longlong2 c[PT_QUADS][2];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const int64_t pix = base + 2 * (threadIdx.x + (int64_t)i * PT_THREADS);
-    const bool ok = pix < p.npix;
-    dv[i] = ok ? *reinterpret_cast<const double2*>(p.delta + pix) : make_double2(0.0, 0.0);
-    vv[i] = (ok && p.vis) ? *reinterpret_cast<const double2*>(p.vis + pix) : make_double2(1.0, 1.0);
-    cin[i] = (ok && !p.sample) ? *reinterpret_cast<const longlong2*>(p.counts_in + pix) : make_longlong2(0, 0);
-  }
+  for (int i = 0; i < PT_QUADS; ++i) {
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const int64_t pix = base + 2 * (threadIdx.x + (int64_t)i * PT_THREADS);
-    if (pix >= p.npix) continue;
-    double n0 = biased(dv[i].x, p.model, p.bias), n1 = biased(dv[i].y, p.model, p.bias);
-    if (p.mean) {
-      n0 = __dsub_rn(n0, mean);
-      n1 = __dsub_rn(n1, mean);
+    for (int h = 0; h < 2; ++h) {
+      const int64_t pix = wbase + i * 128 + 4 * lane + 2 * h;
+      const bool ok = pix < p.npix;
+      dv[i][h] = ok ? *reinterpret_cast<const double2*>(p.delta + pix) : make_double2(0.0, 0.0);
+      vv[i][h] = (ok && VIS) ? *reinterpret_cast<const double2*>(p.vis + pix) : make_double2(1.0, 1.0);
+      c[i][h] = (ok && !SAMPLE) ? *reinterpret_cast<const longlong2*>(p.counts_in + pix) : make_longlong2(0, 0);
     }
-    n0 = __dmul_rn(__dadd_rn(n0, 1.0), p.scale);
-    n1 = __dmul_rn(__dadd_rn(n1, 1.0), p.scale);
-    if (p.vis) {
-      n0 = __dmul_rn(n0, vv[i].x);
-      n1 = __dmul_rn(n1, vv[i].y);
-    }
-    if (p.nbar_out) *reinterpret_cast<double2*>(p.nbar_out + pix) = make_double2(n0, n1);
-    longlong2 c;
-    if (p.sample) {
-      // one Philox call per pixel pair: words (0,1) -> even pixel, (2,3) -> odd pixel
-      const uint64_t pr = (uint64_t)pix >> 1;
-      const Philox4 r = philox4x32_10((uint32_t)pr, (uint32_t)(pr >> 32), p.stream, RNG_TAG_POISSON, p.k0, p.k1);
-      c.x = poisson_from_uniform(fmax(n0, 0.0), u01_closed_open(r.v[0], r.v[1]), p.k0, p.k1, (uint64_t)pix, p.stream);
-      c.y = poisson_from_uniform(fmax(n1, 0.0), u01_closed_open(r.v[2], r.v[3]), p.k0, p.k1, (uint64_t)pix + 1, p.stream);
-    } else {
-      c = cin[i];
-    }
-    *reinterpret_cast<longlong2*>(p.counts + pix) = c;
-    s += c.x + c.y;
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int64_t t = 0;
-    for (int w = 0; w < PT_THREADS / 32; ++w) t += sh[w];
-    p.block_sums[blockIdx.x] = t;
-  }
-}
 
-// exclusive scan of the block sums (single CTA), total written to block_off[n]
-__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const int64_t* __restrict__ sums, int n,
-                                                               int64_t* __restrict__ block_off) {
-  __shared__ int64_t sh[1024];
-  __shared__ int64_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int64_t v = (i < n) ? sums[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int64_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
+  int qn = 0;  // warp-uniform queue length
+#pragma unroll
+  for (int i = 0; i < PT_QUADS; ++i) {
+    const int loc = i * 128 + 4 * lane;
+    const int64_t pix = wbase + loc;
+    double n[4] = {dv[i][0].x, dv[i][0].y, dv[i][1].x, dv[i][1].y};
+    const double vs[4] = {vv[i][0].x, vv[i][0].y, vv[i][1].x, vv[i][1].y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // log-linear bias (expm1, log1p) lives in its own instantiation: the linear / no-bias
+      // streaming path stays free of out-of-line math calls
+      n[e] = LOGLIN ? biased(n[e], BIAS_LOGLINEAR, p.bias) : (p.model == BIAS_LINEAR ? __dmul_rn(p.bias, n[e]) : n[e]);
+      if (p.mean) n[e] = __dsub_rn(n[e], mean);
+      n[e] = __dmul_rn(__dadd_rn(n[e], 1.0), p.scale);
+      if (VIS) n[e] = __dmul_rn(n[e], vs[e]);
     }
-    if (i < n) block_off[i] = carry + sh[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
+    if (p.nbar_out) {
+      if (pix < p.npix) *reinterpret_cast<double2*>(p.nbar_out + pix) = make_double2(n[0], n[1]);
+      if (pix + 2 < p.npix) *reinterpret_cast<double2*>(p.nbar_out + pix + 2) = make_double2(n[2], n[3]);
+    }
+    if (SAMPLE) {
+      *reinterpret_cast<int4*>(s_cnt + warp * PT_WSEG + loc) = make_int4(0, 0, 0, 0);
+      // one Philox call per 4 pixels: word e -> the leading 32 bits of pixel e's uniform
+      const uint64_t qd = (uint64_t)pix >> 2;
+      const Philox4 r = philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), p.stream, RNG_TAG_POISSON, p.k0, p.k1);
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // u < (bits+1) 2^-32; zero galaxies for sure if that bound is <= 1 - lam <= e^{-lam}
+        const double ub = __hiloint2double(0x43300000, (int)r.v[e]) - 4503599627370495.0;  // bits + 1, exact
+        const bool slow =
+            (pix + e < p.npix) && (n[e] > 0.0) && !(n[e] < 10.0 && ub <= fma(-n[e], 4294967296.0, 4294967296.0));
+        const unsigned m = __ballot_sync(full, slow);
+        if (slow) {
+          const int k = qn + __popc(m & lt);
+          s_qlam[warp][k] = n[e];
+          s_qbits[warp][k] = r.v[e];
+          s_qidx[warp][k] = (unsigned short)(loc + e);
+        }
+        qn += __popc(m);
+      }
+    }
   }
-  if (threadIdx.x == 0) block_off[n] = carry;
-}
+  if (SAMPLE) {
+    __syncwarp();
+    // the queued pixels, 32 at a time on dense lanes
+    for (int k = lane; k < qn; k += 32) {
+      const int loc = s_qidx[warp][k];
+      const uint64_t pix = (uint64_t)(wbase + loc);
+      // the other 21 bits of the 53-bit uniform
+      const Philox4 r = philox4x32_10((uint32_t)pix, (uint32_t)(pix >> 32), p.stream, RNG_TAG_POISSON + 0x80u, p.k0, p.k1);
+      const double u = ((double)s_qbits[warp][k] * 2097152.0 + (double)(r.v[0] >> 11)) * (1.0 / 9007199254740992.0);
+      const int64_t v = poisson_slow(s_qlam[warp][k], u, p.k0, p.k1, pix, p.stream);
+      s_cnt[warp * PT_WSEG + loc] = (int)min(v, (int64_t)2147483647);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PT_QUADS; ++i) {
+      const int4 v = *reinterpret_cast<const int4*>(s_cnt + warp * PT_WSEG + i * 128 + 4 * lane);
+      c[i][0] = make_longlong2(v.x, v.y);
+      c[i][1] = make_longlong2(v.z, v.w);
+    }
+  }
 
-// per-pixel exclusive offsets: off[p] = sum_{q<p} counts[q]; off[npix] = total
-__global__ void __launch_bounds__(PT_THREADS) points_offsets_kernel(const int64_t* __restrict__ counts, int64_t npix,
-                                                                    const int64_t* __restrict__ block_off, int nblocks,
-                                                                    int64_t* __restrict__ off) {
-  __shared__ int64_t s_c[PT_TILE];      // counts, then offsets, of the tile
-  __shared__ int64_t sh[PT_THREADS / 32];
-  const int64_t base = (int64_t)blockIdx.x * PT_TILE;
-  const int tid = threadIdx.x;
-  // coalesced load into shared memory
+  // ---- scan: lane-level, then warp totals; the tile prefix comes from the look-back warp ----
+  int64_t ex[PT_QUADS];
+  int64_t run = 0;
 #pragma unroll
-  for (int i = 0; i < PT_ITEMS; ++i) {
-    const int k = tid + i * PT_THREADS;
-    s_c[k] = (base + k < npix) ? counts[base + k] : 0;
+  for (int i = 0; i < PT_QUADS; ++i) {
+    const int64_t s = (c[i][0].x + c[i][0].y) + (c[i][1].x + c[i][1].y);
+    int64_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    ex[i] = run + incl - s;
+    run += __shfl_sync(full, incl, 31);
   }
-  __syncthreads();
-  // thread t owns PT_ITEMS consecutive pixels
-  int64_t c[PT_ITEMS];
-  int64_t s = 0;
+  if (lane == 0) s_wtot[warp] = run;
+  named_arrive(1, NALL);
+  named_sync(3, PT_THREADS);
+  int64_t wpre = 0, agg = 0;
 #pragma unroll
-  for (int i = 0; i < PT_ITEMS; ++i) {
-    c[i] = s_c[tid * PT_ITEMS + i];
-    s += c[i];
+  for (int w = 0; w < PT_WARPS; ++w) {
+    const int64_t t = s_wtot[w];
+    agg += t;
+    if (w < warp) wpre += t;
   }
-  // block scan of the per-thread sums: warp shuffles, then the warp totals
-  int64_t incl = s;
-  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0 && tile > 0) atomicMax(p.status + tile, ST_AGG | (unsigned long long)agg);
+  // the counts do not depend on the prefix: store them while the look-back finishes
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
+  for (int i = 0; i < PT_QUADS; ++i) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t pix = wbase + i * 128 + 4 * lane + 2 * h;
+      if (pix < p.npix) *reinterpret_cast<longlong2*>(p.counts + pix) = c[i][h];
+    }
   }
-  if (lane == 31) sh[warp] = incl;
-  __syncthreads();
-  int64_t woff = 0;
+  named_sync(2, NALL);
+  wpre += s_excl;
 #pragma unroll
-  for (int w = 0; w < PT_THREADS / 32; ++w)
-    if (w < warp) woff += sh[w];
-  int64_t run = block_off[blockIdx.x] + woff + incl - s;
-#pragma unroll
-  for (int i = 0; i < PT_ITEMS; ++i) {
-    s_c[tid * PT_ITEMS + i] = run;
-    run += c[i];
+  for (int i = 0; i < PT_QUADS; ++i) {
+    const int64_t pix = wbase + i * 128 + 4 * lane;
+    const int64_t o0 = wpre + ex[i];
+    const int64_t o1 = o0 + c[i][0].x, o2 = o1 + c[i][0].y, o3 = o2 + c[i][1].x;
+    if (pix < p.npix) *reinterpret_cast<longlong2*>(p.off + pix) = make_longlong2(o0, o1);
+    if (pix + 2 < p.npix) *reinterpret_cast<longlong2*>(p.off + pix + 2) = make_longlong2(o2, o3);
   }
-  __syncthreads();
-  // coalesced store
-#pragma unroll
-  for (int i = 0; i < PT_ITEMS; ++i) {
-    const int k = tid + i * PT_THREADS;
-    if (base + k < npix) off[base + k] = s_c[k];
-  }
-  if (blockIdx.x == nblocks - 1 && tid == 0) off[npix] = block_off[nblocks];
 }
 
 struct FillParams {
@@ -419,6 +512,10 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
     final_sum_kernel<<<1, 1024, 0, st>>>(partial, nblocks, 1.0 / (double)npix, mean);
     count_launch(2);
   }
+  GLB_REQUIRE(npix % 2 == 0, "npix must be even (12 nside^2)");
+  GLB_REQUIRE(((uintptr_t)d_delta | (uintptr_t)d_counts | (uintptr_t)d_off | (uintptr_t)d_vis | (uintptr_t)d_counts_in |
+               (uintptr_t)d_nbar_out) % 16 == 0,
+              "map pointers must be 16-byte aligned");
   CountParams p;
   p.delta = d_delta;
   p.vis = d_vis;
@@ -426,8 +523,11 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
   p.counts_in = d_counts_in;
   p.nbar_out = d_nbar_out;
   p.counts = d_counts;
-  p.block_sums = block_sums;
+  p.off = d_off;
+  p.status = reinterpret_cast<unsigned long long*>(block_sums);
+  p.ticket = reinterpret_cast<unsigned int*>(block_sums + nblocks);
   p.npix = npix;
+  p.ntiles = nblocks;
   p.scale = scale;
   p.bias = bias;
   p.model = bias_model;
@@ -435,11 +535,26 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
   p.k0 = (uint32_t)seed;
   p.k1 = (uint32_t)(seed >> 32);
   p.stream = stream_id;
-  points_count_kernel<<<nblocks, PT_THREADS, 0, st>>>(p);
-  scan_block_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nblocks, block_off);
-  points_offsets_kernel<<<nblocks, PT_THREADS, 0, st>>>(d_counts, npix, block_off, nblocks, d_off);
+  GLB_CUDA_CHECK(cudaMemsetAsync(block_sums, 0, (size_t)(nblocks + 1) * sizeof(int64_t), st));
+  const int grid = nblocks;
+  const int variant = (d_vis ? 4 : 0) | (p.sample ? 2 : 0) | (bias_model == BIAS_LOGLINEAR ? 1 : 0);
+#define GLB_COUNT_LAUNCH(V, VIS, SAMPLE, LOGLIN)                                                           \
+  case V:                                                                                                  \
+    points_count_scan_kernel<VIS, SAMPLE, LOGLIN><<<grid, PT_THREADS + 32, 0, st>>>(p);                     \
+    break;
+  switch (variant) {
+    GLB_COUNT_LAUNCH(0, false, false, false)
+    GLB_COUNT_LAUNCH(1, false, false, true)
+    GLB_COUNT_LAUNCH(2, false, true, false)
+    GLB_COUNT_LAUNCH(3, false, true, true)
+    GLB_COUNT_LAUNCH(4, true, false, false)
+    GLB_COUNT_LAUNCH(5, true, false, true)
+    GLB_COUNT_LAUNCH(6, true, true, false)
+    GLB_COUNT_LAUNCH(7, true, true, true)
+  }
+#undef GLB_COUNT_LAUNCH
   GLB_CUDA_CHECK(cudaGetLastError());
-  count_launch(3);
+  count_launch(1);
   return GLB_OK;
 }
 
