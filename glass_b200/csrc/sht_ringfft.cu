@@ -12,14 +12,18 @@
 //   2. pack   Z[k] = (G[k] + conj G[h-k]) + i e^{2 pi i k/n} (G[k] - conj G[h-k])
 //             so that the length-h complex inverse DFT z of Z holds the real ring as
 //             x[2j] = Re z[j], x[2j+1] = Im z[j]
-//   3. DFT_h  h a power of two: radix-2 DIF in shared memory, output read bit-reversed.
+//   3. DFT_h  h a power of two: register-blocked DIF in shared memory (fft_core.cuh: radix-8
+//             passes + one contiguous radix-16 pass, swizzled conflict-free layout) whose last
+//             pass hands out the result in natural order.
 //             otherwise h = 2L: two length-L DFTs (even/odd k) by Bluestein's chirp-z
 //             with a power-of-two circular convolution of length M >= 2L-1
 //             (forward DIF -> multiply by the precomputed chirp spectrum, stored in the
-//             same bit-reversed order -> inverse DIT: no bit reversal anywhere), then
-//             one radix-2 butterfly.  Intermediate values live in registers so shared
-//             memory only ever holds one M-length buffer.
-//   4. store  coalesced 16-byte stores of (x[2j], x[2j+1]) with the transform applied.
+//             matching order -> inverse DIT: no bit reversal anywhere, and DIF tail, multiply
+//             and DIT head are one pass), then one radix-2 butterfly.  Intermediate values
+//             live in registers so shared memory only ever holds one M-length buffer.
+//   4. store  coalesced 16-byte stores of (x[2j], x[2j+1]) with the transform applied --
+//             for the direct path straight from the registers of the last FFT pass.
+#include "fft_core.cuh"
 #include "plan.h"
 
 namespace glb {
@@ -40,137 +44,11 @@ struct FftParams {
   const int* rowidx;
   int mmax;
   int tw_n;
+  int stash_off;     // offset (double2) of the Bluestein stash behind the FFT buffer
   int kind[4];
   double p0[4];
   double p1[4];
 };
-
-// ---- shared-memory power-of-two FFTs, radix-8 passes (three butterfly levels per pass held in
-// registers: 5 passes instead of 13 for 8192 points, one table twiddle per thread and pass --
-// the others follow by squaring and by constant 8th roots of unity).
-// DIF: natural in -> bit-reversed out.  DIT: bit-reversed in -> natural out.
-// sign: inverse == false -> e^{-2 pi i jk/M}, inverse == true -> e^{+2 pi i jk/M}.
-__device__ __forceinline__ double2 csq(double2 a) { return make_double2(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
-// multiply by e^{-i pi a/4} (forward) or its conjugate (inverse), a = 0..3
-template <int A>
-__device__ __forceinline__ double2 mul_root8(double2 v, bool inverse) {
-  const double h = 0.70710678118654752440;
-  if (A == 0) return v;
-  if (A == 2) return inverse ? make_double2(-v.y, v.x) : make_double2(v.y, -v.x);            // -+ i
-  if (A == 1) return inverse ? make_double2(h * (v.x - v.y), h * (v.x + v.y))                  // (1+i)/sqrt2
-                             : make_double2(h * (v.x + v.y), h * (v.y - v.x));                 // (1-i)/sqrt2
-  return inverse ? make_double2(-h * (v.x + v.y), h * (v.x - v.y))                            // (-1+i)/sqrt2
-                 : make_double2(h * (v.y - v.x), -h * (v.x + v.y));                            // (-1-i)/sqrt2
-}
-
-// one DIF pass fusing K levels with half-spans s, s/2, ..., s/2^(K-1)
-template <int THREADS, int K>
-__device__ __forceinline__ void dif_pass(double2* x, int M, int s, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  constexpr int R = 1 << K;
-  const int q = s >> (K - 1);
-  const int lq = 31 - __clz(q);
-  const int tstep = tw_n / (2 * s);
-  for (int g = threadIdx.x; g < (M >> K); g += THREADS) {
-    const int lo = g & (q - 1);
-    const int base = ((g >> lq) << (lq + K)) + lo;
-    double2 v[R];
-#pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = x[base + t * q];
-    double2 w = __ldg(&tw[lo * tstep]);  // e^{-2 pi i lo/(2s)}
-    if (inverse) w.y = -w.y;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int hs = R >> (j + 1);
-#pragma unroll
-      for (int t = 0; t < R; ++t) {
-        if ((t & hs) == 0) {
-          const double2 u = v[t], z = v[t + hs];
-          v[t] = cadd(u, z);
-          double2 d = cmul(csub(u, z), w);
-          const int a = (t & (hs - 1)) * (4 / hs);  // (t mod hs)/(2hs) turns, in units of 1/8
-          if (a == 1) d = mul_root8<1>(d, inverse);
-          else if (a == 2) d = mul_root8<2>(d, inverse);
-          else if (a == 3) d = mul_root8<3>(d, inverse);
-          v[t + hs] = d;
-        }
-      }
-      w = csq(w);
-    }
-#pragma unroll
-    for (int t = 0; t < R; ++t) x[base + t * q] = v[t];
-  }
-  __syncthreads();
-}
-
-// one DIT pass fusing K levels with half-spans s, 2s, ..., s*2^(K-1)
-template <int THREADS, int K>
-__device__ __forceinline__ void dit_pass(double2* x, int M, int s, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  constexpr int R = 1 << K;
-  const int q = s;
-  const int lq = 31 - __clz(q);
-  const int tstep = tw_n / (q * R);  // top level: span q*R
-  for (int g = threadIdx.x; g < (M >> K); g += THREADS) {
-    const int lo = g & (q - 1);
-    const int base = ((g >> lq) << (lq + K)) + lo;
-    double2 v[R];
-#pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = x[base + t * q];
-    // lo-dependent twiddle of each level: wl[K-1] = e^{-2 pi i lo/(q R)}, wl[j] = wl[j+1]^2
-    double2 wl[K];
-    wl[K - 1] = __ldg(&tw[lo * tstep]);
-    if (inverse) wl[K - 1].y = -wl[K - 1].y;
-#pragma unroll
-    for (int j = K - 2; j >= 0; --j) wl[j] = csq(wl[j + 1]);
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int hs = 1 << j;
-#pragma unroll
-      for (int t = 0; t < R; ++t) {
-        if ((t & hs) == 0) {
-          double2 z = cmul(v[t + hs], wl[j]);
-          const int a = (t & (hs - 1)) * (4 / hs);
-          if (a == 1) z = mul_root8<1>(z, inverse);
-          else if (a == 2) z = mul_root8<2>(z, inverse);
-          else if (a == 3) z = mul_root8<3>(z, inverse);
-          const double2 u = v[t];
-          v[t] = cadd(u, z);
-          v[t + hs] = csub(u, z);
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < R; ++t) x[base + t * q] = v[t];
-  }
-  __syncthreads();
-}
-
-template <int THREADS>
-__device__ __forceinline__ void fft_dif(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  int s = M >> 1;
-  while (s >= 4) {
-    dif_pass<THREADS, 3>(x, M, s, tw, tw_n, inverse);
-    s >>= 3;
-  }
-  if (s == 2)
-    dif_pass<THREADS, 2>(x, M, s, tw, tw_n, inverse);
-  else if (s == 1)
-    dif_pass<THREADS, 1>(x, M, s, tw, tw_n, inverse);
-}
-
-template <int THREADS>
-__device__ __forceinline__ void fft_dit(double2* x, int M, const double2* __restrict__ tw, int tw_n, bool inverse) {
-  int s = 1;
-  while (s * 8 <= M) {
-    dit_pass<THREADS, 3>(x, M, s, tw, tw_n, inverse);
-    s <<= 3;
-  }
-  if (s * 4 == M)
-    dit_pass<THREADS, 2>(x, M, s, tw, tw_n, inverse);
-  else if (s * 2 == M)
-    dit_pass<THREADS, 1>(x, M, s, tw, tw_n, inverse);
-}
 
 __device__ __forceinline__ double apply_transform(double x, int kind, double p0, double p1) {
   if (kind == GLB_T_LOGNORMAL) {
@@ -184,19 +62,46 @@ __device__ __forceinline__ double apply_transform(double x, int kind, double p0,
   return x;
 }
 
+// Roots of unity of one ring from two small shared-memory tables: T(j) = e^{2 pi i j/(2 nphi)},
+// j < 2 nphi, as hi[j >> 6] * lo[j & 63].  Every trigonometric factor of the ring stage is one of
+// them (phase shift e^{i pi m/nphi} = T(m mod 2nphi); real-FFT twiddle e^{2 pi i k/nphi} = T(2k);
+// chirp e^{i pi q^2/L} = T(4 (q^2 mod 2L)); e^{2 pi i q/h} = T(4q)), so a CTA evaluates
+// sincospi ~600 times instead of ~6 times per ring element.
+struct RingTrig {
+  const double2* hi;
+  const double2* lo;
+  __device__ __forceinline__ double2 T(int j) const { return cmul(hi[j >> 6], lo[j & 63]); }
+};
+constexpr int TRIG_HI = 512;  // 2 * 16384 / 64
+template <int THREADS>
+__device__ __forceinline__ RingTrig ring_trig_setup(double2* s_hi, double2* s_lo, int nphi) {
+  const double inv = 1.0 / (double)nphi;  // j/(2 nphi) turns = j/nphi half-turns
+  for (int j = threadIdx.x; j < 64; j += THREADS) s_lo[j] = cispi((double)j * inv);
+  for (int a = threadIdx.x; a * 64 < 2 * nphi; a += THREADS) s_hi[a] = cispi((double)(a * 64) * inv);
+  __syncthreads();
+  RingTrig t;
+  t.hi = s_hi;
+  t.lo = s_lo;
+  return t;
+}
+
 // chirp c[q] = e^{i pi q^2 / L}
 __device__ __forceinline__ double2 chirp(int q, int L) {
   const long long q2 = ((long long)q * q) % (2LL * L);
   return cispi((double)q2 / (double)L);
 }
+// the same from the ring's tables (q < 2^15: q^2 fits 32 bits unsigned)
+__device__ __forceinline__ double2 chirp(const RingTrig& tr, int q, int L) {
+  return tr.T(4 * (int)(((unsigned)q * (unsigned)q) % (unsigned)(2 * L)));
+}
 
 // Z[k] from the folded bins
-__device__ __forceinline__ double2 pack_z(const double2* G, int k, int h, int n) {
+__device__ __forceinline__ double2 pack_z(const RingTrig& tr, const double2* G, int k, int h) {
   const double2 g = G[k];
   const double2 gr = cconj(G[h - k]);
   const double2 s = cadd(g, gr);
   const double2 d = csub(g, gr);
-  const double2 w = cispi(2.0 * (double)k / (double)n);
+  const double2 w = tr.T(2 * k);  // e^{2 pi i k/nphi}
   const double2 wd = cmul(w, d);  // i*wd = (-wd.y, wd.x)
   return make_double2(s.x - wd.y, s.y + wd.x);
 }
@@ -217,7 +122,8 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   double* __restrict__ out = p.maps[b] + d.start;
   const int kind = p.kind[b];
   const double tp0 = p.p0[b], tp1 = p.p1[b];
-  const double inv_n = 1.0 / (double)n;
+  __shared__ double2 s_thi[TRIG_HI], s_tlo[64];
+  const RingTrig tr = ring_trig_setup<THREADS>(s_thi, s_tlo, n);
 
   // ---- 1. fold with phase shift ----
   for (int k = tid; k <= h; k += THREADS) {
@@ -225,12 +131,12 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
     for (int m = k; m <= mlim; m += n) {
       double2 t = F(m);
       if (m == 0) t.y = 0.0;
-      if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
+      if (d.shifted) t = cmul(t, tr.T(m % (2 * n)));
       g = cadd(g, t);
     }
     for (int m = n - k; m <= mlim; m += n) {
       double2 t = F(m);
-      if (d.shifted) t = cmul(t, cispi((double)(m % (2 * n)) * inv_n));
+      if (d.shifted) t = cmul(t, tr.T(m % (2 * n)));
       g = cadd(g, cconj(t));
     }
     buf[k] = g;
@@ -238,78 +144,76 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   __syncthreads();
 
   double2 reg[NREG];
+  const int nfft = 31 - __clz(d.M);  // log2 of the power-of-two FFT length
   if (d.L == 0) {
     // ---- direct power-of-two path ----
 #pragma unroll
     for (int t = 0; t < NREG; ++t) {
       const int k = tid + t * THREADS;
-      if (k < h) reg[t] = pack_z(buf, k, h, n);
+      if (k < h) reg[t] = pack_z(tr, buf, k, h);
     }
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < NREG; ++t) {
       const int k = tid + t * THREADS;
-      if (k < h) buf[k] = reg[t];
+      if (k < h) buf[fft::sw(k, nfft)] = reg[t];
     }
     __syncthreads();
-    fft_dif<THREADS>(buf, h, p.tw, p.tw_n, true);
-    const int lg = 31 - __clz(h);
-    for (int j = tid; j < h; j += THREADS) {
-      const int jr = (lg == 0) ? 0 : (int)(__brev((unsigned)j) >> (32 - lg));
-      const double2 zv = buf[jr];
+    // the last pass emits z[j] in natural order: consecutive lanes, consecutive 16-byte stores
+    fft::dev_fft_dif_emit<THREADS>(buf, nfft, p.tw, p.tw_n, true, [&](int j, double2 zv) {
       double2 o;
       o.x = apply_transform(zv.x, kind, tp0, tp1);
       o.y = apply_transform(zv.y, kind, tp0, tp1);
       *reinterpret_cast<double2*>(out + 2 * j) = o;
-    }
+    });
     return;
   }
 
   // ---- Bluestein path: h = 2L ----
-  const int L = d.L, M = d.M;
+  // even-k sequence in registers, odd-k sequence parked in the shared-memory stash while the
+  // FFT buffer is busy with the other one
+  const int L = d.L;
   constexpr int NQ = NREG / 2;
-  double2* ae = reg;
-  double2* ao = reg + NQ;
+  double2* stash = buf + p.stash_off;
+  double2* ev = reg;
 #pragma unroll
   for (int t = 0; t < NQ; ++t) {
     const int q = tid + t * THREADS;
     if (q < L) {
-      const double2 c = chirp(q, L);
-      ae[t] = cmul(pack_z(buf, 2 * q, h, n), c);
-      ao[t] = cmul(pack_z(buf, 2 * q + 1, h, n), c);
+      const double2 c = chirp(tr, q, L);
+      ev[t] = cmul(pack_z(tr, buf, 2 * q, h), c);
+      stash[q] = cmul(pack_z(tr, buf, 2 * q + 1, h), c);
     }
   }
   __syncthreads();
   const double2* __restrict__ bf = p.bf + d.bf_off;
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    double2* a = pass ? ao : ae;
-    for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < NQ; ++t) {
-      const int q = tid + t * THREADS;
-      if (q < L) buf[q] = a[t];
-    }
-    __syncthreads();
-    fft_dif<THREADS>(buf, M, p.tw, p.tw_n, false);
-    for (int i = tid; i < M; i += THREADS) buf[i] = cmul(buf[i], bf[i]);
-    __syncthreads();
-    fft_dit<THREADS>(buf, M, p.tw, p.tw_n, true);
-#pragma unroll
-    for (int t = 0; t < NQ; ++t) {
-      const int q = tid + t * THREADS;
-      if (q < L) a[t] = buf[q];
-    }
-    __syncthreads();
+  for (int t = 0; t < NQ; ++t) {
+    const int q = tid + t * THREADS;
+    if (q < L) buf[fft::sw(q, nfft)] = ev[t];
   }
+  __syncthreads();
+  fft::dev_bluestein_conv<THREADS>(buf, nfft, p.tw, p.tw_n, bf, L);  // elements >= L count as zero
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) {
+    const int q = tid + t * THREADS;
+    if (q < L) ev[t] = buf[fft::sw(q, nfft)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < NQ; ++t) {
+    const int q = tid + t * THREADS;
+    if (q < L) buf[fft::sw(q, nfft)] = stash[q];
+  }
+  __syncthreads();
+  fft::dev_bluestein_conv<THREADS>(buf, nfft, p.tw, p.tw_n, bf, L);
 #pragma unroll
   for (int t = 0; t < NQ; ++t) {
     const int q = tid + t * THREADS;
     if (q < L) {
-      const double2 c = chirp(q, L);
-      const double2 E = cmul(ae[t], c);
-      const double2 O = cmul(cmul(ao[t], c), cispi(2.0 * (double)q / (double)h));
+      const double2 c = chirp(tr, q, L);
+      const double2 E = cmul(ev[t], c);
+      const double2 O = cmul(cmul(buf[fft::sw(q, nfft)], c), tr.T(4 * q));  // e^{2 pi i q/h}
       const double2 z0 = cadd(E, O), z1 = csub(E, O);
       double2 o;
       o.x = apply_transform(z0.x, kind, tp0, tp1);
@@ -341,6 +245,7 @@ struct FftAnaParams {
   double norm;            // 4 pi / npix
   int mmax;
   int tw_n;
+  int stash_off;
 };
 
 template <int THREADS, int NREG>
@@ -356,62 +261,62 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_analysis_kernel(const Fft
   const double* __restrict__ in = p.maps[b] + d.start;
   double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
   const double wscale = p.norm * (p.ring_w ? p.ring_w[ring] : 1.0);
-  const int lg = 31 - __clz(h);
+  const int nfft = 31 - __clz(d.M);
   bool bitrev_out;
+  __shared__ double2 s_thi[TRIG_HI], s_tlo[64];
+  const RingTrig tr = ring_trig_setup<THREADS>(s_thi, s_tlo, n);
 
   if (d.L == 0) {
-    for (int j = tid; j < h; j += THREADS) buf[j] = *reinterpret_cast<const double2*>(in + 2 * j);
+    for (int j = tid; j < h; j += THREADS) buf[fft::sw(j, nfft)] = *reinterpret_cast<const double2*>(in + 2 * j);
     __syncthreads();
-    fft_dif<THREADS>(buf, h, p.tw, p.tw_n, false);
+    fft::dev_fft_dif<THREADS>(buf, nfft, p.tw, p.tw_n, false);
     bitrev_out = true;
   } else {
-    const int L = d.L, M = d.M;
+    const int L = d.L;
     constexpr int NQ = NREG / 2;
-    double2 reg[NREG];
-    double2* ae = reg;
-    double2* ao = reg + NQ;
+    double2* stash = buf + p.stash_off;
+    double2 ev[NQ], od[NQ];
 #pragma unroll
     for (int t = 0; t < NQ; ++t) {
       const int q = tid + t * THREADS;
       if (q < L) {
-        const double2 c = chirp(q, L);
+        const double2 c = chirp(tr, q, L);
         const double2 ze = *reinterpret_cast<const double2*>(in + 4 * q);
         const double2 zo = *reinterpret_cast<const double2*>(in + 4 * q + 2);
-        ae[t] = cmul(cconj(ze), c);  // forward DFT as conj(IDFT(conj .))
-        ao[t] = cmul(cconj(zo), c);
+        buf[fft::sw(q, nfft)] = cmul(cconj(ze), c);  // forward DFT as conj(IDFT(conj .))
+        stash[q] = cmul(cconj(zo), c);
       }
     }
+    __syncthreads();
     const double2* __restrict__ bf = p.bf + d.bf_off;
+    fft::dev_bluestein_conv<THREADS>(buf, nfft, p.tw, p.tw_n, bf, L);
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      double2* a = pass ? ao : ae;
-      for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
-      __syncthreads();
-#pragma unroll
-      for (int t = 0; t < NQ; ++t) {
-        const int q = tid + t * THREADS;
-        if (q < L) buf[q] = a[t];
-      }
-      __syncthreads();
-      fft_dif<THREADS>(buf, M, p.tw, p.tw_n, false);
-      for (int i = tid; i < M; i += THREADS) buf[i] = cmul(buf[i], bf[i]);
-      __syncthreads();
-      fft_dit<THREADS>(buf, M, p.tw, p.tw_n, true);
-#pragma unroll
-      for (int t = 0; t < NQ; ++t) {
-        const int q = tid + t * THREADS;
-        if (q < L) a[t] = buf[q];
-      }
-      __syncthreads();
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) ev[t] = buf[fft::sw(q, nfft)];
     }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) buf[fft::sw(q, nfft)] = stash[q];
+    }
+    __syncthreads();
+    fft::dev_bluestein_conv<THREADS>(buf, nfft, p.tw, p.tw_n, bf, L);
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int q = tid + t * THREADS;
+      if (q < L) od[t] = buf[fft::sw(q, nfft)];
+    }
+    __syncthreads();
     // Zf[k] = E[k] + w^k O[k], Zf[k+L] = E[k] - w^k O[k], w = e^{-2 pi i / h}; natural order in buf
 #pragma unroll
     for (int t = 0; t < NQ; ++t) {
       const int q = tid + t * THREADS;
       if (q < L) {
-        const double2 c = chirp(q, L);
-        const double2 E = cconj(cmul(ae[t], c));
-        const double2 O = cmul(cconj(cmul(ao[t], c)), cispi(-2.0 * (double)q / (double)h));
+        const double2 c = chirp(tr, q, L);
+        const double2 E = cconj(cmul(ev[t], c));
+        const double2 O = cmul(cconj(cmul(od[t], c)), cconj(tr.T(4 * q)));  // e^{-2 pi i q/h}
         buf[q] = cadd(E, O);
         buf[q + L] = csub(E, O);
       }
@@ -420,27 +325,27 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_analysis_kernel(const Fft
     bitrev_out = false;
   }
 
-  const double inv_n = 1.0 / (double)n;
   for (int m = tid; m <= mlim; m += THREADS) {
     const int k = m % n;
     const int kk = (k <= h) ? k : n - k;
     int i0 = kk % h, i1 = (h - kk) % h;
-    if (bitrev_out && lg > 0) {
-      i0 = (int)(__brev((unsigned)i0) >> (32 - lg));
-      i1 = (int)(__brev((unsigned)i1) >> (32 - lg));
+    if (bitrev_out) {  // logical bit-reversed position, swizzled layout
+      i0 = fft::sw((int)fft::bitrev((unsigned)i0, nfft), nfft);
+      i1 = fft::sw((int)fft::bitrev((unsigned)i1, nfft), nfft);
     }
     const double2 zk = buf[i0];
     const double2 zr = cconj(buf[i1]);
     const double2 sum = cadd(zk, zr), dif = csub(zk, zr);
-    const double2 wd = cmul(cispi(-2.0 * (double)kk * inv_n), dif);  // -i*wd = (wd.y, -wd.x)
+    const double2 wd = cmul(cconj(tr.T(2 * kk)), dif);  // -i*wd = (wd.y, -wd.x)
     double2 X = make_double2(0.5 * (sum.x + wd.y), 0.5 * (sum.y - wd.x));
     if (k > h) X = cconj(X);
-    if (d.shifted) X = cmul(X, cispi(-(double)(m % (2 * n)) * inv_n));
+    if (d.shifted) X = cmul(X, cconj(tr.T(m % (2 * n))));
     F[m] = cscale(X, wscale);
   }
 }
 
-// chirp spectrum  Bf = DIF_M( b_wrapped ) / M,  b[d] = conj(c[d]) = e^{-i pi d^2 / L}
+// chirp spectrum  Bf = DIF_M( b_wrapped ) / M,  b[d] = conj(c[d]) = e^{-i pi d^2 / L}, stored in the
+// block-transposed order the fused Bluestein middle pass reads (fft::bf_index)
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bluestein_spectrum_kernel(const int* Ls, const int* Ms, const int64_t* offs,
                                                                      const double2* tw, int tw_n, double2* bf) {
@@ -448,18 +353,19 @@ __global__ void __launch_bounds__(THREADS) bluestein_spectrum_kernel(const int* 
   double2* buf = reinterpret_cast<double2*>(smem_raw);
   const int tid = threadIdx.x;
   const int L = Ls[blockIdx.x], M = Ms[blockIdx.x];
-  for (int i = tid; i < M; i += THREADS) buf[i] = make_double2(0.0, 0.0);
+  const int nfft = 31 - __clz(M);
+  for (int i = tid; i < M + 8; i += THREADS) buf[i] = make_double2(0.0, 0.0);
   __syncthreads();
   for (int q = tid; q < L; q += THREADS) {
     const double2 c = cconj(chirp(q, L));
-    buf[q] = c;
-    if (q > 0) buf[M - q] = c;
+    buf[fft::sw(q, nfft)] = c;
+    if (q > 0) buf[fft::sw(M - q, nfft)] = c;
   }
   __syncthreads();
-  fft_dif<THREADS>(buf, M, tw, tw_n, false);
+  fft::dev_fft_dif<THREADS>(buf, nfft, tw, tw_n, false);
   const double inv = 1.0 / (double)M;
   double2* o = bf + offs[blockIdx.x];
-  for (int i = tid; i < M; i += THREADS) o[i] = cscale(buf[i], inv);
+  for (int i = tid; i < M; i += THREADS) o[fft::bf_index(i, nfft)] = cscale(buf[fft::sw(i, nfft)], inv);
 }
 
 // -------------------------------------------------------------------------------------
@@ -487,7 +393,7 @@ int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::v
   GLB_CUDA_CHECK(cudaMemcpyAsync(dO, offs.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   int maxM = 0;
   for (int m : Ms) maxM = std::max(maxM, m);
-  const size_t smem = (size_t)maxM * sizeof(double2);
+  const size_t smem = (size_t)(maxM + 8) * sizeof(double2);
   GLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_spectrum_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
   bluestein_spectrum_kernel<512><<<(unsigned)n, 512, smem, st>>>(dL, dM, dO, pl->d_tw, pl->tw_n, pl->d_bf);
@@ -500,9 +406,11 @@ int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::v
 }
 
 template <int THREADS, int NREG>
-static int launch_class(const FftParams& p, int nrings, int nb, int lb, cudaStream_t st) {
+static int launch_class(FftParams p, int nrings, int nb, int lb, cudaStream_t st) {
   if (nrings == 0) return GLB_OK;
-  const size_t smem = (size_t)(lb + 2) * sizeof(double2);
+  // FFT buffer (+8: the swizzle permutes inside aligned groups of 8) and the Bluestein stash (L <= lb/2)
+  p.stash_off = lb + 8;
+  const size_t smem = (size_t)(lb + 8 + lb / 2) * sizeof(double2);
   static bool attr_set = false;
   if (!attr_set) {
     GLB_CUDA_CHECK(cudaFuncSetAttribute(sht_ringfft_synth_kernel<THREADS, NREG>,
@@ -560,9 +468,10 @@ int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* co
 }
 
 template <int THREADS, int NREG>
-static int launch_class_ana(const FftAnaParams& p, int nrings, int nb, int lb, cudaStream_t st) {
+static int launch_class_ana(FftAnaParams p, int nrings, int nb, int lb, cudaStream_t st) {
   if (nrings == 0) return GLB_OK;
-  const size_t smem = (size_t)(lb + 2) * sizeof(double2);
+  p.stash_off = lb + 8;
+  const size_t smem = (size_t)(lb + 8 + lb / 2) * sizeof(double2);
   static bool attr_set = false;
   if (!attr_set) {
     GLB_CUDA_CHECK(cudaFuncSetAttribute(sht_ringfft_analysis_kernel<THREADS, NREG>,
