@@ -42,10 +42,14 @@ inline double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y 
 namespace glb {
 namespace fft {
 
-GLB_FFT_HD int ilog2(int v) {
+GLB_FFT_HD int ilog2(int v) {  // v a power of two
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
   int n = 0;
   while ((1 << n) < v) ++n;
   return n;
+#endif
 }
 
 // bit reversal of the low `bits` bits
@@ -60,11 +64,11 @@ GLB_FFT_HD unsigned bitrev(unsigned v, int bits) {
 }
 
 // physical position of logical element i in a buffer holding a 2^n-point transform
-GLB_FFT_HD int sw(int i, int n) {
-  int f = i >> 4;
-  if (n >= 10) f ^= i >> (n - 3);
-  return i ^ (f & 7);
-}
+GLB_FFT_HD int sw(int i, int n) { return i ^ ((((i >> 4) ^ (i >> (n >= 10 ? n - 3 : 31))) & 7)); }
+
+// the 3-bit XOR mask of sw(): phys(i) = i ^ swmask(i, sh), sh = swshift(n)
+GLB_FFT_HD int swshift(int n) { return n >= 10 ? n - 3 : 31; }
+GLB_FFT_HD int swmask(int i, int sh) { return ((i >> 4) ^ (i >> sh)) & 7; }
 
 GLB_FFT_HD double2 csq(double2 a) { return make_double2(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
 
@@ -151,19 +155,24 @@ GLB_FFT_HD void dif_pass(double2* x, int n, int s, const double2* tw, int tw_n, 
   const int M = 1 << n;
   const int q = s >> (K - 1);
   const int lq = ilog2(q);
-  const int tstep = tw_n / (2 * s);
+  const int tshift = ilog2(tw_n) - ilog2(2 * s);  // twiddle table stride tw_n / (2 s), powers of two
+  // element t of a butterfly group sits at base + t q; base and t q occupy disjoint bits and
+  // q >= 16, so the swizzle mask splits into a per-thread and a per-t (warp-uniform) part:
+  //   phys(base + t q) = ((base ^ mask(base)) ^ mask(t q)) + t q
+  const int sh = swshift(n);
+  int ft[R];
+#pragma unroll
+  for (int t = 0; t < R; ++t) ft[t] = swmask(t * q, sh);
   for (int g = tid; g < (M >> K); g += nthreads) {
     const int lo = g & (q - 1);
     const int base = ((g >> lq) << (lq + K)) + lo;
+    const int b0 = base ^ swmask(base, sh);
     double2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) {
-      const int i = base + t * q;
-      v[t] = (i < nvalid) ? x[sw(i, n)] : make_double2(0.0, 0.0);
-    }
-    dif_butterflies<K, false>(v, load_tw(tw, lo * tstep, inverse), inverse);
+    for (int t = 0; t < R; ++t) v[t] = (base + t * q < nvalid) ? x[(b0 ^ ft[t]) + t * q] : make_double2(0.0, 0.0);
+    dif_butterflies<K, false>(v, load_tw(tw, lo << tshift, inverse), inverse);
 #pragma unroll
-    for (int t = 0; t < R; ++t) x[sw(base + t * q, n)] = v[t];
+    for (int t = 0; t < R; ++t) x[(b0 ^ ft[t]) + t * q] = v[t];
   }
 }
 
@@ -174,20 +183,25 @@ GLB_FFT_HD void dit_pass(double2* x, int n, int s, const double2* tw, int tw_n, 
   const int M = 1 << n;
   const int q = s;
   const int lq = ilog2(q);
-  const int tstep = tw_n / (q * R);
+  const int tshift = ilog2(tw_n) - lq - K;  // tw_n / (q R)
+  const int sh = swshift(n);
+  int ft[R];
+#pragma unroll
+  for (int t = 0; t < R; ++t) ft[t] = swmask(t * q, sh);
   for (int g = tid; g < (M >> K); g += nthreads) {
     const int lo = g & (q - 1);
     const int base = ((g >> lq) << (lq + K)) + lo;
+    const int b0 = base ^ swmask(base, sh);  // see dif_pass
     double2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = x[sw(base + t * q, n)];
+    for (int t = 0; t < R; ++t) v[t] = x[(b0 ^ ft[t]) + t * q];
     double2 wl[K];
-    wl[K - 1] = load_tw(tw, lo * tstep, inverse);
+    wl[K - 1] = load_tw(tw, lo << tshift, inverse);
 #pragma unroll
     for (int j = K - 2; j >= 0; --j) wl[j] = csq(wl[j + 1]);
     dit_butterflies<K, false>(v, wl, inverse);
 #pragma unroll
-    for (int t = 0; t < R; ++t) x[sw(base + t * q, n)] = v[t];
+    for (int t = 0; t < R; ++t) x[(b0 ^ ft[t]) + t * q] = v[t];
   }
 }
 
@@ -231,18 +245,22 @@ GLB_FFT_HD void dit_upper_schedule(int n, Step&& step) {
 }
 
 // ---- contiguous blocks of R = 2^T elements held in registers ----
+// (T == 4: the mask is the same for the 16 elements of a block, phys = 16 g + (t ^ mask))
 template <int T>
 GLB_FFT_HD void block_load(const double2* x, int n, int g, double2* v, int nvalid) {
+  const int fg = (T == 4) ? swmask(g << 4, swshift(n)) : 0;
 #pragma unroll
   for (int t = 0; t < (1 << T); ++t) {
     const int i = (g << T) + t;
-    v[t] = (i < nvalid) ? x[sw(i, n)] : make_double2(0.0, 0.0);
+    const int ph = (T == 4) ? (g << 4) + (t ^ fg) : sw(i, n);
+    v[t] = (i < nvalid) ? x[ph] : make_double2(0.0, 0.0);
   }
 }
 template <int T>
 GLB_FFT_HD void block_store(double2* x, int n, int g, const double2* v) {
+  const int fg = (T == 4) ? swmask(g << 4, swshift(n)) : 0;
 #pragma unroll
-  for (int t = 0; t < (1 << T); ++t) x[sw((g << T) + t, n)] = v[t];
+  for (int t = 0; t < (1 << T); ++t) x[(T == 4) ? (g << 4) + (t ^ fg) : sw((g << T) + t, n)] = v[t];
 }
 
 // DIF tail in place (result in bit-reversed order)

@@ -304,7 +304,38 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
     int k = 0;
 
     if (phase == 0) {
-      while (k < kc) {
+      // blocks of 4 l-pairs with ONE exponent test per block while every ring is still far
+      // (2^-80) below the significance threshold: per step |p| grows by at most ~2^14 (first
+      // steps of a large m), so four unchecked steps can neither overflow nor cross the
+      // threshold.  The exponent tests are integer instructions that would otherwise
+      // outnumber the 2 DFMA per ring and step.
+      while (k + 4 <= kc) {
+        bool near = false;
+#pragma unroll
+        for (int j = 0; j < R; ++j) near |= (sc[j] == 0) && (bexp(p2[j]) >= BEXP_SIG - 80);
+        if (__any_sync(0xffffffffu, near)) break;  // finish with the exact per-step loop below
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC);
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const double rr = fma(ab.x, x2[j], ab.y);
+            const double t = fma(rr, p2[j], -p1[j]);
+            p1[j] = p2[j];
+            p2[j] = t;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (bexp(p2[j]) >= BEXP_BIG) {
+            p1[j] *= SMALL;
+            p2[j] *= SMALL;
+            sc[j] += 1;
+          }
+        }
+        k += 4;
+      }
+      while (phase == 0 && k < kc) {
         bool sig = false;
 #pragma unroll
         for (int j = 0; j < R; ++j) sig |= (sc[j] == 0) && (bexp(p2[j]) >= BEXP_SIG);

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   const int mlim = min(p.mlim[d.pair], p.mmax);
   const int row = p.rowidx ? p.rowidx[ring] : ring;
   const double2* __restrict__ Fb = p.phase + b * p.phase_map_stride + (int64_t)row * p.W;
-  auto F = [&](int m) -> double2 { return Fb[(int64_t)(m % p.G) * p.blk + m / p.G]; };
+  const bool one_gpu = (p.G == 1);  // the m-split layout needs a division per element
+  auto F = [&](int m) -> double2 { return one_gpu ? Fb[m] : Fb[(int64_t)(m % p.G) * p.blk + m / p.G]; };
   double* __restrict__ out = p.maps[b] + d.start;
   const int kind = p.kind[b];
   const double tp0 = p.p0[b], tp1 = p.p1[b];
@@ -128,16 +129,23 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_synth_kernel(const FftPar
   // ---- 1. fold with phase shift ----
   for (int k = tid; k <= h; k += THREADS) {
     double2 g = make_double2(0.0, 0.0);
+    // m = k, k + n, ...: m mod 2n alternates between j and j + n (mod 2n), no division needed
+    int j = k;  // k <= n/2 < 2n
     for (int m = k; m <= mlim; m += n) {
       double2 t = F(m);
       if (m == 0) t.y = 0.0;
-      if (d.shifted) t = cmul(t, tr.T(m % (2 * n)));
+      if (d.shifted) t = cmul(t, tr.T(j));
       g = cadd(g, t);
+      j += n;
+      if (j >= 2 * n) j -= 2 * n;
     }
+    j = n - k;  // n/2 <= n - k <= n
     for (int m = n - k; m <= mlim; m += n) {
       double2 t = F(m);
-      if (d.shifted) t = cmul(t, tr.T(m % (2 * n)));
+      if (d.shifted) t = cmul(t, tr.T(j));
       g = cadd(g, cconj(t));
+      j += n;
+      if (j >= 2 * n) j -= 2 * n;
     }
     buf[k] = g;
   }
