@@ -113,6 +113,29 @@ def _np(a) -> np.ndarray:
     return np.asarray(a)
 
 
+def _gls_to_host(gls):
+    """Host (NumPy) copies of the spectra with ONE device->host transfer for all CUDA tensors.
+
+    The spectra are tiny (<= lmax+1 doubles each) and only feed host-side recursions
+    (cls2cov / iternorm / cltovar); fetching them one by one would synchronise the stream
+    once per spectrum and drain the kernel queue between shells.
+    """
+    idx = [i for i, g in enumerate(gls) if isinstance(g, torch.Tensor) and g.is_cuda and g.numel() > 0]
+    if not idx:
+        return [_np(g) for g in gls]
+    flat = torch.cat([gls[i].detach().reshape(-1).to(torch.float64) for i in idx]).cpu().numpy()
+    out = [None] * len(gls)
+    pos = 0
+    for i in idx:
+        n = gls[i].numel()
+        out[i] = flat[pos : pos + n].reshape(tuple(gls[i].shape))
+        pos += n
+    for i, g in enumerate(gls):
+        if out[i] is None:
+            out[i] = _np(g)
+    return out
+
+
 def iternorm(cov: Iterable) -> Iterator[np.ndarray]:
     """
     Scaling vectors for iterative normal sampling (glass/fields.py:101-188).
@@ -231,6 +254,7 @@ class _ShellSampler:
         self.lib = _lib.load()
         self.device = device
         self.nside = nside
+        gls = _gls_to_host(gls)
         ngrf = nfields_from_nspectra(len(gls))
         self.ngrf = ngrf
         self.ncorr = ngrf - 1 if ncorr is None else ncorr
@@ -404,10 +428,15 @@ def generate(fields: Sequence, gls, nside: int, *, ncorr: int | None = None, rng
         raise ValueError(msg)
 
     variances: dict[int, float] = {}
+    host_autos: dict[int, np.ndarray] = {}
+    if any(isinstance(g, torch.Tensor) and g.is_cuda for g in gls):
+        # one transfer for all auto-spectra instead of a stream synchronisation per shell
+        ii = [i * (i + 1) // 2 for i in range(n)]  # getcl(gls, i, i)
+        host_autos = dict(zip(range(n), _gls_to_host([gls[k] for k in ii])))
 
     def var_of(i: int) -> float:
         if i not in variances:
-            variances[i] = cltovar(getcl(gls, i, i))
+            variances[i] = cltovar(host_autos[i] if i in host_autos else getcl(gls, i, i))
         return variances[i]
 
     def transforms_for(i: int):
