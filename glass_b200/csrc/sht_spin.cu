@@ -264,6 +264,25 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
     int k = 0;  // chunk-local l index; parity slot of k is (k & 1) because SP_KT is even
 
     if (phase == 0) {
+      // blocks of 4 steps with one exponent test while every ring is still 2^-80 below the
+      // significance threshold (see sht_legendre.cu): the tests are integer instructions that
+      // would otherwise outnumber the 4 DFMA per ring and step
+      while (k + 4 <= kc) {
+        bool near = false;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          near |= (sc[j] == 0) && (max(sp_bexp(pp2[j]), sp_bexp(pm2[j])) >= SP_BEXP_SIG - 80);
+        if (__any_sync(0xffffffffu, near)) break;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC);
+#pragma unroll
+          for (int j = 0; j < R; ++j) recur(j, ab.x, ab.y);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) rescale(j);
+        k += 4;
+      }
       while (k < kc) {
         bool sig = false;
 #pragma unroll
