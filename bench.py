@@ -431,6 +431,19 @@ def run_b200(args) -> None:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     total_ms = dev_s * 1e3 / K
+    # DRAM traffic per launch from the committed ncu --set full capture of this same workload
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except OSError:
+        pass
+
+    def traffic_of(kernel):
+        t = traffic.get(kernel)
+        if t and t.get("nside") == nside and t.get("lmax") == lmax and t.get("maps_per_launch") == int(round(maps_per_launch)):
+            return t["bytes_per_launch"]
+        return None
+
     line = {
         "metric": METRIC,
         "value": value,
@@ -467,7 +480,9 @@ def run_b200(args) -> None:
             "peak": peak_tf.value,
             "unit": "TFLOP/s",
             "frac": achieved / peak_tf.value,
-            "traffic": None,
+            "traffic": traffic_of("sht_legendre_synth_kernel"),
+            "bound_note": "FP64 vector pipe (tcgen05 has no FP64 mode; DMMA measured at the same 37 TFLOP/s on the same units, "
+            "tools/microbench/dmma_mix.cu), so neither 'hbm' nor 'tensor' applies",
             "peak_source": "measured live in this run: register-resident DFMA chains on all SMs "
             "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
             "algorithmic_flop_per_launch": alg_flop,
@@ -488,7 +503,7 @@ def run_b200(args) -> None:
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": fft_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
-            "traffic": None,
+            "traffic": traffic_of("sht_ringfft_synth_kernel"),
         },
     }
     if world == 1 and not args.no_extra:

@@ -11,6 +11,9 @@ missing.
 from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, shells  # noqa: F401
 from .fields import (  # noqa: F401
     cls2cov,
+    cltovar,
+    discretized_cls,
+    effective_cls,
     gaussian_fields,
     generate,
     generate_gaussian,
@@ -29,7 +32,7 @@ from .lensing import (  # noqa: F401
     multi_plane_weights,
     shear_from_convergence,
 )
-from .points import linear_bias, loglinear_bias, positions_from_delta  # noqa: F401
+from .points import linear_bias, loglinear_bias, positions_from_delta, uniform_positions  # noqa: F401
 from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
 from .shells import RadialWindow  # noqa: F401
 

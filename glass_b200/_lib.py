@@ -47,6 +47,7 @@ SIGNATURES = {
     "glb_points_fill": (_i, [_i64, _dp, _dp, _i64, _i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp]),
     "glb_ring2ang_uv": (_i, [_i64, _dp, _dp, _dp, _i64, _i, _dp, _dp, _vp]),
     "glb_randang": (_i, [_i64, _dp, _i64, C.c_uint64, C.c_uint32, _i, _dp, _dp, _vp]),
+    "glb_uniform_positions": (_i, [_i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),
     "glb_ang2pix": (_i, [_i64, _dp, _dp, _i64, _i, _dp, _vp]),
     "glb_multiplane_update": (_i, [_dp, _dp, _dp, C.c_double, _i64, C.c_double, C.c_double, _vp]),
     "glb_galaxy_shear": (_i, [_i64, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _i, _dp, _vp]),

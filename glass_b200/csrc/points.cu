@@ -467,6 +467,41 @@ __global__ void __launch_bounds__(256) randang_kernel(int64_t nside, const int64
   }
 }
 
+// glass.uniform_positions (glass/points.py:543-607): lon = uniform(-180, 180), lat = degrees(asin(uniform(-1, 1)))
+// per point; (u1, u2) from Philox keyed by (seed, stream, point index) or supplied arrays.  NumPy's
+// uniform(low, high) is low + (high - low) * random(), reproduced with separately rounded operations.
+__global__ void __launch_bounds__(256) uniform_positions_kernel(int64_t n, const double* __restrict__ u1,
+                                                                const double* __restrict__ u2, uint32_t k0, uint32_t k1,
+                                                                uint32_t stream, double* __restrict__ lon,
+                                                                double* __restrict__ lat) {
+  const double rad2deg = 57.295779513082320877;
+  // two points per thread: 16-byte stores
+  const int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  double a[2], b[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t j = min(i + e, n - 1);
+    if (u1) {
+      a[e] = u1[j];
+      b[e] = u2[j];
+    } else {
+      const Philox4 r = philox4x32_10((uint32_t)j, (uint32_t)((uint64_t)j >> 32), stream, RNG_TAG_POS + 0x40u, k0, k1);
+      a[e] = u01_closed_open(r.v[0], r.v[1]);
+      b[e] = u01_closed_open(r.v[2], r.v[3]);
+    }
+    a[e] = __dadd_rn(-180.0, __dmul_rn(360.0, a[e]));
+    b[e] = __dmul_rn(asin(__dadd_rn(-1.0, __dmul_rn(2.0, b[e]))), rad2deg);
+  }
+  if (i + 1 < n) {
+    *reinterpret_cast<double2*>(lon + i) = make_double2(a[0], a[1]);
+    *reinterpret_cast<double2*>(lat + i) = make_double2(b[0], b[1]);
+  } else {
+    lon[i] = a[0];
+    lat[i] = b[0];
+  }
+}
+
 __global__ void __launch_bounds__(256) ang2pix_kernel(int64_t nside, const double* __restrict__ a, const double* __restrict__ b,
                                                       int64_t n, int lonlat, int64_t* __restrict__ ipix) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -605,6 +640,21 @@ int glb_randang(int64_t nside, const int64_t* d_ipix, int64_t n, uint64_t seed, 
   GLB_REQUIRE(d_ipix && d_out1 && d_out2, "null pointer");
   randang_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       nside, d_ipix, n, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id, lonlat, d_out1, d_out2);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_uniform_positions(int64_t n, const double* d_u1, const double* d_u2, uint64_t seed, uint32_t stream_id,
+                          double* d_lon, double* d_lat, void* stream) {
+  GLB_REQUIRE(n >= 0, "bad size");
+  if (n == 0) return GLB_OK;
+  GLB_REQUIRE(d_lon && d_lat, "null pointer");
+  GLB_REQUIRE((d_u1 == nullptr) == (d_u2 == nullptr), "the two uniform arrays must be given together");
+  GLB_REQUIRE(((uintptr_t)d_lon | (uintptr_t)d_lat) % 16 == 0, "output pointers must be 16-byte aligned");
+  const int64_t nthreads = (n + 1) / 2;
+  uniform_positions_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, d_u1, d_u2, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id, d_lon, d_lat);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;

@@ -16,6 +16,7 @@
 // a final per-m pass adds the tiles in fixed order (deterministic) and applies alpha / the
 // odd recursion.
 #include <algorithm>
+#include <cstdlib>
 
 #include "plan.h"
 
@@ -111,7 +112,7 @@ struct AnaParams {
 };
 
 template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS) legendre_analysis_kernel(const AnaParams p) {
+__global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legendre_analysis_kernel(const AnaParams p) {
   constexpr int NWARPS = THREADS / 32;
   __shared__ __align__(128) double2 s_rec[AN_STAGES][AN_KT];
   __shared__ __align__(8) uint64_t s_full[AN_STAGES];
@@ -374,9 +375,22 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
 int sht_map2phase_group(glb_plan* pl, const double* const* d_maps, int nb, const double* d_ring_w, double2* d_phase,
                         cudaStream_t st);
 
+int plan_items(glb_plan* pl, int tile, int G, int rank, LegItem** d_items, int* nitems);
+
+// ring pairs per thread of the analysis kernel: the cross-lane reduction of a round costs the
+// same for any R, so more rings per thread amortise it better (8: one CTA of 256 threads per SM)
+static int analysis_R(const glb_plan* pl) {
+  int R = (pl->npair >= 2048) ? 8 : 4;
+  if (const char* env = getenv("GLB_AN_R")) {
+    const int r = atoi(env);
+    if (r == 4 || r == 8) R = r;
+  }
+  return R;
+}
+
 int plan_ensure_analysis(glb_plan* pl) {
   if (pl->d_partial) return GLB_OK;
-  const int T = pl->leg_threads * pl->leg_R;
+  const int T = pl->leg_threads * analysis_R(pl);
   pl->ana_ntile = (pl->npair + T - 1) / T;
   const size_t bytes = (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_partial, bytes));
@@ -399,7 +413,11 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
   if ((rc = sht_map2phase_group(pl, maps, 1, d_ring_w, pl->d_phase, st)) != GLB_OK) return rc;
   GLB_CUDA_CHECK(cudaMemsetAsync(pl->d_partial, 0, (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double), st));
   AnaParams p;
-  p.items = pl->d_items;
+  const int R = analysis_R(pl);
+  LegItem* items = nullptr;
+  int nitems = 0;
+  if ((rc = plan_items(pl, R * pl->leg_threads, 1, 0, &items, &nitems)) != GLB_OK) return rc;
+  p.items = items;
   p.rec = reinterpret_cast<const double2*>(pl->d_ab_tab);
   p.roff = pl->d_roff;
   p.z = pl->d_z;
@@ -414,13 +432,21 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
   p.mmax = pl->mmax;
   p.npair = pl->npair;
   p.nring = pl->nring;
-  constexpr int R = 4;
-  if (pl->leg_threads == 64)
-    legendre_analysis_kernel<R, 64><<<pl->nitems, 64, 0, st>>>(p);
-  else if (pl->leg_threads == 128)
-    legendre_analysis_kernel<R, 128><<<pl->nitems, 128, 0, st>>>(p);
-  else
-    legendre_analysis_kernel<R, 256><<<pl->nitems, 256, 0, st>>>(p);
+  if (R == 8) {
+    if (pl->leg_threads == 64)
+      legendre_analysis_kernel<8, 64><<<nitems, 64, 0, st>>>(p);
+    else if (pl->leg_threads == 128)
+      legendre_analysis_kernel<8, 128><<<nitems, 128, 0, st>>>(p);
+    else
+      legendre_analysis_kernel<8, 256><<<nitems, 256, 0, st>>>(p);
+  } else {
+    if (pl->leg_threads == 64)
+      legendre_analysis_kernel<4, 64><<<nitems, 64, 0, st>>>(p);
+    else if (pl->leg_threads == 128)
+      legendre_analysis_kernel<4, 128><<<nitems, 128, 0, st>>>(p);
+    else
+      legendre_analysis_kernel<4, 256><<<nitems, 256, 0, st>>>(p);
+  }
   analysis_finalize_kernel<<<pl->mmax + 1, FIN_THREADS, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff, pl->d_prep_tab,
                                                                  pl->d_partial, pl->ana_ntile, pl->nrec, accumulate,
                                                                  d_alm);

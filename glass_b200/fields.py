@@ -216,6 +216,79 @@ def cltovar(cl) -> float:
     return float(np.sum((2 * ell + 1) / (4 * np.pi) * cl))
 
 
+def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, nside: int | None = None, pixwin=None):
+    """
+    Apply discretisation effects to angular power spectra (glass/fields.py:239-300): truncate
+    to ``lmax``, keep ``ncorr`` correlations, multiply by the squared HEALPix pixel window.
+
+    The reference reads the window from healpy's data files (glass/healpix.py:313-356), which
+    do not exist offline; here ``nside`` needs ``pixwin=`` (array w_l, e.g. ``healpy.pixwin``
+    output) -- everything else is identical.  Host-side: the spectra are tiny.
+    """
+    if len(cls) == 0:
+        return []
+    if ncorr is not None:
+        n = nfields_from_nspectra(len(cls))
+        empty = cls[0][:0]
+        cls = [cls[i * (i + 1) // 2 + j] if j <= ncorr else empty for i in range(n) for j in range(i + 1)]
+    pw = None
+    if nside is not None:
+        if pixwin is None:
+            raise NotImplementedError(
+                "discretized_cls(nside=...) needs the HEALPix pixel window: pass pixwin=w_l "
+                "(healpy's data files, glass/healpix.py:313-356, are not available offline)"
+            )
+        pw = pixwin[: lmax + 1] if lmax is not None else pixwin
+    gls = []
+    for cl in cls:
+        if cl.shape[0] > 0:
+            if lmax is not None:
+                cl = cl[: lmax + 1]
+            if pw is not None:
+                n = min(cl.shape[0], pw.shape[0])
+                w = pw[:n]
+                if isinstance(cl, torch.Tensor) and not isinstance(w, torch.Tensor):
+                    w = torch.as_tensor(np.asarray(w), dtype=cl.dtype, device=cl.device)
+                cl = cl[:n] * w**2
+        gls.append(cl)
+    return gls
+
+
+def effective_cls(cls, weights1, weights2=None, *, lmax: int | None = None):
+    """
+    Effective angular power spectra from weights (glass/fields.py:607-694):
+    ``out[j1 + j2] = sum_{i1, i2} w1[i1, j1] w2[i2, j2] C_l^{i1 i2}``, accumulated in the
+    reference's order (i1 outer, i2 inner) so that the result is bit-identical.
+    """
+    n = nfields_from_nspectra(len(cls))
+    cls = _gls_to_host(cls)
+    if lmax is None:
+        lmax = max((cl.shape[0] for cl in cls), default=0) - 1
+    weights1 = _np(weights1)
+    same = weights2 is None
+    weights2 = weights1 if same else _np(weights2)
+    shape1, shape2 = weights1.shape, weights2.shape
+    for i, shape in enumerate((shape1, shape2)):
+        if not shape or shape[0] != n:
+            msg = f"shape mismatch between fields and weights{i + 1}"
+            raise ValueError(msg)
+    import itertools
+
+    if same:
+        pairs = itertools.combinations_with_replacement(np.ndindex(shape1[1:]), 2)
+    else:
+        pairs = itertools.product(np.ndindex(shape1[1:]), np.ndindex(shape2[1:]))
+    out = np.empty(shape1[1:] + shape2[1:] + (lmax + 1,))
+    c = (slice(None),)
+    for j1, j2 in pairs:
+        w1, w2 = weights1[c + j1], weights2[c + j2]
+        cl = sum(w1[i1] * w2[i2] * getcl(cls, i1, i2, lmax=lmax) for i1 in range(n) for i2 in range(n))
+        out[j1 + j2 + (...,)] = cl
+        if same and j1 != j2:
+            out[j2 + j1 + (...,)] = cl
+    return out
+
+
 def _glass_to_healpix_alm(alm):
     """l-major -> m-major (glass/fields.py:943-962)."""
     if isinstance(alm, torch.Tensor) and alm.is_cuda:

@@ -224,3 +224,57 @@ def positions_from_delta(  # noqa: PLR0913
                     yield lon, lat, n * cmask
                 else:
                     yield lon.cpu().numpy(), lat.cpu().numpy(), n * cmask
+
+
+def uniform_positions(ngal, *, rng=None, xp=None):
+    """
+    Generate positions uniformly over the sphere (glass/points.py:543-607).
+
+    ``ngal`` (scalar or array): expected number of points per arcmin2.  Yields, per entry
+    of ``ngal`` in C order, ``(lon, lat, count)`` with ``lon = uniform(-180, 180)``,
+    ``lat = degrees(asin(uniform(-1, 1)))`` and ``count`` an int (scalar ``ngal``) or an
+    int64 array of ``ngal``'s shape holding the count in that entry's slot.  Arrays are CUDA
+    tensors when ``ngal`` is a CUDA tensor or ``xp is torch``, NumPy arrays otherwise.
+
+    The total counts are Poisson(ARCMIN2_SPHERE * ngal) drawn on the host (a handful of
+    scalars); the two uniforms per point come from Philox keyed by (seed, population, point
+    index), or from ``rng=Deviates(poisson=[counts], uniform=...)`` in parity mode
+    (``uniform``: callable n -> (u1, u2), the deviates of lon and lat).
+    """
+    device, on_device = A.pick_device(ngal)
+    on_device = on_device or (xp is torch)
+    deviates = rng if isinstance(rng, _rng.Deviates) else None
+    seed = _rng.seed_from(rng)
+    lam = ARCMIN2_SPHERE * np.asarray(A.to_np(ngal), dtype=np.float64)
+    if deviates is not None and deviates.poisson is not None:
+        ngal_sphere = np.asarray(deviates.next_poisson(), dtype=np.int64).reshape(lam.shape)
+    else:
+        ngal_sphere = np.random.default_rng(seed).poisson(lam).astype(np.int64)
+    dims = ngal_sphere.shape
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        for ipop, k in enumerate(np.ndindex(dims)):
+            n = int(ngal_sphere[k])
+            lon = torch.empty(n, dtype=torch.float64, device=device)
+            lat = torch.empty(n, dtype=torch.float64, device=device)
+            u1 = u2 = None
+            if deviates is not None and deviates.uniform is not None:
+                a, b = deviates.uniform(n)
+                u1, u2 = A.to_dev(a, device), A.to_dev(b, device)
+            _lib.check(
+                lib.glb_uniform_positions(
+                    n, None if u1 is None else u1.data_ptr(), None if u2 is None else u2.data_ptr(),
+                    C.c_uint64(seed), C.c_uint32(ipop), lon.data_ptr(), lat.data_ptr(), st,
+                ),
+                "glb_uniform_positions",
+            )
+            if dims:
+                count = np.zeros(dims, dtype=np.int64)
+                count[k] = n
+            else:
+                count = n
+            if on_device:
+                yield lon, lat, count
+            else:
+                yield lon.cpu().numpy(), lat.cpu().numpy(), count

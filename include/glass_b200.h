@@ -133,6 +133,11 @@ int glb_ring2ang_uv(int64_t nside, const int64_t* d_ipix, const double* d_u, con
  * call with the same seed, like the reference's fresh default_rng(42) per call. */
 int glb_randang(int64_t nside, const int64_t* d_ipix, int64_t n, uint64_t seed, uint32_t stream_id, int lonlat,
                 double* d_out1, double* d_out2, void* stream);
+/* glass.uniform_positions (glass/points.py:543-607), one population of n points: lon = uniform(-180, 180),
+ * lat = degrees(asin(uniform(-1, 1))) (points.py:594-595).  The two uniforms per point come from Philox
+ * keyed by (seed, stream_id, point index) or from d_u1/d_u2 (parity mode, both or neither). */
+int glb_uniform_positions(int64_t n, const double* d_u1, const double* d_u2, uint64_t seed, uint32_t stream_id,
+                          double* d_lon, double* d_lat, void* stream);
 /* healpix.ang2pix(nside, theta|lon, phi|lat, lonlat)   glass/healpix.py:172 (RING scheme). */
 int glb_ang2pix(int64_t nside, const double* d_a, const double* d_b, int64_t n, int lonlat, int64_t* d_ipix,
                 void* stream);

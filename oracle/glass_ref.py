@@ -305,6 +305,26 @@ class MultiPlaneConvergence:
         return self.kappa3
 
 
+def uniform_positions_from_uniforms(counts, u_lon, u_lat):
+    """glass/points.py:586-604 with supplied deviates: for every population k (C order) of the
+    count array, lon = uniform(-180, 180) = -180 + 360 u (NumPy's low + (high - low) * random()),
+    lat = degrees(arcsin(uniform(-1, 1))); yields (lon, lat, count) like the reference."""
+    counts = np.asarray(counts, dtype=np.int64)
+    dims = counts.shape
+    pos = 0
+    for k in np.ndindex(dims):
+        n = int(counts[k])
+        lon = -180.0 + 360.0 * np.asarray(u_lon[pos : pos + n], dtype=np.float64)
+        lat = np.degrees(np.arcsin(-1.0 + 2.0 * np.asarray(u_lat[pos : pos + n], dtype=np.float64)))
+        pos += n
+        if dims:
+            count = np.zeros(dims, dtype=np.int64)
+            count[k] = n
+        else:
+            count = n
+        yield lon, lat, count
+
+
 def kappa_to_shear_fl(lmax, discretized=False, pw0=None, pw2=None):
     """glass/lensing.py:413-421: combined kappa_lm -> gamma E-mode factor."""
     ell = np.arange(lmax + 1)

@@ -257,6 +257,39 @@ def main():
     out["z_samples"] = glass.redshifts_from_nz(400, z, nz, rng=rr, warn=False)
     out["z_uniform"] = np.random.default_rng(9).uniform(0.0, 1.0, size=400)
 
+    # ---- discretized_cls / effective_cls (glass/fields.py:239-300, 607-694) ----
+    gls_d = synthetic_gls(4, 12, 3)
+    PW = 1.0 / (1.0 + 0.01 * np.arange(20.0) ** 2)
+    import glass.healpix as _ghp
+
+    _ghp.pixwin = lambda nside, lmax=None, pol=False, xp=None: PW[: (lmax + 1) if lmax is not None else None]
+    out["dcl_pw"] = PW
+    for tag, kw in {"lmax": {"lmax": 8}, "ncorr": {"ncorr": 1}, "all": {"lmax": 9, "ncorr": 2, "nside": 4}}.items():
+        res = glass.discretized_cls(gls_d, **kw)
+        out[f"dcl_{tag}_len"] = np.array([r.shape[0] for r in res])
+        out[f"dcl_{tag}"] = np.concatenate(res)
+    w1 = np.random.default_rng(4).random((4, 3))
+    w2 = np.random.default_rng(5).random((4, 2))
+    out["ecl_w1"], out["ecl_w2"] = w1, w2
+    out["ecl_auto"] = glass.effective_cls(gls_d, w1)
+    out["ecl_cross"] = glass.effective_cls(gls_d, w1, w2, lmax=7)
+
+    # ---- uniform_positions (glass/points.py:543-607): two populations, seed 11 ----
+    ngal_u = np.array([2e-6, 5e-6])
+    ups = list(glass.uniform_positions(ngal_u, rng=np.random.default_rng(11), xp=np))
+    out["up_ngal"] = ngal_u
+    out["up_lon"] = np.concatenate([u[0] for u in ups])
+    out["up_lat"] = np.concatenate([u[1] for u in ups])
+    out["up_count"] = np.stack([u[2] for u in ups])
+    # the same stream replayed: Poisson totals first, then per population lon deviates, lat deviates
+    rr = np.random.default_rng(11)
+    tot = rr.poisson(glass.points.ARCMIN2_SPHERE * ngal_u)
+    ul, ub = [], []
+    for n in tot:
+        ul.append(rr.random(int(n)))
+        ub.append(rr.random(int(n)))
+    out["up_totals"], out["up_u_lon"], out["up_u_lat"] = tot, np.concatenate(ul), np.concatenate(ub)
+
     np.savez_compressed(os.path.join(HERE, "glass_reference_vectors.npz"), **out)
     print("wrote", len(out), "arrays,", sum(v.nbytes for v in out.values()) // 1024, "KiB")
 

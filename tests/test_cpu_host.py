@@ -217,3 +217,26 @@ def test_msplit_layout_partitions():
         for rs in lay["rings"]:
             s = set(rs)
             assert all((nring - 1 - r) in s for r in rs)
+
+
+def test_discretized_and_effective_cls_golden():
+    """glass/fields.py:239-300 and 607-694 against vectors made by executing the reference
+    (its healpy pixel window replaced by a supplied array)."""
+    import os
+
+    import glass_b200
+    from helpers import synthetic_gls
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    gls = synthetic_gls(4, 12, 3)
+    for tag, kw in {"lmax": {"lmax": 8}, "ncorr": {"ncorr": 1}, "all": {"lmax": 9, "ncorr": 2, "nside": 4, "pixwin": gold["dcl_pw"]}}.items():
+        res = glass_b200.discretized_cls(gls, **kw)
+        assert np.array_equal(np.array([r.shape[0] for r in res]), gold[f"dcl_{tag}_len"])
+        assert np.array_equal(np.concatenate(res), gold[f"dcl_{tag}"])
+    assert glass_b200.discretized_cls([]) == []
+    with pytest.raises(NotImplementedError):
+        glass_b200.discretized_cls(gls, nside=4)
+    assert np.array_equal(glass_b200.effective_cls(gls, gold["ecl_w1"]), gold["ecl_auto"])
+    assert np.array_equal(glass_b200.effective_cls(gls, gold["ecl_w1"], gold["ecl_w2"], lmax=7), gold["ecl_cross"])
+    with pytest.raises(ValueError, match="shape mismatch between fields and weights1"):
+        glass_b200.effective_cls(gls, np.ones((3, 2)))

@@ -209,3 +209,12 @@ def test_c_oracle_matches_numpy_oracle():
     a = sht_c.alm2map(alm, 128, 300)
     b = sht_c.alm2map(alm, 128, 300, use_mlim=True)
     assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()
+
+
+def test_golden_uniform_positions():
+    """uniform_positions (glass/points.py:543-607) executed from the reference source; the
+    oracle replays it bit-exactly from the same Poisson totals and uniform deviates."""
+    got = list(G.uniform_positions_from_uniforms(GOLD["up_totals"], GOLD["up_u_lon"], GOLD["up_u_lat"]))
+    assert np.array_equal(np.concatenate([g[0] for g in got]), GOLD["up_lon"])
+    assert np.array_equal(np.concatenate([g[1] for g in got]), GOLD["up_lat"])
+    assert np.array_equal(np.stack([g[2] for g in got]), GOLD["up_count"])

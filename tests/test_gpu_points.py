@@ -180,3 +180,41 @@ def test_batch_cut_corner_cases(cuda_device):
         got = list(glass_b200.positions_from_delta(1e-3, np.zeros(npix), rng=Deviates(poisson=[counts], uv=uv), batch=batch))
         assert [g[2] for g in got] == [r[2] for r in ref], batch
         assert sum(g[2] for g in got) == counts.sum()
+
+
+def test_uniform_positions(cuda_device):
+    """glass/points.py:543-607: supplied deviates against the golden vectors of the reference
+    (lon bit-exact, lat to 1 ulp of asin), count semantics, and the Philox draws statistically."""
+    import os
+
+    from scipy import stats
+
+    import glass_b200
+    from glass_b200.rng import Deviates
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    pos = {"i": 0}
+
+    def uniforms(n):
+        a = pos["i"]
+        pos["i"] += n
+        return gold["up_u_lon"][a : a + n], gold["up_u_lat"][a : a + n]
+
+    got = list(glass_b200.uniform_positions(gold["up_ngal"], rng=Deviates(poisson=[gold["up_totals"]], uniform=uniforms)))
+    assert len(got) == 2 and all(isinstance(g[0], np.ndarray) for g in got)
+    assert np.array_equal(np.concatenate([g[0] for g in got]), gold["up_lon"])
+    np.testing.assert_allclose(np.concatenate([g[1] for g in got]), gold["up_lat"], rtol=0, atol=2e-14)
+    assert np.array_equal(np.stack([g[2] for g in got]), gold["up_count"])
+    # scalar density: count is a Python int, arrays follow the input's device
+    (lon, lat, cnt), = list(glass_b200.uniform_positions(torch.tensor(3e-3, device=cuda_device), rng=5))
+    assert isinstance(cnt, int) and lon.is_cuda and lon.numel() == cnt
+    lam = G.ARCMIN2_SPHERE * 3e-3
+    assert abs(cnt - lam) < 6 * np.sqrt(lam)
+    lo, la = lon.cpu().numpy(), lat.cpu().numpy()
+    assert lo.min() >= -180 and lo.max() < 180 and la.min() >= -90 and la.max() <= 90
+    assert stats.kstest(lo, "uniform", args=(-180, 360)).pvalue > 1e-4
+    assert stats.kstest(np.sin(np.radians(la)), "uniform", args=(-1, 2)).pvalue > 1e-4
+    assert abs(np.corrcoef(lo, la)[0, 1]) < 6 / np.sqrt(cnt)
+    # zero density: an empty batch is still yielded, like the reference
+    (lon, lat, cnt), = list(glass_b200.uniform_positions(0.0, rng=1))
+    assert cnt == 0 and lon.size == 0
