@@ -353,6 +353,7 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_dist_rowidx);
   for (int c = 0; c < 3; ++c) cudaFree(pl->d_dist_ring_order[c]);
   cudaFree(pl->d_partial);
+  cudaFree(pl->d_ana_first_tile);
   cudaFree(pl->d_tmpmap);
   cudaFree(pl->d_ab_tab);
   if (pl->h_pin_in) cudaFreeHost(pl->h_pin_in);

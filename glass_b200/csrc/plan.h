@@ -72,10 +72,11 @@ struct glb_plan {
   int64_t rec_capacity = 0;          // doubles available in d_rec
 
   // analysis (map2alm): per-tile partial sums and a scratch map pair, built lazily
-  double* d_partial = nullptr;       // [ana_ntile][nrec][4]
+  double* d_partial = nullptr;       // [ana_ntile][nrec][4], one slab per warp tile
   double* d_tmpmap = nullptr;        // [2][npix]
   double* d_ab_tab = nullptr;        // [nrec] {a_k, b_k} recurrence coefficients (TMA-streamed by the analysis kernel)
-  int ana_ntile = 0;
+  int ana_ntile = 0;                 // warp tiles (ring-pair tiles x warps per CTA)
+  int* d_ana_first_tile = nullptr;   // [mmax+1] first warp tile the analysis kernel writes for m
 
   // m-split distribution over GPUs (glb_dist_setup): this rank computes the Legendre stage for
   // m = rank (mod world) and the Fourier stage for its own ring bands

@@ -12,19 +12,21 @@
 // (the forward recursion is the transpose of the backward one in sht_prep_kernel).
 // A CTA owns (m, tile of ring pairs): threads walk l for their R ring pairs, partial sums for 8
 // consecutive k are held in registers, reduced across the warp by a shuffle transpose
-// (31 adds for 32 values), across warps through shared memory, and written per tile;
-// a final per-m pass adds the tiles in fixed order (deterministic) and applies alpha / the
-// odd recursion.
+// (31 adds for 32 values) and written per WARP tile -- there is no CTA-wide reduction and no
+// barrier in the l loop, so warps in cheap phases (rings near the poles) run ahead instead of
+// waiting for the slowest warp every 64 l-pairs; a final per-m pass adds the warp tiles in
+// fixed order (deterministic) and applies alpha / the odd recursion.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "plan.h"
 
 namespace glb {
 
 constexpr int AN_KT = 256;     // l-pairs per smem chunk (multiple of AN_SK)
-constexpr int AN_KB = 4;       // l-pairs per warp-level reduction round (4 or 8)
-constexpr int AN_SK = 64;      // l-pairs between cross-warp reductions (one CTA-wide sync each)
+constexpr int AN_KB = 8;       // l-pairs per warp-level reduction round (AN_KB * 4 = 32 values = one per lane)
+constexpr int AN_TRS = 34;     // row stride (doubles) of the per-warp transpose buffer
 constexpr int AN_STAGES = 3;
 constexpr int AN_BEXP_BIG = 1023 + 256;
 
@@ -106,7 +108,7 @@ struct AnaParams {
   const double* cm_mant;
   const int* cm_exp;
   const double2* phase;       // [nring][mmax+1] weighted G_m(ring)
-  double* partial;            // [ntile][nrec][4]
+  double* partial;            // [ntile * warps per CTA][nrec][4]: one slab per warp tile
   int64_t nrec;
   int lmax, mmax, npair, nring;
 };
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
   __shared__ __align__(128) double2 s_rec[AN_STAGES][AN_KT];
   __shared__ __align__(8) uint64_t s_full[AN_STAGES];
   __shared__ __align__(8) uint64_t s_empty[AN_STAGES];
-  __shared__ double s_wsum[2][NWARPS][AN_SK * 4];
+  extern __shared__ __align__(16) double s_tr_dyn[];  // [NWARPS][32 * AN_TRS] per-warp transpose buffers of the reduction
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const LegItem item = p.items[blockIdx.x];
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
   const int K = (p.lmax - m) / 2 + 1;
   const int nchunks = (K + AN_KT - 1) / AN_KT;
   const double2* rec_m = p.rec + p.roff[m];
-  double* out_m = p.partial + ((int64_t)item.tile * p.nrec + p.roff[m]) * 4;
+  double* out_m = p.partial + (((int64_t)item.tile * NWARPS + (threadIdx.x >> 5)) * p.nrec + p.roff[m]) * 4;
 
   if (tid == 0) {
 #pragma unroll
@@ -171,7 +173,6 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
     }
   }
   const double SMALL = 7.458340731200207e-155;  // 2^-512
-  int wbuf = 0;
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c % AN_STAGES;
@@ -186,101 +187,80 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
     const double2* ck = &s_rec[s][0];
     const int kc = min(AN_KT, K - c * AN_KT);
 
-    for (int ks = 0; ks < kc; ks += AN_SK) {
-      bool contrib = false;
+    for (int k0 = 0; k0 < kc; k0 += AN_KB) {
+      double part[AN_KB * 4];
 #pragma unroll
-      for (int j = 0; j < R; ++j) contrib |= (sc[j] == 0) && (p2[j] != 0.0);
-      for (int k0 = ks; k0 < min(ks + AN_SK, kc); k0 += AN_KB) {
-        double part[AN_KB * 4];
+      for (int i = 0; i < AN_KB * 4; ++i) part[i] = 0.0;
+      // FAST when every ring of the warp is at scale 0 (no select, no rescale test) and the
+      // round is complete; otherwise the CHECKED form
+      bool allz = (k0 + AN_KB <= kc);
 #pragma unroll
-        for (int i = 0; i < AN_KB * 4; ++i) part[i] = 0.0;
-        // FAST when every ring of the warp is at scale 0 (no select, no rescale test) and the
-        // round is complete; otherwise the CHECKED form
-        bool allz = (k0 + AN_KB <= kc);
+      for (int j = 0; j < R; ++j) allz &= (sc[j] == 0);
+      if (__all_sync(0xffffffffu, allz)) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) allz &= (sc[j] == 0);
-        if (__all_sync(0xffffffffu, allz)) {
+        for (int kk = 0; kk < AN_KB; ++kk) {
+          const double2 ab = ck[k0 + kk];
 #pragma unroll
-          for (int kk = 0; kk < AN_KB; ++kk) {
+          for (int j = 0; j < R; ++j) {
+            part[kk * 4 + 0] = fma(p2[j], ge_r[j], part[kk * 4 + 0]);
+            part[kk * 4 + 1] = fma(p2[j], ge_i[j], part[kk * 4 + 1]);
+            part[kk * 4 + 2] = fma(p2[j], go_r[j], part[kk * 4 + 2]);
+            part[kk * 4 + 3] = fma(p2[j], go_i[j], part[kk * 4 + 3]);
+            const double rr = fma(ab.x, x2[j], ab.y);
+            const double t = fma(rr, p2[j], -p1[j]);
+            p1[j] = p2[j];
+            p2[j] = t;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < AN_KB; ++kk) {
+          if (k0 + kk < kc) {
             const double2 ab = ck[k0 + kk];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-              part[kk * 4 + 0] = fma(p2[j], ge_r[j], part[kk * 4 + 0]);
-              part[kk * 4 + 1] = fma(p2[j], ge_i[j], part[kk * 4 + 1]);
-              part[kk * 4 + 2] = fma(p2[j], go_r[j], part[kk * 4 + 2]);
-              part[kk * 4 + 3] = fma(p2[j], go_i[j], part[kk * 4 + 3]);
+              const double pa = (sc[j] == 0) ? p2[j] : 0.0;
+              part[kk * 4 + 0] = fma(pa, ge_r[j], part[kk * 4 + 0]);
+              part[kk * 4 + 1] = fma(pa, ge_i[j], part[kk * 4 + 1]);
+              part[kk * 4 + 2] = fma(pa, go_r[j], part[kk * 4 + 2]);
+              part[kk * 4 + 3] = fma(pa, go_i[j], part[kk * 4 + 3]);
               const double rr = fma(ab.x, x2[j], ab.y);
               const double t = fma(rr, p2[j], -p1[j]);
               p1[j] = p2[j];
               p2[j] = t;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < AN_KB; ++kk) {
-            if (k0 + kk < kc) {
-              const double2 ab = ck[k0 + kk];
-#pragma unroll
-              for (int j = 0; j < R; ++j) {
-                const double pa = (sc[j] == 0) ? p2[j] : 0.0;
-                part[kk * 4 + 0] = fma(pa, ge_r[j], part[kk * 4 + 0]);
-                part[kk * 4 + 1] = fma(pa, ge_i[j], part[kk * 4 + 1]);
-                part[kk * 4 + 2] = fma(pa, go_r[j], part[kk * 4 + 2]);
-                part[kk * 4 + 3] = fma(pa, go_i[j], part[kk * 4 + 3]);
-                const double rr = fma(ab.x, x2[j], ab.y);
-                const double t = fma(rr, p2[j], -p1[j]);
-                p1[j] = p2[j];
-                p2[j] = t;
-                if (an_bexp(p2[j]) >= AN_BEXP_BIG) {
-                  p1[j] *= SMALL;
-                  p2[j] *= SMALL;
-                  sc[j] += 1;
-                }
+              if (an_bexp(p2[j]) >= AN_BEXP_BIG) {
+                p1[j] *= SMALL;
+                p2[j] *= SMALL;
+                sc[j] += 1;
               }
             }
           }
         }
-        // warp transpose-reduce of the AN_KB*4 values: lane i ends with the warp total of value i
-#define GLB_TR_STEP(O, NH)                                                   \
-  {                                                                          \
-    const bool up = (lane & (O)) != 0;                                       \
-    _Pragma("unroll") for (int i = 0; i < (NH); ++i) {                       \
-      const double send = up ? part[i] : part[i + (NH)];                     \
-      const double keep = up ? part[i + (NH)] : part[i];                     \
-      part[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));              \
-    }                                                                        \
-  }
-        if (AN_KB == 8) {
-          GLB_TR_STEP(16, 16)
-          GLB_TR_STEP(8, 8)
-          GLB_TR_STEP(4, 4)
-          GLB_TR_STEP(2, 2)
-          GLB_TR_STEP(1, 1)
-          s_wsum[wbuf][warp][(k0 - ks) * 4 + lane] = part[0];
-        } else {  // AN_KB == 4: 16 values over 32 lanes
-          GLB_TR_STEP(8, 8)
-          GLB_TR_STEP(4, 4)
-          GLB_TR_STEP(2, 2)
-          GLB_TR_STEP(1, 1)
-          part[0] += __shfl_xor_sync(0xffffffffu, part[0], 16);
-          if (lane < 16) s_wsum[wbuf][warp][(k0 - ks) * 4 + lane] = part[0];
-        }
-#undef GLB_TR_STEP
       }
+      // warp reduction of the AN_KB*4 = 32 values through shared memory: lane L stores value i
+      // at [i][L] (consecutive lanes, conflict-free), then reads row L with 16-byte loads (row
+      // stride 34 doubles: 8 consecutive lanes start in 8 different 16-byte bank groups) and adds
+      // the 32 entries in a fixed order.  79 instructions per round against 217 for the
+      // select-and-shuffle transpose (4 FSEL + 2 SHFL + 1 DADD per output).
+      // value v = kk*4 + q of this round belongs to l-pair k0 + kk: consecutive lanes write
+      // consecutive doubles of this warp tile's slab (always written: no memset, no flags)
+      double* dst = out_m + ((int64_t)c * AN_KT + k0) * 4;
+      double* tr = s_tr_dyn + warp * (32 * AN_TRS);
 #pragma unroll
-      for (int j = 0; j < R; ++j) contrib |= (sc[j] == 0) && (p2[j] != 0.0);
-      const int any = __syncthreads_or(contrib ? 1 : 0);
-      if (any) {
-        // cross-warp sum of the AN_SK*4 staged values, coalesced store to this tile's partials
-        const int nval = (min(ks + AN_SK, kc) - ks) * 4;
-        for (int i = tid; i < nval; i += THREADS) {
-          double tot = 0.0;
+      for (int i = 0; i < AN_KB * 4; ++i) tr[i * AN_TRS + lane] = part[i];
+      __syncwarp();
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-          for (int w = 0; w < NWARPS; ++w) tot += s_wsum[wbuf][w][i];
-          out_m[((int64_t)c * AN_KT + ks) * 4 + i] = tot;
-        }
+      for (int i = 0; i < 32; i += 4) {
+        const double2 a = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i);
+        const double2 b = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i + 2);
+        t0 += a.x;
+        t1 += a.y;
+        t2 += b.x;
+        t3 += b.y;
       }
-      wbuf ^= 1;
+      __syncwarp();
+      if (k0 + (lane >> 2) < kc) dst[lane] = (t0 + t1) + (t2 + t3);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);
@@ -303,6 +283,7 @@ constexpr int FIN_THREADS = 128;
 __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
                                                                         const double* __restrict__ tab,
                                                                         const double* __restrict__ partial, int ntile,
+                                                                        const int* __restrict__ first_tile,
                                                                         int64_t nrec, int accumulate,
                                                                         double2* __restrict__ alm) {
   __shared__ double s_y[2][FIN_CH + 1];   // s1_k * y_k (re, im), then v_k in place
@@ -312,6 +293,7 @@ __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax
   const int K = (lmax - m) / 2 + 1;
   const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;
   const double* t = tab + roff[m] * 5;
+  const int tl0 = first_tile[m];
   if (tid < 2) s_carry[tid] = 0.0;
   __syncthreads();
   for (int klo = 0; klo < K; klo += FIN_CH) {
@@ -320,7 +302,7 @@ __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax
       const int k = klo + i;
       const int l = m + 2 * k;
       double s0 = 0.0, s1v = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int tl = 0; tl < ntile; ++tl) {
+      for (int tl = tl0; tl < ntile; ++tl) {  // warp tiles of CTA tiles without a live ring were never written
         const double4 q = *reinterpret_cast<const double4*>(partial + ((int64_t)tl * nrec + roff[m] + k) * 4);
         s0 += q.x;
         s1v += q.y;
@@ -391,7 +373,15 @@ static int analysis_R(const glb_plan* pl) {
 int plan_ensure_analysis(glb_plan* pl) {
   if (pl->d_partial) return GLB_OK;
   const int T = pl->leg_threads * analysis_R(pl);
-  pl->ana_ntile = (pl->npair + T - 1) / T;
+  const int nwarps = pl->leg_threads / 32;
+  pl->ana_ntile = (pl->npair + T - 1) / T * nwarps;  // warp tiles
+  {
+    // first warp tile written for each m: CTA tiles below rmin[m] / T have no work item
+    std::vector<int> ft(pl->mmax + 1);
+    for (int m = 0; m <= pl->mmax; ++m) ft[m] = std::min(pl->h_rmin[m] / T, (pl->npair + T - 1) / T) * nwarps;
+    GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_ana_first_tile, ft.size() * sizeof(int)));
+    GLB_CUDA_CHECK(cudaMemcpy(pl->d_ana_first_tile, ft.data(), ft.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   const size_t bytes = (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_partial, bytes));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_tmpmap, (size_t)pl->npix * sizeof(double) * 2));
@@ -411,7 +401,6 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
   int rc;
   const double* maps[1] = {d_map};
   if ((rc = sht_map2phase_group(pl, maps, 1, d_ring_w, pl->d_phase, st)) != GLB_OK) return rc;
-  GLB_CUDA_CHECK(cudaMemsetAsync(pl->d_partial, 0, (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double), st));
   AnaParams p;
   const int R = analysis_R(pl);
   LegItem* items = nullptr;
@@ -432,24 +421,36 @@ int sht_analysis_pass(glb_plan* pl, const double* d_map, const double* d_ring_w,
   p.mmax = pl->mmax;
   p.npair = pl->npair;
   p.nring = pl->nring;
+#define GLB_AN_LAUNCH(RR, TT)                                                                                  \
+  {                                                                                                            \
+    const size_t smem = (size_t)(TT / 32) * 32 * AN_TRS * sizeof(double);                                      \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      GLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<RR, TT>,                                    \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    legendre_analysis_kernel<RR, TT><<<nitems, TT, smem, st>>>(p);                                             \
+  }
   if (R == 8) {
     if (pl->leg_threads == 64)
-      legendre_analysis_kernel<8, 64><<<nitems, 64, 0, st>>>(p);
+      GLB_AN_LAUNCH(8, 64)
     else if (pl->leg_threads == 128)
-      legendre_analysis_kernel<8, 128><<<nitems, 128, 0, st>>>(p);
+      GLB_AN_LAUNCH(8, 128)
     else
-      legendre_analysis_kernel<8, 256><<<nitems, 256, 0, st>>>(p);
+      GLB_AN_LAUNCH(8, 256)
   } else {
     if (pl->leg_threads == 64)
-      legendre_analysis_kernel<4, 64><<<nitems, 64, 0, st>>>(p);
+      GLB_AN_LAUNCH(4, 64)
     else if (pl->leg_threads == 128)
-      legendre_analysis_kernel<4, 128><<<nitems, 128, 0, st>>>(p);
+      GLB_AN_LAUNCH(4, 128)
     else
-      legendre_analysis_kernel<4, 256><<<nitems, 256, 0, st>>>(p);
+      GLB_AN_LAUNCH(4, 256)
   }
+#undef GLB_AN_LAUNCH
   analysis_finalize_kernel<<<pl->mmax + 1, FIN_THREADS, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff, pl->d_prep_tab,
-                                                                 pl->d_partial, pl->ana_ntile, pl->nrec, accumulate,
-                                                                 d_alm);
+                                                                 pl->d_partial, pl->ana_ntile, pl->d_ana_first_tile,
+                                                                 pl->nrec, accumulate, d_alm);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch(2);
   return GLB_OK;
