@@ -249,7 +249,7 @@ def uniform_positions(ngal, *, rng=None, xp=None):
     if deviates is not None and deviates.poisson is not None:
         ngal_sphere = np.asarray(deviates.next_poisson(), dtype=np.int64).reshape(lam.shape)
     else:
-        ngal_sphere = np.random.default_rng(seed).poisson(lam).astype(np.int64)
+        ngal_sphere = np.asarray(np.random.default_rng(seed).poisson(lam), dtype=np.int64)
     dims = ngal_sphere.shape
     lib = _lib.load()
     with torch.cuda.device(device):
