@@ -218,3 +218,32 @@ def test_uniform_positions(cuda_device):
     # zero density: an empty batch is still yielded, like the reference
     (lon, lat, cnt), = list(glass_b200.uniform_positions(0.0, rng=1))
     assert cnt == 0 and lon.size == 0
+
+
+def test_poisson_with_visibility_and_bias_variants(cuda_device):
+    """The sampling instantiations of the fused count/offset kernel (visibility, log-linear bias,
+    monopole removal): zero where the visibility is zero, Poisson moments elsewhere, and offsets
+    that are the exclusive scan of the counts."""
+    from glass_b200.points import _Population, linear_bias, loglinear_bias
+
+    nside = 64
+    npix = 12 * nside**2
+    rng = np.random.default_rng(2)
+    delta = np.expm1(0.4 * rng.standard_normal(npix) - 0.08)
+    vis = (np.arange(npix) % 3 != 0).astype(float) * 0.5
+    for model, bias, rm in ((linear_bias, 0.9, False), (loglinear_bias, 1.4, False), (linear_bias, 0.9, True)):
+        ngal = 6.0 / (G.ARCMIN2_SPHERE / npix)
+        pop = _Population(delta, vis, ngal, bias, model, rm, 77, 3, None, cuda_device, want_nbar=True)
+        c = pop.counts.cpu().numpy()
+        nbar = np.clip(pop.nbar.cpu().numpy(), 0, None)
+        name = "linear" if model is linear_bias else "loglinear"
+        ref = G.expected_count(delta, ngal, bias, vis, name, rm)
+        np.testing.assert_allclose(pop.nbar.cpu().numpy(), ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+        assert np.all(c[vis == 0] == 0)
+        assert abs(c.sum() - nbar.sum()) < 6 * np.sqrt(nbar.sum())
+        # per-pixel standardised residuals have unit variance for Poisson draws
+        m = nbar > 0.5
+        zres = (c[m] - nbar[m]) / np.sqrt(nbar[m])
+        assert abs(zres.var() - 1.0) < 0.05 and abs(zres.mean()) < 0.02
+        off = pop.off.cpu().numpy()
+        assert off[-1] == c.sum() and np.array_equal(off[:-1], np.cumsum(c) - c)
