@@ -303,6 +303,7 @@ def run_b200(args) -> None:
     import glass_b200
     from glass_b200 import _lib
     from glass_b200.healpix import get_plan
+    from glass_b200.sharding import shard_shells
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,6 +312,16 @@ def run_b200(args) -> None:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host threads: the per-shell host work (iternorm on (lmax+1, ncorr+1) arrays) gains nothing
+    # from BLAS/OpenMP threads, and world ranks x all cores oversubscribes the box
+    per_rank = max(1, (os.cpu_count() or 1) // max(1, world))
+    torch.set_num_threads(per_rank)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=per_rank)
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -321,7 +332,7 @@ def run_b200(args) -> None:
     nshell_total = world * S * nsteps
     gls = synthetic_gls(nshell_total, lmax, NCORR)
     fields = [glass_b200.grf.Lognormal(1.0)] * nshell_total
-    mine = range(rank, nshell_total, world)
+    mine = shard_shells(nshell_total, rank, world)  # contiguous block of S * nsteps shells per rank
     lib = _lib.load()
     plan = get_plan(nside, lmax, max_batch=4, device=dev)
 

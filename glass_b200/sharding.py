@@ -4,19 +4,31 @@ glass_b200.sharding -- how the path is split over the GPUs of one box (one proce
 The per-shell chain (a_lm draw/combine -> synthesis -> transformation -> Poisson/positions)
 has no exchange step: shell j depends on other shells only through the random normals
 z_{j-ncorr..j}, which are a pure function of (seed, shell, index) and are regenerated locally.
-So shells are dealt round-robin to the ranks and nothing crosses NVLink on the data path;
+So every rank takes a contiguous block of shells and nothing crosses NVLink on the data path;
 torch.distributed is used only for the barrier and the max-over-ranks timing.
 """
 
 from __future__ import annotations
 
 
-def shard_shells(nshells: int, rank: int, world: int) -> range:
-    """Shell indices owned by ``rank`` (round-robin, so every rank's shells span the same
-    redshift range and cost)."""
+def shard_shells(nshells: int, rank: int, world: int, mode: str = "block") -> range:
+    """Shell indices owned by ``rank``.
+
+    ``"block"`` (default): contiguous blocks of ceil/floor(nshells / world) shells.  Every shell
+    costs the same (one nside, one lmax), and a block re-uses the normal deviates of its own
+    preceding shells, so a rank regenerates only the ``ncorr`` deviates before its block --
+    dealt ``"round-robin"`` (``rank, rank + world, ...``) it regenerates ``ncorr`` per shell
+    (measured at nside 4096, ncorr 3: +0.37 ms per regenerated shell) and walks ``world`` times
+    more of the host-side iternorm recursion per produced shell."""
     if not (0 <= rank < world):
         raise ValueError("rank must be in [0, world)")
-    return range(rank, nshells, world)
+    if mode == "round-robin":
+        return range(rank, nshells, world)
+    if mode != "block":
+        raise ValueError("mode must be 'block' or 'round-robin'")
+    base, extra = divmod(nshells, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
 
 
 def neighbours_needed(shells, ncorr: int) -> set[int]:

@@ -154,6 +154,8 @@ def test_shell_sharding_world2_gloo():
         mine = gathered[rank]
         assert set(mine) <= set(need) and all(0 <= s < nshell for s in need)
         assert all(any(0 <= j - s <= ncorr for j in mine) for s in need)
+        # contiguous blocks: only the ncorr shells before the block are regenerated
+        assert mine == list(range(mine[0], mine[-1] + 1)) and len(need) <= len(mine) + ncorr
 
 
 def _msplit_worker(rank, world, port, nside, lmax, q):
