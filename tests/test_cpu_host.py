@@ -242,3 +242,21 @@ def test_discretized_and_effective_cls_golden():
     assert np.array_equal(glass_b200.effective_cls(gls, gold["ecl_w1"], gold["ecl_w2"], lmax=7), gold["ecl_cross"])
     with pytest.raises(ValueError, match="shape mismatch between fields and weights1"):
         glass_b200.effective_cls(gls, np.ones((3, 2)))
+
+
+def test_fft_core_host_build_and_run(tmp_path):
+    """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
+    per-thread functions: compile them for the host and check every pass, thread by thread,
+    against a long-double reference (DIF, reordering DIF tail, DIT, fused Bluestein middle)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "fft_core_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-o", str(exe), os.path.join(root, "tests", "native", "fft_core_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fft_core ok" in r.stdout, r.stdout + r.stderr
