@@ -23,7 +23,7 @@ from .fields import (  # noqa: F401
     lognormal_fields,
     nfields_from_nspectra,
 )
-from .galaxies import galaxy_shear, redshifts, redshifts_from_nz  # noqa: F401
+from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_nz  # noqa: F401
 from .harmonics import multalm  # noqa: F401
 from .lensing import (  # noqa: F401
     MultiPlaneConvergence,

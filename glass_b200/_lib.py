@@ -52,6 +52,7 @@ SIGNATURES = {
     "glb_multiplane_update": (_i, [_dp, _dp, _dp, C.c_double, _i64, C.c_double, C.c_double, _vp]),
     "glb_galaxy_shear": (_i, [_i64, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _i, _dp, _vp]),
     "glb_ellipticity": (_i, [_i, C.c_double, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
+    "glb_gaussian_phz": (_i, [_dp, _dp, C.c_double, _dp, C.c_double, _dp, C.c_double, _dp, _i, _i64, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),
     "glb_redshifts_from_cdf": (_i, [_dp, _dp, _i, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_alm2map_host": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_dist_setup": (_i, [_vp, _i, _i, _ip, _ip, _i]),

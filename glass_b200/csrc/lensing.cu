@@ -80,6 +80,42 @@ __device__ __forceinline__ double2 philox_normal_pair(uint32_t k0, uint32_t k1, 
   return make_double2(rad * c, rad * s);
 }
 
+// glass.gaussian_phz (glass/galaxies.py:350-455): zphot = normal(z, (1 + z) sigma_0), re-drawn while
+// outside [lower, upper] (plain rejection, like the reference's while loop).  sigma_0 / lower / upper
+// are arrays or scalars.  Philox mode: the whole rejection loop runs in the thread (attempt number in
+// the counter).  Supplied-deviate mode replays the reference's rounds: one launch per round with that
+// round's full-size normal array; redraw_only = 0 draws every element, 1 only those still out of
+// bounds; nbad counts the elements out of bounds after the round.
+__global__ void __launch_bounds__(256) gaussian_phz_kernel(const double* __restrict__ z, const double* __restrict__ sigma0_arr,
+                                                           double sigma0, const double* __restrict__ lower_arr, double lower,
+                                                           const double* __restrict__ upper_arr, double upper,
+                                                           const double* __restrict__ normals, int redraw_only, int64_t n,
+                                                           uint32_t k0, uint32_t k1, uint32_t stream,
+                                                           double* __restrict__ zphot, unsigned long long* __restrict__ nbad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double zi = z[i];
+  const double s0 = sigma0_arr ? sigma0_arr[i] : sigma0;
+  const double lo = lower_arr ? lower_arr[i] : lower;
+  const double hi = upper_arr ? upper_arr[i] : upper;
+  const double sigma = __dmul_rn(__dadd_rn(1.0, zi), s0);  // xp.add(1, z) * sigma_0
+  if (normals) {
+    double v = zphot[i];
+    if (!redraw_only || v < lo || v > hi) v = __dadd_rn(zi, __dmul_rn(sigma, normals[i]));  // loc + scale * N(0,1)
+    zphot[i] = v;
+    if (v < lo || v > hi) atomicAdd(nbad, 1ull);
+    return;
+  }
+  double v = zi;
+  for (uint32_t attempt = 0; attempt < 4096; ++attempt) {
+    // two normals per Philox call: even attempts use .x, odd attempts .y
+    const double2 nn = philox_normal_pair(k0, k1, (uint64_t)i, stream, RNG_TAG_REDSHIFT + 0x10u + (attempt >> 1));
+    v = __dadd_rn(zi, __dmul_rn(sigma, (attempt & 1) ? nn.y : nn.x));
+    if (!(v < lo || v > hi)) break;
+  }
+  zphot[i] = v;
+}
+
 // mode 0: intrinsic-normal (shapes.py:323-362), sigma = sigma_eta; mode 1: clipped Gaussian
 // (shapes.py:255-285), re-drawn until |e| <= 1.  normals (optional): supplied complex deviates.
 __global__ void __launch_bounds__(256) ellipticity_kernel(int mode, double sigma, const double2* __restrict__ normals,
@@ -167,6 +203,21 @@ int glb_galaxy_shear(int64_t nside, const double* d_lon, const double* d_lat, co
   galaxy_shear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       nside, d_lon, d_lat, d_ipix, reinterpret_cast<const double2*>(d_eps), n, d_kappa, d_gamma1, d_gamma2,
       reduced_shear, reinterpret_cast<double2*>(d_out));
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_gaussian_phz(const double* d_z, const double* d_sigma0, double sigma0, const double* d_lower, double lower,
+                     const double* d_upper, double upper, const double* d_normals, int redraw_only, int64_t n,
+                     uint64_t seed, uint32_t stream_id, double* d_zphot, int64_t* d_nbad, void* stream) {
+  GLB_REQUIRE(n >= 0, "bad size");
+  if (n == 0) return GLB_OK;
+  GLB_REQUIRE(d_z && d_zphot, "null pointer");
+  GLB_REQUIRE(!d_normals || d_nbad, "a supplied-deviate round needs the out-of-bounds counter");
+  gaussian_phz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_z, d_sigma0, sigma0, d_lower, lower, d_upper, upper, d_normals, redraw_only, n, (uint32_t)seed,
+      (uint32_t)(seed >> 32), stream_id, d_zphot, reinterpret_cast<unsigned long long*>(d_nbad));
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;

@@ -32,6 +32,10 @@
 
 namespace glb {
 
+#ifndef GLB_LEG_UNROLL
+#define GLB_LEG_UNROLL 2
+#endif
+constexpr int LEG_UNROLL = GLB_LEG_UNROLL;  // unroll factor of the FAST loop (development knob)
 constexpr int LEG_KT = 64;      // l-pairs per smem chunk
 constexpr int LEG_STAGES = 4;   // chunks in flight
 constexpr int SCALE_BITS = 512;
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
       }
     }
     if (phase == 2) {
-#pragma unroll 2
+#pragma unroll LEG_UNROLL
       for (; k < kc; ++k) {
         const double* rk = ck + k * REC;
         const double2 ab = *reinterpret_cast<const double2*>(rk);

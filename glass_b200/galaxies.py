@@ -116,3 +116,78 @@ def galaxy_shear(lon, lat, eps, kappa, gamma1, gamma2, *, reduced_shear: bool = 
             "glb_galaxy_shear",
         )
     return out if on_device else out.cpu().numpy()
+
+
+def gaussian_phz(z, sigma_0, *, lower=None, upper=None, rng=None, xp=None):
+    r"""
+    Photometric redshifts assuming a Gaussian error :math:`\sigma(z) = (1 + z) \sigma_0`
+    (glass/galaxies.py:350-455), with plain rejection sampling outside ``[lower, upper]``.
+
+    Returns an array of the broadcast shape of ``z`` and ``sigma_0`` (CUDA tensor if an input is
+    one or ``xp is torch``, else NumPy).  Parity mode: ``rng=Deviates(normal=[n_0, n_1, ...])``
+    supplies the standard normals of the reference's successive rounds (full-size arrays).
+    """
+    device, on_device = A.pick_device(z, sigma_0, lower, upper)
+    on_device = on_device or (xp is torch)
+    deviates = rng if isinstance(rng, _rng.Deviates) else None
+    seed = _rng.seed_from(rng)
+
+    def dev(a):  # keeps 0-d inputs 0-d (A.to_dev goes through ascontiguousarray, which makes them 1-d)
+        if isinstance(a, torch.Tensor):
+            return a.to(device=device, dtype=torch.float64)
+        return torch.as_tensor(np.asarray(a, dtype=np.float64), device=device)
+
+    z_d, s_d = dev(z), dev(sigma_0)
+    dims = tuple(torch.broadcast_shapes(z_d.shape, s_d.shape))
+    lo_d = dev(0.0 if lower is None else lower)
+    hi_d = dev(float("inf") if upper is None else upper)
+    if lower is None and upper is not None:
+        lo_d = torch.zeros_like(hi_d)
+    if upper is None and lower is not None:
+        hi_d = torch.full_like(lo_d, float("inf"))
+    if (lo_d.ndim == hi_d.ndim != 0) and not (tuple(lo_d.shape) == tuple(hi_d.shape) == dims):
+        msg = "lower and upper must best scalars or have the same shape as z"
+        raise ValueError(msg)
+    if not bool(torch.all(lo_d < hi_d).item()):
+        msg = "requires lower < upper"
+        raise ValueError(msg)
+    n = int(np.prod(dims)) if dims else 1
+    z_f = z_d.expand(dims).contiguous().reshape(-1) if dims else z_d.reshape(1)
+
+    def per_galaxy(t):  # (device array or None, scalar)
+        if t.ndim == 0:
+            return None, float(t.item())
+        return t.expand(dims).contiguous().reshape(-1), 0.0
+
+    s_arr, s_val = per_galaxy(s_d)
+    lo_arr, lo_val = per_galaxy(lo_d)
+    hi_arr, hi_val = per_galaxy(hi_d)
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    lib = _lib.load()
+    call = next(_CALLS)
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+
+        def launch(normals, redraw_only, nbad):
+            _lib.check(
+                lib.glb_gaussian_phz(
+                    z_f.data_ptr(), ptr(s_arr), s_val, ptr(lo_arr), lo_val, ptr(hi_arr), hi_val, ptr(normals), redraw_only, n,
+                    C.c_uint64(seed), C.c_uint32(call & 0xFFFFFFFF), out.data_ptr(), ptr(nbad), st,
+                ),
+                "glb_gaussian_phz",
+            )
+
+        if deviates is not None and deviates.normal is not None:
+            rounds = iter(deviates.normal)
+            first = True
+            while True:
+                nbad = torch.zeros(1, dtype=torch.int64, device=device)
+                launch(dev(next(rounds)).expand(dims).contiguous().reshape(-1) if dims else dev(next(rounds)).reshape(1), 0 if first else 1, nbad)
+                first = False
+                if int(nbad.item()) == 0:
+                    break
+        else:
+            launch(None, 0, None)
+    res = out.reshape(dims) if dims else out.reshape(())
+    return res if on_device else res.cpu().numpy()

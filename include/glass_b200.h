@@ -138,6 +138,15 @@ int glb_randang(int64_t nside, const int64_t* d_ipix, int64_t n, uint64_t seed, 
  * keyed by (seed, stream_id, point index) or from d_u1/d_u2 (parity mode, both or neither). */
 int glb_uniform_positions(int64_t n, const double* d_u1, const double* d_u2, uint64_t seed, uint32_t stream_id,
                           double* d_lon, double* d_lat, void* stream);
+/* glass.gaussian_phz (glass/galaxies.py:350-455): zphot = normal(z, (1+z) sigma_0) with rejection outside
+ * [lower, upper].  sigma_0 / lower / upper: device array (per galaxy) or, if the pointer is NULL, the scalar.
+ * d_normals == NULL: Philox deviates keyed by (seed, stream_id, galaxy, attempt), whole rejection loop in
+ * one launch.  d_normals != NULL (parity mode): ONE round of the reference's loop with that round's
+ * full-size normal array; redraw_only = 0 draws every element, 1 only those out of bounds; *d_nbad (int64,
+ * caller-zeroed) receives the number of elements still out of bounds. */
+int glb_gaussian_phz(const double* d_z, const double* d_sigma0, double sigma0, const double* d_lower, double lower,
+                     const double* d_upper, double upper, const double* d_normals, int redraw_only, int64_t n,
+                     uint64_t seed, uint32_t stream_id, double* d_zphot, int64_t* d_nbad, void* stream);
 /* healpix.ang2pix(nside, theta|lon, phi|lat, lonlat)   glass/healpix.py:172 (RING scheme). */
 int glb_ang2pix(int64_t nside, const double* d_a, const double* d_b, int64_t n, int lonlat, int64_t* d_ipix,
                 void* stream);

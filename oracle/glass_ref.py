@@ -426,3 +426,20 @@ def redshifts_from_nz_uniform(z, nz, u):
     cdf = np.concatenate([[0.0], np.cumsum((nz[1:] + nz[:-1]) * 0.5 * np.diff(z))])  # arraytools.py:197-226
     cdf /= cdf[-1]
     return np.interp(u, cdf, z)
+
+
+def gaussian_phz_from_normals(z, sigma_0, normals, lower=None, upper=None):
+    """glass/galaxies.py:411-455 for array z with supplied standard normals: ``normals`` is the
+    list of full-size arrays the reference's successive ``xrng.normal(z, sigma)`` calls would be
+    built from (normal(loc, scale) = loc + scale * standard_normal)."""
+    z = np.asarray(z, dtype=np.float64)
+    sigma = (1 + z) * np.asarray(sigma_0, dtype=np.float64)
+    lo = np.asarray(0.0 if lower is None else lower, dtype=np.float64)
+    hi = np.asarray(np.inf if upper is None else upper, dtype=np.float64)
+    rounds = iter(normals)
+    zphot = z + sigma * next(rounds)
+    trunc = (zphot < lo) | (zphot > hi)
+    while np.count_nonzero(trunc) > 0:
+        zphot = np.where(trunc, z + sigma * next(rounds), zphot)
+        trunc = (zphot < lo) | (zphot > hi)
+    return zphot

@@ -274,6 +274,13 @@ def main():
     out["ecl_auto"] = glass.effective_cls(gls_d, w1)
     out["ecl_cross"] = glass.effective_cls(gls_d, w1, w2, lmax=7)
 
+    # ---- gaussian_phz (glass/galaxies.py:350-455): array z, bounds that force several rounds ----
+    zt = np.random.default_rng(21).uniform(0.0, 1.5, size=300)
+    out["phz_z"] = zt
+    out["phz_out"] = glass.gaussian_phz(zt, 0.2, lower=0.1, upper=1.2, rng=np.random.default_rng(22), xp=np)
+    rr = np.random.default_rng(22)
+    out["phz_normals"] = np.stack([rr.standard_normal(300) for _ in range(40)])
+
     # ---- uniform_positions (glass/points.py:543-607): two populations, seed 11 ----
     ngal_u = np.array([2e-6, 5e-6])
     ups = list(glass.uniform_positions(ngal_u, rng=np.random.default_rng(11), xp=np))

@@ -218,3 +218,11 @@ def test_golden_uniform_positions():
     assert np.array_equal(np.concatenate([g[0] for g in got]), GOLD["up_lon"])
     assert np.array_equal(np.concatenate([g[1] for g in got]), GOLD["up_lat"])
     assert np.array_equal(np.stack([g[2] for g in got]), GOLD["up_count"])
+
+
+def test_golden_gaussian_phz():
+    """gaussian_phz (glass/galaxies.py:350-455) executed from the reference source with bounds
+    that need several rejection rounds; the oracle replays it from the same normal deviates."""
+    got = G.gaussian_phz_from_normals(GOLD["phz_z"], 0.2, list(GOLD["phz_normals"]), 0.1, 1.2)
+    assert np.array_equal(got, GOLD["phz_out"])
+    assert got.min() >= 0.1 and got.max() <= 1.2
