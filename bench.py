@@ -303,7 +303,7 @@ def run_b200(args) -> None:
     import glass_b200
     from glass_b200 import _lib
     from glass_b200.healpix import get_plan
-    from glass_b200.sharding import shard_shells
+    from glass_b200.sharding import bind_to_local_cpus, shard_shells
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -314,6 +314,7 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local)
     # host threads: the per-shell host work (iternorm on (lmax+1, ncorr+1) arrays) gains nothing
     # from BLAS/OpenMP threads, and world ranks x all cores oversubscribes the box
+    local_cpus = bind_to_local_cpus(local) if world > 1 else None  # NUMA-local pinned staging buffers
     per_rank = max(1, (os.cpu_count() or 1) // max(1, world))
     torch.set_num_threads(per_rank)
     try:
@@ -477,6 +478,7 @@ def run_b200(args) -> None:
             "shells_per_step_per_rank": S,
             "l2": "inputs larger than L2 (a_lm 0.54 GB, phases 2.1 GB, map 1.6 GB per shell)",
             "parallelism": f"shell-sharded x{world}, no data-path collective",
+            "host_binding": (f"rank 0 bound to {len(local_cpus)} GPU-local cores (NVML affinity)" if local_cpus else "none"),
         },
         "clocks": clk,
         "e2e": {

@@ -31,6 +31,31 @@ def shard_shells(nshells: int, rank: int, world: int, mode: str = "block") -> ra
     return range(lo, lo + base + (1 if rank < extra else 0))
 
 
+def bind_to_local_cpus(device_index: int) -> list[int] | None:
+    """Pin this process to the CPU cores NVML reports as local to the GPU (same NUMA node /
+    PCIe root), BEFORE any pinned host buffer is allocated: page-locked staging memory is then
+    first-touched on the GPU's own socket and the device->host copies of several ranks do not
+    cross the inter-socket link.  Returns the cores, or None if NVML / affinity is unavailable
+    (then nothing is changed)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def neighbours_needed(shells, ncorr: int) -> set[int]:
     """Shells whose normal deviates a rank must (re)generate: its own and the ``ncorr``
     preceding ones of each (glass/fields.py:410-420)."""
