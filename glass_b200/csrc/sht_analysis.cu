@@ -29,6 +29,7 @@ constexpr int AN_KB = 8;       // l-pairs per warp-level reduction round (AN_KB 
 constexpr int AN_TRS = 34;     // row stride (doubles) of the per-warp transpose buffer
 constexpr int AN_STAGES = 3;
 constexpr int AN_BEXP_BIG = 1023 + 256;
+constexpr int AN_BEXP_SIG = 1023 - 70;   // as BEXP_SIG of the synthesis kernel
 
 __device__ __forceinline__ int an_bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
     }
   }
   const double SMALL = 7.458340731200207e-155;  // 2^-512
+  bool skipping = true;  // warp-uniform: no ring has come near significance yet
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c % AN_STAGES;
@@ -188,6 +190,42 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
     const int kc = min(AN_KT, K - c * AN_KT);
 
     for (int k0 = 0; k0 < kc; k0 += AN_KB) {
+      double* dst = out_m + ((int64_t)c * AN_KT + k0) * 4;
+      if (skipping && k0 + AN_KB <= kc) {
+        // SKIP round: while no ring of the warp is both at scale 0 and within 2^-120 of the
+        // significance threshold 2^-70 (the synthesis kernel's rule, sht_legendre.cu), nothing
+        // can contribute during the next AN_KB steps (per step |p| grows by at most ~2^14):
+        // run the recurrence only -- 2 DFMA per ring and step instead of 6 plus selects and
+        // exponent tests -- and write the round's zeros.  One rescale test per round is enough
+        // (|p| < 2^256 before, < 2^368 after eight steps).
+        bool near = false;
+#pragma unroll
+        for (int j = 0; j < R; ++j) near |= (sc[j] == 0) && (an_bexp(p2[j]) >= AN_BEXP_SIG - 120);
+        if (!__any_sync(0xffffffffu, near)) {
+#pragma unroll
+          for (int kk = 0; kk < AN_KB; ++kk) {
+            const double2 ab = ck[k0 + kk];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const double rr = fma(ab.x, x2[j], ab.y);
+              const double t = fma(rr, p2[j], -p1[j]);
+              p1[j] = p2[j];
+              p2[j] = t;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            if (an_bexp(p2[j]) >= AN_BEXP_BIG) {
+              p1[j] *= SMALL;
+              p2[j] *= SMALL;
+              sc[j] += 1;
+            }
+          }
+          dst[lane] = 0.0;
+          continue;
+        }
+        skipping = false;
+      }
       double part[AN_KB * 4];
 #pragma unroll
       for (int i = 0; i < AN_KB * 4; ++i) part[i] = 0.0;
@@ -244,7 +282,6 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
       // select-and-shuffle transpose (4 FSEL + 2 SHFL + 1 DADD per output).
       // value v = kk*4 + q of this round belongs to l-pair k0 + kk: consecutive lanes write
       // consecutive doubles of this warp tile's slab (always written: no memset, no flags)
-      double* dst = out_m + ((int64_t)c * AN_KT + k0) * 4;
       double* tr = s_tr_dyn + warp * (32 * AN_TRS);
 #pragma unroll
       for (int i = 0; i < AN_KB * 4; ++i) tr[i * AN_TRS + lane] = part[i];

@@ -36,6 +36,12 @@ class MultiPlaneConvergence:
         self.kappa2 = None
         self.kappa3 = None
         self._host = False
+        self._like = None  # map-shaped tensor sizing the hand-off of an empty block (dist.multi_plane_block)
+
+    def _set_state_map(self, name: str, value) -> None:
+        """Install a received map (delta3, kappa2, kappa3) of the recurrence state
+        (glass_b200.dist.recv_multi_plane_state)."""
+        setattr(self, name, value)
 
     def add_window(self, delta, w) -> None:
         """Add a mass plane from a window function (glass/lensing.py:489-509)."""

@@ -260,3 +260,137 @@ def test_fft_core_host_build_and_run(tmp_path):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fft_core ok" in r.stdout, r.stdout + r.stderr
+
+
+class _CpuMultiPlane:
+    """Test double with the state layout of glass_b200.MultiPlaneConvergence and the reference's
+    arithmetic (glass/lensing.py:535-586) on CPU tensors: exercises the rank-to-rank hand-off of
+    glass_b200.dist.multi_plane_block without a GPU."""
+
+    def __init__(self, cosmo):
+        self.cosmo = cosmo
+        self.z2 = self.z3 = self.x3 = self.w3 = 0.0
+        self.r23 = 1.0
+        self.delta3 = self.kappa2 = self.kappa3 = None
+        self._like = None
+
+    def _set_state_map(self, name, value):
+        setattr(self, name, value)
+
+    def add_window(self, delta, w):
+        za, wa, zeff = w
+        self.add_plane(delta, zeff, float(np.trapezoid(wa, za) / np.interp(zeff, za, wa)))
+
+    def add_plane(self, delta, zsrc, wlens=1.0):
+        import torch
+
+        delta2, self.delta3 = self.delta3, delta
+        z1, self.z2, self.z3 = self.z2, self.z3, zsrc
+        w2, self.w3 = self.w3, wlens
+        x2, self.x3 = self.x3, self.cosmo.transverse_comoving_distance(self.z3) / self.cosmo.hubble_distance
+        r12 = self.r23
+        r13, self.r23 = np.asarray(self.cosmo.transverse_comoving_distance([z1, self.z2], self.z3)) / (self.cosmo.hubble_distance * self.x3)
+        t = float(r13 / r12)
+        f = float(3 * self.cosmo.Omega_m0 / 2 * x2 * self.r23 * (1 + self.z2) / self.cosmo.H_over_H0(self.z2) * w2)
+        if self.kappa2 is None:
+            self.kappa2, self.kappa3 = torch.zeros_like(delta), torch.zeros_like(delta)
+        self.kappa2, self.kappa3 = self.kappa3, self.kappa2
+        self.kappa3 *= 1 - t
+        self.kappa3 += t * self.kappa2
+        if delta2 is not None:
+            self.kappa3 += f * delta2
+
+    @property
+    def kappa(self):
+        return self.kappa3
+
+
+class _MockCosmo:  # reference tests/fixtures/domain.py:36-97
+    Omega_m0 = 0.3
+    hubble_distance = 4.4e3
+
+    def H_over_H0(self, z):  # noqa: N802
+        return (self.Omega_m0 * (1 + z) ** 3 + 1 - self.Omega_m0) ** 0.5
+
+    def transverse_comoving_distance(self, z, z2=None):
+        if z2 is None:
+            return self.hubble_distance * np.asarray(z) * 1_000
+        return self.hubble_distance * (np.asarray(z2) - np.asarray(z)) * 1_000
+
+
+def _mp_inputs(nshell, npix):
+    import torch
+
+    g = torch.Generator().manual_seed(7)
+    deltas = [torch.randn(npix, dtype=torch.float64, generator=g) for _ in range(nshell)]
+    dz = 1.0 / (nshell + 1)
+    wins = [(np.array([i, i + 1.0, i + 2.0]) * dz, np.array([0.0, 1.0, 0.0]), (i + 1.0) * dz) for i in range(nshell)]
+    return deltas, wins
+
+
+def _multiplane_worker(rank, world, port, nshell, npix, q):
+    import torch
+    import torch.distributed as dist
+
+    from glass_b200.dist import multi_plane_block
+    from glass_b200.sharding import shard_shells
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    deltas, wins = _mp_inputs(nshell, npix)
+    mine = shard_shells(nshell, rank, world)
+    conv = _CpuMultiPlane(_MockCosmo())
+    conv._like = torch.empty(npix, dtype=torch.float64)
+    kappas = multi_plane_block(conv, [deltas[i] for i in mine], [wins[i] for i in mine])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, list(mine), [k.numpy() for k in kappas]))
+
+
+@pytest.mark.parametrize("world,nshell", [(2, 7), (3, 2)])
+def test_multi_plane_pipeline_gloo(world, nshell):
+    """Shell-sharded multi-plane recurrence: the state handed from rank to rank (five scalars,
+    three maps) reproduces the serial recurrence bit for bit, including an empty last block."""
+    import torch.multiprocessing as mp
+
+    npix = 48
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_multiplane_worker, args=(r, world, port, nshell, npix, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    deltas, wins = _mp_inputs(nshell, npix)
+    conv = _CpuMultiPlane(_MockCosmo())
+    serial = []
+    for d, w in zip(deltas, wins):
+        conv.add_window(d, w)
+        serial.append(conv.kappa.clone().numpy())
+    seen = set()
+    for rank, mine, kappas in res:
+        assert len(mine) == len(kappas)
+        for i, k in zip(mine, kappas):
+            assert np.array_equal(k, serial[i])
+            seen.add(i)
+    assert seen == set(range(nshell))
+
+
+def test_expm1_fast_host_build_and_run(tmp_path):
+    """csrc/expm1_fast.cuh (the lognormal transform fused into the ring-FFT store) against
+    80-bit expm1l on the host: <= 2 ulp over [-40, 40], tiny arguments, reduction boundaries,
+    and the library's results for out-of-range / non-finite arguments."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "expm1_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), os.path.join(root, "tests", "native", "expm1_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "expm1_fast ok" in r.stdout, r.stdout + r.stderr

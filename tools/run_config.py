@@ -10,8 +10,11 @@ of examples/2-advanced/stage_4_galaxies.ipynb cell 13), device-re
             z = redshifts(count, shell_i); eps = ellipticity_intnorm(count, sigma_e)
             she = galaxy_shear(lon, lat, eps, kappa_i, gamma1, gamma2)
 
-    python tools/run_config.py 1|2|3 [--shells S] [--niter K]
-Prints per-stage device times (CUDA events) and totals as one JSON line.
+    python tools/run_config.py 1|2|3|4 [--shells S] [--niter K] [--lensing]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/run_config.py 4 --lensing            # N GPUs: contiguous blocks of shells per rank,
+                                                   # multi-plane recurrence pipelined over the ranks
+Prints per-stage device times (CUDA events) and totals as one JSON line (rank 0).
 """
 import argparse
 import json
@@ -53,7 +56,15 @@ def main():
     S, nside, lmax, lensing = CONFIGS[args.config]
     S = args.shells or S
     lensing = lensing or args.lensing
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    mine = list(glass_b200.sharding.shard_shells(S, rank, world))
     npix = 12 * nside * nside
     dz = 1.0 / (S + 1)
     shells = [glass_b200.RadialWindow(np.array([i, i + 1.0, i + 2.0]) * dz, np.array([0.0, 1.0, 0.0]), (i + 1.0) * dz) for i in range(S)]
@@ -71,15 +82,27 @@ def main():
 
     pend = []
     conv = glass_b200.MultiPlaneConvergence(MockCosmology())
-    matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=3, rng=42)
+    matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=3, rng=42, shells=mine if world > 1 else None)
     ngal_tot = 0
+    if world > 1:
+        import torch.distributed as dist
+        from glass_b200.dist import multi_plane_block
+
+        # the hand-off below is the first NCCL point-to-point of each pair: open the channels
+        # outside the timed region (communicator setup, not the path)
+        tok = torch.zeros(1, device=dev)
+        if rank > 0:
+            dist.recv(tok, rank - 1)
+        if rank + 1 < world:
+            dist.send(tok, rank + 1)
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(S):
-        delta = timed("generate", lambda: next(matter))
+
+    def per_shell(i, delta, kappa):
+        nonlocal ngal_tot
+        g1 = g2 = None
         if lensing:
-            timed("multiplane", lambda: conv.add_window(delta, shells[i]))
-            kappa = conv.kappa
             g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
         it = glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
         while True:
@@ -92,16 +115,49 @@ def main():
             if lensing:
                 eps = timed("ellipticity", lambda: glass_b200.ellipticity_intnorm(cnt, 0.27, rng=i, xp=torch))
                 she = timed("galaxy_shear", lambda: glass_b200.galaxy_shear(lon, lat, eps, kappa, g1, g2))
+
+    if world == 1:
+        for i in range(S):
+            delta = timed("generate", lambda: next(matter))
+            kappa = None
+            if lensing:
+                timed("multiplane", lambda: conv.add_window(delta, shells[i]))
+                kappa = conv.kappa
+            per_shell(i, delta, kappa)
+    else:
+        # 1. matter planes of the block (no communication)  2. multi-plane recurrence, pipelined
+        # over the ranks (dist.multi_plane_block)  3. transforms and galaxies (no communication)
+        deltas = [timed("generate", lambda: next(matter)) for _ in mine]
+        kappas = [None] * len(mine)
+        if lensing:
+            conv._like = torch.empty(npix, dtype=torch.float64, device=dev)
+            kappas = timed("multiplane", lambda: multi_plane_block(conv, deltas, [shells[i] for i in mine]))
+        for i, delta, kappa in zip(mine, deltas, kappas):
+            per_shell(i, delta, kappa)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     for name, a, b in pend:
         stages[name] += a.elapsed_time(b)
+    if world > 1:
+        # whole-job numbers: wall = max over ranks, galaxies = sum, stage times = max over ranks
+        t = torch.tensor([wall] + [stages[k] for k in stages], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+        for k, v in zip(stages, t[1:].tolist()):
+            stages[k] = v
+        g = torch.tensor([int(ngal_tot)], dtype=torch.int64, device=dev)
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        ngal_tot = int(g[0])
     out = {
-        "config": args.config, "shells": S, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
+        "config": args.config, "n_gpus": world, "shells": S, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
         "galaxies": int(ngal_tot), "wall_s": wall, "shells_per_s": S / wall, "galaxies_per_s": ngal_tot / wall,
         "stage_ms_total": {k: round(v, 2) for k, v in stages.items()},
     }
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
