@@ -8,7 +8,7 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, shells  # noqa: F401
+from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells  # noqa: F401
 from .fields import (  # noqa: F401
     cls2cov,
     cltovar,

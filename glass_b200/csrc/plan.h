@@ -98,7 +98,7 @@ struct glb_plan {
   int64_t bf_total = 0;
 
   // workspace
-  double* d_rec = nullptr;           // Legendre records  [nrec * (2 + 4*B)]
+  double* d_rec = nullptr;           // Legendre records  [nrec * (4 + 4*B)]
   double2* d_phase = nullptr;        // [max_batch][nring][mmax+1]
   int64_t workspace_bytes = 0;
 

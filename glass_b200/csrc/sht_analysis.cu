@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "plan.h"
+#include "sht_tables.cuh"
 
 namespace glb {
 
@@ -32,36 +33,6 @@ constexpr int AN_BEXP_BIG = 1023 + 256;
 constexpr int AN_BEXP_SIG = 1023 - 70;   // as BEXP_SIG of the synthesis kernel
 
 __device__ __forceinline__ int an_bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
-
-__host__ __device__ __forceinline__ double an_eps(int l, int m) {
-  if (l <= m) return 0.0;
-  const double dl = (double)l, dm = (double)m;
-  return sqrt(((dl - dm) * (dl + dm)) / (4.0 * dl * dl - 1.0));
-}
-
-// recurrence coefficients only: rec[roff[m] + k] = {a_k, b_k}
-__global__ void __launch_bounds__(128) analysis_coef_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
-                                                            double2* __restrict__ rec) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m > mmax) return;
-  const int K = (lmax - m) / 2 + 1;
-  double2* r = rec + roff[m];
-  double alpha_km1 = 0.0, alpha_k = 1.0;
-  double e_lm1 = 0.0, e_l = 0.0, e_lp1 = an_eps(m + 1, m), e_lp2 = an_eps(m + 2, m);
-  for (int k = 0; k < K; ++k) {
-    const int l = m + 2 * k;
-    const double e_lp3 = an_eps(l + 3, m), e_lp4 = an_eps(l + 4, m);
-    const double alpha_kp1 = (k == 0) ? 1.0 : alpha_km1 * ((e_l * e_lm1) / (e_lp1 * e_lp2));
-    const double a = alpha_k / (e_lp1 * e_lp2 * alpha_kp1);
-    r[k] = make_double2(a, -(e_lp1 * e_lp1 + e_l * e_l) * a);
-    alpha_km1 = alpha_k;
-    alpha_k = alpha_kp1;
-    e_lm1 = e_lp1;
-    e_l = e_lp2;
-    e_lp1 = e_lp3;
-    e_lp2 = e_lp4;
-  }
-}
 
 __device__ __forceinline__ void an_lam_mm_scaled(int m, double sth, double cm_mant, int cm_exp, double& val, int& scale) {
   int e;
@@ -101,7 +72,7 @@ __device__ __forceinline__ void an_lam_mm_scaled(int m, double sth, double cm_ma
 
 struct AnaParams {
   const LegItem* items;
-  const double2* rec;         // {a_k, b_k}
+  const double2* rec;         // two pairs per l-pair: {a_k, b_k}, {-a_k, a_k + b_k}
   const int64_t* roff;
   const double* z;
   const double* sth;
@@ -117,7 +88,7 @@ struct AnaParams {
 template <int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legendre_analysis_kernel(const AnaParams p) {
   constexpr int NWARPS = THREADS / 32;
-  __shared__ __align__(128) double2 s_rec[AN_STAGES][AN_KT];
+  __shared__ __align__(128) double2 s_rec[AN_STAGES][2 * AN_KT];
   __shared__ __align__(8) uint64_t s_full[AN_STAGES];
   __shared__ __align__(8) uint64_t s_empty[AN_STAGES];
   extern __shared__ __align__(16) double s_tr_dyn[];  // [NWARPS][32 * AN_TRS] per-warp transpose buffers of the reduction
@@ -127,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
   const int m = item.m;
   const int K = (p.lmax - m) / 2 + 1;
   const int nchunks = (K + AN_KT - 1) / AN_KT;
-  const double2* rec_m = p.rec + p.roff[m];
+  const double2* rec_m = p.rec + 2 * p.roff[m];
   double* out_m = p.partial + (((int64_t)item.tile * NWARPS + (threadIdx.x >> 5)) * p.nrec + p.roff[m]) * 4;
 
   if (tid == 0) {
@@ -142,9 +113,9 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
   auto issue = [&](int c) {
     const int s = c % AN_STAGES;
     const int kc = min(AN_KT, K - c * AN_KT);
-    const uint32_t bytes = (uint32_t)(kc * sizeof(double2));
+    const uint32_t bytes = (uint32_t)(kc * 2 * sizeof(double2));
     mbar_arrive_expect_tx(&s_full[s], bytes);
-    bulk_g2s(&s_rec[s][0], rec_m + (int64_t)c * AN_KT, bytes, &s_full[s]);
+    bulk_g2s(&s_rec[s][0], rec_m + (int64_t)c * (2 * AN_KT), bytes, &s_full[s]);
   };
   if (tid == 0)
     for (int c = 0; c < AN_STAGES - 1 && c < nchunks; ++c) issue(c);
@@ -154,6 +125,9 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
   const int pair0 = item.tile * (THREADS * R) + tid * R;
   const double cm_mant = p.cm_mant[m];
   const int cm_exp = p.cm_exp[m];
+  // warp-uniform recurrence variable, as in the synthesis kernel: u = sin^2 where z^2 >= 1/2
+  const double zw = p.z[min(item.tile * (THREADS * R) + (tid & ~31) * R, p.npair - 1)];
+  const bool use_u = zw * zw >= 0.5;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int r = pair0 + j;
@@ -162,8 +136,9 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
     sc[j] = 0;
     if (live) {
       const double zz = p.z[r];
-      x2[j] = zz * zz;
-      an_lam_mm_scaled(m, p.sth[r], cm_mant, cm_exp, p2[j], sc[j]);
+      const double sth = p.sth[r];
+      x2[j] = use_u ? sth * sth : zz * zz;  // the warp's recurrence variable, see sht_prep_tables_kernel
+      an_lam_mm_scaled(m, sth, cm_mant, cm_exp, p2[j], sc[j]);
       const double2 gn = p.phase[(int64_t)r * (p.mmax + 1) + m];
       double2 gs = make_double2(0.0, 0.0);
       if (r != p.npair - 1) gs = p.phase[(int64_t)(p.nring - 1 - r) * (p.mmax + 1) + m];
@@ -186,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
       }
     }
     mbar_wait(&s_full[s], (c / AN_STAGES) & 1);
-    const double2* ck = &s_rec[s][0];
+    const double2* ck = &s_rec[s][use_u ? 1 : 0];  // pair of l-pair k at ck[2 k]
     const int kc = min(AN_KT, K - c * AN_KT);
 
     for (int k0 = 0; k0 < kc; k0 += AN_KB) {
@@ -204,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
         if (!__any_sync(0xffffffffu, near)) {
 #pragma unroll
           for (int kk = 0; kk < AN_KB; ++kk) {
-            const double2 ab = ck[k0 + kk];
+            const double2 ab = ck[2 * (k0 + kk)];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
               const double rr = fma(ab.x, x2[j], ab.y);
@@ -237,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
       if (__all_sync(0xffffffffu, allz)) {
 #pragma unroll
         for (int kk = 0; kk < AN_KB; ++kk) {
-          const double2 ab = ck[k0 + kk];
+          const double2 ab = ck[2 * (k0 + kk)];
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             part[kk * 4 + 0] = fma(p2[j], ge_r[j], part[kk * 4 + 0]);
@@ -254,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
 #pragma unroll
         for (int kk = 0; kk < AN_KB; ++kk) {
           if (k0 + kk < kc) {
-            const double2 ab = ck[k0 + kk];
+            const double2 ab = ck[2 * (k0 + kk)];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
               const double pa = (sc[j] == 0) ? p2[j] : 0.0;
@@ -286,29 +261,41 @@ __global__ void __launch_bounds__(THREADS, (R > 4 ? 256 : 512) / THREADS) legend
 #pragma unroll
       for (int i = 0; i < AN_KB * 4; ++i) tr[i * AN_TRS + lane] = part[i];
       __syncwarp();
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      // eight independent chains of four adds, then a three-level tree (11 dependent DADDs
+      // became 7): the adds sit between two rounds of FMAs with nothing else to overlap
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0, t6 = 0.0, t7 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 32; i += 8) {
         const double2 a = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i);
         const double2 b = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i + 2);
+        const double2 cc = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i + 4);
+        const double2 dd = *reinterpret_cast<const double2*>(tr + lane * AN_TRS + i + 6);
         t0 += a.x;
         t1 += a.y;
         t2 += b.x;
         t3 += b.y;
+        t4 += cc.x;
+        t5 += cc.y;
+        t6 += dd.x;
+        t7 += dd.y;
       }
       __syncwarp();
-      if (k0 + (lane >> 2) < kc) dst[lane] = (t0 + t1) + (t2 + t3);
+      if (k0 + (lane >> 2) < kc) dst[lane] = ((t0 + t1) + (t2 + t3)) + ((t4 + t5) + (t6 + t7));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);
   }
 }
 
-// rec[i] = {a_k, b_k} gathered from the static prep table (once per plan)
+// rec[2i], rec[2i+1] = {a_k, b_k}, {-a_k, a_k + b_k} gathered from the static prep table (once per plan)
 __global__ void __launch_bounds__(256) analysis_ab_gather_kernel(const double* __restrict__ tab, int64_t nrec,
                                                                  double2* __restrict__ ab) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nrec) ab[i] = make_double2(tab[i * 5], tab[i * 5 + 1]);
+  if (i < nrec) {
+    const double* t = tab + i * PREP_TAB;
+    ab[2 * i] = make_double2(t[TAB_A], t[TAB_B]);
+    ab[2 * i + 1] = make_double2(-t[TAB_A], t[TAB_AB]);
+  }
 }
 
 // One CTA per m: add the tiles in fixed order (coalesced, deterministic), a_{m+2k} = alpha_k ce_k,
@@ -329,7 +316,7 @@ __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax
   const int m = blockIdx.x, tid = threadIdx.x;
   const int K = (lmax - m) / 2 + 1;
   const int64_t base = (int64_t)m * (2 * lmax + 1 - m) / 2;
-  const double* t = tab + roff[m] * 5;
+  const double* t = tab + roff[m] * PREP_TAB;
   const int tl0 = first_tile[m];
   if (tid < 2) s_carry[tid] = 0.0;
   __syncthreads();
@@ -346,8 +333,8 @@ __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax
         s2 += q.z;
         s3 += q.w;
       }
-      const double* tk = t + (int64_t)k * 5;
-      const double alpha = tk[2], s1 = tk[3];
+      const double* tk = t + (int64_t)k * PREP_TAB;
+      const double alpha = tk[TAB_ALPHA], s1 = tk[TAB_S1];
       double2 ev = make_double2(alpha * s0, (m == 0) ? 0.0 : alpha * s1v);
       if (accumulate) {
         const double2 o = alm[base + l];
@@ -357,7 +344,7 @@ __global__ void __launch_bounds__(FIN_THREADS) analysis_finalize_kernel(int lmax
       alm[base + l] = ev;
       s_y[0][i] = s1 * s2;
       s_y[1][i] = s1 * s3;
-      s_c[i] = (k > 0) ? t[(int64_t)(k - 1) * 5 + 4] : 0.0;
+      s_c[i] = (k > 0) ? t[(int64_t)(k - 1) * PREP_TAB + TAB_C] : 0.0;
     }
     __syncthreads();
     if (tid < 2) {
@@ -422,7 +409,7 @@ int plan_ensure_analysis(glb_plan* pl) {
   const size_t bytes = (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_partial, bytes));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_tmpmap, (size_t)pl->npix * sizeof(double) * 2));
-  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_ab_tab, (size_t)pl->nrec * sizeof(double2)));
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_ab_tab, (size_t)pl->nrec * 2 * sizeof(double2)));
   analysis_ab_gather_kernel<<<(unsigned)((pl->nrec + 255) / 256), 256>>>(pl->d_prep_tab, pl->nrec,
                                                                         reinterpret_cast<double2*>(pl->d_ab_tab));
   GLB_CUDA_CHECK(cudaGetLastError());

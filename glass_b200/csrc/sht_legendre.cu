@@ -29,6 +29,7 @@
 #include <cstdlib>
 
 #include "plan.h"
+#include "sht_tables.cuh"
 
 namespace glb {
 
@@ -44,53 +45,34 @@ constexpr int BEXP_SIG = 1023 - 70;   // "significant" when scale==0 and |p| >= 
 
 __device__ __forceinline__ int bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
-__host__ __device__ __forceinline__ double eps_lm(int l, int m) {
-  // e_l = sqrt((l^2-m^2)/(4 l^2-1)); exact integer products in double
-  if (l <= m) return 0.0;  // also covers l == m (zero) and l < m
-  const double dl = (double)l, dm = (double)m;
-  return sqrt(((dl - dm) * (dl + dm)) / (4.0 * dl * dl - 1.0));
-}
 
 // -------------------------------------------------------------------------------------
 // static per-plan tables (depend on l, m only), one thread per m, run once at plan creation:
-//   tab[roff[m]+k] = {a_k, b_k, alpha_k, s1_k = alpha_k/e_{l+1}, c_k = e_{l+2}/e_{l+3}},  l = m+2k
+//   tab[roff[m]+k] = {a_k, b_k, a_k + b_k, alpha_k, s1_k = alpha_k/e_{l+1}, c_k = e_{l+2}/e_{l+3}},  l = m+2k
+// computed in double-double and rounded once (sht_tables.cuh explains why that matters).
+//
+// Conditioning.  p_k is a polynomial of degree k in y = x^2 and, like any such polynomial, is
+// sensitive to its argument at BOTH ends of [0, 1]: |dp_k/dy| ~ k / sqrt(y (1 - y)).  The factor
+// of the recurrence is therefore evaluated per warp in the variable that is known to RELATIVE
+// precision at the warp's rings:
+//     y <  1/2 (towards the equator):  a_k y + b_k            with y = z^2
+//     y >= 1/2 (towards the poles):    (a_k + b_k) - a_k u    with u = sin^2(theta) = t (2 - t),
+//                                                             t = i^2 / (3 nside^2)
+// Both are ONE FMA on a coefficient pair of the record, {a_k, b_k} or {-a_k, a_k + b_k}, chosen by
+// a warp-uniform offset.  With y = fl(z z) everywhere the ABSOLUTE error 1e-16 of y near the
+// poles, the same in every step, cost 2e-9 of the map at l = 8191 (d lambda_l0 / dz = l^2 / 2
+// there); with u everywhere the rings next to the equator lose as much (measured:
+// tests/test_gpu_fullsize.py, tests/test_gpu_sht.py::test_alm2map_vs_long_double_oracle).
 // -------------------------------------------------------------------------------------
-constexpr int PREP_TAB = 5;
-
-__global__ void __launch_bounds__(128) sht_prep_tables_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
-                                                              double* __restrict__ tab) {
+__global__ void __launch_bounds__(64) sht_prep_tables_kernel(int lmax, int mmax, const int64_t* __restrict__ roff,
+                                                             double* __restrict__ tab) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m > mmax) return;
-  const int K = (lmax - m) / 2 + 1;
-  double* t = tab + roff[m] * PREP_TAB;
-  double alpha_km1 = 0.0, alpha_k = 1.0;
-  double e_lm1 = 0.0;              // e_{l-1}
-  double e_l = 0.0;                // e_l   (l = m: zero)
-  double e_lp1 = eps_lm(m + 1, m);
-  double e_lp2 = eps_lm(m + 2, m);
-  for (int k = 0; k < K; ++k) {
-    const int l = m + 2 * k;
-    const double e_lp3 = eps_lm(l + 3, m);
-    const double e_lp4 = eps_lm(l + 4, m);
-    const double alpha_kp1 = (k == 0) ? 1.0 : alpha_km1 * ((e_l * e_lm1) / (e_lp1 * e_lp2));
-    const double a = alpha_k / (e_lp1 * e_lp2 * alpha_kp1);
-    double* tk = t + (int64_t)k * PREP_TAB;
-    tk[0] = a;
-    tk[1] = -(e_lp1 * e_lp1 + e_l * e_l) * a;
-    tk[2] = alpha_k;
-    tk[3] = alpha_k / e_lp1;
-    tk[4] = e_lp2 / e_lp3;
-    alpha_km1 = alpha_k;
-    alpha_k = alpha_kp1;
-    e_lm1 = e_lp1;
-    e_l = e_lp2;
-    e_lp1 = e_lp3;
-    e_lp2 = e_lp4;
-  }
+  prep_tables_for_m(lmax, m, tab + roff[m] * PREP_TAB);
 }
 
 // -------------------------------------------------------------------------------------
-// prep: a_lm (m-major) -> per-m record stream {a_k, b_k, (Ae_re, Ae_im, Ao_re, Ao_im) x B}
+// prep: a_lm (m-major) -> per-m record stream {a_k, b_k, -a_k, a_k + b_k, (Ae_re, Ae_im, Ao_re, Ao_im) x B}
 //   Ae_k = alpha_k a_{m+2k};  Ao_k = s1_k t_k,  t_k = a_{m+2k+1} - c_k t_{k+1}  (backward in k)
 // One CTA per m.  Chunks of PREP_CH l-pairs, from the top: coalesced loads into shared memory,
 // the short sequential recursion by 2B threads (one per map and re/im), coalesced record
@@ -103,7 +85,7 @@ template <int B>
 __global__ void __launch_bounds__(PREP_THREADS) sht_prep_kernel(const double2* __restrict__ alm, int64_t alm_stride,
                                                                  int lmax, int mmax, const int64_t* __restrict__ roff,
                                                                  const double* __restrict__ tab, double* __restrict__ rec) {
-  constexpr int REC = 2 + 4 * B;
+  constexpr int REC = 4 + 4 * B;
   __shared__ double s_t[2 * B][PREP_CH + 1];  // odd-coefficient stream, then t_k in place (+1: no bank conflicts)
   __shared__ double s_c[PREP_CH];
   __shared__ double s_carry[2 * B];
@@ -122,7 +104,7 @@ __global__ void __launch_bounds__(PREP_THREADS) sht_prep_kernel(const double2* _
     for (int i = tid; i < n; i += PREP_THREADS) {
       const int k = klo + i;
       const int l = m + 2 * k;
-      s_c[i] = t[(int64_t)k * PREP_TAB + 4];
+      s_c[i] = t[(int64_t)k * PREP_TAB + TAB_C];
 #pragma unroll
       for (int bb = 0; bb < B; ++bb) {
         double2 o = make_double2(0.0, 0.0);
@@ -148,18 +130,20 @@ __global__ void __launch_bounds__(PREP_THREADS) sht_prep_kernel(const double2* _
       const int k = klo + i;
       const int l = m + 2 * k;
       const double* tk = t + (int64_t)k * PREP_TAB;
-      const double alpha = tk[2], s1 = tk[3];
+      const double alpha = tk[TAB_ALPHA], s1 = tk[TAB_S1];
       double* rk = r + (int64_t)k * REC;
-      rk[0] = tk[0];
-      rk[1] = tk[1];
+      rk[0] = tk[TAB_A];
+      rk[1] = tk[TAB_B];
+      rk[2] = -tk[TAB_A];
+      rk[3] = tk[TAB_AB];
 #pragma unroll
       for (int bb = 0; bb < B; ++bb) {
         double2 v = alm[bb * alm_stride + base + l];
         if (m == 0) v.y = 0.0;  // a_l0 is real (healpy ignores the imaginary part)
-        rk[2 + 4 * bb + 0] = v.x * alpha;
-        rk[2 + 4 * bb + 1] = v.y * alpha;
-        rk[2 + 4 * bb + 2] = s_t[2 * bb][i] * s1;
-        rk[2 + 4 * bb + 3] = s_t[2 * bb + 1][i] * s1;
+        rk[4 + 4 * bb + 0] = v.x * alpha;
+        rk[4 + 4 * bb + 1] = v.y * alpha;
+        rk[4 + 4 * bb + 2] = s_t[2 * bb][i] * s1;
+        rk[4 + 4 * bb + 3] = s_t[2 * bb + 1][i] * s1;
       }
     }
     __syncthreads();
@@ -228,7 +212,7 @@ struct LegParams {
 
 template <int R, int B, int THREADS>
 __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegParams p) {
-  constexpr int REC = 2 + 4 * B;
+  constexpr int REC = 4 + 4 * B;
   constexpr int CHUNK_DOUBLES = LEG_KT * REC;
   constexpr int NWARPS = THREADS / 32;
   __shared__ __align__(128) double s_rec[LEG_STAGES][CHUNK_DOUBLES];
@@ -272,6 +256,12 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
   const int pair0 = item.tile * (THREADS * R) + tid * R;
   const double cm_mant = p.cm_mant[m];
   const int cm_exp = p.cm_exp[m];
+  // warp-uniform choice of the recurrence variable (see sht_prep_tables_kernel): u = sin^2 for
+  // warps whose first ring has z^2 >= 1/2, y = z^2 otherwise; `ab_off` selects the matching
+  // coefficient pair of the record
+  const double zw = p.z[min(item.tile * (THREADS * R) + (tid & ~31) * R, p.npair - 1)];
+  const bool use_u = zw * zw >= 0.5;
+  const int ab_off = use_u ? 2 : 0;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int r = pair0 + j;
@@ -283,8 +273,9 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
     zz[j] = 0.0;
     if (live[j]) {
       zz[j] = p.z[r];
-      x2[j] = zz[j] * zz[j];
-      lam_mm_scaled(m, p.sth[r], cm_mant, cm_exp, p2[j], sc[j]);
+      const double sth = p.sth[r];
+      x2[j] = use_u ? sth * sth : zz[j] * zz[j];  // the warp's recurrence variable: u or y
+      lam_mm_scaled(m, sth, cm_mant, cm_exp, p2[j], sc[j]);
     }
 #pragma unroll
     for (int b = 0; b < B; ++b) acc[j][b][0] = acc[j][b][1] = acc[j][b][2] = acc[j][b][3] = 0.0;
@@ -320,7 +311,7 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
         if (__any_sync(0xffffffffu, near)) break;  // finish with the exact per-step loop below
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC);
+          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC + ab_off);
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const double rr = fma(ab.x, x2[j], ab.y);
@@ -347,7 +338,7 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
           phase = 1;
           break;
         }
-        const double2 ab = *reinterpret_cast<const double2*>(ck + k * REC);
+        const double2 ab = *reinterpret_cast<const double2*>(ck + k * REC + ab_off);
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const double rr = fma(ab.x, x2[j], ab.y);
@@ -373,12 +364,12 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
           break;
         }
         const double* rk = ck + k * REC;
-        const double2 ab = *reinterpret_cast<const double2*>(rk);
+        const double2 ab = *reinterpret_cast<const double2*>(rk + ab_off);
         double2 ce[B], co[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-          ce[b] = *reinterpret_cast<const double2*>(rk + 2 + 4 * b);
-          co[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+          ce[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+          co[b] = *reinterpret_cast<const double2*>(rk + 6 + 4 * b);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -407,12 +398,12 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
 #pragma unroll LEG_UNROLL
       for (; k < kc; ++k) {
         const double* rk = ck + k * REC;
-        const double2 ab = *reinterpret_cast<const double2*>(rk);
+        const double2 ab = *reinterpret_cast<const double2*>(rk + ab_off);
         double2 ce[B], co[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-          ce[b] = *reinterpret_cast<const double2*>(rk + 2 + 4 * b);
-          co[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+          ce[b] = *reinterpret_cast<const double2*>(rk + 4 + 4 * b);
+          co[b] = *reinterpret_cast<const double2*>(rk + 6 + 4 * b);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -539,7 +530,7 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, bool
 // static tables of the prep stage (once per plan)
 int sht_build_prep_tables(glb_plan* pl, cudaStream_t st) {
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_prep_tab, (size_t)pl->nrec * PREP_TAB * sizeof(double)));
-  const int threads = 128;
+  const int threads = 64;  // one thread per m, sequential in l: small blocks spread the long m over the SMs
   sht_prep_tables_kernel<<<(pl->mmax + threads) / threads, threads, 0, st>>>(pl->lmax, pl->mmax, pl->d_roff,
                                                                              pl->d_prep_tab);
   GLB_CUDA_CHECK(cudaGetLastError());

@@ -394,3 +394,21 @@ def test_expm1_fast_host_build_and_run(tmp_path):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "expm1_fast ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_legendre_tables_host_build_and_run(tmp_path):
+    """csrc/sht_tables.cuh + dd.cuh (double-double coefficient tables of the Legendre stages):
+    every entry within 0.51 ulp of the 80-bit value and no systematic offset in the product
+    a_k a_{k-1} (the k^2-amplified error source found at lmax 8191)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "tables_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "native", "tables_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "tables ok" in r.stdout, r.stdout + r.stderr
