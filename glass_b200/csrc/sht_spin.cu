@@ -11,6 +11,12 @@
 // map2(0,B) = map1(B,0)).  Both functions follow the three-term recurrence in l of
 // d^l_{m,-s}; rescaled by sigma_l (sigma_{l+1} = C_l sigma_{l-1}) it becomes
 //     p+-_{l+1} = (x A'_l +- B'_l) p+-_l - p+-_{l-1}            (2 DFMA per function per l)
+// The factor is evaluated per warp in the variable that is known to relative precision at its
+// rings: x A' +- B' with x = cos(theta) where x < 1/2, (A' +- B') - A' t with t = 1 - x =
+// 2 sin^2(theta/2) where x >= 1/2 (the absolute rounding error of x next to the poles, the same
+// in every step, is amplified by l^2/2 -- 4e-10 of the functions at l = 8191, 2e-11 with t;
+// same reasoning as in sht_legendre.cu).  Both are one FMA on a coefficient triple of the
+// record, {A', B', -B'} or {-A', A'+B', A'-B'}, chosen by a warp-uniform offset.
 // and the southern ring of a pair needs no second recurrence:
 //     lam+(pi-theta) = (-1)^{l+s} lam-(theta)
 // so sums are kept separately for even and odd (l+m+s).  Everything else -- one thread per
@@ -69,13 +75,13 @@ __global__ void __launch_bounds__(128) spin_tables_kernel(int lmax, int mmax, in
   }
 }
 
-// ---- prep (per call, fully parallel): records {A'_l, B'_l, E_l sigma_l [, B_l sigma_l]} ----
+// ---- prep (per call, fully parallel): records {A', B', -B', 0, -A', A'+B', A'-B', 0, E_l sigma_l [, B_l sigma_l]} ----
 // grid: (ceil((lmax+1)/256), mmax+1): blockIdx.y = m, threads over l
 template <int NB>
 __global__ void __launch_bounds__(256) spin_prep_kernel(const double2* __restrict__ alm1, const double2* __restrict__ alm2,
                                                          int lmax, int spin, const int64_t* __restrict__ soff,
                                                          const double* __restrict__ tab, double* __restrict__ rec) {
-  constexpr int REC = 2 + 2 * NB;
+  constexpr int REC = 8 + 2 * NB;
   const int m = blockIdx.y;
   const int l0 = max(m, spin);
   const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,17 +91,24 @@ __global__ void __launch_bounds__(256) spin_prep_kernel(const double2* __restric
   const double* tk = tab + i * 3;
   const double sig = tk[2];
   double* rk = rec + i * REC;
-  rk[0] = tk[0];
-  rk[1] = tk[1];
+  const double A = tk[0], B = tk[1];
+  rk[0] = A;
+  rk[1] = B;
+  rk[2] = -B;
+  rk[3] = 0.0;
+  rk[4] = -A;
+  rk[5] = A + B;
+  rk[6] = A - B;
+  rk[7] = 0.0;
   double2 e = alm1[base + l];
   if (m == 0) e.y = 0.0;
-  rk[2] = e.x * sig;
-  rk[3] = e.y * sig;
+  rk[8] = e.x * sig;
+  rk[9] = e.y * sig;
   if (NB == 2) {
     double2 b = alm2[base + l];
     if (m == 0) b.y = 0.0;
-    rk[4] = b.x * sig;
-    rk[5] = b.y * sig;
+    rk[10] = b.x * sig;
+    rk[11] = b.y * sig;
   }
 }
 
@@ -144,7 +157,7 @@ struct SpinParams {
 
 template <int R, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256) ? 512 / THREADS : 1) spin_legendre_synth_kernel(const SpinParams p) {
-  constexpr int REC = 2 + 2 * NB;
+  constexpr int REC = 8 + 2 * NB;
   constexpr int CHUNK_DOUBLES = SP_KT * REC;
   constexpr int NWARPS = THREADS / 32;
   __shared__ __align__(128) double s_rec[SP_STAGES][CHUNK_DOUBLES];
@@ -188,6 +201,9 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
   const double sn_mant = p.sn_mant[m];
   const int sn_exp = p.sn_exp[m];
   const int ea = abs(m - s), eb = m + s;
+  // warp-uniform recurrence variable: t = 1 - x for warps whose first ring has x >= 1/2
+  const bool use_t = p.z[min(item.tile * (THREADS * R) + (tid & ~31) * R, p.npair - 1)] >= 0.5;
+  const int c_off = use_t ? 4 : 0;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int r = pair0 + j;
@@ -195,8 +211,8 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
     pp1[j] = pp2[j] = pm1[j] = pm2[j] = xx[j] = 0.0;
     sc[j] = 0;
     if (live[j]) {
-      xx[j] = p.z[r];
       const double ch = p.ch[r], sh = p.sh[r];
+      xx[j] = use_t ? 2.0 * sh * sh : p.z[r];  // t = 1 - x = 2 sin^2(theta/2), or x
       double mca, msb, mcb, msa;
       int eca, esb, ecb, esa;
       pow_scaled(ch, ea, mca, eca);  // ch^|m-s|
@@ -229,9 +245,10 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
   int phase = 0;
 
   // one l step with accumulation into parity slot Q (compile time) using multiplier-selected p
-  auto recur = [&](int j, double A, double B) {
-    const double rp = fma(xx[j], A, B);
-    const double rm = fma(xx[j], A, -B);
+  // P, Qp, Qm = {A', B', -B'} (variable x) or {-A', A'+B', A'-B'} (variable t)
+  auto recur = [&](int j, double P, double Qp, double Qm) {
+    const double rp = fma(xx[j], P, Qp);
+    const double rm = fma(xx[j], P, Qm);
     const double tp = fma(rp, pp2[j], -pp1[j]);
     const double tm = fma(rm, pm2[j], -pm1[j]);
     pp1[j] = pp2[j];
@@ -275,9 +292,10 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
         if (__any_sync(0xffffffffu, near)) break;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC);
+          const double2 ab = *reinterpret_cast<const double2*>(ck + (k + u) * REC + c_off);
+          const double qm = ck[(k + u) * REC + c_off + 2];
 #pragma unroll
-          for (int j = 0; j < R; ++j) recur(j, ab.x, ab.y);
+          for (int j = 0; j < R; ++j) recur(j, ab.x, ab.y, qm);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) rescale(j);
@@ -292,10 +310,11 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
           phase = 1;
           break;
         }
-        const double2 ab = *reinterpret_cast<const double2*>(ck + k * REC);
+        const double2 ab = *reinterpret_cast<const double2*>(ck + k * REC + c_off);
+        const double qm = ck[k * REC + c_off + 2];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          recur(j, ab.x, ab.y);
+          recur(j, ab.x, ab.y, qm);
           rescale(j);
         }
         ++k;
@@ -304,10 +323,11 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
     // generic (runtime parity) accumulate step used by the CHECK phase and odd leftovers
     auto check_step = [&](int kk) {
       const double* rk = ck + kk * REC;
-      const double2 ab = *reinterpret_cast<const double2*>(rk);
+      const double2 ab = *reinterpret_cast<const double2*>(rk + c_off);
+      const double qm = rk[c_off + 2];
       double2 e[NB];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) e[b] = *reinterpret_cast<const double2*>(rk + 2 + 2 * b);
+      for (int b = 0; b < NB; ++b) e[b] = *reinterpret_cast<const double2*>(rk + 8 + 2 * b);
       const bool odd = kk & 1;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
           acc[j][b][1][2] = fma(a1m, e[b].x, acc[j][b][1][2]);
           acc[j][b][1][3] = fma(a1m, e[b].y, acc[j][b][1][3]);
         }
-        recur(j, ab.x, ab.y);
+        recur(j, ab.x, ab.y, qm);
         rescale(j);
       }
     };
@@ -350,10 +370,11 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const double* rk = ck + (k + q) * REC;
-          const double2 ab = *reinterpret_cast<const double2*>(rk);
+          const double2 ab = *reinterpret_cast<const double2*>(rk + c_off);
+          const double qm = rk[c_off + 2];
           double2 e[NB];
 #pragma unroll
-          for (int b = 0; b < NB; ++b) e[b] = *reinterpret_cast<const double2*>(rk + 2 + 2 * b);
+          for (int b = 0; b < NB; ++b) e[b] = *reinterpret_cast<const double2*>(rk + 8 + 2 * b);
 #pragma unroll
           for (int j = 0; j < R; ++j) {
 #pragma unroll
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
               acc[j][b][q][2] = fma(pm2[j], e[b].x, acc[j][b][q][2]);
               acc[j][b][q][3] = fma(pm2[j], e[b].y, acc[j][b][q][3]);
             }
-            recur(j, ab.x, ab.y);
+            recur(j, ab.x, ab.y, qm);
           }
         }
       }
@@ -513,7 +534,7 @@ int plan_ensure_spin(glb_plan* pl, int spin) {
     soff[pl->mmax + 1] = acc;
     pl->nrec_spin = acc;
     if ((rc = upload_vec(&pl->d_soff, soff)) != GLB_OK) return rc;
-    if (acc * 6 > pl->rec_capacity) {
+    if (acc * 12 > pl->rec_capacity) {
       set_last_error("internal: record workspace too small for the spin transform");
       return GLB_ERR_NOMEM;
     }

@@ -117,6 +117,115 @@ def test_single_harmonics_fullsize(cuda_device):
     assert err < 1e-10, err  # BASELINE.json north_star: maps from identical alm within 1e-10 relative
 
 
+def exact_half_angles(nside):
+    """cos(theta/2), sin(theta/2) of all rings in extended precision (1 - z is exact in the caps)."""
+    n = int(nside)
+    i = np.arange(1, 4 * n, dtype=np.int64)
+    ip = np.where(i > 3 * n, 4 * n - i, i).astype(LD)
+    cap = (i < n) | (i > 3 * n)
+    t = ip * ip / (LD(3) * n * n)
+    zeq = (LD(2) * n - i.astype(LD)) * 2 / (LD(3) * n)
+    omz = np.where(cap, np.where(i > 3 * n, 2 - t, t), 1 - zeq)  # 1 - z
+    opz = np.where(cap, np.where(i > 3 * n, t, 2 - t), 1 + zeq)  # 1 + z
+    return np.sqrt(opz / 2), np.sqrt(omz / 2)
+
+
+def wigner_d_single(l, m, mp, z, ch, sh):
+    """d^l_{m,mp}(theta) on all rings in the precision of ``z``: oracle.healpix_ref.wigner_d_l
+    (three-term recurrence in l) keeping two rows.  80-bit range covers sin^(m+s)(theta/2) down
+    to 1e-4900, enough for the small m used here."""
+    T = z.dtype.type
+    j = max(abs(m), abs(mp))
+    a, b, sign = m, mp, 1.0
+    if abs(a) < abs(b):
+        a, b = b, a
+        sign *= (-1.0) ** (a - b)
+    if a < 0:
+        sign *= (-1.0) ** (a - b)
+        a, b = -a, -b
+    lognorm = T(0.5) * (T(math.lgamma(2 * j + 1.0)) - T(math.lgamma(j + b + 1.0)) - T(math.lgamma(j - b + 1.0)))
+    # exact norm for small j: sqrt((2j)! / ((j+b)! (j-b)!))
+    if j <= 20:
+        lognorm = T(0.5) * np.log(T(math.factorial(2 * j)) / (T(math.factorial(j + b)) * T(math.factorial(j - b))))
+    with np.errstate(divide="ignore"):
+        mag = np.exp(lognorm + (j + b) * np.log(ch) + (j - b) * np.log(sh))
+    cur = T(sign * (-1.0) ** (j - b)) * mag
+    if l == j:
+        return cur
+    prev = np.zeros_like(cur)
+    for ll in range(j, l):
+        den = T(ll) * np.sqrt(((T(ll) + 1) ** 2 - T(m) * m) * ((T(ll) + 1) ** 2 - T(mp) * mp)) if ll > 0 else T(1)
+        if ll == 0:
+            nxt = z * cur
+        else:
+            t1 = (2 * T(ll) + 1) * (T(ll) * (T(ll) + 1) * z - T(m) * mp)
+            t2 = (T(ll) + 1) * np.sqrt((T(ll) * ll - T(m) * m) * (T(ll) * ll - T(mp) * mp))
+            nxt = (t1 * cur - t2 * prev) / den
+        prev, cur = cur, nxt
+    return cur
+
+
+def slam_single(l, m, s, z, ch, sh):
+    """sY_lm(theta, 0) = (-1)^s sqrt((2l+1)/4pi) d^l_{m,-s}(theta) (oracle.healpix_ref.slam_lm)."""
+    T = z.dtype.type
+    pi = T("3.14159265358979323846264338327950288") if T is LD else T(math.pi)
+    return T((-1.0) ** s) * np.sqrt((2 * T(l) + 1) / (4 * pi)) * wigner_d_single(l, m, -s, z, ch, sh)
+
+
+def spin_mode_maps(modes, spin, nside, ring, j, nphi_p, shifted, z, ch, sh, dev, mlim_ring=None):
+    """Expected (map1, map2) of E-only single modes [(l, m, e)]: P = map1 + i map2 =
+    sum_m P_m e^{i m phi} with P_m = -e sY_{l,m}, P_{-m} = -(-1)^m conj(e) sY_{l,-m}
+    (oracle.healpix_ref.alm2map_spin)."""
+    npix = 12 * nside * nside
+    w1 = torch.zeros(npix, dtype=torch.float64, device=dev)
+    w2 = torch.zeros(npix, dtype=torch.float64, device=dev)
+    for l, m, e in modes:
+        yp = slam_single(l, m, spin, z, ch, sh).astype(np.float64)
+        if mlim_ring is not None:
+            yp = np.where(mlim_ring < m, 0.0, yp)
+        yp_t = torch.as_tensor(yp, device=dev)[ring]
+        if m == 0:
+            w1 += -e.real * yp_t
+            continue
+        yn = slam_single(l, -m, spin, z, ch, sh).astype(np.float64)
+        if mlim_ring is not None:
+            yn = np.where(mlim_ring < m, 0.0, yn)
+        yn_t = torch.as_tensor(yn, device=dev)[ring]
+        num = (2 * m * j + m * shifted) % (2 * nphi_p)
+        ang = math.pi * num.to(torch.float64) / nphi_p.to(torch.float64)
+        c, sn = torch.cos(ang), torch.sin(ang)
+        sg = (-1.0) ** m
+        # P_m e^{i a} + P_{-m} e^{-i a},  P_m = -(er + i ei) yp,  P_{-m} = -sg (er - i ei) yn
+        w1 += -(e.real * c - e.imag * sn) * yp_t - sg * (e.real * c - e.imag * sn) * yn_t
+        w2 += -(e.real * sn + e.imag * c) * yp_t + sg * (e.real * sn + e.imag * c) * yn_t
+    return w1, w2
+
+
+def test_spin2_single_harmonics_fullsize(cuda_device):
+    """Spin-2 synthesis (kappa -> shear) at nside 4096 against 80-bit spin-weighted harmonics on
+    exact ring geometry: low m, where the polar rings amplify rounding of cos(theta) by l^2/2."""
+    from glass_b200 import healpix as hp
+
+    dev = cuda_device
+    ri = H.ring_info(NSIDE)
+    zx, _ = exact_ring_geometry(NSIDE)
+    chx, shx = exact_half_angles(NSIDE)
+    modes = [(2, 0, 1.0 + 0j), (8191, 0, 0.8 + 0j), (8000, 1, 0.5 - 0.4j), (8191, 2, -0.7 + 0.2j), (6000, 3, 0.3 + 0.9j), (4097, 40, 0.6 - 0.1j)]
+    alm = np.zeros(H.alm_size(LMAX), dtype=np.complex128)
+    for l, m, e in modes:
+        alm[H.alm_index(LMAX, l, m)] = e
+    g1, g2 = hp.alm2map_spin([torch.as_tensor(alm).to(dev), None], NSIDE, 2, LMAX)
+    nphi = torch.as_tensor(ri["nphi"], device=dev)
+    ring = torch.repeat_interleave(torch.arange(nphi.numel(), device=dev), nphi)
+    j = torch.arange(12 * NSIDE * NSIDE, device=dev) - torch.as_tensor(ri["start"], device=dev)[ring]
+    nphi_p = nphi[ring]
+    shifted = torch.as_tensor(ri["shifted"].astype(np.int64), device=dev)[ring]
+    w1, w2 = spin_mode_maps(modes, 2, NSIDE, ring, j, nphi_p, shifted, zx, chx, shx, dev)
+    scale = max(w1.abs().max().item(), w2.abs().max().item())
+    err = max((g1 - w1).abs().max().item(), (g2 - w2).abs().max().item()) / scale
+    assert err < 1e-10, err
+
+
 def test_linearity_and_batching_fullsize(cuda_device):
     """S(a) + S(b) == S(a + b) to rounding, and a map does not depend on its batch slot."""
     from glass_b200.healpix import alm2map_batch
