@@ -42,6 +42,7 @@ SIGNATURES = {
     "glb_alm_draw": (_i, [_i, C.c_uint64, C.c_uint32, _dp, _vp]),
     "glb_alm_glass_to_healpix": (_i, [_i, _dp, _dp, _vp]),
     "glb_alm_combine": (_i, [_i, _i, _vp, _dp, _i, _dp, _vp]),
+    "glb_iternorm_step": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
     "glb_points_workspace_bytes": (C.c_size_t, [_i64]),
     "glb_points_counts": (_i, [_i64, _dp, _dp, _i, C.c_double, C.c_double, _i, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp, _vp]),
     "glb_points_fill": (_i, [_i64, _dp, _dp, _i64, _i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp]),

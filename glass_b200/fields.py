@@ -313,6 +313,61 @@ def _glass_to_healpix_alm(alm):
 # --------------------------------------------------------------------------------------
 
 
+#: from this many correlated shells on, the iterative-normal recursion runs on the device (K1,
+#: ``glb_iternorm_step``): the NumPy recursion costs O(n k^2) host time per shell -- 19 ms at
+#: k = 19, 180 ms at k = 59 for lmax 8191 -- which passes the shell's 39 ms of GPU time near
+#: k = 25.  Below it the host recursion is kept: its weights are bit-identical to the
+#: reference's NumPy arithmetic, which the bit-exact a_lm parity tests rely on.
+ITERNORM_DEVICE_MIN_NCORR = 8
+
+
+class _DeviceIterNorm:
+    """glass/fields.py:101-188 with the state (m, a, s) resident on the GPU; ``step`` consumes
+    one row of ``cls2cov`` and returns the weights ``[a, s]`` as a device tensor (n, k+1).
+    "covariance matrix is not positive definite" is recorded per step in ``flags`` and raised
+    by :meth:`check` (one device read per batch of shells instead of one per shell)."""
+
+    def __init__(self, n: int, k: int, nsteps: int, device):
+        self.lib = _lib.load()
+        self.n, self.k, self.device = int(n), int(k), device
+        kk = max(self.k, 1)
+        self.m = torch.zeros((kk, kk, self.n), dtype=torch.float64, device=device)
+        self.a = torch.zeros((kk, self.n), dtype=torch.float64, device=device)
+        self.s = torch.ones(self.n, dtype=torch.float64, device=device)
+        self.tmp = torch.empty((kk, self.n), dtype=torch.float64, device=device)
+        self.flags = torch.zeros(max(int(nsteps), 1), dtype=torch.int32, device=device)
+        self.i = 0
+        self.checked = 0
+
+    def step(self, row: np.ndarray) -> torch.Tensor:
+        row = np.ascontiguousarray(row, dtype=np.float64)
+        if row.shape[-1] - 1 != self.k or row.shape[0] != self.n:
+            raise ValueError("shape mismatch in covariance")
+        dev = self.device
+        rd = torch.from_numpy(row.copy()).pin_memory().to(dev, non_blocking=True)  # cls2cov re-yields one buffer
+        w = torch.empty((self.n, self.k + 1), dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(
+            self.lib.glb_iternorm_step(self.n, self.k, 1 if self.i == 0 else 0, rd.data_ptr(), self.m.data_ptr(), self.a.data_ptr(),
+                                       self.s.data_ptr(), self.tmp.data_ptr(), w.data_ptr(), self.flags[self.i :].data_ptr(), st),
+            "glb_iternorm_step",
+        )
+        self.i += 1
+        return w
+
+    def first_failure(self):
+        """Index of the first step whose covariance was not positive definite, or None
+        (synchronises with the stream)."""
+        if self.i == self.checked:
+            return None
+        f = self.flags[self.checked : self.i].cpu().numpy()
+        bad = np.nonzero(f)[0]
+        if bad.size:
+            return self.checked + int(bad[0])
+        self.checked = self.i
+        return None
+
+
 class _ShellSampler:
     """Device-side state of _generate_grf: z history, iternorm weights, alm of each shell.
 
@@ -338,7 +393,12 @@ class _ShellSampler:
         self.nalm = self.n * (self.n + 1) // 2
         self.deviates = rng if isinstance(rng, _rng.Deviates) else None
         self.seed = _rng.seed_from(rng)
-        self.witer = iternorm(cls2cov(gls, self.n, ngrf, self.ncorr))
+        self.dnorm = None
+        if self.ncorr >= ITERNORM_DEVICE_MIN_NCORR:
+            self.dnorm = _DeviceIterNorm(self.n, self.ncorr, ngrf, device)
+            self.witer = cls2cov(gls, self.n, ngrf, self.ncorr)  # rows; the recursion runs on the device
+        else:
+            self.witer = iternorm(cls2cov(gls, self.n, ngrf, self.ncorr))
         self.wanted = wanted
         self.zcache: dict[int, torch.Tensor] = {}
         self.shell = 0
@@ -368,6 +428,9 @@ class _ShellSampler:
                 w = next(self.witer)
             except StopIteration:
                 return None
+            if self.dnorm is not None:
+                self.h2d_bytes += w.nbytes
+                w = self.dnorm.step(w)  # device tensor (n, ncorr + 1)
             j = self.shell
             self.shell += 1
             if self.wanted is None or self.wanted(j):
@@ -379,16 +442,26 @@ class _ShellSampler:
         zs = [self._z(s) for s in range(j - nterms + 1, j + 1)]
         for s in [s for s in self.zcache if s < j - self.ncorr]:
             del self.zcache[s]
-        wh = np.ascontiguousarray(w[:, mis:], dtype=np.float64)
-        # pinned staging + async copy: a pageable H2D would block the host until the stream drains
-        wd = torch.from_numpy(wh).pin_memory().to(dev, non_blocking=True)
-        self.h2d_bytes += wh.nbytes
+        if self.dnorm is not None:
+            wd, stride = w, w.shape[-1]
+            wptr = wd.data_ptr() + 8 * mis
+        else:
+            wh = np.ascontiguousarray(w[:, mis:], dtype=np.float64)
+            # pinned staging + async copy: a pageable H2D would block the host until the stream drains
+            wd = torch.from_numpy(wh).pin_memory().to(dev, non_blocking=True)
+            self.h2d_bytes += wh.nbytes
+            stride, wptr = nterms, wd.data_ptr()
         zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in zs])
         _lib.check(
-            lib.glb_alm_combine(self.lmax, nterms, zptrs, wd.data_ptr(), nterms, out.data_ptr(), st),
+            lib.glb_alm_combine(self.lmax, nterms, zptrs, wptr, stride, out.data_ptr(), st),
             "glb_alm_combine",
         )
         return j
+
+    def first_failure(self):
+        """Shell index at which the device recursion found a non positive definite covariance
+        (None if none so far, or when the recursion runs on the host, which raises itself)."""
+        return None if self.dnorm is None else self.dnorm.first_failure()
 
 
 def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=None):
@@ -429,6 +502,12 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                         exhausted = True
                         break
                     idx.append(j)
+                bad = sampler.first_failure()
+                if bad is not None:
+                    # the reference raises when it reaches shell `bad`: yield the earlier ones first
+                    idx = [j for j in idx if j < bad]
+                    state["error"] = ValueError("covariance matrix is not positive definite")
+                    exhausted = True
                 nb = len(idx)
                 if nb == 0:
                     break

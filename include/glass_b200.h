@@ -94,6 +94,13 @@ int glb_almxfl(int lmax, double* d_alm, const double* d_fl, int nfl, void* strea
 int glb_alm_draw(int lmax, uint64_t seed, uint32_t shell, double* d_z, void* stream);
 /* _glass_to_healpix_alm   fields.py:943-962: l-major -> m-major gather (for supplied z). */
 int glb_alm_glass_to_healpix(int lmax, const double* d_in, double* d_out, void* stream);
+/* iternorm   fields.py:101-188, one step (one shell) for all n = lmax+1 multipoles at once.
+ * State (caller-allocated, zero-initialised, kept between steps): d_m [k][k][n], d_a [k][n],
+ * d_s [n]; d_tmp [k][n] scratch.  d_row: [n][k+1] row of cls2cov (fields.py:191-236), d_w:
+ * [n][k+1] result [a, s].  first != 0 on the first step.  *d_flag is OR-ed with 1 where the
+ * reference raises "covariance matrix is not positive definite" (fields.py:184-186). */
+int glb_iternorm_step(int n, int k, int first, const double* d_row, double* d_m, double* d_a, double* d_s,
+                      double* d_tmp, double* d_w, int* d_flag, void* stream);
 /* alm = sum_i multalm(z_i, w[:, i])   fields.py:420 + harmonics.py:46-47, then the m = 0
  * fix alm = Re + Im (fields.py:425).  h_zptrs: HOST array of nterms DEVICE pointers to
  * m-major z arrays, oldest first; d_w: [lmax+1][w_stride] float64, column i scales z_i.

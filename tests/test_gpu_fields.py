@@ -116,6 +116,51 @@ def test_generate_errors(cuda_device):
         next(g)
 
 
+@pytest.mark.parametrize("nshell,lmax,ncorr", [(14, 40, 9), (12, 25, 11), (5, 12, 0), (9, 300, 8)])
+def test_device_iternorm_vs_host(cuda_device, nshell, lmax, ncorr):
+    """K1 (glb_iternorm_step) against the host recursion (glass/fields.py:101-188) on the rows
+    of cls2cov, shell by shell.  Tolerance 1e-11 relative: the summation order of NumPy's
+    batched matmul is not specified, so this path is not bit-exact by construction."""
+    from glass_b200.fields import _DeviceIterNorm, cls2cov, iternorm
+
+    gls = synthetic_gls(nshell, lmax, ncorr, ragged=True)
+    host = [w.copy() for w in iternorm(cls2cov(gls, lmax + 1, nshell, ncorr))]
+    dn = _DeviceIterNorm(lmax + 1, ncorr, nshell, cuda_device)
+    for j, row in enumerate(cls2cov(gls, lmax + 1, nshell, ncorr)):
+        w = dn.step(row).cpu().numpy()
+        assert w.shape == host[j].shape
+        assert np.abs(w - host[j]).max() <= 1e-11 * np.abs(host[j]).max(), j
+    assert dn.first_failure() is None
+
+
+def test_generate_device_iternorm_matches_host_path(cuda_device, monkeypatch):
+    """generate() with many correlated shells (device recursion) against the same call forced
+    onto the host recursion, and the reference's error when a covariance is not positive
+    definite: shells before the failing one are still yielded."""
+    import glass_b200
+    from glass_b200 import fields as F
+
+    nshell, lmax, nside, ncorr = 12, 48, 16, 10
+    gls = synthetic_gls(nshell, lmax, ncorr)
+    flds = [glass_b200.grf.Lognormal()] * nshell
+    dev_maps = [np.array(m) for m in glass_b200.generate(flds, gls, nside, ncorr=ncorr, rng=5)]
+    monkeypatch.setattr(F, "ITERNORM_DEVICE_MIN_NCORR", 10**9)
+    host_maps = [np.array(m) for m in glass_b200.generate(flds, gls, nside, ncorr=ncorr, rng=5)]
+    monkeypatch.undo()
+    assert len(dev_maps) == len(host_maps) == nshell
+    for a, b in zip(dev_maps, host_maps):
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    # shell 2 is more strongly correlated with shell 1 than a positive definite matrix allows
+    bad = [g.copy() for g in gls]
+    bad[2 * 3 // 2 + 1] = 3.0 * gls[0]
+    g = glass_b200.generate(flds, bad, nside, ncorr=ncorr, rng=5)
+    got = []
+    with pytest.raises(ValueError, match="covariance matrix is not positive definite"):
+        for m in g:
+            got.append(m)
+    assert len(got) == 2
+
+
 def test_philox_normals_statistics(cuda_device):
     """Random draws are validated statistically (north_star): recovered C_l within
     cosmic variance, seed reproducibility, shell independence."""

@@ -52,6 +52,8 @@ def main():
     ap.add_argument("--niter", type=int, default=3)
     ap.add_argument("--ngal", type=float, default=None, help="galaxies per arcmin^2 per shell")
     ap.add_argument("--lensing", action="store_true")
+    ap.add_argument("--ncorr", type=int, default=3, help="correlated shells (59 = all 60 shells of config 4 fully correlated)")
+    ap.add_argument("--no-galaxies", action="store_true")
     args = ap.parse_args()
     S, nside, lmax, lensing = CONFIGS[args.config]
     S = args.shells or S
@@ -68,7 +70,7 @@ def main():
     npix = 12 * nside * nside
     dz = 1.0 / (S + 1)
     shells = [glass_b200.RadialWindow(np.array([i, i + 1.0, i + 2.0]) * dz, np.array([0.0, 1.0, 0.0]), (i + 1.0) * dz) for i in range(S)]
-    gls = [torch.as_tensor(g).to(dev) for g in synthetic_gls(S, lmax, 3)]
+    gls = [torch.as_tensor(g).to(dev) for g in synthetic_gls(S, lmax, args.ncorr)]
     ngal = args.ngal if args.ngal is not None else 0.083 * npix / glass_b200.points.ARCMIN2_SPHERE * (4096 / nside) ** 2 * 0 + 6.7335 / 60
     stages = {k: 0.0 for k in ("generate", "multiplane", "shear_from_convergence", "positions", "redshifts", "ellipticity", "galaxy_shear")}
 
@@ -82,7 +84,7 @@ def main():
 
     pend = []
     conv = glass_b200.MultiPlaneConvergence(MockCosmology())
-    matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=3, rng=42, shells=mine if world > 1 else None)
+    matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=args.ncorr, rng=42, shells=mine if world > 1 else None)
     ngal_tot = 0
     if world > 1:
         import torch.distributed as dist
@@ -104,7 +106,7 @@ def main():
         g1 = g2 = None
         if lensing:
             g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
-        it = glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
+        it = iter(()) if args.no_galaxies else glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
         while True:
             try:
                 lon, lat, cnt = timed("positions", lambda: next(it))
@@ -149,7 +151,7 @@ def main():
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
         ngal_tot = int(g[0])
     out = {
-        "config": args.config, "n_gpus": world, "shells": S, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
+        "config": args.config, "n_gpus": world, "shells": S, "ncorr": args.ncorr, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
         "galaxies": int(ngal_tot), "wall_s": wall, "shells_per_s": S / wall, "galaxies_per_s": ngal_tot / wall,
         "stage_ms_total": {k: round(v, 2) for k, v in stages.items()},
     }
