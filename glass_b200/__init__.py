@@ -27,12 +27,13 @@ from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_nz  
 from .harmonics import multalm  # noqa: F401
 from .lensing import (  # noqa: F401
     MultiPlaneConvergence,
+    deflect,
     from_convergence,
     multi_plane_matrix,
     multi_plane_weights,
     shear_from_convergence,
 )
-from .points import linear_bias, loglinear_bias, positions_from_delta, uniform_positions  # noqa: F401
+from .points import displace, displacement, linear_bias, loglinear_bias, positions_from_delta, uniform_positions  # noqa: F401
 from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
 from .shells import RadialWindow  # noqa: F401
 

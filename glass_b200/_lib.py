@@ -51,6 +51,8 @@ SIGNATURES = {
     "glb_uniform_positions": (_i, [_i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),
     "glb_ang2pix": (_i, [_i64, _dp, _dp, _i64, _i, _dp, _vp]),
     "glb_multiplane_update": (_i, [_dp, _dp, _dp, C.c_double, _i64, C.c_double, C.c_double, _vp]),
+    "glb_displace": (_i, [_dp, _dp, _dp, _dp, _i64, _i, _i64, _dp, _dp, _vp]),
+    "glb_displacement": (_i, [_dp, _dp, _dp, _dp, _i64, _dp, _vp]),
     "glb_galaxy_shear": (_i, [_i64, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _i, _dp, _vp]),
     "glb_ellipticity": (_i, [_i, C.c_double, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_gaussian_phz": (_i, [_dp, _dp, C.c_double, _dp, C.c_double, _dp, C.c_double, _dp, _i, _i64, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),

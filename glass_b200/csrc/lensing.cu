@@ -70,6 +70,54 @@ __global__ void __launch_bounds__(256) galaxy_shear_kernel(int64_t nside, const 
   out[i] = g;
 }
 
+// glass.displace (glass/points.py:654-716, sign = +1) and glass.deflect (glass/lensing.py:687-778,
+// sign = -1): the exponential map on the sphere.  The point (lon, lat) moves the angular distance
+// |alpha| along the geodesic with bearing arg(alpha); same formulas and operation order as the
+// reference (great-circle navigation, lat instead of co-lat).
+__global__ void __launch_bounds__(256) displace_kernel(const double* __restrict__ lon, const double* __restrict__ lat,
+                                                       const double* __restrict__ a1, const double* __restrict__ a2,
+                                                       int64_t a_stride, double sign, int64_t n,
+                                                       double* __restrict__ out_lon, double* __restrict__ out_lat) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double pi = 3.141592653589793;
+  const double t = lat[i] / 180.0 * pi;
+  double ct, st;
+  sincos(t, &ct, &st);  // sin and cos flipped: lat, not co-lat
+  const double x = a1[i * a_stride], y = a2[i * a_stride];
+  const double a = hypot(x, y);
+  const double g = atan2(y, x);
+  double sa, ca, sg, cg;
+  sincos(a, &sa, &ca);
+  sincos(g, &sg, &cg);
+  const double tp = atan2(ct * ca + st * sa * cg, hypot(ct * sa - st * ca * cg, st * sg));
+  const double d = atan2(sa * sg, st * ca - ct * sa * cg);
+  out_lon[i] = lon[i] + sign * (d / pi * 180.0);
+  out_lat[i] = tp / pi * 180.0;
+}
+
+// glass.displacement (glass/points.py:719-772): the complex displacement that takes
+// (from_lon, from_lat) to (to_lon, to_lat): r e^{i x}.
+__global__ void __launch_bounds__(256) displacement_kernel(const double* __restrict__ from_lon,
+                                                           const double* __restrict__ from_lat,
+                                                           const double* __restrict__ to_lon,
+                                                           const double* __restrict__ to_lat, int64_t n,
+                                                           double2* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double rad = 0.017453292519943295;
+  double sa, ca, sb, cb, sg, cg;
+  sincos(from_lat[i] * rad, &sa, &ca);
+  sincos(to_lat[i] * rad, &sb, &cb);
+  sincos((to_lon[i] - from_lon[i]) * rad, &sg, &cg);
+  const double u = cb * sg, v = ca * sb - sa * cb * cg;
+  const double r = atan2(hypot(u, v), sa * sb + ca * cb * cg);
+  const double x = atan2(u, v);
+  double sx, cx;
+  sincos(x, &sx, &cx);
+  out[i] = make_double2(r * cx, r * sx);
+}
+
 __device__ __forceinline__ double2 philox_normal_pair(uint32_t k0, uint32_t k1, uint64_t idx, uint32_t stream, uint32_t tag) {
   const Philox4 r = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), stream, tag, k0, k1);
   const double u1 = u01_open_closed(r.v[0], r.v[1]);
@@ -203,6 +251,30 @@ int glb_galaxy_shear(int64_t nside, const double* d_lon, const double* d_lat, co
   galaxy_shear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       nside, d_lon, d_lat, d_ipix, reinterpret_cast<const double2*>(d_eps), n, d_kappa, d_gamma1, d_gamma2,
       reduced_shear, reinterpret_cast<double2*>(d_out));
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_displace(const double* d_lon, const double* d_lat, const double* d_alpha1, const double* d_alpha2,
+                 int64_t alpha_stride, int deflect, int64_t n, double* d_out_lon, double* d_out_lat, void* stream) {
+  GLB_REQUIRE(n >= 0 && alpha_stride >= 1, "bad size");
+  if (n == 0) return GLB_OK;
+  GLB_REQUIRE(d_lon && d_lat && d_alpha1 && d_alpha2 && d_out_lon && d_out_lat, "null pointer");
+  displace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_lon, d_lat, d_alpha1, d_alpha2, alpha_stride, deflect ? -1.0 : 1.0, n, d_out_lon, d_out_lat);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_displacement(const double* d_from_lon, const double* d_from_lat, const double* d_to_lon,
+                     const double* d_to_lat, int64_t n, double* d_out, void* stream) {
+  GLB_REQUIRE(n >= 0, "bad size");
+  if (n == 0) return GLB_OK;
+  GLB_REQUIRE(d_from_lon && d_from_lat && d_to_lon && d_to_lat && d_out, "null pointer");
+  displacement_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_from_lon, d_from_lat, d_to_lon, d_to_lat, n, reinterpret_cast<double2*>(d_out));
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;

@@ -252,3 +252,11 @@ def shear_from_convergence(kappa, lmax: int | None = None, *, discretized: bool 
     alm = hp.almxfl(alm, fl, inplace=True)
     g1, g2 = hp.alm2map_spin([alm, None], nside, 2, lmax)
     return [g1, g2] if on_device else [g1.cpu().numpy(), g2.cpu().numpy()]
+
+
+def deflect(lon, lat, alpha, xp=None):
+    """Apply deflections to positions (glass/lensing.py:687-778; deprecated in the reference in
+    favour of ``glass.displace``, which moves the longitude the other way)."""
+    from .points import _displace
+
+    return _displace(lon, lat, alpha, deflect=True)

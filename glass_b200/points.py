@@ -278,3 +278,72 @@ def uniform_positions(ngal, *, rng=None, xp=None):
                 yield lon, lat, count
             else:
                 yield lon.cpu().numpy(), lat.cpu().numpy(), count
+
+
+def _alpha_parts(alpha, device):
+    """(alpha1, alpha2, stride) device views of a displacement given as a complex array or with a
+    leading axis of size 2 (glass/points.py:692-696)."""
+    is_complex = (isinstance(alpha, torch.Tensor) and alpha.is_complex()) or (
+        not isinstance(alpha, torch.Tensor) and np.iscomplexobj(alpha)
+    )
+    if is_complex:
+        a = A.to_dev(alpha, device, torch.complex128)
+        r = torch.view_as_real(a.contiguous())  # [..., 2] float64, interleaved
+        return a.shape, r, r.data_ptr(), r.data_ptr() + 8, 2
+    a = A.to_dev(alpha, device)
+    if a.shape[0] != 2:
+        raise ValueError("alpha must be complex-valued or have a leading axis of size 2")
+    a = a.contiguous()
+    return a.shape[1:], a, a[0].data_ptr(), a[1].data_ptr(), 1
+
+
+def _displace(lon, lat, alpha, deflect: bool):
+    device, on_device = A.pick_device(lon, lat, alpha)
+    shape_a, keep, p1, p2, stride = _alpha_parts(alpha, device)
+    lon_d, lat_d = A.to_dev(lon, device), A.to_dev(lat, device)
+    shape = torch.broadcast_shapes(lon_d.shape, lat_d.shape, tuple(shape_a))
+    if tuple(shape_a) != tuple(shape):
+        # broadcast the displacement (rare: scalar alpha): materialise it as complex128
+        if stride == 2:
+            full = torch.view_as_complex(keep).expand(shape).contiguous()
+        else:
+            full = torch.complex(keep[0], keep[1]).expand(shape).contiguous()
+        keep = torch.view_as_real(full)
+        p1, p2, stride = keep.data_ptr(), keep.data_ptr() + 8, 2
+    lon_d = lon_d.expand(shape).contiguous()
+    lat_d = lat_d.expand(shape).contiguous()
+    n = lon_d.numel()
+    out_lon = torch.empty(shape, dtype=torch.float64, device=device)
+    out_lat = torch.empty(shape, dtype=torch.float64, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(
+            lib.glb_displace(lon_d.data_ptr(), lat_d.data_ptr(), p1, p2, stride, int(deflect), n, out_lon.data_ptr(), out_lat.data_ptr(), st),
+            "glb_displace",
+        )
+    if on_device:
+        return out_lon, out_lat
+    return out_lon.cpu().numpy(), out_lat.cpu().numpy()
+
+
+def displace(lon, lat, alpha):
+    """Displace positions on the sphere (glass/points.py:654-716): the exponential map.  ``alpha``
+    complex, or real with a leading axis of size 2.  One kernel, 48 bytes per point."""
+    return _displace(lon, lat, alpha, deflect=False)
+
+
+def displacement(from_lon, from_lat, to_lon, to_lat):
+    """Complex displacement between two sets of positions in degrees (glass/points.py:719-772)."""
+    device, on_device = A.pick_device(from_lon, from_lat, to_lon, to_lat)
+    ts = torch.broadcast_tensors(*(A.to_dev(x, device) for x in (from_lon, from_lat, to_lon, to_lat)))
+    ts = [t.contiguous() for t in ts]
+    out = torch.empty(ts[0].shape, dtype=torch.complex128, device=device)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(
+            lib.glb_displacement(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), out.numel(), out.data_ptr(), st),
+            "glb_displacement",
+        )
+    return out if on_device else out.cpu().numpy()

@@ -171,6 +171,15 @@ int glb_multiplane_update(double* d_kappa3, const double* d_kappa2, const double
 int glb_galaxy_shear(int64_t nside, const double* d_lon, const double* d_lat, const int64_t* d_ipix,
                      const double* d_eps, int64_t n, const double* d_kappa, const double* d_gamma1,
                      const double* d_gamma2, int reduced_shear, double* d_out, void* stream);
+/* glass.displace (glass/points.py:654-716; deflect = 0) and glass.deflect (glass/lensing.py:687-778;
+ * deflect = 1, the displaced longitude is lon - d instead of lon + d): exponential map on the
+ * sphere, degrees in and out.  alpha = d_alpha1 + i d_alpha2, element i at [i * alpha_stride]
+ * (stride 2 with d_alpha2 = d_alpha1 + 1 for a complex128 array, stride 1 for two real arrays). */
+int glb_displace(const double* d_lon, const double* d_lat, const double* d_alpha1, const double* d_alpha2,
+                 int64_t alpha_stride, int deflect, int64_t n, double* d_out_lon, double* d_out_lat, void* stream);
+/* glass.displacement (glass/points.py:719-772): complex displacement from -> to, d_out complex128 [n]. */
+int glb_displacement(const double* d_from_lon, const double* d_from_lat, const double* d_to_lon,
+                     const double* d_to_lat, int64_t n, double* d_out, void* stream);
 /* ellipticity_intnorm (glass/shapes.py:323-362; mode 0, sigma = sigma_eta computed by the
  * caller) / ellipticity_gaussian (shapes.py:255-285; mode 1, redraw while |e| > 1).
  * d_normals (mode 0 only, may be NULL): supplied complex standard normals. */

@@ -35,6 +35,7 @@ def install_shims():
         return np
 
     aac.array_namespace = array_namespace
+    aac.get_namespace = array_namespace
     aac.is_jax_array = lambda x: False
     aac.is_numpy_array = lambda x: isinstance(x, np.ndarray)
     aac.is_array_api_obj = lambda x: isinstance(x, np.ndarray)
@@ -301,5 +302,45 @@ def main():
     print("wrote", len(out), "arrays,", sum(v.nbytes for v in out.values()) // 1024, "KiB")
 
 
+def main_displace():
+    """Second file (kept separate so that adding it did not rewrite the first):
+    displace / displacement / deflect of glass/points.py:654-772 and glass/lensing.py:687-778."""
+    install_shims()
+    sys.path.insert(0, REF)
+    import glass  # the reference itself
+    import glass.lensing
+    import glass.points
+
+    rr = np.random.default_rng(77)
+    n = 2000
+    lon = rr.uniform(-180.0, 360.0, n)
+    lat = np.degrees(np.arcsin(rr.uniform(-1.0, 1.0, n)))
+    alpha = (rr.standard_normal(n) + 1j * rr.standard_normal(n)) * 10.0 ** rr.uniform(-6, -0.3, n)
+    # edge cases: zero displacement, poles, due north / south / east
+    lon[:6] = [0.0, 10.0, 20.0, 30.0, 40.0, 50.0]
+    lat[:6] = [0.0, 90.0, -90.0, 45.0, -30.0, 89.999]
+    alpha[:6] = [0.0, 0.1 + 0.0j, 0.2j, -0.3 + 0.0j, 0.0 + 0.25j, 0.01 + 0.01j]
+    out = {"lon": lon, "lat": lat, "alpha": alpha}
+    dlon, dlat = glass.points.displace(lon, lat, alpha)
+    out["displace_lon"], out["displace_lat"] = dlon, dlat
+    dlon2, dlat2 = glass.points.displace(lon, lat, np.stack([alpha.real, alpha.imag]))
+    assert np.array_equal(dlon, dlon2) and np.array_equal(dlat, dlat2)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        flon, flat = glass.lensing.deflect(lon, lat, alpha)
+    out["deflect_lon"], out["deflect_lat"] = flon, flat
+    to_lon = rr.uniform(-180.0, 360.0, n)
+    to_lat = np.degrees(np.arcsin(rr.uniform(-1.0, 1.0, n)))
+    out["to_lon"], out["to_lat"] = to_lon, to_lat
+    out["displacement"] = glass.points.displacement(lon, lat, to_lon, to_lat)
+    np.savez_compressed(os.path.join(HERE, "glass_reference_displace.npz"), **out)
+    print("wrote", len(out), "arrays to glass_reference_displace.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--displace" in sys.argv:
+        main_displace()
+    else:
+        main()

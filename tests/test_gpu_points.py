@@ -247,3 +247,59 @@ def test_poisson_with_visibility_and_bias_variants(cuda_device):
         assert abs(zres.var() - 1.0) < 0.05 and abs(zres.mean()) < 0.02
         off = pop.off.cpu().numpy()
         assert off[-1] == c.sum() and np.array_equal(off[:-1], np.cumsum(c) - c)
+
+
+def _unit(lon, lat):
+    lo, la = np.radians(lon), np.radians(lat)
+    return np.stack([np.cos(la) * np.cos(lo), np.cos(la) * np.sin(lo), np.sin(la)])
+
+
+def test_displace_deflect_displacement_golden(cuda_device):
+    """glass.displace / glass.deflect / glass.displacement against vectors produced by executing
+    the reference's own source (tests/golden/make_golden.py --displace).  Transcendental
+    functions differ from NumPy's libm in the last bits: 1e-11 degrees, and the displaced POINT
+    (unit vector) to 1e-13 where the longitude itself is ill-conditioned (poles)."""
+    import os
+
+    import glass_b200
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glass_reference_displace.npz"))
+    lon, lat, alpha = g["lon"], g["lat"], g["alpha"]
+    ok = np.abs(lat) < 89.9
+    for fn, key in ((glass_b200.displace, "displace"), (glass_b200.deflect, "deflect")):
+        a, b = fn(lon, lat, alpha)
+        assert isinstance(a, np.ndarray) and a.shape == lon.shape
+        ra, rb = g[key + "_lon"], g[key + "_lat"]
+        assert np.abs(_unit(a, b) - _unit(ra, rb)).max() < 1e-13
+        okk = ok & (np.abs(rb) < 89.9)
+        assert np.abs(a - ra)[okk].max() < 1e-11 and np.abs(b - rb)[okk].max() < 1e-11
+        a2, b2 = fn(lon, lat, np.stack([alpha.real, alpha.imag]))  # leading axis of size 2
+        assert np.array_equal(a, a2) and np.array_equal(b, b2)
+    d = glass_b200.displacement(lon, lat, g["to_lon"], g["to_lat"])
+    assert d.dtype == np.complex128
+    assert np.abs(d - g["displacement"]).max() < 1e-12
+    # CUDA tensors in -> CUDA tensors out
+    tl, tb = glass_b200.displace(torch.as_tensor(lon).to(cuda_device), torch.as_tensor(lat).to(cuda_device), torch.as_tensor(alpha).to(cuda_device))
+    assert tl.is_cuda and np.array_equal(tl.cpu().numpy(), glass_b200.displace(lon, lat, alpha)[0])
+
+
+def test_displace_roundtrip_large(cuda_device):
+    """Size-independent property on 2e7 points: displacing by the displacement between two
+    positions lands on the second one."""
+    import glass_b200
+
+    n = 20_000_000
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(3)
+    lon = 360.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g)
+    lat = torch.rad2deg(torch.asin(2.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g) - 1.0))
+    lon2 = 360.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g)
+    lat2 = torch.rad2deg(torch.asin(2.0 * torch.rand(n, dtype=torch.float64, device=cuda_device, generator=g) - 1.0))
+    a = glass_b200.displacement(lon, lat, lon2, lat2)
+    lo, la = glass_b200.displace(lon, lat, a)
+
+    def unit(lo, la):
+        lo, la = torch.deg2rad(lo), torch.deg2rad(la)
+        return torch.stack([torch.cos(la) * torch.cos(lo), torch.cos(la) * torch.sin(lo), torch.sin(la)])
+
+    assert (unit(lo, la) - unit(lon2, lat2)).abs().max().item() < 1e-12
