@@ -8,7 +8,7 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells  # noqa: F401
+from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, user  # noqa: F401
 from .fields import (  # noqa: F401
     cls2cov,
     cltovar,
@@ -36,5 +36,6 @@ from .lensing import (  # noqa: F401
 from .points import displace, displacement, linear_bias, loglinear_bias, positions_from_delta, uniform_positions  # noqa: F401
 from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
 from .shells import RadialWindow  # noqa: F401
+from .user import load_cls, save_cls, write_catalog  # noqa: F401
 
 __version__ = "0.1.0"

@@ -412,3 +412,37 @@ def test_legendre_tables_host_build_and_run(tmp_path):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "tables ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_write_catalog_fits_roundtrip_host(tmp_path):
+    """glass.write_catalog mirror (glass/user.py:169-205) with host arrays: a conforming FITS
+    file (2880-byte blocks, primary HDU + one BINTABLE), rows in write order, NAXIS2 patched."""
+    import glass_b200
+    from glass_b200.user import read_catalog
+
+    rng = np.random.default_rng(4)
+    path = tmp_path / "cat.fits"
+    parts = []
+    with glass_b200.write_catalog(path, ext="CATALOG") as out:
+        for n in (5, 0, 1234, 77):
+            cols = {"RA": rng.uniform(0, 360, n), "DEC": rng.uniform(-90, 90, n), "Z": rng.random(n).astype(np.float32),
+                    "ID": rng.integers(0, 2**40, n), "G": rng.standard_normal(n) + 1j * rng.standard_normal(n)}
+            out.write(**cols)
+            parts.append(cols)
+    raw = path.read_bytes()
+    assert len(raw) % 2880 == 0 and raw[:30].startswith(b"SIMPLE  =                    T")
+    assert raw[2880:2880 + 20] == b"XTENSION= 'BINTABLE'"
+    cat = read_catalog(path)
+    assert cat["__extname__"] == "CATALOG"
+    for name in ("RA", "DEC", "Z", "ID", "G"):
+        want = np.concatenate([p[name] for p in parts])
+        assert cat[name].dtype == want.dtype and np.array_equal(cat[name], want)
+    # save_cls / load_cls (glass/user.py:41-86)
+    cls = [np.arange(5.0), np.zeros(0), np.arange(3.0) + 10]
+    glass_b200.save_cls(tmp_path / "cls.npz", cls)
+    back = glass_b200.load_cls(tmp_path / "cls.npz")
+    assert len(back) == 3 and all(np.array_equal(a, b) for a, b in zip(cls, back))
+    with pytest.raises(ValueError, match="columns differ"):
+        with glass_b200.write_catalog(tmp_path / "bad.fits") as out:
+            out.write(A=np.zeros(2))
+            out.write(B=np.zeros(2))
