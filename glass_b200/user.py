@@ -92,7 +92,7 @@ class _FitsWriter:
             return
         bufs, ev, n = slot
         ev.synchronize()
-        self._append_host({name: bufs[name][:n].numpy() for name in self.names})
+        self._append_host({name: buf[:n].numpy() for name, buf in bufs.items()})
         self._slots[k] = (bufs, ev, None)
 
     def _stage_cuda(self, columns: dict) -> None:
