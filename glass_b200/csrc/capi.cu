@@ -26,27 +26,6 @@ static int timing_collect(glb_plan* pl) {
   }
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   pl->ev_pool.clear();
-  // split calls (glb_alm2map_prepare / glb_alm2map_finish): pairs -> stage 0, triples -> stages 1, 2
-  for (size_t i = 0; i + 1 < pl->ev_pool_prep.size(); i += 2) {
-    GLB_CUDA_CHECK(cudaEventSynchronize(pl->ev_pool_prep[i + 1]));
-    float ms = 0.f;
-    GLB_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_pool_prep[i], pl->ev_pool_prep[i + 1]));
-    pl->stage_ms[0] += ms;
-    pl->stage_launches[0] += 1;
-  }
-  for (cudaEvent_t e : pl->ev_pool_prep) cudaEventDestroy(e);
-  pl->ev_pool_prep.clear();
-  for (size_t i = 0; i + 2 < pl->ev_pool_fin.size(); i += 3) {
-    GLB_CUDA_CHECK(cudaEventSynchronize(pl->ev_pool_fin[i + 2]));
-    for (int s = 0; s < 2; ++s) {
-      float ms = 0.f;
-      GLB_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_pool_fin[i + s], pl->ev_pool_fin[i + s + 1]));
-      pl->stage_ms[1 + s] += ms;
-      pl->stage_launches[1 + s] += 1;
-    }
-  }
-  for (cudaEvent_t e : pl->ev_pool_fin) cudaEventDestroy(e);
-  pl->ev_pool_fin.clear();
   return GLB_OK;
 }
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
@@ -159,70 +138,6 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
       if (plan->ev_pool.size() > 4096) timing_collect(plan);
     }
     done += g;
-  }
-  return GLB_OK;
-}
-
-// The two halves of glb_alm2map for one group of 1, 2 or 4 maps, so that a caller can run the
-// prep stage of the NEXT group on a second (high-priority) stream while the Legendre kernel of
-// the current group owns the FP64 pipe: prep is latency-bound (sequential in l per m) and its
-// CTAs fit next to a resident Legendre CTA.  `slot` selects one of two record buffers.
-int glb_alm2map_prepare(glb_plan* plan, const double* d_alm, int nmaps, int slot, void* stream) {
-  GLB_REQUIRE(plan && d_alm, "null pointer");
-  GLB_REQUIRE(nmaps == 1 || nmaps == 2 || nmaps == 4, "nmaps must be 1, 2 or 4");
-  GLB_REQUIRE(nmaps <= plan->max_batch, "nmaps exceeds max_batch");
-  GLB_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
-  cudaStream_t st = (cudaStream_t)stream;
-  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
-  if (slot == 1 && !plan->d_rec_alt) {
-    GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_rec_alt, (size_t)plan->rec_capacity * sizeof(double)));
-    plan->workspace_bytes += plan->rec_capacity * (int64_t)sizeof(double);
-  }
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  if (plan->timing) {
-    for (int i = 0; i < 2; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
-    GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
-  }
-  double* saved = plan->d_rec;
-  if (slot == 1) plan->d_rec = plan->d_rec_alt;
-  const int rc = sht_prep_group(plan, reinterpret_cast<const double2*>(d_alm), nmaps, st);
-  plan->d_rec = saved;
-  if (rc != GLB_OK) return rc;
-  if (plan->timing) {
-    GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
-    for (int i = 0; i < 2; ++i) plan->ev_pool_prep.push_back(ev[i]);
-  }
-  return GLB_OK;
-}
-
-int glb_alm2map_finish(glb_plan* plan, int nmaps, int slot, double* d_map, const int* h_transform,
-                       const double* h_tparams, void* stream) {
-  GLB_REQUIRE(plan && d_map, "null pointer");
-  GLB_REQUIRE(nmaps == 1 || nmaps == 2 || nmaps == 4, "nmaps must be 1, 2 or 4");
-  GLB_REQUIRE(nmaps <= plan->max_batch, "nmaps exceeds max_batch");
-  GLB_REQUIRE(slot == 0 || (slot == 1 && plan->d_rec_alt), "slot was not prepared");
-  cudaStream_t st = (cudaStream_t)stream;
-  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  if (plan->timing) {
-    for (int i = 0; i < 3; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
-    GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
-  }
-  double* saved = plan->d_rec;
-  if (slot == 1) plan->d_rec = plan->d_rec_alt;
-  int rc = sht_legendre_group(plan, nmaps, plan->d_phase, st);
-  plan->d_rec = saved;
-  if (rc != GLB_OK) return rc;
-  if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
-  double* outs[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int b = 0; b < nmaps; ++b) outs[b] = d_map + (int64_t)b * plan->npix;
-  rc = sht_phase2map_group(plan, plan->d_phase, nmaps, outs, h_transform, h_tparams, nullptr, st);
-  if (rc != GLB_OK) return rc;
-  if (plan->timing) {
-    GLB_CUDA_CHECK(cudaEventRecord(ev[2], st));
-    for (int i = 0; i < 3; ++i) plan->ev_pool_fin.push_back(ev[i]);
-    plan->stage_maps += nmaps;
-    if (plan->ev_pool_fin.size() > 3000) timing_collect(plan);
   }
   return GLB_OK;
 }

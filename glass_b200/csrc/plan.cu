@@ -340,7 +340,6 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_tw);
   cudaFree(pl->d_bf);
   cudaFree(pl->d_rec);
-  cudaFree(pl->d_rec_alt);
   cudaFree(pl->d_phase);
   cudaFree(pl->d_ch);
   cudaFree(pl->d_sh);
@@ -363,10 +362,6 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_stage_map);
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   pl->ev_pool.clear();
-  for (cudaEvent_t e : pl->ev_pool_prep) cudaEventDestroy(e);
-  pl->ev_pool_prep.clear();
-  for (cudaEvent_t e : pl->ev_pool_fin) cudaEventDestroy(e);
-  pl->ev_pool_fin.clear();
 }
 
 }  // namespace glb

@@ -99,15 +99,12 @@ struct glb_plan {
 
   // workspace
   double* d_rec = nullptr;           // Legendre records  [nrec * (4 + 4*B)]
-  double* d_rec_alt = nullptr;       // second record buffer (glb_alm2map_prepare slot 1), allocated on first use
   double2* d_phase = nullptr;        // [max_batch][nring][mmax+1]
   int64_t workspace_bytes = 0;
 
   // optional per-stage timing (CUDA events on the launch stream): prep, legendre, ringfft
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;     // recorded quadruples e0..e3 per group
-  std::vector<cudaEvent_t> ev_pool_prep;  // pairs around the prep stage of glb_alm2map_prepare
-  std::vector<cudaEvent_t> ev_pool_fin;   // triples around Legendre and ring FFT of glb_alm2map_finish
   double stage_ms[3] = {0.0, 0.0, 0.0};
   int64_t stage_launches[3] = {0, 0, 0};
   int64_t stage_maps = 0;               // maps transformed while timing was on

@@ -139,27 +139,6 @@ def alm2map_batch(alms: torch.Tensor, nside: int, lmax: int | None = None, trans
     return out
 
 
-def alm2map_prepare(pl: "Plan", alms: torch.Tensor, slot: int) -> None:
-    """First half of :func:`alm2map_batch` for a group of 1, 2 or 4 maps on the CURRENT stream:
-    a_lm -> Legendre records in record buffer ``slot`` (``glb_alm2map_prepare``)."""
-    with torch.cuda.device(alms.device):
-        st = torch.cuda.current_stream(alms.device).cuda_stream
-        _lib.check(pl.lib.glb_alm2map_prepare(pl.handle, alms.data_ptr(), alms.shape[0], int(slot), st), "glb_alm2map_prepare")
-
-
-def alm2map_finish(pl: "Plan", nmaps: int, slot: int, transforms=None, out=None, device=None) -> torch.Tensor:
-    """Second half: records of ``slot`` -> maps [nmaps, npix] on the CURRENT stream
-    (``glb_alm2map_finish``)."""
-    device = device if device is not None else torch.device("cuda", pl.device)
-    if out is None:
-        out = torch.empty((nmaps, pl.npix), dtype=torch.float64, device=device)
-    kinds, params, _keep = _transform_args(transforms)
-    with torch.cuda.device(device):
-        st = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(pl.lib.glb_alm2map_finish(pl.handle, int(nmaps), int(slot), out.data_ptr(), kinds, params, st), "glb_alm2map_finish")
-    return out
-
-
 def alm2map(
     alms,
     nside: int,

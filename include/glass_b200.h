@@ -71,14 +71,6 @@ int glb_plan_info(const glb_plan* plan, int* nside, int* lmax, int64_t* npix, in
 int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map,
                 const int* h_transform, const double* h_tparams, void* stream);
 
-/* glb_alm2map in two halves for one group of 1, 2 or 4 maps (same results, bit for bit):
- * prepare = a_lm -> Legendre records into record buffer `slot` (0 or 1); finish = records of
- * `slot` -> phases -> ring FFT (+ fused pixel transform) -> d_map [nmaps][npix].  Lets the caller
- * run `prepare` of the next group on a second stream while `finish` of the current one owns the
- * FP64 pipe (glass_b200/fields.py does; healpy.alm2map, glass/healpix.py:71). */
-int glb_alm2map_prepare(glb_plan* plan, const double* d_alm, int nmaps, int slot, void* stream);
-int glb_alm2map_finish(glb_plan* plan, int nmaps, int slot, double* d_map, const int* h_transform,
-                       const double* h_tparams, void* stream);
 /* healpy.alm2map_spin([alm1, alm2], nside, spin, lmax)   glass/healpix.py:107
  * (called from glass/lensing.py:343,366,428).  d_alm2 may be NULL (B-modes zero, which
  * is what GLASS always passes). */
