@@ -38,6 +38,7 @@ SIGNATURES = {
     "glb_alm2map": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_alm2map_spin": (_i, [_vp, _dp, _dp, _i, _dp, _dp, _vp]),
     "glb_map2alm": (_i, [_vp, _dp, _dp, _i, _dp, _vp]),
+    "glb_map2alm_batch": (_i, [_vp, _dp, _i, _dp, _i, _dp, _vp]),
     "glb_almxfl": (_i, [_i, _dp, _dp, _i, _vp]),
     "glb_alm_draw": (_i, [_i, C.c_uint64, C.c_uint32, _dp, _vp]),
     "glb_alm_glass_to_healpix": (_i, [_i, _dp, _dp, _vp]),

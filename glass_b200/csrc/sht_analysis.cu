@@ -408,14 +408,14 @@ int plan_ensure_analysis(glb_plan* pl) {
   }
   const size_t bytes = (size_t)pl->ana_ntile * pl->nrec * 4 * sizeof(double);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_partial, bytes));
-  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_tmpmap, (size_t)pl->npix * sizeof(double) * 2));
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_tmpmap, (size_t)pl->npix * sizeof(double) * (pl->max_batch + 1)));
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_ab_tab, (size_t)pl->nrec * 2 * sizeof(double2)));
   analysis_ab_gather_kernel<<<(unsigned)((pl->nrec + 255) / 256), 256>>>(pl->d_prep_tab, pl->nrec,
                                                                         reinterpret_cast<double2*>(pl->d_ab_tab));
   GLB_CUDA_CHECK(cudaGetLastError());
   GLB_CUDA_CHECK(cudaDeviceSynchronize());
   count_launch();
-  pl->workspace_bytes += (int64_t)bytes + pl->npix * 16;
+  pl->workspace_bytes += (int64_t)bytes + pl->npix * 8 * (pl->max_batch + 1);
   return GLB_OK;
 }
 

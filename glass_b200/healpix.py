@@ -302,20 +302,31 @@ def map2alm(maps, *, lmax: int | None = None, pol: bool = True, use_pixel_weight
     Jacobi refinements ``alm += A(map - S(alm))`` (healpy's default ``iter=3``).
     """
     single = not isinstance(maps, (list, tuple)) and getattr(maps, "ndim", 1) == 1
-    if not single:
-        if pol:
-            raise NotImplementedError("polarised (TQU) map2alm is outside the GLASS hot path; pass pol=False")
-        return [map2alm(m, lmax=lmax, pol=False, use_pixel_weights=use_pixel_weights, niter=niter, ring_weights=ring_weights) for m in maps]
-    dev, on_device = _dev_and_kind(maps)
-    m = _to(maps, dev, torch.float64)
-    nside = npix2nside(m.numel())
+    if not single and pol:
+        raise NotImplementedError("polarised (TQU) map2alm is outside the GLASS hot path; pass pol=False")
+    seq = [maps] if single else list(maps)
+    dev, on_device = _dev_and_kind(*seq)
+    ms = [_to(m, dev, torch.float64).reshape(-1) for m in seq]
+    nside = npix2nside(ms[0].numel())
+    if any(m.numel() != ms[0].numel() for m in ms):
+        raise ValueError("all maps must have the same size")
     lmax = 3 * nside - 1 if lmax is None else int(lmax)
-    pl = get_plan(nside, lmax, max_batch=1, device=dev)
-    alm = torch.empty(pl.nalm, dtype=torch.complex128, device=dev)
+    nmaps = len(ms)
+    pl = get_plan(nside, lmax, max_batch=4 if nmaps >= 4 else (2 if nmaps >= 2 else 1), device=dev)
+    alms = torch.empty((nmaps, pl.nalm), dtype=torch.complex128, device=dev)
     w = None if ring_weights is None else _to(ring_weights, dev, torch.float64)
     if w is not None and w.numel() != 4 * nside - 1:
         raise ValueError("ring_weights must have 4*nside-1 entries")
     with torch.cuda.device(dev):
-        rc = pl.lib.glb_map2alm(pl.handle, m.data_ptr(), None if w is None else w.data_ptr(), int(niter), alm.data_ptr(), pl.stream_ptr())
-    _lib.check(rc, "glb_map2alm")
-    return _out(alm, on_device)
+        done = 0
+        while done < nmaps:  # groups of 4, 2, 1: the refinement syntheses of a group share one recurrence
+            g = 4 if nmaps - done >= 4 else (2 if nmaps - done >= 2 else 1)
+            grp = ms[done] if g == 1 else torch.stack(ms[done : done + g])
+            grp = grp.contiguous()
+            rc = pl.lib.glb_map2alm_batch(pl.handle, grp.data_ptr(), g, None if w is None else w.data_ptr(), int(niter),
+                                          alms[done:].data_ptr(), pl.stream_ptr())
+            _lib.check(rc, "glb_map2alm_batch")
+            done += g
+    if single:
+        return _out(alms[0], on_device)
+    return [_out(alms[b], on_device) for b in range(nmaps)]

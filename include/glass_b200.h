@@ -82,6 +82,11 @@ int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2,
  * [4*nside-1] or NULL (uniform); niter Jacobi refinements (healpy default 3). */
 int glb_map2alm(glb_plan* plan, const double* d_map, const double* d_ring_weights, int niter,
                 double* d_alm, void* stream);
+/* The same for nb = 1, 2 or 4 maps at once (d_maps [nb][npix], d_alms [nb][nalm], nb <= the
+ * plan's max_batch): healpy.map2alm accepts a sequence of maps (pol=False).  The synthesis of
+ * every refinement runs as one batched transform. */
+int glb_map2alm_batch(glb_plan* plan, const double* d_maps, int nb, const double* d_ring_weights, int niter,
+                      double* d_alms, void* stream);
 
 /* healpy.almxfl(alm, fl)   glass/healpix.py:136 (called from glass/lensing.py:322,339,363,425)
  * in place; fl has nfl entries, treated as zero beyond. */

@@ -189,3 +189,31 @@ def test_gaussian_phz(cuda_device):
         glass_b200.gaussian_phz(z, 0.1, lower=1.0, upper=0.5)
     with pytest.raises(ValueError, match="lower and upper must best scalars"):
         glass_b200.gaussian_phz(z, 0.1, lower=torch.zeros(3, device=cuda_device), upper=torch.ones(3, device=cuda_device))
+
+
+def test_batched_map2alm_and_shear_match_single(cuda_device):
+    """healpy.map2alm accepts a sequence of maps; here up to four maps of a group share the
+    recurrence of every refinement synthesis.  Results against the one-map-at-a-time path
+    (1e-10: the batched synthesis kernel accumulates in the same order, its ring FFT too)."""
+    import glass_b200
+    from glass_b200 import healpix as hp
+
+    nside, lmax = 32, 64
+    rng = np.random.default_rng(12)
+    maps = 0.01 * rng.standard_normal((7, 12 * nside**2))
+    singles = [hp.map2alm(m, lmax=lmax, pol=False, niter=2) for m in maps]
+    batched = hp.map2alm(list(maps), lmax=lmax, pol=False, niter=2)  # groups of 4 + 2 + 1
+    assert len(batched) == 7
+    for a, b in zip(batched, singles):
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    ref = H.map2alm(maps[5], lmax=lmax, niter=2)
+    assert np.abs(batched[5] - ref).max() <= 1e-10 * np.abs(ref).max()
+    g1, g2 = glass_b200.shear_from_convergence(maps[:3], lmax, discretized=False, niter=1)
+    assert g1.shape == g2.shape == (3, 12 * nside**2)
+    for b in range(3):
+        s1, s2 = glass_b200.shear_from_convergence(maps[b], lmax, discretized=False, niter=1)
+        assert np.abs(g1[b] - s1).max() <= 1e-10 * np.abs(s1).max()
+        assert np.abs(g2[b] - s2).max() <= 1e-10 * np.abs(s2).max()
+    kd = torch.as_tensor(maps[:2]).to(cuda_device)
+    d1, d2 = glass_b200.shear_from_convergence(kd, lmax, discretized=False, niter=1)
+    assert d1.is_cuda and np.abs(d1.cpu().numpy() - g1[:2]).max() <= 1e-12 * np.abs(g1).max()

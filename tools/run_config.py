@@ -101,10 +101,12 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
 
-    def per_shell(i, delta, kappa):
+    def per_shell(i, delta, kappa, shear=None):
         nonlocal ngal_tot
         g1 = g2 = None
-        if lensing:
+        if lensing and shear is not None:
+            g1, g2 = shear
+        elif lensing:
             g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
         it = iter(()) if args.no_galaxies else glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
         while True:
@@ -134,8 +136,16 @@ def main():
         if lensing:
             conv._like = torch.empty(npix, dtype=torch.float64, device=dev)
             kappas = timed("multiplane", lambda: multi_plane_block(conv, deltas, [shells[i] for i in mine]))
+        shears = {}
+        if lensing:
+            # kappa -> shear for up to four planes of the block at once (batched refinement syntheses)
+            for a in range(0, len(mine), 4):
+                grp = kappas[a : a + 4]
+                g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(torch.stack(grp), lmax, discretized=False, niter=args.niter))
+                for b in range(len(grp)):
+                    shears[mine[a + b]] = (g1[b], g2[b])
         for i, delta, kappa in zip(mine, deltas, kappas):
-            per_shell(i, delta, kappa)
+            per_shell(i, delta, kappa, shears.get(i))
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     for name, a, b in pend:
