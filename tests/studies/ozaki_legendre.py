@@ -8,7 +8,7 @@ tcgen05.mma kind::i8 with int32 accumulators does) and the partial sums of the t
 FP64.  Reported: relative error of F against the FP64 contraction as a function of the number of
 slices d (all pairs i + j <= d + 1 are used: d (d + 1) / 2 integer products).
 
-    python tools/studies/ozaki_legendre.py [nside] [tile]
+    python tests/studies/ozaki_legendre.py [nside] [tile]
 
 This is design evidence for DESIGN.md section 7, not part of the product.
 """
