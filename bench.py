@@ -372,6 +372,27 @@ def run_b200(args) -> None:
     peak_tf, peak_ms = C.c_double(), C.c_double()
     _lib.check(lib.glb_measure_fp64_peak(local, C.byref(peak_tf), C.byref(peak_ms), None), "glb_measure_fp64_peak")
 
+    # second FP64 figure: cuBLAS DGEMM 8192^3 through torch.matmul, rank 0 only
+    dgemm_tf = None
+    if rank == 0:
+        try:
+            n_g = 8192
+            ga = torch.randn((n_g, n_g), dtype=torch.float64, device=dev)
+            gb = torch.randn((n_g, n_g), dtype=torch.float64, device=dev)
+            torch.matmul(ga, gb)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                torch.matmul(ga, gb)
+            g1.record()
+            torch.cuda.synchronize()
+            dgemm_tf = 3 * 2.0 * n_g**3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
+            del ga, gb
+            torch.cuda.empty_cache()
+        except Exception:  # a library figure for context only: never fail the bench on it
+            dgemm_tf = None
+
     # ---- device-resident arm: gls on the device -> maps stay in HBM ----
     gls_dev = [torch.as_tensor(g).to(dev) for g in gls]
     checksum = torch.zeros((), dtype=torch.float64, device=dev)
@@ -503,6 +524,7 @@ def run_b200(args) -> None:
             "tools/microbench/dmma_mix.cu), so neither 'hbm' nor 'tensor' applies",
             "peak_source": "measured live in this run: register-resident DFMA chains on all SMs "
             "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+            "peak_cublas_dgemm_8192": dgemm_tf,
             "algorithmic_flop_per_launch": alg_flop,
             "maps_per_launch": maps_per_launch,
             "ms_per_launch": leg_ms,
