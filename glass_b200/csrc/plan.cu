@@ -244,7 +244,7 @@ int plan_build(glb_plan* pl) {
   // ---- workspace ----
   const int gb = std::min(pl->max_batch, 4);
   const int gmax = gb >= 4 ? 4 : (gb >= 2 ? 2 : 1);
-  // records: scalar synthesis needs nrec*(2+4B) doubles, the spin transform (E and B) 6 per (l,m)
+  // records: scalar synthesis needs nrec*(4+4B) doubles, the spin transform (E and B) 12 per (l,m)
   pl->rec_capacity = std::max<int64_t>(pl->nrec * (4 + 4 * gmax), pl->nalm * 12);
   const size_t rec_bytes = (size_t)pl->rec_capacity * sizeof(double);
   const size_t phase_bytes = (size_t)std::max(gmax, 2) * pl->nring * (pl->mmax + 1) * sizeof(double2);

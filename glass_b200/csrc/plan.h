@@ -74,7 +74,7 @@ struct glb_plan {
   // analysis (map2alm): per-tile partial sums and a scratch map pair, built lazily
   double* d_partial = nullptr;       // [ana_ntile][nrec][4], one slab per warp tile
   double* d_tmpmap = nullptr;        // [max_batch + 1][npix]: synthesised maps of a Jacobi step, residual
-  double* d_ab_tab = nullptr;        // [nrec] {a_k, b_k} recurrence coefficients (TMA-streamed by the analysis kernel)
+  double* d_ab_tab = nullptr;        // [nrec][2] {a_k, b_k}, {-a_k, a_k+b_k} recurrence coefficients (TMA-streamed by the analysis kernel)
   int ana_ntile = 0;                 // warp tiles (ring-pair tiles x warps per CTA)
   int* d_ana_first_tile = nullptr;   // [mmax+1] first warp tile the analysis kernel writes for m
 

@@ -15,7 +15,7 @@
 //    with coefficients (Ae, Ao) obtained from a_lm by an O(lmax) pass per m
 //    (sht_prep_kernel).  North and south ring of a pair share everything but the sign.
 //  * one thread owns R adjacent ring pairs and walks l; a CTA owns (m, tile of ring
-//    pairs); the per-m record stream {a_k, b_k, Ae_k, Ao_k} is staged through shared
+//    pairs); the per-m record stream {a_k, b_k, -a_k, a_k+b_k, Ae_k, Ao_k} is staged through shared
 //    memory by the TMA engine (cp.async.bulk + mbarrier, multi-stage), every thread
 //    reads it with broadcast LDS.128.  The inner loop is pure DFMA: (2 + 4B) per ring
 //    pair per l-pair for B maps batched on one recurrence.
