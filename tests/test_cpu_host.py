@@ -446,3 +446,22 @@ def test_write_catalog_fits_roundtrip_host(tmp_path):
         with glass_b200.write_catalog(tmp_path / "bad.fits") as out:
             out.write(A=np.zeros(2))
             out.write(B=np.zeros(2))
+
+
+def test_legendre_recurrence_host_replay(tmp_path):
+    """Host replay of the synthesis kernel's recurrence arithmetic at nside 4096, lmax 8191
+    (double-double tables, per-ring recurrence variable, FMA chain) against 80-bit arithmetic on
+    exact ring geometry: 9e-12 of the function's maximum -- the figure measured on the GPU by
+    tests/test_gpu_fullsize.py -- and >= 10x worse for the two discarded formulations."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "legendre_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "native", "legendre_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "legendre recurrence ok" in r.stdout, r.stdout + r.stderr
