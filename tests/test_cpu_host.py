@@ -465,3 +465,20 @@ def test_legendre_recurrence_host_replay(tmp_path):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "legendre recurrence ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_spin_recurrence_host_replay(tmp_path):
+    """Host replay of the spin-2 synthesis kernel's recurrence arithmetic at nside 4096, lmax 8191
+    (per-ring variable x or t = 1 - x) against 80-bit arithmetic on exact ring geometry."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "spin_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "native", "spin_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "spin recurrence ok" in r.stdout, r.stdout + r.stderr
