@@ -15,8 +15,9 @@ scaling is weak.
 Printed JSON line (rank 0): value = device-resident throughput (maps stay in HBM),
 e2e = same through the public API with HOST buffers (NumPy gls in, NumPy maps out; the
 device->host copy of every map is inside the timed region), roofline = the Legendre
-kernel against the FP64 DFMA peak measured in this run, cpu_baseline = the oracle's C
-port of the path timed on the host cores (N=1 only).
+kernel against the FP64 DFMA peak measured in this run, cpu_baseline = the CPU arm (GLASS's
+NumPy steps + the SIMD/OpenMP synthesis of oracle/sht_fast.cpp standing in for healpy) timed on
+the host cores (N=1 only).
 """
 
 from __future__ import annotations
@@ -113,54 +114,75 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm (oracle port): the reference path for one lognormal shell on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> float:
-    """One shell of the reference path on the CPU: NumPy normals + banded combine +
-    l-major->m-major (glass/fields.py:404-425), C-oracle alm2map standing in for healpy
-    (glass/healpix.py:71), NumPy expm1 (grf/_transformations.py:83-89)."""
+def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> tuple[float, float]:
+    """One shell of the reference path on the CPU, as (seconds of the NumPy part, seconds of the
+    transform): NumPy normals + banded combine + l-major->m-major (glass/fields.py:404-425) and
+    NumPy expm1 (grf/_transformations.py:83-89) on one thread, exactly as GLASS runs them; the
+    SIMD/OpenMP synthesis of oracle/sht_fast.cpp standing in for healpy.alm2map
+    (glass/healpix.py:71) on ``nthreads`` threads."""
     from oracle import glass_ref as G
     from oracle import sht_c
 
     gls = synthetic_gls(NCORR + 1, lmax, NCORR)
     rng = np.random.default_rng(42)
     n = (lmax + 1) * (lmax + 2) // 2
-    zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR + 1)]
+    zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR)]
     t0 = time.perf_counter()
     # the (ncorr+1)-th shell has the full set of correlated terms, like every later shell
-    z_new = rng.standard_normal((n, 2)) @ np.array([1, 1j])
-    zs[-1] = z_new
-    alm = G.generate_alms(gls, NCORR, zs)[-1]
-    # only the last shell's combine+reorder is "this shell's" work; the loop above did
-    # NCORR+1 of them, so charge 1/(NCORR+1) of that part
+    zs.append(rng.standard_normal((n, 2)) @ np.array([1, 1j]))
     t1 = time.perf_counter()
-    m = sht_c.alm2map(alm, nside, lmax, use_mlim=True, nthreads=nthreads)
+    alm = G.generate_alms(gls, NCORR, zs)[-1]
+    # only the last shell's combine+reorder is "this shell's" work; generate_alms did
+    # NCORR+1 of them, so charge 1/(NCORR+1) of that part
+    t2 = time.perf_counter()
+    del zs
+    m = sht_c.alm2map_fast(alm, nside, lmax, nthreads=nthreads)
+    t3 = time.perf_counter()
     var = G.cltovar(gls[0])
     m = G.lognormal(m, var, 1.0)
-    t2 = time.perf_counter()
-    return (t1 - t0) / (NCORR + 1) + (t2 - t1)
+    t4 = time.perf_counter()
+    return (t1 - t0) + (t2 - t1) / (NCORR + 1) + (t4 - t3), t3 - t2
+
+
+def cpu_sample(budget_s: float, nthreads: int):
+    """(nside, numpy seconds, transform seconds) of the largest sample whose predicted time fits
+    ``budget_s``: the NumPy part scales with nside^2, the Legendre transform with nside^3."""
+    cpu_shell_seconds(256, 511, nthreads)  # thread pool start-up, first-touch of the libraries
+    p_np, p_sht = cpu_shell_seconds(512, 1023, nthreads)
+    ns = NSIDE
+    while ns > 512 and p_np * (ns / 512) ** 2 + p_sht * (ns / 512) ** 3 > budget_s:
+        ns //= 2
+    return ns, p_np, p_sht
+
+
+def cpu_extrapolate(ns: int, t_np: float, t_sht: float) -> tuple[float, str]:
+    """Seconds per shell at NSIDE from a sample at ``ns`` and the words that say how."""
+    if ns == NSIDE:
+        return t_np + t_sht, ""
+    r = NSIDE / ns
+    return t_np * r**2 + t_sht * r**3, f"; extrapolated to nside={NSIDE}: NumPy part x{r**2:.0f} (~nside^2), transform x{r**3:.0f} (~nside^3)"
+
+
+CPU_NOTE = (
+    "CPU restatement of the reference path (healpy/libsharp2 unavailable offline): GLASS's NumPy steps on one "
+    "thread as in the reference; alm2map = oracle/sht_fast.cpp (AVX-512 across rings, register-blocked "
+    "recurrence, mlim ring skipping, OpenMP over m)"
+)
 
 
 def cpu_baseline(budget_s: float = 25.0) -> dict:
     from oracle import sht_c
 
     cores = sht_c.max_threads()
-    # probe at nside=512 to choose the largest sample that fits the budget (cost ~ nside^3)
-    t512 = cpu_shell_seconds(512, 1023, cores)
-    ns = 4096
-    while ns > 512 and t512 * (ns / 512) ** 3 > budget_s:
-        ns //= 2
-    t = t512 if ns == 512 else cpu_shell_seconds(ns, 2 * ns - 1, cores)
-    scale = (NSIDE / ns) ** 3
-    sample = f"1 lognormal shell (alm draw+combine, alm2map, expm1) at nside={ns} lmax={2*ns-1}: {t:.2f} s on {cores} threads"
-    if ns != NSIDE:
-        sample += f"; extrapolated to nside={NSIDE} by (nside ratio)^3 = x{scale:.0f}"
-    return {
-        "value": 1.0 / (t * scale),
-        "unit": UNIT,
-        "cores": cores,
-        "kind": "port",
-        "sample": sample,
-        "note": "C/NumPy restatement of the reference path (healpy/libsharp2 unavailable offline); scalar double loops + OpenMP over m",
-    }
+    ns, t_np, t_sht = cpu_sample(budget_s, cores)
+    if ns != 512:
+        t_np, t_sht = cpu_shell_seconds(ns, 2 * ns - 1, cores)
+    t, how = cpu_extrapolate(ns, t_np, t_sht)
+    sample = (
+        f"1 lognormal shell (alm draw+combine, alm2map, expm1) at nside={ns} lmax={2*ns-1}: "
+        f"{t_np:.2f} s NumPy (1 thread) + {t_sht:.2f} s alm2map on {cores} threads" + how
+    )
+    return {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE}
 
 
 def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
@@ -258,22 +280,20 @@ def run_reference(args) -> None:
     from oracle import sht_c
 
     cores = sht_c.max_threads()
-    t512 = cpu_shell_seconds(512, 1023, cores)
-    ns = 4096
-    per_step_budget = 15.0
-    while ns > 512 and t512 * (ns / 512) ** 3 > per_step_budget:
-        ns //= 2
+    ns, _, _ = cpu_sample(20.0, cores)  # seconds of CPU work per step
     for _ in range(args.warmup):
         cpu_shell_seconds(ns, 2 * ns - 1, cores)
-    t0 = time.perf_counter()
+    t_np = t_sht = 0.0
     for _ in range(args.steps):
-        cpu_shell_seconds(ns, 2 * ns - 1, cores)
-    dt = (time.perf_counter() - t0) / args.steps
-    scale = (NSIDE / ns) ** 3
-    value = 1.0 / (dt * scale)
-    sample = f"each step = 1 lognormal shell at nside={ns} lmax={2*ns-1} ({dt:.2f} s on {cores} threads)"
-    if ns != NSIDE:
-        sample += f", extrapolated to nside={NSIDE} by x{scale:.0f} (cost ~ nside^3)"
+        a, b = cpu_shell_seconds(ns, 2 * ns - 1, cores)
+        t_np += a / args.steps
+        t_sht += b / args.steps
+    dt, how = cpu_extrapolate(ns, t_np, t_sht)
+    value = 1.0 / dt
+    sample = (
+        f"each step = 1 lognormal shell at nside={ns} lmax={2*ns-1} "
+        f"({t_np:.2f} s NumPy on 1 thread + {t_sht:.2f} s alm2map on {cores} threads)" + how
+    )
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -282,14 +302,14 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": dt * scale * 1e3,
+        "ms_per_step": dt * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"lognormal shells nside={NSIDE} lmax={LMAX} ncorr={NCORR} (CPU arm: oracle port on host cores)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

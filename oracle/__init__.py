@@ -25,4 +25,7 @@ Parity status (see DESIGN.md "Oracle"):
   pixel centres).  The reference's own tests for these functions are purely
   differential against the live library (``tests/core/test_healpix.py``), hold
   no stored vectors, so for these functions: **parity unpinned**.
+* ``oracle/sht_fast.cpp`` is not a checker but the TIMED CPU arm of ``bench.py`` (a SIMD /
+  OpenMP synthesis with the structure of libsharp, so that the CPU baseline is a fair one); it
+  is itself pinned against ``sht_ref.c`` in ``tests/test_cpu_oracle.py``.
 """

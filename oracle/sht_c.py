@@ -1,4 +1,5 @@
-"""ctypes wrapper of the C oracle (oracle/sht_ref.c).  TEST INFRASTRUCTURE ONLY."""
+"""ctypes wrapper of the C oracle (oracle/sht_ref.c, the checker) and of the timed CPU arm
+(oracle/sht_fast.cpp).  TEST INFRASTRUCTURE ONLY."""
 
 from __future__ import annotations
 
@@ -29,10 +30,10 @@ def _lib(long_double: bool) -> C.CDLL:
         stamp = _HERE / "_build" / "host.txt"
         host = os.uname().nodename + ":" + str(os.cpu_count())
         # -march=native objects must be rebuilt when the snapshot lands on another host
-        if not path.exists() or not stamp.exists() or stamp.read_text() != host:
+        if not stamp.exists() or stamp.read_text() != host:
             subprocess.run(["make", "-C", os.fspath(_HERE), "clean"], capture_output=True)
-            build()
-            stamp.write_text(host)
+        build()  # make: a no-op when the libraries are newer than their sources
+        stamp.write_text(host)
         lib = C.CDLL(os.fspath(path))
         for fn in (lib.ref_alm2map, lib.ref_alm2phase):
             fn.restype = C.c_int
@@ -40,6 +41,36 @@ def _lib(long_double: bool) -> C.CDLL:
         lib.ref_max_threads.restype = C.c_int
         _LIBS[long_double] = lib
     return _LIBS[long_double]
+
+
+_FAST: list = []
+
+
+def _fast() -> C.CDLL:
+    if not _FAST:
+        _lib(False)  # (re)builds everything for this host
+        lib = C.CDLL(os.fspath(_HERE / "_build" / "liboracle_sht_fast.so"))
+        lib.fast_alm2map.restype = C.c_int
+        lib.fast_alm2map.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.fast_alm2map_timed.restype = C.c_int
+        lib.fast_alm2map_timed.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _FAST.append(lib)
+    return _FAST[0]
+
+
+def alm2map_fast(alm, nside: int, lmax: int, *, nthreads: int = 0, timings: dict | None = None):
+    """The timed CPU arm: same result as ``alm2map(..., use_mlim=True)`` from the SIMD / register
+    blocked implementation in sht_fast.cpp.  ``timings`` receives the seconds of the two stages."""
+    alm = np.ascontiguousarray(alm, dtype=np.complex128)
+    assert alm.size == (lmax + 1) * (lmax + 2) // 2
+    out = np.empty(12 * nside * nside)
+    tl, tf = C.c_double(0), C.c_double(0)
+    rc = _fast().fast_alm2map_timed(nside, lmax, alm.ctypes.data, out.ctypes.data, nthreads, C.byref(tl), C.byref(tf))
+    if rc != 0:
+        raise MemoryError("fast_alm2map") if rc == -1 else ValueError("fast_alm2map: nside must be a power of two >= 2")
+    if timings is not None:
+        timings["legendre_s"], timings["fft_s"] = tl.value, tf.value
+    return out
 
 
 def max_threads() -> int:

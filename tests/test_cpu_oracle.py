@@ -211,6 +211,25 @@ def test_c_oracle_matches_numpy_oracle():
     assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()
 
 
+def test_timed_cpu_arm_matches_checker():
+    """oracle/sht_fast.cpp (the SIMD/OpenMP synthesis that bench.py times as the CPU arm) against
+    the scalar C oracle and the 80-bit one, incl. high-m rings that start scaled down, a band
+    limit above 2 nside and the smallest supported nside."""
+    from oracle import sht_c
+
+    for nside, lmax in [(2, 5), (4, 11), (16, 47), (64, 191), (128, 255), (256, 700)]:
+        alm = _alm(lmax, nside)
+        ref = sht_c.alm2map(alm, nside, lmax, use_mlim=True)
+        tm = {}
+        got = sht_c.alm2map_fast(alm, nside, lmax, nthreads=2, timings=tm)
+        assert np.abs(got - ref).max() < 2e-12 * np.abs(ref).max(), (nside, lmax)
+        assert tm["legendre_s"] >= 0 and tm["fft_s"] >= 0
+    truth = sht_c.alm2map(alm, 256, 700, use_mlim=True, long_double=True)
+    assert np.abs(got - truth).max() < 1e-11 * np.abs(truth).max()
+    with pytest.raises(ValueError):
+        sht_c.alm2map_fast(_alm(5, 0), 3, 5)
+
+
 def test_golden_uniform_positions():
     """uniform_positions (glass/points.py:543-607) executed from the reference source; the
     oracle replays it bit-exactly from the same Poisson totals and uniform deviates."""
