@@ -10,18 +10,25 @@ missing.
 
 from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, user  # noqa: F401
 from .fields import (  # noqa: F401
+    check_posdef_spectra,
     cls2cov,
     cltovar,
+    cov_from_spectra,
     discretized_cls,
     effective_cls,
+    enumerate_spectra,
     gaussian_fields,
     generate,
     generate_gaussian,
     generate_lognormal,
     getcl,
+    glass_to_healpix_spectra,
+    healpix_to_glass_spectra,
     iternorm,
     lognormal_fields,
+    lognormal_shift_hilbert2011,
     nfields_from_nspectra,
+    spectra_indices,
 )
 from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_nz  # noqa: F401
 from .harmonics import multalm  # noqa: F401
@@ -33,7 +40,15 @@ from .lensing import (  # noqa: F401
     multi_plane_weights,
     shear_from_convergence,
 )
-from .points import displace, displacement, linear_bias, loglinear_bias, positions_from_delta, uniform_positions  # noqa: F401
+from .points import (  # noqa: F401
+    displace,
+    displacement,
+    linear_bias,
+    loglinear_bias,
+    position_weights,
+    positions_from_delta,
+    uniform_positions,
+)
 from .shapes import ellipticity_gaussian, ellipticity_intnorm  # noqa: F401
 from .shells import RadialWindow  # noqa: F401
 from .user import load_cls, save_cls, write_catalog  # noqa: F401

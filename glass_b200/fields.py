@@ -209,6 +209,65 @@ def getcl(cls, i: int, j: int, lmax: int | None = None):
     return cl
 
 
+def enumerate_spectra(entries):
+    """Iterate over two-point functions in standard ("Christmas tree") order, yielding
+    ``(i, j, entry)`` (glass/fields.py:563-581)."""
+    for k, cl in enumerate(entries):
+        i = int((2 * k + 0.25) ** 0.5 - 0.5)
+        j = i * (i + 3) // 2 - k
+        yield i, j, cl
+
+
+def spectra_indices(n: int, *, xp=None) -> np.ndarray:
+    """Index pairs ``(i, j)`` in standard order for ``n`` fields, one per row
+    (glass/fields.py:584-604)."""
+    i, j = np.tril_indices(n)
+    out = np.stack([i, i - j]).T
+    return torch.as_tensor(out) if xp is torch else out
+
+
+def glass_to_healpix_spectra(spectra):
+    """Reorder spectra from GLASS order to (new) HEALPix order: all auto-spectra, then all
+    first off-diagonals, ... (glass/fields.py:897-917)."""
+    n = nfields_from_nspectra(len(spectra))
+    comb = {(int(i), int(j)): pos for pos, (i, j) in enumerate(spectra_indices(n))}
+    return [spectra[comb[(i + k, i)]] for k in range(n) for i in range(n - k)]
+
+
+def healpix_to_glass_spectra(spectra):
+    """Reorder spectra from (new) HEALPix order to GLASS order (glass/fields.py:920-940)."""
+    n = nfields_from_nspectra(len(spectra))
+    comb = {(i + k, i): pos for pos, (k, i) in enumerate((k, i) for k in range(n) for i in range(n - k))}
+    return [spectra[comb[(int(i), int(j))]] for i, j in spectra_indices(n)]
+
+
+def lognormal_shift_hilbert2011(z: float) -> float:
+    """Lognormal shift of Hilbert et al. (2011) for convergence fields (glass/fields.py:965-982)."""
+    return z * (8e-3 + z * (2.9e-2 + z * (-7.9e-3 + z * 6.5e-4)))
+
+
+def cov_from_spectra(spectra, *, lmax: int | None = None) -> np.ndarray:
+    """Covariance matrices ``cov[l, i, j]`` from spectra in standard order; ragged or empty
+    spectra leave zeros (glass/fields.py:985-1032).  Host-side: (lmax+1) x n x n doubles."""
+    n = nfields_from_nspectra(len(spectra))
+    spectra = _gls_to_host(spectra)
+    k = max((cl.shape[0] for cl in spectra), default=0) if lmax is None else lmax + 1
+    cov = np.zeros((k, n, n), dtype=spectra[0].dtype if spectra else np.float64)
+    for i, j, cl in enumerate_spectra(spectra):
+        size = min(k, cl.shape[0])
+        flat = np.reshape(cl, (-1,))
+        cov[:size, i, j] = flat[:size]
+        cov[:size, j, i] = flat[:size]
+    return cov
+
+
+def check_posdef_spectra(spectra) -> bool:
+    """Whether the spectra form positive semi-definite matrices at every l
+    (glass/fields.py:1035-1052)."""
+    cov = cov_from_spectra(spectra)
+    return bool(np.all(np.linalg.eigvalsh(cov) >= 0))
+
+
 def cltovar(cl) -> float:
     """transformcl.cltovar as used at glass/fields.py:890: sum_l (2l+1)/(4 pi) C_l."""
     cl = _np(cl)

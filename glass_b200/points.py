@@ -42,6 +42,26 @@ def loglinear_bias(delta, b):
     return np.expm1(delta_g)
 
 
+def position_weights(densities, bias=None):
+    """Relative weight of each shell for angular clustering: densities normalised over the first
+    (shell) axis, times an optional linear bias per shell (glass/points.py:610-651).  A handful
+    of numbers per shell: host arithmetic on NumPy arrays, torch arithmetic on tensors."""
+    is_t = isinstance(densities, torch.Tensor) or isinstance(bias, torch.Tensor)
+    xp_asarray = (lambda a: torch.as_tensor(a, dtype=torch.float64)) if is_t else (lambda a: np.asarray(a, dtype=np.float64))
+    densities = xp_asarray(densities)
+    if bias is not None:
+        bias = xp_asarray(bias)
+        # broadcast_first (glass/arraytools.py:24-44): the first axis is common, the others broadcast
+        mv = torch.movedim if is_t else np.moveaxis
+        bc = torch.broadcast_tensors if is_t else np.broadcast_arrays
+        moved = [mv(a, 0, -1) if a.ndim else a for a in (densities, bias)]
+        densities, bias = (mv(a, -1, 0) if a.ndim else a for a in bc(*moved))
+    densities = densities / densities.sum(0)
+    if bias is not None:
+        densities = densities * bias
+    return densities
+
+
 _BIAS_NONE, _BIAS_LINEAR, _BIAS_LOGLINEAR = 0, 1, 2
 
 

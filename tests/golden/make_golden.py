@@ -339,8 +339,52 @@ def main_displace():
     print("wrote", len(out), "arrays to glass_reference_displace.npz")
 
 
+def main_spectra():
+    """Third file: the spectra-order helpers of glass/fields.py:563-604, 897-1052 and
+    position_weights of glass/points.py:610-651."""
+    install_shims()
+    sys.path.insert(0, REF)
+    import glass  # the reference itself
+    import glass.fields
+    import glass.points
+
+    # array_api_extra.tril_indices is reached through glass._array_api_utils.XPAdditions
+    out = {}
+    for n in (1, 2, 3, 5):
+        out[f"indices_{n}"] = np.asarray(glass.fields.spectra_indices(n, xp=np))
+    labels = np.arange(15)  # 5 fields, entries are their own positions
+    out["enum_15"] = np.array([(i, j, int(c)) for i, j, c in glass.fields.enumerate_spectra(list(labels))])
+    out["g2h_15"] = np.array(glass.fields.glass_to_healpix_spectra(list(labels)))
+    out["h2g_15"] = np.array(glass.fields.healpix_to_glass_spectra(list(labels)))
+    zz = np.linspace(0.0, 3.0, 13)
+    out["hilbert_z"] = zz
+    out["hilbert_shift"] = np.array([glass.fields.lognormal_shift_hilbert2011(float(z)) for z in zz])
+    gls = synthetic_gls(4, 12, 2, ragged=True)
+    out["cov_gls_len"] = np.array([g.shape[0] for g in gls])
+    out["cov_gls"] = np.concatenate(gls)
+    out["cov_full"] = glass.fields.cov_from_spectra(gls)
+    out["cov_lmax5"] = glass.fields.cov_from_spectra(gls, lmax=5)
+    out["cov_lmax20"] = glass.fields.cov_from_spectra(gls, lmax=20)
+    out["posdef_good"] = np.asarray(bool(glass.fields.check_posdef_spectra(gls)))
+    bad = [np.array([1.0, 1.0]), np.array([1.0, 1.0]), np.array([0.5, 1.5])]  # |rho| > 1 at l = 1
+    out["posdef_bad"] = np.asarray(bool(glass.fields.check_posdef_spectra(bad)))
+    r = np.random.default_rng(8)
+    d1, b1 = r.random(5), r.random(5)
+    d2, b2 = r.random((5, 3, 2)), r.random((5, 2))
+    out["pw_d1"], out["pw_b1"], out["pw_d2"], out["pw_b2"] = d1, b1, d2, b2
+    out["pw_1"] = glass.points.position_weights(d1)
+    out["pw_1b"] = glass.points.position_weights(d1, b1)
+    out["pw_1f"] = glass.points.position_weights(d1, 1.7)
+    out["pw_2b"] = glass.points.position_weights(d2, b2)
+    out["pw_2b1"] = glass.points.position_weights(d2, b1)
+    np.savez_compressed(os.path.join(HERE, "glass_reference_spectra.npz"), **out)
+    print("wrote", len(out), "arrays to glass_reference_spectra.npz")
+
+
 if __name__ == "__main__":
-    if "--displace" in sys.argv:
+    if "--spectra" in sys.argv:
+        main_spectra()
+    elif "--displace" in sys.argv:
         main_displace()
     else:
         main()

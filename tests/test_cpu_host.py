@@ -244,6 +244,41 @@ def test_discretized_and_effective_cls_golden():
         glass_b200.effective_cls(gls, np.ones((3, 2)))
 
 
+def test_spectra_helpers_and_position_weights_golden():
+    """Spectra-order helpers (glass/fields.py:563-604, 897-1052) and position_weights
+    (glass/points.py:610-651) against vectors from executing the reference's source
+    (tests/golden/make_golden.py --spectra): bit-identical."""
+    import glass_b200 as glass
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_spectra.npz"))
+    for n in (1, 2, 3, 5):
+        assert np.array_equal(glass.spectra_indices(n), g[f"indices_{n}"])
+    labels = list(np.arange(15))
+    assert np.array_equal(np.array([(i, j, int(c)) for i, j, c in glass.enumerate_spectra(labels)]), g["enum_15"])
+    assert np.array_equal(np.array(glass.glass_to_healpix_spectra(labels)), g["g2h_15"])
+    assert np.array_equal(np.array(glass.healpix_to_glass_spectra(labels)), g["h2g_15"])
+    assert glass.healpix_to_glass_spectra(glass.glass_to_healpix_spectra(labels)) == labels
+    with pytest.raises(ValueError, match="invalid number of spectra: 4"):
+        glass.glass_to_healpix_spectra(labels[:4])
+    assert np.array_equal(np.array([glass.lognormal_shift_hilbert2011(float(z)) for z in g["hilbert_z"]]), g["hilbert_shift"])
+    gls = np.split(g["cov_gls"], np.cumsum(g["cov_gls_len"])[:-1])
+    assert np.array_equal(glass.cov_from_spectra(gls), g["cov_full"])
+    assert np.array_equal(glass.cov_from_spectra(gls, lmax=5), g["cov_lmax5"])
+    assert np.array_equal(glass.cov_from_spectra(gls, lmax=20), g["cov_lmax20"])
+    assert glass.check_posdef_spectra(gls) == bool(g["posdef_good"]) is True
+    bad = [np.array([1.0, 1.0]), np.array([1.0, 1.0]), np.array([0.5, 1.5])]
+    assert glass.check_posdef_spectra(bad) == bool(g["posdef_bad"]) is False
+    assert np.array_equal(glass.position_weights(g["pw_d1"]), g["pw_1"])
+    assert np.array_equal(glass.position_weights(g["pw_d1"], g["pw_b1"]), g["pw_1b"])
+    assert np.array_equal(glass.position_weights(g["pw_d1"], 1.7), g["pw_1f"])
+    assert np.array_equal(glass.position_weights(g["pw_d2"], g["pw_b2"]), g["pw_2b"])
+    assert np.array_equal(glass.position_weights(g["pw_d2"], g["pw_b1"]), g["pw_2b1"])
+    import torch
+
+    t = glass.position_weights(torch.as_tensor(g["pw_d2"]), torch.as_tensor(g["pw_b2"]))
+    assert np.allclose(t.numpy(), g["pw_2b"], rtol=1e-14, atol=0)  # torch sums in another order
+
+
 def test_fft_core_host_build_and_run(tmp_path):
     """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
     per-thread functions: compile them for the host and check every pass, thread by thread,
