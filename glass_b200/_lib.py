@@ -62,6 +62,10 @@ SIGNATURES = {
     "glb_dist_setup": (_i, [_vp, _i, _i, _ip, _ip, _i]),
     "glb_dist_alm2phase": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_dist_phase2map": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
+    "glb_dist_p2p_alloc": (_i, [_vp, _i, _vp]),
+    "glb_dist_p2p_open": (_i, [_vp, _vp, _ip]),
+    "glb_dist_alm2phase_p2p": (_i, [_vp, _dp, _i, _i, _vp]),
+    "glb_dist_p2p_recv": (_i, [_vp, _i, C.POINTER(_vp)]),
     "glb_plan_timing_enable": (_i, [_vp, _i]),
     "glb_plan_timing_read": (_i, [_vp, _dp, _vp, _vp]),
     "glb_kernel_launch_count": (C.c_uint64, []),

@@ -1,4 +1,6 @@
 // capi.cu -- extern "C" entry points declared in include/glass_b200.h.
+#include <algorithm>
+#include <cstring>
 #include <new>
 
 #include "plan.h"
@@ -9,7 +11,7 @@ int plan_build(glb_plan* pl);
 void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
-int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false);
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false, int p2p_buffer = -1);
 unsigned long long launch_count();
 int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
 
@@ -265,6 +267,94 @@ int glb_dist_phase2map(glb_plan* plan, const double* d_recv, int nmaps, double* 
   for (int b = 0; b < nmaps; ++b) outs[b] = d_map + (int64_t)b * plan->npix;
   return sht_phase2map_group(plan, reinterpret_cast<const double2*>(d_recv), nmaps, outs, h_transform, h_tparams,
                              nullptr, (cudaStream_t)stream, true);
+}
+
+// ---- fused Legendre + transpose over peer memory ---------------------------------------------
+// bytes of ONE receive buffer of a rank owning `rows` rings, rounded so that the second buffer
+// of the block stays 256-byte aligned
+static size_t p2p_buffer_bytes(const glb_plan* plan, int nmaps_max, int rows) {
+  const size_t b = (size_t)nmaps_max * plan->dist_world * std::max(rows, 1) * plan->dist_W * sizeof(double2);
+  return (b + 255) / 256 * 256;
+}
+
+int glb_dist_p2p_alloc(glb_plan* plan, int nmaps_max, void* h_handle) {
+  GLB_REQUIRE(plan && h_handle, "null pointer");
+  GLB_REQUIRE(plan->dist_W > 0, "glb_dist_setup has not been called");
+  GLB_REQUIRE(nmaps_max >= 1 && nmaps_max <= 4, "nmaps_max must be in [1, 4]");
+  GLB_REQUIRE(plan->dist_world <= glb::P2P_MAX_WORLD, "peer stores support at most 8 ranks");
+  GLB_REQUIRE(plan->p2p_nb == 0, "receive buffers already allocated");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const size_t bytes = p2p_buffer_bytes(plan, nmaps_max, plan->dist_rows_local);
+  // ONE plain cudaMalloc block for both buffers (CUDA IPC cannot export memory of a stream-ordered
+  // pool; one allocation = one handle for the peers to open).  Zeroed once: entries no rank ever
+  // writes (rings beyond mlim) stay zero, the others are rewritten by every transform.
+  char* block = nullptr;
+  GLB_CUDA_CHECK(cudaMalloc((void**)&block, glb::P2P_NBUF * bytes));
+  GLB_CUDA_CHECK(cudaMemset(block, 0, glb::P2P_NBUF * bytes));
+  for (int i = 0; i < glb::P2P_NBUF; ++i) plan->d_p2p_recv[i] = reinterpret_cast<double2*>(block + i * bytes);
+  cudaIpcMemHandle_t h;
+  GLB_CUDA_CHECK(cudaIpcGetMemHandle(&h, block));
+  memcpy(h_handle, &h, 64);
+  GLB_CUDA_CHECK(cudaDeviceSynchronize());
+  plan->p2p_nb = nmaps_max;
+  return GLB_OK;
+}
+
+int glb_dist_p2p_open(glb_plan* plan, const void* h_all_handles, const int* h_rows) {
+  GLB_REQUIRE(plan && h_all_handles && h_rows, "null pointer");
+  GLB_REQUIRE(plan->p2p_nb > 0, "glb_dist_p2p_alloc has not been called");
+  GLB_REQUIRE(plan->d_p2p_tab == nullptr, "peer buffers already opened");
+  GLB_REQUIRE(h_rows[plan->dist_rank] == plan->dist_rows_local, "h_rows disagrees with glb_dist_setup");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const int world = plan->dist_world;
+  glb::LegP2P tab[glb::P2P_NBUF];
+  memset(tab, 0, sizeof(tab));
+  for (int i = 0; i < glb::P2P_NBUF; ++i) {
+    tab[i].rank = plan->dist_rank;
+    tab[i].world = world;
+    for (int d = 0; d < world; ++d) tab[i].rowstart[d + 1] = tab[i].rowstart[d] + h_rows[d];
+    for (int d = world; d < glb::P2P_MAX_WORLD; ++d) tab[i].rowstart[d + 1] = tab[i].rowstart[world];
+    GLB_REQUIRE(tab[i].rowstart[world] == plan->nring, "h_rows does not add up to the number of rings");
+  }
+  for (int d = 0; d < world; ++d) {
+    char* block = reinterpret_cast<char*>(plan->d_p2p_recv[0]);
+    if (d != plan->dist_rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(h_all_handles) + 64 * (size_t)d, 64);
+      void* ptr = nullptr;
+      GLB_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      plan->p2p_peer[d] = ptr;
+      block = static_cast<char*>(ptr);
+    }
+    // every rank allocated with the same nmaps_max, so the peer's buffer size follows from its rows
+    const size_t bytes_d = p2p_buffer_bytes(plan, plan->p2p_nb, h_rows[d]);
+    for (int i = 0; i < glb::P2P_NBUF; ++i) tab[i].base[d] = reinterpret_cast<double2*>(block + i * bytes_d);
+  }
+  GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_p2p_tab, sizeof(tab)));
+  GLB_CUDA_CHECK(cudaMemcpy(plan->d_p2p_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+  return GLB_OK;
+}
+
+int glb_dist_alm2phase_p2p(glb_plan* plan, const double* d_alm, int nmaps, int buffer, void* stream) {
+  GLB_REQUIRE(plan && d_alm, "null pointer");
+  GLB_REQUIRE(nmaps == 1 || nmaps == 2 || nmaps == 4, "nmaps must be 1, 2 or 4");
+  GLB_REQUIRE(nmaps <= plan->max_batch && nmaps <= plan->p2p_nb, "nmaps exceeds max_batch or the receive buffers");
+  GLB_REQUIRE(plan->d_p2p_tab != nullptr, "glb_dist_p2p_open has not been called");
+  GLB_REQUIRE(buffer >= 0 && buffer < glb::P2P_NBUF, "buffer must be 0 or 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  int rc = sht_prep_group(plan, reinterpret_cast<const double2*>(d_alm), nmaps, st);
+  if (rc != GLB_OK) return rc;
+  return sht_legendre_group(plan, nmaps, nullptr, st, true, buffer);
+}
+
+int glb_dist_p2p_recv(glb_plan* plan, int buffer, double** d_recv) {
+  GLB_REQUIRE(plan && d_recv, "null pointer");
+  GLB_REQUIRE(plan->p2p_nb > 0, "glb_dist_p2p_alloc has not been called");
+  GLB_REQUIRE(buffer >= 0 && buffer < glb::P2P_NBUF, "buffer must be 0 or 1");
+  *d_recv = reinterpret_cast<double*>(plan->d_p2p_recv[buffer]);
+  return GLB_OK;
 }
 
 int glb_plan_timing_enable(glb_plan* plan, int enable) {

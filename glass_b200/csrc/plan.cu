@@ -352,6 +352,11 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_dist_rowmap);
   cudaFree(pl->d_dist_rowidx);
   for (int c = 0; c < 3; ++c) cudaFree(pl->d_dist_ring_order[c]);
+  // peer mappings first (the owners free the memory itself), then this rank's receive buffers
+  for (int d = 0; d < P2P_MAX_WORLD; ++d)
+    if (pl->p2p_peer[d]) cudaIpcCloseMemHandle(pl->p2p_peer[d]);
+  cudaFree(pl->d_p2p_recv[0]);  // one block holds both buffers
+  cudaFree(pl->d_p2p_tab);
   cudaFree(pl->d_partial);
   cudaFree(pl->d_ana_first_tile);
   cudaFree(pl->d_tmpmap);

@@ -26,6 +26,17 @@ struct RingDesc {
   int64_t bf_off;  // offset (in double2) of the chirp spectrum in d_bf, -1 if direct
 };
 
+// m-split with peer stores: where the Legendre kernel of rank `rank` puts F_m(ring) -- straight
+// into the receive buffer [map][src rank][local row][W] of the rank that owns the ring, through
+// peer mappings of those buffers (NVLink).  One table per receive buffer, in device memory.
+constexpr int P2P_MAX_WORLD = 8;
+constexpr int P2P_NBUF = 2;
+struct LegP2P {
+  double2* base[P2P_MAX_WORLD];       // receive buffer of every rank as mapped into THIS process
+  int rowstart[P2P_MAX_WORLD + 1];    // first row (permuted send order) owned by each rank
+  int rank, world;
+};
+
 }  // namespace glb
 
 struct glb_plan {
@@ -87,6 +98,12 @@ struct glb_plan {
   int* d_dist_rowidx = nullptr;      // [nring] local row of each owned ring (-1 otherwise)
   int* d_dist_ring_order[3] = {nullptr, nullptr, nullptr};
   int n_dist_ring_class[3] = {0, 0, 0};
+  // fused Legendre + transpose (glb_dist_p2p_*): receive buffers allocated here with cudaMalloc
+  // (CUDA IPC needs that), the peers' buffers opened through their IPC handles
+  int p2p_nb = 0;                                                // maps a receive buffer holds
+  double2* d_p2p_recv[glb::P2P_NBUF] = {nullptr, nullptr};       // [p2p_nb][world][rows_local][W], halves of ONE cudaMalloc block
+  void* p2p_peer[glb::P2P_MAX_WORLD] = {};                       // the peers' blocks as opened here (null: own rank)
+  glb::LegP2P* d_p2p_tab = nullptr;                              // [P2P_NBUF]
 
   // ring FFT
   glb::RingDesc* d_rings = nullptr;  // [nring]

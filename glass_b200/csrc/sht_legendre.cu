@@ -208,9 +208,14 @@ struct LegParams {
   // phase layout: row(ring) * W + m / G.  Single GPU: G = 1, W = mmax+1, rowmap = null (identity).
   int G, W;
   const int* rowmap;
+  // P2P instantiation only (appended, so the layout seen by the other instantiations is unchanged)
+  const LegP2P* p2p;
 };
 
-template <int R, int B, int THREADS>
+// P2P = true: m-split over GPUs with the transpose fused into the store -- every F_m(ring) goes
+// straight to the receive buffer of the rank that owns the ring (peer-mapped over NVLink) instead
+// of a local send buffer that an all-to-all moves afterwards.
+template <int R, int B, int THREADS, bool P2P = false>
 __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegParams p) {
   constexpr int REC = 4 + 4 * B;
   constexpr int CHUNK_DOUBLES = LEG_KT * REC;
@@ -426,22 +431,50 @@ __global__ void __launch_bounds__(THREADS) sht_legendre_synth_kernel(const LegPa
   }
 
   // ---- write F_m for the north and south ring of every live pair ----
+  if constexpr (P2P) {
+    const LegP2P* __restrict__ t = p.p2p;
+    const int world = __ldg(&t->world), me = __ldg(&t->rank);
+    const int slot = m / p.G;
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    if (!live[j]) continue;
-    const int r = pair0 + j;
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      const double er = acc[j][b][0], ei = acc[j][b][1];
-      const double orr = acc[j][b][2] * zz[j], oi = acc[j][b][3] * zz[j];
-      double2* ph = p.phase + b * p.phase_map_stride;
-      const int slot = m / p.G;
+    for (int j = 0; j < R; ++j) {
+      if (!live[j]) continue;
+      const int r = pair0 + j;
       const int rs = p.nring - 1 - r;
-      const int row_n = p.rowmap ? p.rowmap[r] : r;
-      ph[(int64_t)row_n * p.W + slot] = make_double2(er + orr, ei + oi);
-      if (r != p.npair - 1) {
-        const int row_s = p.rowmap ? p.rowmap[rs] : rs;
-        ph[(int64_t)row_s * p.W + slot] = make_double2(er - orr, ei - oi);
+      // a ring and its mirror have the same owner (msplit_layout), consecutive pairs mostly too
+      const int row_n = p.rowmap[r];
+      int d = 0;
+      while (row_n >= __ldg(&t->rowstart[d + 1])) ++d;
+      const int first = __ldg(&t->rowstart[d]);
+      const int64_t rows_d = __ldg(&t->rowstart[d + 1]) - first;
+      double2* base = reinterpret_cast<double2*>(__ldg(reinterpret_cast<const unsigned long long*>(&t->base[d])));
+      const int row_s = r != p.npair - 1 ? p.rowmap[rs] : -1;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const double er = acc[j][b][0], ei = acc[j][b][1];
+        const double orr = acc[j][b][2] * zz[j], oi = acc[j][b][3] * zz[j];
+        double2* dst = base + (int64_t)(b * world + me) * rows_d * p.W + slot;
+        dst[(int64_t)(row_n - first) * p.W] = make_double2(er + orr, ei + oi);
+        if (row_s >= 0) dst[(int64_t)(row_s - first) * p.W] = make_double2(er - orr, ei - oi);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!live[j]) continue;
+      const int r = pair0 + j;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const double er = acc[j][b][0], ei = acc[j][b][1];
+        const double orr = acc[j][b][2] * zz[j], oi = acc[j][b][3] * zz[j];
+        double2* ph = p.phase + b * p.phase_map_stride;
+        const int slot = m / p.G;
+        const int rs = p.nring - 1 - r;
+        const int row_n = p.rowmap ? p.rowmap[r] : r;
+        ph[(int64_t)row_n * p.W + slot] = make_double2(er + orr, ei + oi);
+        if (r != p.npair - 1) {
+          const int row_s = p.rowmap ? p.rowmap[rs] : rs;
+          ph[(int64_t)row_s * p.W + slot] = make_double2(er - orr, ei - oi);
+        }
       }
     }
   }
@@ -460,8 +493,9 @@ static int launch_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
 }
 
 template <int B>
-static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, bool dist = false) {
+static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, bool dist = false, int p2p_buffer = -1) {
   LegParams p;
+  p.p2p = p2p_buffer >= 0 ? pl->d_p2p_tab + p2p_buffer : nullptr;
   p.items = pl->d_items;
   p.rec = pl->d_rec;
   p.roff = pl->d_roff;
@@ -504,10 +538,22 @@ static int launch_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, bool
     launched = true;                                                             \
   }
   bool launched = false;
+  if (p.p2p) {  // fused transpose: the default configurations only
+#define GLB_LEG_LAUNCH_P2P(RR, TT)                                               \
+  if (R == RR && threads == TT) {                                                \
+    sht_legendre_synth_kernel<RR, B, TT, true><<<nitems, TT, 0, st>>>(p);        \
+    launched = true;                                                             \
+  }
+    GLB_LEG_LAUNCH_P2P(4, 64)
+    GLB_LEG_LAUNCH_P2P(4, 128)
+    GLB_LEG_LAUNCH_P2P(4, 256)
+#undef GLB_LEG_LAUNCH_P2P
+  } else {
   GLB_LEG_LAUNCH(4, 64)
   GLB_LEG_LAUNCH(4, 128)
   GLB_LEG_LAUNCH(4, 256)
-  if (B == 4) {
+  }
+  if (B == 4 && !p.p2p) {
     GLB_LEG_LAUNCH(2, 512)
     GLB_LEG_LAUNCH(2, 256)
     GLB_LEG_LAUNCH(3, 384)
@@ -552,11 +598,11 @@ int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st) 
 }
 
 // records -> phase [nb][nring][mmax+1]  (dist: [nb][nring (permuted rows)][W], this rank's m only)
-int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist) {
+int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist, int p2p_buffer) {
   switch (nb) {
-    case 1: return launch_legendre<1>(pl, d_phase, st, dist);
-    case 2: return launch_legendre<2>(pl, d_phase, st, dist);
-    case 4: return launch_legendre<4>(pl, d_phase, st, dist);
+    case 1: return launch_legendre<1>(pl, d_phase, st, dist, p2p_buffer);
+    case 2: return launch_legendre<2>(pl, d_phase, st, dist, p2p_buffer);
+    case 4: return launch_legendre<4>(pl, d_phase, st, dist, p2p_buffer);
     default:
       set_last_error("internal: batch group must be 1, 2 or 4");
       return GLB_ERR_INVALID_ARG;
@@ -566,7 +612,7 @@ int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, 
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
   const int rc = sht_prep_group(pl, d_alm, nb, st);
   if (rc != GLB_OK) return rc;
-  return sht_legendre_group(pl, nb, d_phase, st, false);
+  return sht_legendre_group(pl, nb, d_phase, st, false, -1);
 }
 
 }  // namespace glb

@@ -1,8 +1,10 @@
 """
 glass_b200.dist -- ONE spherical-harmonic synthesis spread over the GPUs of a box
 (axis 2): the Legendre stage is sharded by m, the ring FFT and everything in
-pixel space by ring band, with one NCCL all-to-all of the phase array over NVLink between
-them.  Use it when a single shell has to finish quickly (latency) or for the largest nside;
+pixel space by ring band.  The m -> ring transpose between them is either one NCCL all-to-all
+of the phase array over NVLink (default), or -- ``p2p=True`` -- fused into the Legendre kernel,
+which then stores every F_m(ring) straight into the owning rank's receive buffer through
+NVLink peer mappings, so the transfer overlaps the FP64 work and only a barrier remains.  Use it when a single shell has to finish quickly (latency) or for the largest nside;
 for throughput over many shells the communication-free shell sharding of
 ``glass_b200.generate(..., shells=...)`` is the better split.
 """
@@ -23,7 +25,7 @@ from .sharding import msplit_layout, owned_pixel_ranges
 class MSplitTransform:
     """alm (replicated on every rank) -> the rank's ring bands of the map."""
 
-    def __init__(self, nside: int, lmax: int, group=None, max_batch: int = 4, device=None):
+    def __init__(self, nside: int, lmax: int, group=None, max_batch: int = 4, device=None, p2p: bool = False):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -41,6 +43,39 @@ class MSplitTransform:
         self.rows = lay["rows"]
         self.nring = 4 * self.nside - 1
         self.pixel_ranges = owned_pixel_ranges(self.nside, lay, self.rank)
+        self.p2p = bool(p2p)
+        if self.p2p:
+            self._p2p_setup(min(int(max_batch), 4))
+
+    def _p2p_setup(self, nb_max: int) -> None:
+        """Receive buffers in IPC-exportable memory, handles exchanged over the process group,
+        peers opened (C ABI: glb_dist_p2p_alloc / glb_dist_p2p_open)."""
+        pl = self.plan
+        mine = (C.c_ubyte * 64)()
+        _lib.check(pl.lib.glb_dist_p2p_alloc(pl.handle, nb_max, mine), "glb_dist_p2p_alloc")
+        every = gather_bytes(bytes(mine), self.group, pl.torch_device)
+        rows = np.ascontiguousarray(self.rows, dtype=np.int32)
+        _lib.check(pl.lib.glb_dist_p2p_open(pl.handle, b"".join(every), rows.ctypes.data), "glb_dist_p2p_open")
+        self._flag = torch.zeros(1, dtype=torch.int32, device=pl.torch_device)
+        self._buffer = 0
+        dist.barrier(group=self.group)  # nobody stores before every receive buffer is zeroed and mapped
+
+    def _alm2map_p2p(self, alms: torch.Tensor, transforms, out: torch.Tensor) -> torch.Tensor:
+        pl, nb = self.plan, alms.shape[0]
+        buf, self._buffer = self._buffer, self._buffer ^ 1
+        with torch.cuda.device(alms.device):
+            st = pl.stream_ptr()
+            _lib.check(pl.lib.glb_dist_alm2phase_p2p(pl.handle, alms.data_ptr(), nb, buf, st), "glb_dist_alm2phase_p2p")
+            # barrier ordered on the stream: when it completes here, the Legendre kernel of every
+            # rank has ended, i.e. all stores into this rank's receive buffer are done.  With the two
+            # buffers alternating it also keeps a fast rank from overwriting the buffer that a slow
+            # rank's ring FFT of the previous transform is still reading.
+            dist.all_reduce(self._flag, group=self.group)
+            recv = C.c_void_p()
+            _lib.check(pl.lib.glb_dist_p2p_recv(pl.handle, buf, C.byref(recv)), "glb_dist_p2p_recv")
+            kinds, params, _keep = hp._transform_args(transforms)
+            _lib.check(pl.lib.glb_dist_phase2map(pl.handle, recv, nb, out.data_ptr(), kinds, params, st), "glb_dist_phase2map")
+        return out
 
     def alm2map(self, alms: torch.Tensor, transforms=None, out: torch.Tensor | None = None) -> torch.Tensor:
         """alms [nb, nalm] complex128 CUDA (same on every rank), nb in {1, 2, 4}.  Returns
@@ -48,11 +83,13 @@ class MSplitTransform:
         pl, dev = self.plan, alms.device
         nb = alms.shape[0]
         alms = alms.contiguous()
+        if out is None:
+            out = torch.zeros((nb, pl.npix), dtype=torch.float64, device=dev)
+        if self.p2p:
+            return self._alm2map_p2p(alms, transforms, out)
         send = torch.empty((nb, self.nring, self.W), dtype=torch.complex128, device=dev)
         rows_me = self.rows[self.rank]
         recv = torch.empty((nb, self.world, rows_me, self.W), dtype=torch.complex128, device=dev)
-        if out is None:
-            out = torch.zeros((nb, pl.npix), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             st = pl.stream_ptr()
             _lib.check(pl.lib.glb_dist_alm2phase(pl.handle, alms.data_ptr(), nb, send.data_ptr(), st), "glb_dist_alm2phase")
@@ -80,6 +117,17 @@ class MSplitTransform:
             full[:, a:b] = maps[:, a:b]
         dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
         return full
+
+
+def gather_bytes(mine: bytes, group=None, device=None) -> list[bytes]:
+    """All-gather of one fixed-size byte string per rank (the IPC handles of the receive buffers);
+    ``device``: where the staging tensors live (a CUDA device under NCCL, None/cpu under gloo)."""
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, t, group=group)
+    return [bytes(p.cpu().numpy().tobytes()) for p in parts]
 
 
 # ------------------------------------------------------------------------------------------

@@ -213,6 +213,26 @@ int glb_dist_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d
 int glb_dist_phase2map(glb_plan* plan, const double* d_recv, int nmaps, double* d_map,
                        const int* h_transform, const double* h_tparams, void* stream);
 
+/* Fused form of the same split: the Legendre kernel stores every F_m(ring) straight into the
+ * receive buffer of the rank that owns the ring, through peer mappings of those buffers
+ * (NVLink / NVSwitch, CUDA IPC between the per-GPU processes), so the m -> ring transpose
+ * overlaps the FP64 work tile by tile and no all-to-all runs afterwards.
+ *   1. glb_dist_setup, then glb_dist_p2p_alloc (same nmaps_max on every rank): two receive
+ *      buffers [nmaps_max][world][rows][W] are allocated as one block; h_handle receives its
+ *      64-byte IPC handle;
+ *   2. the caller gathers the handles of all ranks (any host exchange) and calls
+ *      glb_dist_p2p_open(all handles [world][64], rows per rank [world]);
+ *   3. per transform: glb_dist_alm2phase_p2p(buffer = 0/1 alternating), a barrier over the
+ *      ranks ordered on `stream` (every rank's stores are complete when its kernel has ended),
+ *      then glb_dist_phase2map on the pointer glb_dist_p2p_recv returns.  Alternating the two
+ *      buffers makes that one barrier per transform also protect the buffer a slower rank is
+ *      still reading.
+ * Same kernels and the same bits as the all-to-all form (and as one GPU). */
+int glb_dist_p2p_alloc(glb_plan* plan, int nmaps_max, void* h_handle);
+int glb_dist_p2p_open(glb_plan* plan, const void* h_all_handles, const int* h_rows);
+int glb_dist_alm2phase_p2p(glb_plan* plan, const double* d_alm, int nmaps, int buffer, void* stream);
+int glb_dist_p2p_recv(glb_plan* plan, int buffer, double** d_recv);
+
 /* ---- measurement hooks (bench.py) --------------------------------------------------- */
 /* Per-stage device time of glb_alm2map, from CUDA events recorded on the launch stream:
  * ms3 / launches3 = {prep, Legendre, ring FFT}; nmaps = maps transformed since enable. */

@@ -22,7 +22,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
-    sizes = [int(a) for a in sys.argv[1:]] or [8, 64, 256]
+    p2p = "--p2p" in sys.argv  # fused Legendre + transpose over peer memory instead of the NCCL all-to-all
+    sizes = [int(a) for a in sys.argv[1:] if a != "--p2p"] or [8, 64, 256]
     ok = True
     for nside in sizes:
         lmax = 2 * nside - 1 if nside > 8 else 3 * nside - 1
@@ -32,7 +33,7 @@ def main():
             g.manual_seed(1234 + nside)  # same alm on every rank
             alm = torch.view_as_complex(torch.randn((nb, nalm, 2), dtype=torch.float64, device=dev, generator=g))
             tr = [(_lib.T_LOGNORMAL, 0.1, 1.0)] * nb if nside <= 1024 else None
-            ms = MSplitTransform(nside, lmax, max_batch=nb, device=dev)
+            ms = MSplitTransform(nside, lmax, max_batch=nb, device=dev, p2p=p2p)
             out = ms.alm2map(alm, transforms=tr)
             torch.cuda.synchronize()
             ref = alm2map_batch(alm, nside, lmax, transforms=tr)
@@ -46,6 +47,12 @@ def main():
             ok &= int(tot.item()) == 12 * nside * nside
             full = ms.gather(out)
             ok &= bool(torch.equal(full, ref))
+            if p2p:  # both receive buffers, and a changed input through a buffer that was used before
+                for scale in (1.0, -0.5, 2.0):
+                    out2 = ms.alm2map(alm * scale, transforms=None)
+                    torch.cuda.synchronize()
+                    ref2 = alm2map_batch(alm * scale, nside, lmax, transforms=None)
+                    ok &= all(bool(torch.equal(out2[:, a:b], ref2[:, a:b])) for a, b in ms.pixel_ranges)
             # timing
             for _ in range(2):
                 ms.alm2map(alm, transforms=tr, out=out)
@@ -58,7 +65,7 @@ def main():
                 alm2map_batch(alm, nside, lmax, transforms=tr, out=ref)
             torch.cuda.synchronize(); t1 = (time.perf_counter() - t0) / 3
             if rank == 0:
-                print(f"nside={nside} lmax={lmax} nb={nb} world={world}: m-split {t*1e3:.2f} ms vs single GPU {t1*1e3:.2f} ms "
+                print(f"nside={nside} lmax={lmax} nb={nb} world={world} {'peer stores' if p2p else 'all-to-all'}: m-split {t*1e3:.2f} ms vs single GPU {t1*1e3:.2f} ms "
                       f"(speed-up {t1/t:.2f}x), bands identical: {ok}", flush=True)
             del ms
     flag = torch.tensor([1 if ok else 0], device=dev)

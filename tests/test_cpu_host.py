@@ -181,9 +181,47 @@ def _msplit_worker(rank, world, port, nside, lmax, q):
     for row, ring in enumerate(lay["rings"][rank]):
         for m in range(lmax + 1):
             ok &= recv[m % world, row, m // world].item() == ring * 10000.0 + m
+    # the handle exchange of the peer-store form: one fixed-size byte string per rank, in rank order
+    from glass_b200.dist import gather_bytes
+
+    every = gather_bytes(bytes([rank + 1]) * 128, None, None)
+    ok &= every == [bytes([r + 1]) * 128 for r in range(world)]
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok)))
+
+
+def test_msplit_peer_store_addressing():
+    """Address algebra of the fused Legendre + transpose (sht_legendre_synth_kernel<.., P2P>):
+    writer g puts F(ring, m) at ((b*world + g)*rows_d + (row - rowstart[d]))*W + m // world of rank
+    d's receive buffer, d = owner of the ring's row.  Replayed on the host for every (g, ring, m,
+    b): each rank's buffer must end up exactly as the all-to-all form delivers it,
+    [b][src rank][local row][slot], every needed entry written once."""
+    from glass_b200.sharding import msplit_layout
+
+    for nside, lmax, world, nb in [(4, 9, 2, 2), (8, 20, 3, 1), (16, 31, 8, 4), (2, 5, 2, 1)]:
+        lay = msplit_layout(nside, lmax, world)
+        nring, W, rows = 4 * nside - 1, lay["W"], lay["rows"]
+        rowstart = np.concatenate([[0], np.cumsum(rows)])
+        assert rowstart[-1] == nring
+        bufs = [np.full(nb * world * max(rows[d], 1) * W, np.nan) for d in range(world)]
+        for g in range(world):  # the writer's kernel
+            for ring in range(nring):
+                row = int(lay["rowmap"][ring])
+                d = 0
+                while row >= rowstart[d + 1]:
+                    d += 1
+                for m in range(g, lmax + 1, world):
+                    for b in range(nb):
+                        off = ((b * world + g) * rows[d] + (row - rowstart[d])) * W + m // world
+                        assert np.isnan(bufs[d][off])  # nobody else writes here
+                        bufs[d][off] = (b * 1000 + ring) * 10000.0 + m
+        for d in range(world):  # the reader: glb_dist_phase2map's view of its receive buffer
+            recv = bufs[d].reshape(nb, world, max(rows[d], 1), W)
+            for lr, ring in enumerate(lay["rings"][d]):
+                for m in range(lmax + 1):
+                    for b in range(nb):
+                        assert recv[b, m % world, lr, m // world] == (b * 1000 + ring) * 10000.0 + m
 
 
 def test_msplit_alltoall_layout_world2_gloo():
