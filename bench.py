@@ -280,7 +280,7 @@ def run_reference(args) -> None:
     from oracle import sht_c
 
     cores = sht_c.max_threads()
-    ns, _, _ = cpu_sample(20.0, cores)  # seconds of CPU work per step
+    ns, _, _ = cpu_sample(12.0, cores)  # timed seconds of CPU work per step (drawing the earlier shells' normals adds about as much untimed)
     for _ in range(args.warmup):
         cpu_shell_seconds(ns, 2 * ns - 1, cores)
     t_np = t_sht = 0.0
