@@ -8,11 +8,12 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, user  # noqa: F401
+from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, transformcl, user  # noqa: F401
 from .fields import (  # noqa: F401
     check_posdef_spectra,
     cls2cov,
     cltovar,
+    compute_gaussian_spectra,
     cov_from_spectra,
     discretized_cls,
     effective_cls,
@@ -26,8 +27,10 @@ from .fields import (  # noqa: F401
     healpix_to_glass_spectra,
     iternorm,
     lognormal_fields,
+    lognormal_gls,
     lognormal_shift_hilbert2011,
     nfields_from_nspectra,
+    solve_gaussian_spectra,
     spectra_indices,
 )
 from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_nz  # noqa: F401

@@ -348,6 +348,103 @@ def effective_cls(cls, weights1, weights2=None, *, lmax: int | None = None):
     return out
 
 
+def compute_gaussian_spectra(fields, spectra):
+    """
+    Band-limited Gaussian angular power spectra for the target ``spectra`` after transformation
+    by ``fields`` (glass/fields.py:743-775): ``grf.compute`` per non-empty spectrum.
+    """
+    n = len(fields)
+    if len(spectra) != n * (n + 1) // 2:
+        msg = "mismatch between number of fields and spectra"
+        raise ValueError(msg)
+    return [grf.compute(cl, fields[i], fields[j]) if cl.shape[0] > 0 else 0 * cl for i, j, cl in enumerate_spectra(spectra)]
+
+
+def _stack_transformations(ts, device):
+    """One transformation object whose parameters are per-column tensors, for a group of
+    transformations of the same built-in class; None for anything else."""
+    cls = type(ts[0])
+    if any(type(t) is not cls for t in ts) or cls not in (grf.Normal, grf.Lognormal, grf.SquaredNormal):
+        return None
+    if cls is grf.Normal:
+        return grf.Normal()
+    col = lambda name: torch.tensor([float(getattr(t, name)) for t in ts], dtype=torch.float64, device=device)  # noqa: E731
+    if cls is grf.Lognormal:
+        return grf.Lognormal(col("lamda"))
+    return grf.SquaredNormal(col("a"), col("lamda"))
+
+
+def solve_gaussian_spectra(fields, spectra):
+    """
+    Solve a sequence of Gaussian angular power spectra (glass/fields.py:778-836): after
+    transformation by ``fields`` the two-point statistics recover ``spectra`` for a
+    non-band-limited transform.  Per spectrum the reference's choices are kept -- zero padding
+    ``2 n``, monopole pinned to zero when the target monopole is zero, a warning when the
+    solver does not converge.
+
+    The reference runs S(S+1)/2 independent solves one after the other on the CPU.  Here the
+    spectra that share a length and a pair of built-in transformation classes become the
+    columns of ONE batched Gauss-Newton run (``grf.solve_columns``: every C_l <-> C(theta)
+    transform is one FP64 DGEMM over all columns, step halving and stopping are per column);
+    user-defined transformations are solved one by one.
+    """
+    from . import transformcl as tcl
+
+    n = len(fields)
+    if len(spectra) != n * (n + 1) // 2:
+        msg = "mismatch between number of fields and spectra"
+        raise ValueError(msg)
+    if len(spectra) == 0:
+        return []
+    device, _ = tcl._compute_device(*spectra)
+    out: list = [None] * len(spectra)
+    groups: dict[tuple, list[int]] = {}
+    pairs = [(i, j) for i, j, _cl in enumerate_spectra(spectra)]
+    for k, cl in enumerate(spectra):
+        if cl.shape[0] == 0:
+            out[k] = 0 * cl  # a copy of the empty array
+            continue
+        i, j = pairs[k]
+        groups.setdefault((cl.shape[0], type(fields[i]), type(fields[j])), []).append(k)
+    for (length, _c1, _c2), members in groups.items():
+        t1 = _stack_transformations([fields[pairs[k][0]] for k in members], device)
+        t2 = _stack_transformations([fields[pairs[k][1]] for k in members], device)
+        if t1 is None or t2 is None:  # user-defined transformations: the reference's own loop
+            for k in members:
+                i, j = pairs[k]
+                cl = spectra[k]
+                monopole = 0.0 if float(cl[0]) == 0 else None
+                gl, _cl_out, info = grf.solve(cl, fields[i], fields[j], pad=2 * length, monopole=monopole)
+                if info == 0:
+                    warnings.warn(f"Gaussian spectrum for fields ({i}, {j}) did not converge", stacklevel=2)
+                out[k] = gl
+            continue
+        cols = torch.stack([A_to_dev(spectra[k], device) for k in members], dim=1)
+        mono = torch.where(cols[0] == 0, torch.zeros_like(cols[0]), torch.full_like(cols[0], float("nan")))
+        gl, _rl, info = grf.solve_columns(cols, t1, t2, pad=2 * length, fix_monopole=mono)
+        info = info.cpu().numpy()
+        for c, k in enumerate(members):
+            if info[c] == 0:
+                i, j = pairs[k]
+                warnings.warn(f"Gaussian spectrum for fields ({i}, {j}) did not converge", stacklevel=2)
+            g = gl[:, c].contiguous()
+            out[k] = g if (isinstance(spectra[k], torch.Tensor) and spectra[k].is_cuda) else g.cpu().numpy()
+    return out
+
+
+def A_to_dev(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64)
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+
+
+@deprecated("use glass.lognormal_fields() and glass.solve_gaussian_spectra() instead")
+def lognormal_gls(cls, shift: float = 1.0):
+    """Gaussian spectra for lognormal fields of one shift (glass/fields.py:304-331)."""
+    n = nfields_from_nspectra(len(cls))
+    return solve_gaussian_spectra([grf.Lognormal(shift) for _ in range(n)], cls)
+
+
 def _glass_to_healpix_alm(alm):
     """l-major -> m-major (glass/fields.py:943-962)."""
     if isinstance(alm, torch.Tensor) and alm.is_cuda:

@@ -317,6 +317,142 @@ def test_spectra_helpers_and_position_weights_golden():
     assert np.allclose(t.numpy(), g["pw_2b"], rtol=1e-14, atol=0)  # torch sums in another order
 
 
+@pytest.fixture()
+def transforms_on_cpu(monkeypatch):
+    """The spectra solver is device-agnostic torch + GEMM; the PRODUCT insists on a CUDA device
+    (transformcl._compute_device raises without one).  For the CPU suite the device choice is
+    patched so that the same code runs on CPU tensors."""
+    import torch
+
+    import glass_b200.transformcl as tcl
+
+    monkeypatch.setattr(tcl, "_compute_device", lambda *a: (torch.device("cpu"), False))
+    tcl.clear_tables()
+    yield tcl
+    tcl.clear_tables()
+
+
+def test_transformcl_needs_cuda():
+    import torch
+
+    import glass_b200
+    from glass_b200._lib import GlassB200Error
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(GlassB200Error, match="no CPU fallback"):
+        glass_b200.transformcl.cltocorr(np.ones(8))
+    with pytest.raises(GlassB200Error, match="no CPU fallback"):
+        glass_b200.grf.solve(np.ones(8), glass_b200.grf.Lognormal())
+
+
+def test_transformcl_pair(transforms_on_cpu):
+    """cltocorr / corrtocl (the transformcl interface, glass/grf/_solver.py:100-130): definition
+    by direct Legendre sums, exact inverse, Gauss-Legendre projection of a non-polynomial function,
+    columns transformed together."""
+    from scipy.special import eval_legendre
+
+    tcl = transforms_on_cpu
+    for n in (1, 2, 3, 8, 101, 400):
+        rng = np.random.default_rng(n)
+        cl = rng.standard_normal(n) / (1 + np.arange(n)) ** 2
+        c = tcl.cltocorr(cl)
+        x = np.cos(tcl.theta(n))
+        direct = sum((2 * l + 1) / (4 * np.pi) * cl[l] * eval_legendre(l, x) for l in range(n))
+        assert np.abs(c - direct).max() <= 1e-13 * max(np.abs(direct).max(), 1e-300)
+        assert np.abs(tcl.corrtocl(c) - cl).max() <= 1e-14 * np.abs(cl).max()
+    both = tcl.cltocorr(np.stack([cl, -2 * cl], 1))
+    assert np.allclose(both[:, 0], c, rtol=1e-13, atol=1e-18) and np.allclose(both[:, 1], -2 * c, rtol=1e-13, atol=1e-18)
+    n = 64
+    f = np.exp(np.cos(tcl.theta(n)))
+    xg, wg = np.polynomial.legendre.leggauss(200)
+    ref = np.array([2 * np.pi * np.sum(wg * np.exp(xg) * eval_legendre(l, xg)) for l in range(20)])
+    assert np.abs(tcl.corrtocl(f)[:20] - ref).max() < 1e-12
+    assert abs(tcl.cltovar(cl) - np.sum((2 * np.arange(cl.size) + 1) / (4 * np.pi) * cl)) < 1e-18
+    assert tcl.cltocorr(np.zeros(0)).shape == (0,)
+    with pytest.raises(NotImplementedError):
+        tcl.cltocorr(cl, closed=True)
+
+
+def test_grf_solve_reference_properties(transforms_on_cpu):
+    """The reference's own solver tests (tests/core/grf/test_solver.py:24-131) and the transformation
+    pairs of tests/core/grf/test_transformations.py, on the batched GPU formulation."""
+    from glass_b200 import grf
+
+    lmax = 100
+    ell = np.arange(lmax + 1)
+    cl = 1e-2 / (2 * ell + 1) ** 2
+    rng = np.random.default_rng(42)
+    t = grf.Lognormal(rng.random())
+    # test_one_transformation, test_pad, test_initial, test_no_iterations
+    assert np.array_equal(grf.solve(cl, t)[0], grf.solve(cl, t, t)[0])
+    assert grf.solve(cl, t, pad=2 * cl.shape[0])[1].shape[0] == 3 * cl.shape[0]
+    with pytest.raises(ValueError, match="pad must be a positive integer"):
+        grf.solve(cl, t, pad=-1)
+    assert np.array_equal(grf.solve(cl, t)[0], grf.solve(cl, t, initial=grf.compute(cl, t))[0])
+    assert np.array_equal(grf.compute(cl, grf.Lognormal()), grf.solve(cl, grf.Lognormal(), maxiter=0)[0])
+    # test_lognormal
+    gl0, cltol = rng.random(), 1e-7
+    gl, cl_, info = grf.solve(cl, grf.Lognormal(), grf.Lognormal(), monopole=gl0, cltol=cltol)
+    assert info > 0 and gl[0] == gl0
+    assert np.allclose(cl_[1 : cl.shape[0]], cl[1:], atol=0.0, rtol=cltol)
+    assert np.allclose(grf.compute(cl_, grf.Lognormal(), grf.Lognormal())[1 : gl.shape[0]], gl[1:])
+    # test_monopole
+    c2 = cl.copy()
+    c2[0] = rng.random()
+    gl, cl_out, _ = grf.solve(c2, grf.Lognormal(), monopole=None, gltol=1e-8)
+    assert gl[0] != 0.0 and np.allclose(cl_out[0], c2[0])
+    gl, cl_out, _ = grf.solve(c2, grf.Lognormal(), monopole=gl0, gltol=1e-8)
+    assert gl[0] == gl0 and not np.allclose(cl_out[0], c2[0])
+    # corr / icorr / dcorr pairs: inverse and derivative relations, NotImplemented dispatch
+    x = np.linspace(-0.2, 0.5, 29)
+    for t1, t2 in [(grf.Normal(), grf.Normal()), (grf.Lognormal(0.6), grf.Lognormal(1.4)), (grf.Lognormal(0.6), grf.Normal()),
+                   (grf.Normal(), grf.Lognormal(0.6)), (grf.SquaredNormal(0.8, 1.2), grf.SquaredNormal(0.6, 0.7))]:
+        y = grf.corr(t1, t2, x)
+        assert np.allclose(grf.icorr(t1, t2, y), x, rtol=1e-12, atol=1e-14)
+        h = 1e-6
+        assert np.allclose((grf.corr(t1, t2, x + h) - grf.corr(t1, t2, x - h)) / (2 * h), grf.dcorr(t1, t2, x), rtol=1e-7)
+    with pytest.raises(NotImplementedError, match="SquaredNormal x Normal"):
+        grf.corr(grf.SquaredNormal(0.8), grf.Normal(), x)
+
+
+def test_solve_gaussian_spectra_batched_equals_single(transforms_on_cpu):
+    """solve_gaussian_spectra (glass/fields.py:778-836): the batched run over all spectra follows,
+    column by column, the solve the reference would run on each spectrum alone (padding 2n, zero
+    monopole pinned, empty spectra passed through, mixed transformation pairs)."""
+    import glass_b200 as glass
+    from glass_b200 import grf
+
+    lmax = 60
+    base = 1e-2 / (2 * np.arange(lmax + 1) + 1) ** 2
+    fields = [grf.Lognormal(1.0), grf.Lognormal(0.7), grf.Normal(), grf.Lognormal(1.3)]
+    spectra = []
+    for i in range(4):
+        for j in range(i, -1, -1):
+            c = 0.5 ** (i - j) * base * (1 + 0.1 * i)
+            if i == 1:
+                c[0] = 0.0
+            spectra.append(c if i - j <= 2 else np.zeros(0))
+    gls = glass.solve_gaussian_spectra(fields, spectra)
+    assert len(gls) == len(spectra)
+    for k, (i, j, cl) in enumerate(glass.enumerate_spectra(spectra)):
+        if cl.shape[0] == 0:
+            assert gls[k].shape == (0,)
+            continue
+        g, _, info = grf.solve(cl, fields[i], fields[j], pad=2 * cl.shape[0], monopole=0.0 if cl[0] == 0 else None)
+        assert info > 0
+        assert np.abs(g - gls[k]).max() <= 1e-12 * np.abs(g).max()
+        if cl[0] == 0:
+            assert gls[k][0] == 0.0
+    with pytest.raises(ValueError, match="mismatch between number of fields and spectra"):
+        glass.solve_gaussian_spectra(fields, spectra[:-1])
+    assert glass.solve_gaussian_spectra([], []) == []
+    cg = glass.compute_gaussian_spectra(fields, spectra)
+    assert np.array_equal(cg[0], grf.compute(spectra[0], fields[0], fields[0])) and cg[-1].shape == (0,)
+    with pytest.warns(DeprecationWarning):
+        assert len(glass.lognormal_gls(spectra[:3])) == 3
+
+
 def test_fft_core_host_build_and_run(tmp_path):
     """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
     per-thread functions: compile them for the host and check every pass, thread by thread,

@@ -1,0 +1,54 @@
+"""GPU tests of the spectra side: C_l <-> C(theta) as FP64 DGEMMs and the
+batched Gauss-Newton solver.  Same properties as the CPU suite checks on CPU tensors
+(tests/test_cpu_host.py), here on the device the product uses.  Named to sort last: these
+were written after the round's GPU minutes were spent and have not run on a GPU yet."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_transform_pair_on_device():
+    import torch
+    from scipy.special import eval_legendre
+
+    from glass_b200 import transformcl as tcl
+
+    for n in (3, 101, 1024):
+        rng = np.random.default_rng(n)
+        cl = rng.standard_normal(n) / (1 + np.arange(n)) ** 2
+        c = tcl.cltocorr(cl)
+        assert isinstance(c, np.ndarray)
+        if n <= 101:
+            x = np.cos(tcl.theta(n))
+            direct = sum((2 * l + 1) / (4 * np.pi) * cl[l] * eval_legendre(l, x) for l in range(n))
+            assert np.abs(c - direct).max() <= 1e-12 * np.abs(direct).max()
+        assert np.abs(tcl.corrtocl(c) - cl).max() <= 1e-12 * np.abs(cl).max()
+    d = torch.as_tensor(cl, device="cuda")
+    back = tcl.corrtocl(tcl.cltocorr(d))
+    assert back.is_cuda and torch.allclose(back, d, rtol=0, atol=1e-12 * float(d.abs().max()))
+    tcl.clear_tables()
+
+
+def test_solver_on_device():
+    import torch
+
+    import glass_b200 as glass
+    from glass_b200 import grf
+
+    lmax = 100
+    cl = 1e-2 / (2 * np.arange(lmax + 1) + 1) ** 2
+    t = grf.Lognormal(0.8)
+    gl, cl_out, info = grf.solve(cl, t, pad=2 * cl.shape[0], cltol=1e-7)
+    assert info > 0 and cl_out.shape[0] == 3 * cl.shape[0]
+    assert np.allclose(cl_out[1 : cl.shape[0]], cl[1:], atol=0.0, rtol=1e-7)
+    assert np.allclose(grf.solve(cl, t, maxiter=0)[0], grf.compute(cl, t), rtol=1e-12, atol=1e-18)
+    fields = [grf.Lognormal(1.0), grf.Lognormal(0.7), grf.Normal()]
+    spectra = [torch.as_tensor(0.5 ** (i - j) * cl * (1 + 0.1 * i), device="cuda") for i in range(3) for j in range(i, -1, -1)]
+    gls = glass.solve_gaussian_spectra(fields, spectra)
+    assert all(g.is_cuda and g.shape[0] == cl.shape[0] for g in gls)
+    for k, (i, j, s) in enumerate(glass.enumerate_spectra(spectra)):
+        g, _, info = grf.solve(s, fields[i], fields[j], pad=2 * s.shape[0])
+        assert info > 0
+        assert float((g - gls[k]).abs().max()) <= 1e-10 * float(g.abs().max())
+    glass.transformcl.clear_tables()
