@@ -8,7 +8,7 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, transformcl, user  # noqa: F401
+from . import algorithm, fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, transformcl, user  # noqa: F401
 from .fields import (  # noqa: F401
     check_posdef_spectra,
     cls2cov,
@@ -30,6 +30,7 @@ from .fields import (  # noqa: F401
     lognormal_gls,
     lognormal_shift_hilbert2011,
     nfields_from_nspectra,
+    regularized_spectra,
     solve_gaussian_spectra,
     spectra_indices,
 )

@@ -268,6 +268,30 @@ def check_posdef_spectra(spectra) -> bool:
     return bool(np.all(np.linalg.eigvalsh(cov) >= 0))
 
 
+def regularized_spectra(spectra, *, lmax: int | None = None, method: str = "nearest", **method_kwargs):
+    """
+    Regularise a complete set of spectra so that at every l the matrix C_l^{ij} is a valid
+    positive semi-definite covariance (glass/fields.py:1055-1112).  ``method``: "nearest"
+    (``algorithm.cov_nearest``) or "clip" (``algorithm.cov_clip``); the (lmax+1) matrices are
+    processed as one batch on the device.
+    """
+    from . import algorithm
+
+    if method == "clip":
+        cov_method = algorithm.cov_clip
+    elif method == "nearest":
+        cov_method = algorithm.cov_nearest
+    else:
+        msg = f"unknown method '{method}'"
+        raise ValueError(msg)
+    on_device = any(isinstance(cl, torch.Tensor) and cl.is_cuda for cl in spectra)
+    cov = cov_from_spectra(spectra, lmax=lmax)
+    if on_device:
+        cov = torch.as_tensor(cov, device=next(cl.device for cl in spectra if isinstance(cl, torch.Tensor) and cl.is_cuda))
+    cov = cov_method(cov, **method_kwargs)
+    return [cov[:, i, j] for i, j in spectra_indices(cov.shape[-1])]
+
+
 def cltovar(cl) -> float:
     """transformcl.cltovar as used at glass/fields.py:890: sum_l (2l+1)/(4 pi) C_l."""
     cl = _np(cl)

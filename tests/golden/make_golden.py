@@ -377,6 +377,27 @@ def main_spectra():
     out["pw_1f"] = glass.points.position_weights(d1, 1.7)
     out["pw_2b"] = glass.points.position_weights(d2, b2)
     out["pw_2b1"] = glass.points.position_weights(d2, b1)
+    # ---- regularisation (glass/algorithm.py:111-277, glass/fields.py:1055-1112) ----
+    import glass.algorithm
+
+    r = np.random.default_rng(12)
+    a = r.standard_normal((6, 4, 4))
+    covs = a @ np.swapaxes(a, -1, -2)
+    covs[1, 0, 1] = covs[1, 1, 0] = 1.5 * np.sqrt(covs[1, 0, 0] * covs[1, 1, 1])  # |rho| > 1
+    covs[4, 2, 3] = covs[4, 3, 2] = -1.2 * np.sqrt(covs[4, 2, 2] * covs[4, 3, 3])
+    out["reg_cov"] = covs
+    out["reg_clip"] = glass.algorithm.cov_clip(covs)
+    out["reg_clip_rtol"] = glass.algorithm.cov_clip(covs, rtol=0.1)
+    out["reg_nearest"] = glass.algorithm.cov_nearest(covs)
+    corr = covs / np.sqrt(np.einsum("...ii,...jj->...ij", covs, covs))
+    out["reg_nearcorr"] = glass.algorithm.nearcorr(corr)
+    bad = synthetic_gls(3, 8, 2)
+    bad[2] = 1.4 * bad[0]  # cross-spectrum (1, 0) larger than the auto-spectra allow
+    out["reg_gls_len"] = np.array([g.shape[0] for g in bad])
+    out["reg_gls"] = np.concatenate(bad)
+    for m in ("nearest", "clip"):
+        out[f"reg_spectra_{m}"] = np.stack(glass.fields.regularized_spectra(bad, method=m))
+    out["reg_spectra_lmax5"] = np.stack(glass.fields.regularized_spectra(bad, lmax=5, method="clip"))
     np.savez_compressed(os.path.join(HERE, "glass_reference_spectra.npz"), **out)
     print("wrote", len(out), "arrays to glass_reference_spectra.npz")
 

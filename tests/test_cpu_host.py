@@ -453,6 +453,38 @@ def test_solve_gaussian_spectra_batched_equals_single(transforms_on_cpu):
         assert len(glass.lognormal_gls(spectra[:3])) == 3
 
 
+def test_regularized_spectra_golden(transforms_on_cpu):
+    """cov_clip / nearcorr / cov_nearest (glass/algorithm.py:111-277) and regularized_spectra
+    (glass/fields.py:1055-1112) against vectors from executing the reference's source; the batched
+    eigendecomposition is another library than the reference's LAPACK call, hence a tolerance."""
+    import glass_b200 as glass
+    from glass_b200 import algorithm
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_spectra.npz"))
+    close = lambda a, b: np.allclose(a, b, rtol=1e-10, atol=1e-12 * np.abs(b).max())  # noqa: E731
+    covs = g["reg_cov"]
+    assert close(algorithm.cov_clip(covs), g["reg_clip"])
+    assert close(algorithm.cov_clip(covs, rtol=0.1), g["reg_clip_rtol"])
+    assert close(algorithm.cov_nearest(covs), g["reg_nearest"])
+    corr = covs / np.sqrt(np.einsum("...ii,...jj->...ij", covs, covs))
+    near = algorithm.nearcorr(corr)
+    assert close(near, g["reg_nearcorr"])
+    assert np.allclose(np.einsum("...ii->...i", near), 1.0) and np.linalg.eigvalsh(near).min() > -1e-12
+    with pytest.raises(ValueError, match="negative values on the diagonal"):
+        algorithm.cov_nearest(-covs)
+    with pytest.raises(ValueError, match="non-square matrix"):
+        algorithm.nearcorr(np.ones((3, 2)))
+    bad = np.split(g["reg_gls"], np.cumsum(g["reg_gls_len"])[:-1])
+    assert not glass.check_posdef_spectra(bad)
+    for m in ("nearest", "clip"):
+        reg = glass.regularized_spectra(bad, method=m)
+        assert close(np.stack(reg), g[f"reg_spectra_{m}"])
+        assert glass.check_posdef_spectra([np.asarray(r) * (1 + 1e-12 * (i == 0 or i == 1 or i == 3)) for i, r in enumerate(reg)])
+    assert close(np.stack(glass.regularized_spectra(bad, lmax=5, method="clip")), g["reg_spectra_lmax5"])
+    with pytest.raises(ValueError, match="unknown method 'foo'"):
+        glass.regularized_spectra(bad, method="foo")
+
+
 def test_fft_core_host_build_and_run(tmp_path):
     """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
     per-thread functions: compile them for the host and check every pass, thread by thread,

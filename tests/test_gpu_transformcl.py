@@ -52,3 +52,22 @@ def test_solver_on_device():
         assert info > 0
         assert float((g - gls[k]).abs().max()) <= 1e-10 * float(g.abs().max())
     glass.transformcl.clear_tables()
+
+
+def test_regularized_spectra_on_device():
+    import os
+
+    import torch
+
+    import glass_b200 as glass
+    from glass_b200 import algorithm
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_spectra.npz"))
+    close = lambda a, b: np.allclose(a, b, rtol=1e-8, atol=1e-10 * np.abs(b).max())  # noqa: E731
+    assert close(algorithm.cov_clip(g["reg_cov"]), g["reg_clip"])
+    assert close(algorithm.cov_nearest(g["reg_cov"]), g["reg_nearest"])
+    bad = np.split(g["reg_gls"], np.cumsum(g["reg_gls_len"])[:-1])
+    assert close(np.stack(glass.regularized_spectra(bad, method="clip")), g["reg_spectra_clip"])
+    reg = glass.regularized_spectra([torch.as_tensor(b, device="cuda") for b in bad], method="nearest")
+    assert all(r.is_cuda for r in reg)
+    assert close(torch.stack(reg).cpu().numpy(), g["reg_spectra_nearest"])
