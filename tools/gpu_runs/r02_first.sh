@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round 2, first 1-GPU call: everything written at the end of round 1 without a GPU.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_runs/r02_first.sh'
+set -x
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r02_tests.log
+python bench.py --impl reference --steps 2 --warmup 1 | tee gpurun_out/r02_bench_reference.json
+python bench.py | tee gpurun_out/r02_bench_1gpu.json
+python tools/probe_solver.py 60 8191 3 | tee gpurun_out/r02_solver_ncorr3.json
+python tools/probe_solver.py 60 8191 59 | tee gpurun_out/r02_solver_full.json
