@@ -52,7 +52,7 @@ def main():
     out["roundtrip_err"] = float((b - big).abs().max() / big.abs().max())
     gls, out["solve_s"] = sync_time(lambda: glass.solve_gaussian_spectra(fields, spectra))
     # the solution reproduces the targets: realised spectrum of shell 0
-    g = gls[0]
+    g = torch.as_tensor(gls[0], device=dev)
     rl = tcl.corrtocl_dev(grf.corr(fields[0], fields[0], tcl.cltocorr_dev(torch.nn.functional.pad(g, (0, 2 * n)))))[:n]
     out["max_rel_err_cl_shell0"] = float(((rl - spectra[0]) / spectra[0]).abs().max())
     print(json.dumps(out))
