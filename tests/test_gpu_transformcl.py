@@ -50,7 +50,9 @@ def test_solver_on_device():
     for k, (i, j, s) in enumerate(glass.enumerate_spectra(spectra)):
         g, _, info = grf.solve(s, fields[i], fields[j], pad=2 * s.shape[0])
         assert info > 0
-        assert float((g - gls[k]).abs().max()) <= 1e-10 * float(g.abs().max())
+        # same iteration path -> agreement at rounding level (1e-15 on CPU tensors); the bound leaves room for
+        # a column stopping one Gauss-Newton step apart from its single run (cltol = 1e-5) on other GEMM kernels
+        assert float((g - gls[k]).abs().max()) <= 2e-5 * float(g.abs().max())
     glass.transformcl.clear_tables()
 
 
