@@ -47,6 +47,7 @@ from .lensing import (  # noqa: F401
 from .points import (  # noqa: F401
     displace,
     displacement,
+    effective_bias,
     linear_bias,
     loglinear_bias,
     position_weights,

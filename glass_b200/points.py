@@ -42,6 +42,25 @@ def loglinear_bias(delta, b):
     return np.expm1(delta_g)
 
 
+def _trapezoid_product(f, *ff):
+    """Trapezoidal integral of a product of piecewise-linear functions on the union of their
+    grids, restricted to the common support (glass/arraytools.py:158-194)."""
+    x, _ = f
+    for x_, _y in ff:
+        x = np.union1d(x[(x >= x_[0]) & (x <= x_[-1])], x_[(x_ >= x[0]) & (x_ <= x[-1])])
+    y = np.interp(x, *f)
+    for f_ in ff:
+        y *= np.interp(x, *f_)
+    return np.trapezoid(y, x)
+
+
+def effective_bias(z, bz, w):
+    r"""Effective bias :math:`\bar b = \int b(z) w(z) dz / \int w(z) dz` of a redshift-dependent
+    bias for a radial window (glass/points.py:75-112).  A few hundred numbers: host arithmetic."""
+    z, bz, za, wa = (np.asarray(A.to_np(a), dtype=np.float64) for a in (z, bz, w.za, w.wa))
+    return _trapezoid_product((z, bz), (za, wa)) / np.trapezoid(wa, za)
+
+
 def position_weights(densities, bias=None):
     """Relative weight of each shell for angular clustering: densities normalised over the first
     (shell) axis, times an optional linear bias per shell (glass/points.py:610-651).  A handful

@@ -84,6 +84,7 @@ def install_shims():
         return out
 
     xpx.apply_where = apply_where
+    xpx.union1d = lambda a, b, /, *, xp=None: np.union1d(a, b)
     sys.modules["array_api_extra"] = xpx
 
     # ---- transformcl --------------------------------------------------------
@@ -377,6 +378,16 @@ def main_spectra():
     out["pw_1f"] = glass.points.position_weights(d1, 1.7)
     out["pw_2b"] = glass.points.position_weights(d2, b2)
     out["pw_2b1"] = glass.points.position_weights(d2, b1)
+    # ---- effective_bias (glass/points.py:75-112) ----
+    zb = np.linspace(0.0, 2.0, 41)
+    bzv = 1.0 + 0.5 * zb**2
+    win = glass.RadialWindow(np.array([0.33, 0.5, 0.71, 0.9]), np.array([0.0, 1.0, 0.6, 0.0]), 0.6)
+    out["eb_z"], out["eb_bz"], out["eb_za"], out["eb_wa"] = zb, bzv, np.asarray(win.za), np.asarray(win.wa)
+    out["eb"] = np.asarray(glass.points.effective_bias(zb, bzv, win))
+    wide = glass.RadialWindow(np.array([-0.5, 1.0, 2.5]), np.array([0.0, 1.0, 0.0]), 1.0)  # wider than b(z)
+    out["eb_wide_za"], out["eb_wide_wa"] = np.asarray(wide.za), np.asarray(wide.wa)
+    out["eb_wide"] = np.asarray(glass.points.effective_bias(zb, bzv, wide))
+
     # ---- regularisation (glass/algorithm.py:111-277, glass/fields.py:1055-1112) ----
     import glass.algorithm
 

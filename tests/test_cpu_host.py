@@ -311,6 +311,9 @@ def test_spectra_helpers_and_position_weights_golden():
     assert np.array_equal(glass.position_weights(g["pw_d1"], 1.7), g["pw_1f"])
     assert np.array_equal(glass.position_weights(g["pw_d2"], g["pw_b2"]), g["pw_2b"])
     assert np.array_equal(glass.position_weights(g["pw_d2"], g["pw_b1"]), g["pw_2b1"])
+    for tag in ("", "_wide"):
+        w = glass.RadialWindow(g[f"eb{tag}_za"], g[f"eb{tag}_wa"], 1.0)
+        assert np.array_equal(np.asarray(glass.effective_bias(g["eb_z"], g["eb_bz"], w)), g[f"eb{tag}"])
     import torch
 
     t = glass.position_weights(torch.as_tensor(g["pw_d2"]), torch.as_tensor(g["pw_b2"]))
