@@ -34,7 +34,7 @@ from .fields import (  # noqa: F401
     solve_gaussian_spectra,
     spectra_indices,
 )
-from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_nz  # noqa: F401
+from .galaxies import galaxy_shear, gaussian_phz, redshifts, redshifts_from_bins, redshifts_from_nz  # noqa: F401
 from .harmonics import multalm  # noqa: F401
 from .lensing import (  # noqa: F401
     MultiPlaneConvergence,

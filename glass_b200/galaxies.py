@@ -84,6 +84,40 @@ def redshifts_from_nz(count, z, nz, *, rng=None, warn: bool = True):
     return out if on_device else out.cpu().numpy()
 
 
+def redshifts_from_bins(bins, z, nz_dict, *, rng=None):
+    """
+    Redshifts for galaxies with tomographic bin labels (glass/galaxies.py:122-185): every
+    galaxy draws from the n(z) of its bin.  The labels are tallied (sorted unique labels and their
+    counts), one run of inverse-CDF draws is made per label with the redshift kernel
+    (:func:`redshifts_from_nz`), and the runs are scattered back to the galaxies' positions with
+    one stable argsort -- the same order of draws as the reference, so supplied uniform deviates
+    reproduce it bit for bit.  CUDA ``bins`` keep everything on the device.  N-D label arrays are
+    handled in flattened (C) order; the reference's argsort pair works along the last axis only and
+    is meaningful for 1-D labels.
+    """
+    keys, values = list(nz_dict.keys()), list(nz_dict.values())
+    on_device = A.is_cuda(bins) or A.is_cuda(z)
+    b = bins if isinstance(bins, torch.Tensor) else torch.as_tensor(np.asarray(bins))
+    labels, inverse, counts = torch.unique(b.reshape(-1), sorted=True, return_inverse=True, return_counts=True)
+    labels_h, counts_h = labels.cpu().numpy(), counts.cpu().numpy()
+    runs = []
+    for x, k in zip(labels_h, counts_h):
+        idx = next(i for i, key in enumerate(keys) if np.all(A.to_np(key) == x))  # labels need not be hashable
+        runs.append(redshifts_from_nz(int(k), z, values[idx], rng=rng, warn=False))
+    if on_device:
+        dev = next(t.device for t in (bins, z) if A.is_cuda(t))
+        red = torch.cat([torch.as_tensor(r, device=dev) for r in runs]) if runs else torch.empty(0, dtype=torch.float64, device=dev)
+        order = torch.argsort(inverse.to(dev), stable=True)  # positions of the galaxies, bin by bin
+        out = torch.empty_like(red)
+        out[order] = red
+        return out.reshape(b.shape)
+    red = np.concatenate([A.to_np(r) for r in runs]) if runs else np.empty(0)
+    order = np.argsort(inverse.cpu().numpy(), kind="stable")
+    out = np.empty_like(red)
+    out[order] = red
+    return out.reshape(tuple(b.shape))
+
+
 def galaxy_shear(lon, lat, eps, kappa, gamma1, gamma2, *, reduced_shear: bool = True, ipix=None):
     """
     Observed galaxy shears from weak lensing (glass/galaxies.py:271-347).

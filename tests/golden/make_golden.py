@@ -378,6 +378,18 @@ def main_spectra():
     out["pw_1f"] = glass.points.position_weights(d1, 1.7)
     out["pw_2b"] = glass.points.position_weights(d2, b2)
     out["pw_2b1"] = glass.points.position_weights(d2, b1)
+    # ---- redshifts_from_bins (glass/galaxies.py:122-185): three bins, seed 31 ----
+    import glass.galaxies
+
+    zg = np.linspace(0.0, 2.0, 51)
+    nzd = {5: zg * np.exp(-zg), 2: zg**2 * np.exp(-2 * zg), 9: np.exp(-((zg - 1.0) ** 2) / 0.1)}
+    binlab = np.random.default_rng(30).choice([2, 5, 9], size=200)  # 1-D: the reference's double argsort runs along the LAST axis,
+    # so for N-D labels it ranks within rows and indexes only the first few draws
+    out["rb_bins"], out["rb_z"] = binlab, zg
+    out["rb_nz"] = np.stack([nzd[2], nzd[5], nzd[9]])
+    out["rb_out"] = glass.galaxies.redshifts_from_bins(binlab, zg, nzd, rng=np.random.default_rng(31))
+    out["rb_uniform"] = np.random.default_rng(31).uniform(0.0, 1.0, size=binlab.size)  # one stream: bin 2, 5, 9 runs in turn
+
     # ---- effective_bias (glass/points.py:75-112) ----
     zb = np.linspace(0.0, 2.0, 41)
     bzv = 1.0 + 0.5 * zb**2

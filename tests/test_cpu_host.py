@@ -488,6 +488,37 @@ def test_regularized_spectra_golden(transforms_on_cpu):
         glass.regularized_spectra(bad, method="foo")
 
 
+def test_redshifts_from_bins_order_golden(monkeypatch):
+    """redshifts_from_bins (glass/galaxies.py:122-185): the tally / run / scatter logic against the
+    reference executed with a seeded NumPy stream.  The per-bin draw (the redshift kernel, covered by
+    the GPU tests) is replaced here by its definition interp(u, cdf, z) fed from the same stream."""
+    import glass_b200.galaxies as gal
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_spectra.npz"))
+    stream = iter(g["rb_uniform"])
+
+    def draw(count, z, nz, *, rng=None, warn=True):
+        cdf = gal._cumulative_trapezoid(nz, z)
+        cdf /= cdf[-1]
+        return np.interp(np.array([next(stream) for _ in range(int(count))]), cdf, z)
+
+    monkeypatch.setattr(gal, "redshifts_from_nz", draw)
+    nzd = {5: g["rb_nz"][1], 2: g["rb_nz"][0], 9: g["rb_nz"][2]}  # dictionary order is not label order
+    out = gal.redshifts_from_bins(g["rb_bins"], g["rb_z"], nzd)
+    assert out.shape == g["rb_bins"].shape
+    # every bin receives exactly the reference's run of draws; WITHIN a bin the reference hands them out
+    # in the tie order of NumPy's unstable argsort (which depends on the CPU's sort kernels), here in
+    # galaxy order -- the draws of a run are i.i.d., so only the per-bin sets are comparable
+    for label in (2, 5, 9):
+        sel = g["rb_bins"] == label
+        assert np.array_equal(np.sort(out[sel]), np.sort(g["rb_out"][sel]))
+    first = {label: np.flatnonzero(g["rb_bins"] == label) for label in (2, 5, 9)}
+    runs = np.split(g["rb_uniform"], np.cumsum([first[2].size, first[5].size])[:2])
+    for label, u in zip((2, 5, 9), runs):  # galaxy order within the bin = draw order
+        cdf = gal._cumulative_trapezoid(nzd[label], g["rb_z"])
+        assert np.array_equal(out[first[label]], np.interp(u, cdf / cdf[-1], g["rb_z"]))
+
+
 def test_fft_core_host_build_and_run(tmp_path):
     """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
     per-thread functions: compile them for the host and check every pass, thread by thread,
