@@ -519,6 +519,48 @@ def test_redshifts_from_bins_order_golden(monkeypatch):
         assert np.array_equal(out[first[label]], np.interp(u, cdf / cdf[-1], g["rb_z"]))
 
 
+def test_batch_cut_rule_closed_form_on_cpu():
+    """points._Population.cuts -- the closed form of the reference's 1000-pixel stepping loop
+    (glass/points.py:409-437) -- replayed on CPU tensors: against the batch sizes recorded from the
+    reference's source (golden) and against the oracle's restatement of the loop on corner cases
+    (exact fit at a group boundary, empty batches before an oversize pixel, trailing zeros,
+    random sparse and dense maps, batch = 1)."""
+    import torch
+
+    from glass_b200.points import _Population
+    from oracle import glass_ref as G
+
+    def cuts_of(counts, batch):
+        pop = object.__new__(_Population)
+        pop.npix = counts.size
+        pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64))
+        pop.total = int(counts.sum())
+        return [n for _a, _b, n in pop.cuts(batch)], [(a, b) for a, b, _n in pop.cuts(batch)]
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    for batch in (1_000_000, 500, 37, 1):
+        sizes, _ = cuts_of(gold["pt_counts"], batch)
+        assert sizes == list(gold[f"pt_batches_{batch}"]), batch
+    npix = 12 * 16**2
+    cases = []
+    c = np.zeros(npix, dtype=np.int64)
+    c[0], c[1500], c[1501], c[2999] = 5, 9, 1, 2
+    cases.append((c, 5))
+    c = np.zeros(npix, dtype=np.int64)
+    c[999], c[1000], c[2500] = 3, 2, 4
+    cases.append((c, 3))
+    cases.append((np.random.default_rng(0).poisson(0.01, npix), 2))
+    cases.append((np.random.default_rng(1).poisson(2.0, npix), 1000))
+    cases.append((np.random.default_rng(2).poisson(0.5, npix), 1))
+    cases.append((np.random.default_rng(3).poisson(0.3, 5 * npix), 977))
+    for counts, batch in cases:
+        ref = G.batch_cuts(counts, batch)
+        sizes, ranges = cuts_of(counts, batch)
+        assert sizes == [r[2] for r in ref], batch
+        assert ranges == [(r[0], r[1]) for r in ref], batch
+        assert sum(sizes) == counts.sum()
+
+
 def test_fft_core_host_build_and_run(tmp_path):
     """The shared-memory FFT passes of the ring-FFT kernels (csrc/fft_core.cuh) are plain
     per-thread functions: compile them for the host and check every pass, thread by thread,
