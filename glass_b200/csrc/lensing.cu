@@ -9,6 +9,7 @@
 //   ellipticity_intnorm / ellipticity_gaussian         glass/shapes.py:323-362, 255-285
 //   redshifts_from_nz inverse-CDF draw                 glass/galaxies.py:77-89
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "healpix_geom.cuh"
@@ -248,6 +249,18 @@ int glb_galaxy_shear(int64_t nside, const double* d_lon, const double* d_lat, co
   GLB_REQUIRE(nside >= 1 && n >= 0, "bad size");
   if (n == 0) return GLB_OK;
   GLB_REQUIRE((d_ipix || (d_lon && d_lat)) && d_eps && d_kappa && d_gamma1 && d_gamma2 && d_out, "null pointer");
+  // Experiment knob (off unless set): GLB_L2_FETCH_BYTES=32 asks the L2 for 32-byte instead of 64-byte
+  // fetches.  The three map gathers of a galaxy use 8 bytes of what they pull (ncu: 243 B of DRAM reads
+  // per galaxy at 87 % of peak DRAM throughput).  Device-wide hint, set once and left in place.
+  static const int fetch_bytes = [] {
+    const char* env = getenv("GLB_L2_FETCH_BYTES");
+    return env ? atoi(env) : 0;
+  }();
+  static bool fetch_set = false;
+  if (fetch_bytes > 0 && !fetch_set) {
+    GLB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch_bytes));
+    fetch_set = true;
+  }
   galaxy_shear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       nside, d_lon, d_lat, d_ipix, reinterpret_cast<const double2*>(d_eps), n, d_kappa, d_gamma1, d_gamma2,
       reduced_shear, reinterpret_cast<double2*>(d_out));
