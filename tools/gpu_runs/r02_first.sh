@@ -9,3 +9,6 @@ python bench.py --impl reference --steps 2 --warmup 1 | tee gpurun_out/r02_bench
 python bench.py | tee gpurun_out/r02_bench_1gpu.json
 python tools/probe_solver.py 60 8191 3 | tee gpurun_out/r02_solver_ncorr3.json
 python tools/probe_solver.py 60 8191 59 | tee gpurun_out/r02_solver_full.json
+# K12 with 64-byte (default) and 32-byte L2 fetches
+python tools/probe_sampling.py 2>&1 | tail -4 | tee gpurun_out/r02_sampling_default.log
+GLB_L2_FETCH_BYTES=32 python tools/probe_sampling.py 2>&1 | tail -4 | tee gpurun_out/r02_sampling_fetch32.log
