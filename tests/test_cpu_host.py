@@ -191,6 +191,95 @@ def _msplit_worker(rank, world, port, nside, lmax, q):
     q.put((rank, bool(ok)))
 
 
+def _p2p_host_flow_worker(rank, world, port, q):
+    """MSplitTransform(p2p=True) end to end on the HOST side, under gloo, against a fake library that
+    records the C-ABI calls: handle exchange, open, alternating buffers, barrier, phase2map."""
+    import contextlib
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import glass_b200.dist as gd
+    import glass_b200.healpix as hp
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    calls = []
+
+    class FakeLib:
+        def glb_dist_setup(self, handle, w, r, rowmap, mine, n):
+            calls.append(("setup", w, r, n))
+            return 0
+
+        def glb_dist_p2p_alloc(self, handle, nb, out):
+            assert len(out) == 64
+            for i in range(64):
+                out[i] = 16 * (rank + 1)
+            calls.append(("alloc", nb))
+            return 0
+
+        def glb_dist_p2p_open(self, handle, blob, rows_ptr):
+            assert blob == b"".join(bytes([16 * (r + 1)]) * 64 for r in range(world))
+            rows = (C.c_int32 * world).from_address(rows_ptr)
+            calls.append(("open", list(rows)))
+            return 0
+
+        def glb_dist_alm2phase_p2p(self, handle, alm, nb, buf, st):
+            calls.append(("legendre", nb, buf))
+            return 0
+
+        def glb_dist_p2p_recv(self, handle, buf, out):
+            out._obj.value = 1000 + buf
+            calls.append(("recv", buf))
+            return 0
+
+        def glb_dist_phase2map(self, handle, recv, nb, out, kinds, params, st):
+            calls.append(("fft", recv.value, nb))
+            return 0
+
+    class FakePlan:
+        def __init__(self, nside, lmax, max_batch=1, device=None):
+            self.lib, self.handle, self.npix = FakeLib(), C.c_void_p(1), 12 * nside * nside
+            self.torch_device = torch.device("cpu")
+
+        def stream_ptr(self):
+            return 0
+
+    hp.Plan = FakePlan
+    torch.cuda.device = lambda d: contextlib.nullcontext()
+    ms = gd.MSplitTransform(8, 15, max_batch=4, p2p=True)
+    alm = torch.zeros((2, 136), dtype=torch.complex128)
+    for _ in range(3):
+        out = ms.alm2map(alm)
+    ok = out.shape == (2, 768)
+    rows = ms.layout["rows"]
+    ok &= calls[:3] == [("setup", world, rank, rows[rank]), ("alloc", 4), ("open", rows)]
+    want = []
+    for i in range(3):
+        want += [("legendre", 2, i % 2), ("recv", i % 2), ("fft", 1000 + i % 2, 2)]
+    ok &= calls[3:] == want
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_msplit_peer_store_host_flow_world2_gloo():
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_p2p_host_flow_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _r, ok in res)
+
+
 def test_msplit_peer_store_addressing():
     """Address algebra of the fused Legendre + transpose (sht_legendre_synth_kernel<.., P2P>):
     writer g puts F(ring, m) at ((b*world + g)*rows_d + (row - rowstart[d]))*W + m // world of rank
