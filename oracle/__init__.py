@@ -25,6 +25,10 @@ Parity status (see DESIGN.md "Oracle"):
   pixel centres).  The reference's own tests for these functions are purely
   differential against the live library (``tests/core/test_healpix.py``), hold
   no stored vectors, so for these functions: **parity unpinned**.
+* ``oracle/transformcl_ref.py``: restatement of the absent third-party ``transformcl`` pair that
+  the reference's spectra solver calls; it is the module under which ``make_golden.py --solver``
+  executes the reference's own solver source (so the solver LOGIC is pinned by the reference),
+  and the independent checker of ``glass_b200.transformcl``.  transformcl itself: unpinned.
 * ``oracle/sht_fast.cpp`` is not a checker but the TIMED CPU arm of ``bench.py`` (a SIMD /
   OpenMP synthesis with the structure of libsharp, so that the CPU baseline is a fair one); it
   is itself pinned against ``sht_ref.c`` in ``tests/test_cpu_oracle.py``.

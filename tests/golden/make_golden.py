@@ -340,6 +340,55 @@ def main_displace():
     print("wrote", len(out), "arrays to glass_reference_displace.npz")
 
 
+def main_solver():
+    """Fourth file: the reference's OWN spectra solver (glass/grf/_solver.py:27-148,
+    glass/grf/_core.py:141-179, glass/fields.py:743-836) executed from source, with the oracle's
+    restatement of the absent third-party transformcl as its transform pair."""
+    install_shims()
+    from oracle import transformcl_ref as tref
+
+    tcl = sys.modules["transformcl"]
+    tcl.cltocorr, tcl.corrtocl, tcl.cltovar = tref.cltocorr, tref.corrtocl, tref.cltovar
+    sys.path.insert(0, REF)
+    import glass  # the reference itself
+    import glass.fields
+    import glass.grf
+
+    out = {}
+    lmax = 40
+    ell = np.arange(lmax + 1)
+    cl = 1e-2 / (2 * ell + 1) ** 2
+    out["cl"] = cl
+    cases = {
+        "ln": (glass.grf.Lognormal(0.8), None, {}),
+        "ln_pad": (glass.grf.Lognormal(0.8), glass.grf.Lognormal(1.3), {"pad": 2 * (lmax + 1)}),
+        "ln_mono": (glass.grf.Lognormal(), None, {"pad": 2 * (lmax + 1), "monopole": 0.0, "cltol": 1e-9, "gltol": 1e-9}),
+        "ln_normal": (glass.grf.Lognormal(0.6), glass.grf.Normal(), {"pad": lmax + 1}),
+        "sq": (glass.grf.SquaredNormal(0.9, 1.1), glass.grf.SquaredNormal(0.8, 0.7), {"pad": lmax + 1, "cltol": 1e-8}),
+        "iter2": (glass.grf.Lognormal(0.5), None, {"pad": lmax + 1, "maxiter": 2, "cltol": 1e-14, "gltol": 1e-14}),
+    }
+    for tag, (t1, t2, kw) in cases.items():
+        gl, rl, info = glass.grf.solve(cl.copy(), t1, t2, **kw)
+        out[f"solve_{tag}_gl"], out[f"solve_{tag}_rl"], out[f"solve_{tag}_info"] = gl, rl, np.asarray(info)
+    out["compute_ln"] = glass.grf.compute(cl.copy(), glass.grf.Lognormal(0.8))
+    # solve_gaussian_spectra: 3 fields (two lognormal, one normal), a zero monopole, an empty spectrum
+    fields = [glass.grf.Lognormal(1.0), glass.grf.Lognormal(0.7), glass.grf.Normal()]
+    spectra = []
+    for i in range(3):
+        for j in range(i, -1, -1):
+            c = 0.5 ** (i - j) * cl * (1 + 0.1 * i)
+            if i == 1:
+                c[0] = 0.0
+            spectra.append(c if (i, j) != (2, 0) else np.zeros(0))
+    gls = glass.fields.solve_gaussian_spectra(fields, spectra)
+    out["sgs_len"] = np.array([g.shape[0] for g in gls])
+    out["sgs_gls"] = np.concatenate(gls)
+    out["sgs_spectra_len"] = np.array([c.shape[0] for c in spectra])
+    out["sgs_spectra"] = np.concatenate(spectra)
+    np.savez_compressed(os.path.join(HERE, "glass_reference_solver.npz"), **out)
+    print("wrote", len(out), "arrays to glass_reference_solver.npz")
+
+
 def main_spectra():
     """Third file: the spectra-order helpers of glass/fields.py:563-604, 897-1052 and
     position_weights of glass/points.py:610-651."""
@@ -426,7 +475,9 @@ def main_spectra():
 
 
 if __name__ == "__main__":
-    if "--spectra" in sys.argv:
+    if "--solver" in sys.argv:
+        main_solver()
+    elif "--spectra" in sys.argv:
         main_spectra()
     elif "--displace" in sys.argv:
         main_displace()

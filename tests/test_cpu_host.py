@@ -508,6 +508,47 @@ def test_grf_solve_reference_properties(transforms_on_cpu):
         grf.corr(grf.SquaredNormal(0.8), grf.Normal(), x)
 
 
+def test_solver_against_reference_source_golden(transforms_on_cpu):
+    """The product's transform pair against the oracle's independent restatement
+    (oracle/transformcl_ref.py), and the batched solver against vectors produced by executing the
+    reference's OWN solver source on top of that oracle (tests/golden/make_golden.py --solver):
+    same info flags (same stopping point and halvings), gl and the realised cl to 1e-9."""
+    import glass_b200 as glass
+    from glass_b200 import grf
+    from oracle import transformcl_ref as tref
+
+    tcl = transforms_on_cpu
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 41, 123):
+        x = rng.standard_normal(n) / (1 + np.arange(n))
+        assert np.allclose(tcl.cltocorr(x), tref.cltocorr(x), rtol=1e-12, atol=1e-14)
+        c = tref.cltocorr(x)
+        assert np.allclose(tcl.corrtocl(c), tref.corrtocl(c), rtol=1e-10, atol=1e-13)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_solver.npz"))
+    cl, lmax = g["cl"], g["cl"].shape[0] - 1
+    cases = {
+        "ln": (grf.Lognormal(0.8), None, {}),
+        "ln_pad": (grf.Lognormal(0.8), grf.Lognormal(1.3), {"pad": 2 * (lmax + 1)}),
+        "ln_mono": (grf.Lognormal(), None, {"pad": 2 * (lmax + 1), "monopole": 0.0, "cltol": 1e-9, "gltol": 1e-9}),
+        "ln_normal": (grf.Lognormal(0.6), grf.Normal(), {"pad": lmax + 1}),
+        "sq": (grf.SquaredNormal(0.9, 1.1), grf.SquaredNormal(0.8, 0.7), {"pad": lmax + 1, "cltol": 1e-8}),
+        "iter2": (grf.Lognormal(0.5), None, {"pad": lmax + 1, "maxiter": 2, "cltol": 1e-14, "gltol": 1e-14}),
+    }
+    for tag, (t1, t2, kw) in cases.items():
+        gl, rl, info = grf.solve(cl.copy(), t1, t2, **kw)
+        assert info == int(g[f"solve_{tag}_info"]), tag
+        assert np.allclose(gl, g[f"solve_{tag}_gl"], rtol=1e-9, atol=1e-9 * np.abs(gl).max()), tag
+        assert np.allclose(rl, g[f"solve_{tag}_rl"], rtol=1e-9, atol=1e-9 * np.abs(rl).max()), tag
+    assert np.allclose(grf.compute(cl.copy(), grf.Lognormal(0.8)), g["compute_ln"], rtol=1e-10, atol=1e-15)
+    fields = [grf.Lognormal(1.0), grf.Lognormal(0.7), grf.Normal()]
+    spectra = np.split(g["sgs_spectra"], np.cumsum(g["sgs_spectra_len"])[:-1])
+    gls = glass.solve_gaussian_spectra(fields, spectra)
+    ref = np.split(g["sgs_gls"], np.cumsum(g["sgs_len"])[:-1])
+    assert [x.shape[0] for x in gls] == [x.shape[0] for x in ref]
+    for a, b in zip(gls, ref):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * max(np.abs(b).max(), 1e-300) if b.size else 0)
+
+
 def test_solve_gaussian_spectra_batched_equals_single(transforms_on_cpu):
     """solve_gaussian_spectra (glass/fields.py:778-836): the batched run over all spectra follows,
     column by column, the solve the reference would run on each spectrum alone (padding 2n, zero
