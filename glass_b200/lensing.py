@@ -178,6 +178,22 @@ def _pixwin_ratio(nside, lmax, pixwin):
     return pw2 / pw0
 
 
+def _convergence_factors(nside, lmax, discretized, pixwin):
+    """The three successive ``almxfl`` factors of glass/lensing.py:316-363, with the reference's
+    arithmetic: kappa -> psi ``-2 / (l (l+1))``, psi -> alpha ``sqrt(l (l+1))``, alpha -> gamma
+    ``sqrt((l-1)(l+2)) / 2 [* pw2 / pw0]`` (zero at l = 0)."""
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    f_psi = np.zeros(lmax + 1)
+    f_psi[1:] = -2.0 / (ell[1:] * (ell[1:] + 1))
+    f_alpha = np.sqrt(ell * (ell + 1))
+    f_gamma = np.zeros(lmax + 1)
+    f_gamma[1:] = np.sqrt((ell[1:] - 1) * (ell[1:] + 2))
+    f_gamma /= 2
+    if discretized:
+        f_gamma *= _pixwin_ratio(nside, lmax, pixwin)
+    return f_psi, f_alpha, f_gamma
+
+
 def from_convergence(  # noqa: PLR0913
     kappa,
     lmax: int | None = None,
@@ -201,36 +217,31 @@ def from_convergence(  # noqa: PLR0913
     if not (potential or deflection or shear):
         return ()
     alm, nside, lmax, device, on_device = _kappa_alm(kappa, lmax, niter, ring_weights)
-    ell = np.arange(lmax + 1, dtype=np.float64)
+    if shear:
+        f_psi, f_alpha, f_gamma = _convergence_factors(nside, lmax, discretized, pixwin)
+    else:
+        f_psi, f_alpha, _ = _convergence_factors(nside, lmax, False, None)
     results = ()
 
     def out(t):
         return t if on_device else t.cpu().numpy()
 
     # convert convergence to potential (lensing.py:316-322)
-    fl = np.zeros(lmax + 1)
-    fl[1:] = -2.0 / (ell[1:] * (ell[1:] + 1))
-    alm = hp.almxfl(alm, fl, inplace=True)
+    alm = hp.almxfl(alm, f_psi, inplace=True)
     if potential:
         psi = hp.alm2map_batch(alm[None], nside, lmax)[0]
         results += (out(psi),)
     if not (deflection or shear):
         return results
     # deflection alms (lensing.py:337-339)
-    fl = np.sqrt(ell * (ell + 1))
-    alm = hp.almxfl(alm, fl, inplace=True)
+    alm = hp.almxfl(alm, f_alpha, inplace=True)
     if deflection:
         a1, a2 = hp.alm2map_spin([alm, None], nside, 1, lmax)
         results += (out(torch.complex(a1, a2)),)
     if not shear:
         return results
     # shear alms (lensing.py:353-363)
-    fl = np.zeros(lmax + 1)
-    fl[1:] = np.sqrt((ell[1:] - 1) * (ell[1:] + 2))
-    fl /= 2
-    if discretized:
-        fl *= _pixwin_ratio(nside, lmax, pixwin)
-    alm = hp.almxfl(alm, fl, inplace=True)
+    alm = hp.almxfl(alm, f_gamma, inplace=True)
     g1, g2 = hp.alm2map_spin([alm, None], nside, 2, lmax)
     results += (out(torch.complex(g1, g2)),)
     return results

@@ -340,6 +340,72 @@ def main_displace():
     print("wrote", len(out), "arrays to glass_reference_displace.npz")
 
 
+def main_lensing_factors():
+    """Fifth file: the l-dependent factors of glass/lensing.py:296-371, 403-428 as the reference's
+    own source hands them to healpy.almxfl, and the alm it passes on to the spin transforms -- the
+    transforms themselves are recording shims (healpy is absent), so this pins the GLASS-side
+    arithmetic between them."""
+    install_shims()
+    sys.path.insert(0, REF)
+    hpy = sys.modules["healpy"]
+    rec = {"fl": [], "spin": [], "scalar": []}
+    nside, lmax = 4, 9
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    r = np.random.default_rng(17)
+    alm0 = r.standard_normal(nalm) + 1j * r.standard_normal(nalm)
+    lof = np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)])  # l of every m-major entry
+    PW0 = 1.0 / (1.0 + 0.010 * np.arange(lmax + 1.0) ** 2)
+    PW2 = 1.0 / (1.0 + 0.013 * np.arange(lmax + 1.0) ** 2)
+
+    def map2alm(m, lmax=None, pol=True, use_pixel_weights=False, **kw):
+        return alm0.copy()
+
+    def almxfl(alm, fl, mmax=None, inplace=False):
+        rec["fl"].append(np.array(fl, copy=True))
+        out = alm if inplace else alm.copy()
+        out *= np.asarray(fl)[lof]
+        return out
+
+    def alm2map(alm, nside, lmax=None, **kw):
+        rec["scalar"].append(np.array(alm, copy=True))
+        return np.zeros(12 * nside * nside)
+
+    def alm2map_spin(alms, nside, spin, lmax, mmax=None):
+        rec["spin"].append((spin, np.array(alms[0], copy=True), np.array(alms[1], copy=True)))
+        return [np.zeros(12 * nside * nside), np.zeros(12 * nside * nside)]
+
+    hpy.map2alm, hpy.almxfl, hpy.alm2map, hpy.alm2map_spin = map2alm, almxfl, alm2map, alm2map_spin
+    hpy.get_nside = lambda m: H.npix2nside(np.asarray(m).shape[-1])
+    hpy.pixwin = lambda nside, pol=False, lmax=None: (PW0[: lmax + 1], PW2[: lmax + 1]) if pol else PW0[: lmax + 1]
+    import glass  # the reference itself
+    import glass.healpix as ghp
+    import glass.lensing
+
+    ghp.pixwin = lambda nside, lmax=None, pol=False, xp=None: (PW0[: lmax + 1], PW2[: lmax + 1]) if pol else PW0[: lmax + 1]
+    kappa = np.zeros(12 * nside * nside)
+    out = {"alm0": alm0, "pw0": PW0, "pw2": PW2, "lmax": np.asarray(lmax)}
+    for tag, disc in (("plain", False), ("disc", True)):
+        for k in rec:
+            rec[k].clear()
+        glass.lensing.from_convergence(kappa, lmax, potential=True, deflection=True, shear=True, discretized=disc)
+        out[f"fc_{tag}_fl"] = np.stack(rec["fl"])  # psi, alpha, gamma factors
+        out[f"fc_{tag}_psi_alm"] = rec["scalar"][0]
+        out[f"fc_{tag}_alpha_alm"] = rec["spin"][0][1]
+        out[f"fc_{tag}_gamma_alm"] = rec["spin"][1][1]
+        assert rec["spin"][0][0] == 1 and rec["spin"][1][0] == 2 and not rec["spin"][1][2].any()
+        for k in rec:
+            rec[k].clear()
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            glass.lensing.shear_from_convergence(kappa, lmax, discretized=disc)
+        out[f"sfc_{tag}_fl"] = rec["fl"][0]
+        out[f"sfc_{tag}_alm"] = rec["spin"][0][1]
+    np.savez_compressed(os.path.join(HERE, "glass_reference_lensing_factors.npz"), **out)
+    print("wrote", len(out), "arrays to glass_reference_lensing_factors.npz")
+
+
 def main_solver():
     """Fourth file: the reference's OWN spectra solver (glass/grf/_solver.py:27-148,
     glass/grf/_core.py:141-179, glass/fields.py:743-836) executed from source, with the oracle's
@@ -475,7 +541,9 @@ def main_spectra():
 
 
 if __name__ == "__main__":
-    if "--solver" in sys.argv:
+    if "--lensing-factors" in sys.argv:
+        main_lensing_factors()
+    elif "--solver" in sys.argv:
         main_solver()
     elif "--spectra" in sys.argv:
         main_spectra()

@@ -508,6 +508,68 @@ def test_grf_solve_reference_properties(transforms_on_cpu):
         grf.corr(grf.SquaredNormal(0.8), grf.Normal(), x)
 
 
+def test_lensing_factor_chain_golden(monkeypatch):
+    """from_convergence / shear_from_convergence between the transforms (glass/lensing.py:296-371,
+    403-428): the l-dependent factors and the alm handed to the spin transforms, against what the
+    reference's own source produced with recording shims in place of healpy
+    (tests/golden/make_golden.py --lensing-factors).  The transforms are faked here too, so the
+    host-side control flow of the product runs on the CPU; oracle factors are checked alongside."""
+    import torch
+
+    import glass_b200.lensing as L
+    from oracle import glass_ref as G
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_lensing_factors.npz"))
+    lmax, nside = int(g["lmax"]), 4
+    lof = np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)])
+    rec = {"fl": [], "scalar": [], "spin": []}
+
+    def almxfl(alm, fl, *, inplace=False):
+        rec["fl"].append(np.array(fl, copy=True))
+        alm *= torch.as_tensor(np.asarray(fl)[lof])
+        return alm
+
+    def alm2map_batch(alms, nside, lmax=None, transforms=None, out=None):
+        rec["scalar"].append(alms[0].numpy().copy())
+        return torch.zeros((alms.shape[0], 12 * nside * nside), dtype=torch.float64)
+
+    def alm2map_spin(alms, nside, spin, lmax):
+        assert alms[1] is None  # E-only, like the reference's zero blm
+        rec["spin"].append((spin, alms[0].numpy().copy()))
+        return torch.zeros(12 * nside * nside, dtype=torch.float64), torch.zeros(12 * nside * nside, dtype=torch.float64)
+
+    monkeypatch.setattr(L.hp, "almxfl", almxfl)
+    monkeypatch.setattr(L.hp, "alm2map_batch", alm2map_batch)
+    monkeypatch.setattr(L.hp, "alm2map_spin", alm2map_spin)
+    monkeypatch.setattr(L, "_kappa_alm", lambda kappa, lmax_, niter, rw: (torch.as_tensor(g["alm0"].copy()), nside, lmax, torch.device("cpu"), True))
+    kappa = np.zeros(12 * nside * nside)
+    for tag, disc in (("plain", False), ("disc", True)):
+        pixwin = (g["pw0"], g["pw2"]) if disc else None
+        for k in rec:
+            rec[k].clear()
+        res = L.from_convergence(kappa, lmax, potential=True, deflection=True, shear=True, discretized=disc, pixwin=pixwin)
+        assert len(res) == 3 and res[1].is_complex() and res[2].is_complex()
+        assert np.array_equal(np.stack(rec["fl"]), g[f"fc_{tag}_fl"])
+        assert np.array_equal(rec["scalar"][0], g[f"fc_{tag}_psi_alm"])
+        assert rec["spin"][0][0] == 1 and np.array_equal(rec["spin"][0][1], g[f"fc_{tag}_alpha_alm"])
+        assert rec["spin"][1][0] == 2 and np.array_equal(rec["spin"][1][1], g[f"fc_{tag}_gamma_alm"])
+        for k in rec:
+            rec[k].clear()
+        g1g2 = L.shear_from_convergence(kappa, lmax, discretized=disc, pixwin=pixwin)
+        assert len(g1g2) == 2
+        assert np.array_equal(rec["fl"][0], g[f"sfc_{tag}_fl"]) and np.array_equal(rec["spin"][0][1], g[f"sfc_{tag}_alm"])
+        # the oracle's restatement of the same factors
+        pw = {"pw0": g["pw0"], "pw2": g["pw2"]} if disc else {}
+        assert all(np.array_equal(a, b) for a, b in zip(G.from_convergence_factors(lmax, discretized=disc, **pw), g[f"fc_{tag}_fl"]))
+    assert np.array_equal(G.kappa_to_shear_fl(lmax), g["sfc_plain_fl"])
+    # potential only: the pixel window is not needed (and not asked for)
+    for k in rec:
+        rec[k].clear()
+    assert len(L.from_convergence(kappa, lmax, potential=True)) == 1 and len(rec["fl"]) == 1
+    with pytest.raises(NotImplementedError, match="pixel window"):
+        L.from_convergence(kappa, lmax, shear=True)
+
+
 def test_solver_against_reference_source_golden(transforms_on_cpu):
     """The product's transform pair against the oracle's independent restatement
     (oracle/transformcl_ref.py), and the batched solver against vectors produced by executing the
