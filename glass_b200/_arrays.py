@@ -24,7 +24,10 @@ def pick_device(*arrays) -> tuple[torch.device, bool]:
 def to_dev(x, device, dtype=torch.float64) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(x)
+    if not a.flags.writeable:  # broadcast views: torch warns about wrapping read-only memory
+        a = a.copy()
+    return torch.as_tensor(a).to(device=device, dtype=dtype).contiguous()
 
 
 def to_np(x) -> np.ndarray:

@@ -508,6 +508,88 @@ def test_grf_solve_reference_properties(transforms_on_cpu):
         grf.corr(grf.SquaredNormal(0.8), grf.Normal(), x)
 
 
+def test_multi_plane_host_scalars_golden(monkeypatch):
+    """The REAL glass_b200.MultiPlaneConvergence on CPU tensors with only the K9 kernel replaced
+    (by the reference's three NumPy passes acting on the same buffers): window weight, extrapolation
+    law t, lensing weight f, buffer cycling -- against the kappa planes the reference's own source
+    produced with MockCosmology (golden mpc_*), bit for bit; plus the error of a non-increasing
+    source redshift."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.lensing as L
+
+    def arr(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    class FakeLib:
+        def glb_multiplane_update(self, k3, k2, d2, _zero, n, t, f, st):
+            kappa3, kappa2 = arr(k3, n), arr(k2, n)
+            kappa3 *= 1 - np.asarray(t)  # glass/lensing.py:584-586
+            kappa3 += np.asarray(t) * kappa2
+            if d2 is not None:
+                kappa3 += np.asarray(f) * arr(d2, n)
+            return 0
+
+    monkeypatch.setattr(L._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(L.A, "pick_device", lambda *a: (torch.device("cpu"), True))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    deltas = gold["mpc_deltas"]
+    conv = L.MultiPlaneConvergence(_MockCosmo())
+    assert conv.kappa is None and conv.delta is None
+    for i in range(deltas.shape[0]):
+        w = types.SimpleNamespace(za=np.array([i, i + 1.0, i + 2.0]), wa=np.array([0.0, 1.0, 0.0]), zeff=i + 1.0)
+        conv.add_window(torch.as_tensor(deltas[i].copy()), w)
+        assert np.array_equal(conv.kappa.numpy(), gold["mpc_kappas"][i]), i
+        assert conv.zsrc == i + 1.0 and conv.wlens == 1.0 and np.array_equal(conv.delta.numpy(), deltas[i])
+    with pytest.raises(ValueError, match="source redshift must be increasing"):
+        conv.add_plane(torch.as_tensor(deltas[0].copy()), 5.0)
+
+
+def test_redshifts_host_cdf_golden(monkeypatch):
+    """redshifts_from_nz (glass/galaxies.py:188-268, 77-89): the host side of the product -- broadcast
+    of count / z / nz, cumulative-trapezoid CDF, its normalisation -- with the inverse-CDF kernel
+    replaced by its definition interp(u, cdf, z) on the same buffers, against the reference's own
+    source fed the same uniform deviates (golden z_*), bit for bit."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.galaxies as gal
+    from glass_b200.rng import Deviates
+
+    def arr(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    class FakeLib:
+        def glb_redshifts_from_cdf(self, cdf, z, ncdf, u, n, seed, call, pos, out, st):
+            arr(out, n)[:] = np.interp(arr(u, n), arr(cdf, ncdf), arr(z, ncdf))
+            return 0
+
+    monkeypatch.setattr(gal._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(gal.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    got = gal.redshifts_from_nz(400, gold["z_grid"], gold["z_nz"], rng=Deviates(uniform=gold["z_uniform"]), warn=False)
+    assert isinstance(got, np.ndarray) and np.array_equal(got, gold["z_samples"])
+    with pytest.warns(UserWarning, match="redshifts_from_nz"):
+        gal.redshifts_from_nz(3, gold["z_grid"], gold["z_nz"], rng=Deviates(uniform=gold["z_uniform"]))
+    # two populations with their own n(z): runs concatenated in population order
+    nz2 = np.stack([gold["z_nz"], gold["z_nz"][::-1]])
+    got2 = gal.redshifts_from_nz(np.array([150, 250]), gold["z_grid"], nz2, rng=Deviates(uniform=gold["z_uniform"]), warn=False)
+    assert got2.shape == (400,) and np.array_equal(got2[:150], gold["z_samples"][:150])
+    w = types.SimpleNamespace(za=gold["z_grid"], wa=gold["z_nz"], zeff=1.0)
+    assert np.array_equal(gal.redshifts(400, w, rng=Deviates(uniform=gold["z_uniform"])), gold["z_samples"])
+
+
 def test_lensing_factor_chain_golden(monkeypatch):
     """from_convergence / shear_from_convergence between the transforms (glass/lensing.py:296-371,
     403-428): the l-dependent factors and the alm handed to the spin transforms, against what the
