@@ -406,6 +406,52 @@ def main_lensing_factors():
     print("wrote", len(out), "arrays to glass_reference_lensing_factors.npz")
 
 
+def main_positions():
+    """Sixth file: the whole glass.positions_from_delta (glass/points.py:443-540) executed from the
+    reference's source for populations with leading axes -- ngal (2,), delta (npix,), bias (3, 1),
+    vis (npix,) -> dims (3, 2) -- with the Poisson count maps it drew recorded, so that the
+    product can be replayed from the same counts; in-pixel positions are pixel centres
+    (healpix.randang shim, u = v = 1/2)."""
+    install_shims()
+    sys.path.insert(0, REF)
+    import glass  # the reference itself
+    import glass.points
+
+    nside = 4
+    npix = 12 * nside**2
+    r = np.random.default_rng(23)
+    delta = np.expm1(0.4 * r.standard_normal(npix) - 0.08)
+    vis = (r.random(npix) > 0.2) * r.random(npix)
+    ngal = np.array([6e-4, 1.5e-3])
+    bias = np.array([[0.5], [1.0], [1.7]])
+    drawn = []
+    real = glass.points._sample_number_galaxies
+
+    def recording(n, *, rng=None):
+        c = real(n, rng=rng)
+        drawn.append(np.array(c, copy=True))
+        return c
+
+    glass.points._sample_number_galaxies = recording
+    out = {"delta": delta, "vis": vis, "ngal": ngal, "bias": bias}
+    for tag, kw in {"lin": {}, "loglin_rm": {"bias_model": glass.loglinear_bias, "remove_monopole": True}}.items():
+        drawn.clear()
+        res = list(glass.positions_from_delta(ngal, delta, bias, vis, batch=40, rng=np.random.default_rng(5), **kw))
+        out[f"{tag}_counts"] = np.stack(drawn)  # one count map per population, in iteration order
+        out[f"{tag}_batch_count"] = np.stack([c for _lo, _la, c in res])  # (nbatch, 3, 2) one-hot x size
+        out[f"{tag}_lon"] = np.concatenate([lo for lo, _la, _c in res])
+        out[f"{tag}_lat"] = np.concatenate([la for _lo, la, _c in res])
+    # scalar inputs: count is a plain int
+    drawn.clear()
+    res = list(glass.positions_from_delta(2e-3, delta, None, None, batch=1000, rng=np.random.default_rng(6)))
+    out["scalar_counts"] = drawn[0]
+    out["scalar_batch_count"] = np.array([c for _lo, _la, c in res])
+    assert all(isinstance(c, (int, np.integer)) for _lo, _la, c in res)
+    out["scalar_lon"] = np.concatenate([lo for lo, _la, _c in res])
+    np.savez_compressed(os.path.join(HERE, "glass_reference_positions.npz"), **out)
+    print("wrote", len(out), "arrays to glass_reference_positions.npz")
+
+
 def main_solver():
     """Fourth file: the reference's OWN spectra solver (glass/grf/_solver.py:27-148,
     glass/grf/_core.py:141-179, glass/fields.py:743-836) executed from source, with the oracle's
@@ -541,7 +587,9 @@ def main_spectra():
 
 
 if __name__ == "__main__":
-    if "--lensing-factors" in sys.argv:
+    if "--positions" in sys.argv:
+        main_positions()
+    elif "--lensing-factors" in sys.argv:
         main_lensing_factors()
     elif "--solver" in sys.argv:
         main_solver()

@@ -551,6 +551,74 @@ def test_multi_plane_host_scalars_golden(monkeypatch):
         conv.add_plane(torch.as_tensor(deltas[0].copy()), 5.0)
 
 
+def test_positions_from_delta_host_flow_golden(monkeypatch):
+    """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
+    their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
+    the population axes, iteration order, the one-hot batch counts, batch cuts and the concatenated
+    positions against the reference's own source run on the same count maps (golden positions file)."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.points as P
+    from glass_b200.rng import Deviates
+    from oracle import healpix_ref as H
+
+    def f64(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    def i64(ptr, n):
+        return np.ctypeslib.as_array((C.c_int64 * n).from_address(ptr))
+
+    seen = []
+
+    class FakeLib:
+        def glb_points_workspace_bytes(self, npix):
+            return 64
+
+        def glb_points_counts(self, npix, d, v, code, bias, scale, rm, cin, seed, stream, nbar, counts, off, ws, st):
+            seen.append((code, bias, bool(rm), v is not None, stream.value))
+            c = i64(cin, npix)
+            i64(counts, npix)[:] = c
+            o = i64(off, npix + 1)
+            o[0] = 0
+            o[1:] = np.cumsum(c)
+            return 0
+
+        def glb_points_fill(self, nside, counts, off, start, stop, u, v, seed, stream, lon, lat, ipix, st):
+            npix = 12 * nside * nside
+            c, o = i64(counts, npix), i64(off, npix + 1)
+            n = int(o[stop] - o[start])
+            pix = np.repeat(np.arange(start, stop), c[start:stop])
+            lo, la = H.ring2ang_uv(nside, pix, f64(u, n), f64(v, n), lonlat=True)
+            f64(lon, n)[:], f64(lat, n)[:] = lo, la
+            return 0
+
+    monkeypatch.setattr(P._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(P.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_positions.npz"))
+    centre = lambda n: (np.full(n, 0.5), np.full(n, 0.5))  # noqa: E731
+    for tag, kw in {"lin": {}, "loglin_rm": {"bias_model": P.loglinear_bias, "remove_monopole": True}}.items():
+        seen.clear()
+        res = list(P.positions_from_delta(g["ngal"], g["delta"], g["bias"], g["vis"], batch=40,
+                                          rng=Deviates(poisson=list(g[f"{tag}_counts"]), uv=centre), **kw))
+        assert np.array_equal(np.stack([c for _lo, _la, c in res]), g[f"{tag}_batch_count"])
+        assert np.array_equal(np.concatenate([lo for lo, _la, _c in res]), g[f"{tag}_lon"])
+        assert np.array_equal(np.concatenate([la for _lo, la, _c in res]), g[f"{tag}_lat"])
+        # six populations in C order of dims (3, 2): bias varies along the first axis, every one sees vis
+        assert [s[1] for s in seen] == [0.5, 0.5, 1.0, 1.0, 1.7, 1.7] and [s[4] for s in seen] == list(range(6))
+        assert all(s[0] == (2 if tag == "loglin_rm" else 1) and s[2] == (tag == "loglin_rm") and s[3] for s in seen)
+    res = list(P.positions_from_delta(2e-3, g["delta"], None, None, batch=1000, rng=Deviates(poisson=[g["scalar_counts"]], uv=centre)))
+    assert all(isinstance(c, int) for _lo, _la, c in res) and [c for _lo, _la, c in res] == list(g["scalar_batch_count"])
+    assert np.array_equal(np.concatenate([lo for lo, _la, _c in res]), g["scalar_lon"])
+    with pytest.raises(TypeError, match="bias_model must be callable"):
+        next(P.positions_from_delta(1e-3, g["delta"], bias_model=0))
+
+
 def test_redshifts_host_cdf_golden(monkeypatch):
     """redshifts_from_nz (glass/galaxies.py:188-268, 77-89): the host side of the product -- broadcast
     of count / z / nz, cumulative-trapezoid CDF, its normalisation -- with the inverse-CDF kernel
