@@ -644,17 +644,22 @@ class _ShellSampler:
         return None if self.dnorm is None else self.dnorm.first_failure()
 
 
+def _pick_device(gls) -> tuple[torch.device, bool]:
+    """(device, on_device): the device of the first CUDA spectrum, else the current CUDA device
+    (raises without one); on_device decides the array rule of the module docstring."""
+    for gl in gls:
+        if isinstance(gl, torch.Tensor) and gl.is_cuda:
+            return gl.device, True
+    return torch.device("cuda", hp._device_index()), False
+
+
 def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=None):
     """
     Core of _generate_grf / generate.  ``transforms_for(i)`` returns the fused
     (kind, p0, p1) descriptor for shell i or None for "no fused transform".
     Yields (i, map) with map a CUDA tensor or a NumPy array (array rule above).
     """
-    on_device = any(isinstance(gl, torch.Tensor) and gl.is_cuda for gl in gls)
-    if on_device:
-        device = next(gl.device for gl in gls if isinstance(gl, torch.Tensor) and gl.is_cuda)
-    else:
-        device = torch.device("cuda", hp._device_index())
+    device, on_device = _pick_device(gls)
     wanted = None
     if shells is not None:
         wanted = shells if callable(shells) else (lambda j, _s=frozenset(int(i) for i in shells): j in _s)

@@ -551,6 +551,101 @@ def test_multi_plane_host_scalars_golden(monkeypatch):
         conv.add_plane(torch.as_tensor(deltas[0].copy()), 5.0)
 
 
+def test_generate_host_flow_golden(monkeypatch):
+    """The REAL glass_b200.generate / _generate_grf on CPU tensors with the kernels replaced by their
+    definitions (l-major -> m-major, sum_i z_i w[l, i] + the m = 0 fix) and the synthesis by a
+    recorder: iternorm weights, the z history and its trimming, the `mis` offset into the weights,
+    shell batching and the fused transformation descriptors -- the alm handed to the synthesis
+    against the alm the reference's own source handed to healpy.alm2map (golden grf_alm_*), bit
+    for bit; shell selection (sharding) and the deferred error on a bad spectrum."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.fields as F
+    from glass_b200 import _lib as L
+    from glass_b200 import grf
+    from glass_b200.rng import Deviates
+    from helpers import synthetic_gls
+
+    def c128(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * (2 * n)).from_address(ptr)).view(np.complex128)
+
+    def f64(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    def order(lmax):  # m-major position -> l-major index, and l of every m-major entry
+        ls = np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)])
+        ms = np.concatenate([np.full(lmax + 1 - m, m) for m in range(lmax + 1)])
+        return ls * (ls + 1) // 2 + ms, ls
+
+    class FakeLib:
+        def glb_alm_glass_to_healpix(self, lmax, src, dst, st):
+            n = (lmax + 1) * (lmax + 2) // 2
+            c128(dst, n)[:] = c128(src, n)[order(lmax)[0]]
+            return 0
+
+        def glb_alm_combine(self, lmax, nterms, zptrs, w, stride, out, st):
+            n = (lmax + 1) * (lmax + 2) // 2
+            ls = order(lmax)[1]
+            wmat = f64(w, (lmax + 1) * stride).reshape(lmax + 1, stride)
+            alm = sum(c128(zptrs[i], n) * wmat[ls, i] for i in range(nterms))
+            alm[: lmax + 1] = alm[: lmax + 1].real + alm[: lmax + 1].imag + 0j
+            c128(out, n)[:] = alm
+            return 0
+
+    fed = []
+
+    def alm2map_batch(alms, nside, lmax=None, transforms=None, out=None):
+        fed.append((alms.numpy().copy(), list(transforms)))
+        return torch.zeros((alms.shape[0], 12 * nside * nside), dtype=torch.float64)
+
+    monkeypatch.setattr(F._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(F, "_pick_device", lambda gls: (torch.device("cpu"), True))
+    monkeypatch.setattr(F.hp, "alm2map_batch", alm2map_batch)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    for name, (nshell, lmax, ncorr, ragged) in {"a": (4, 12, 2, False), "b": (5, 9, None, False), "c": (4, 10, 1, True)}.items():
+        nc = nshell - 1 if ncorr is None else ncorr
+        gls = synthetic_gls(nshell, lmax, nc, ragged)
+        rng = np.random.default_rng(42)
+        n = (lmax + 1) * (lmax + 2) // 2
+        zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(nshell)]
+        fed.clear()
+        maps = list(F._generate_grf(gls, 4, ncorr=ncorr, rng=Deviates(normal_alm=zs)))
+        assert len(maps) == nshell and all(m.shape == (192,) for m in maps)
+        assert np.array_equal(np.concatenate([a for a, _t in fed]), gold[f"grf_alm_{name}"])
+        assert [a.shape[0] for a, _t in fed] == ([4] if nshell == 4 else [4, 1])  # batches of SHT_BATCH shells
+        assert all(t == (L.T_NORMAL, 0.0, 1.0) for _a, tr in fed for t in tr)
+        # a rank's shard: only its shells are synthesised, from the same deviates
+        fed.clear()
+        mine = [1, 3]
+        list(F.generate([grf.Normal()] * nshell, gls, 4, ncorr=ncorr, rng=Deviates(normal_alm=zs), shells=mine))
+        assert np.array_equal(np.concatenate([a for a, _t in fed]), gold[f"grf_alm_{name}"][mine])
+    # fused descriptors: Lognormal(lamda) -> (kind, var/2, lamda) with var = sum (2l+1)/(4 pi) g_l of the auto-spectrum
+    gls = synthetic_gls(3, 8, 2)
+    fields = [grf.Lognormal(0.7), grf.Normal(), grf.SquaredNormal(0.3, 1.5)]
+    fed.clear()
+    zs = [np.zeros(45, dtype=complex)] * 3
+    list(F.generate(fields, gls, 4, rng=Deviates(normal_alm=zs)))
+    var0 = F.cltovar(gls[0])
+    assert fed[0][1] == [(L.T_LOGNORMAL, var0 / 2, 0.7), (L.T_NORMAL, 0.0, 1.0), (L.T_SQUARED_NORMAL, 0.3, 1.5)]
+    with pytest.raises(ValueError, match="mismatch between number of fields and gls"):
+        next(F.generate(fields[:2], gls, 4))
+    # a negative auto-spectrum in the third shell: the first two shells are still produced, then the error
+    bad = [g.copy() for g in gls]
+    bad[3][2] = -1.0
+    got = []
+    with pytest.raises(ValueError, match="negative values in cl"):
+        for m in F.generate(fields, bad, 4, rng=Deviates(normal_alm=zs)):
+            got.append(m)
+    assert len(got) == 2
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
