@@ -646,6 +646,54 @@ def test_generate_host_flow_golden(monkeypatch):
     assert len(got) == 2
 
 
+def test_ellipticity_host_flow_golden(monkeypatch):
+    """ellipticity_intnorm (glass/shapes.py:288-362) with the kernel replaced by its definition
+    (e = sigma_eta n, e *= tanh(r/2)/r): the host side -- admissibility check, the sigma -> sigma_eta
+    fit, population order and offsets -- against the reference's own source on the same normals."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.shapes as S
+    from glass_b200.rng import Deviates
+
+    def c128(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * (2 * n)).from_address(ptr)).view(np.complex128)
+
+    calls = []
+
+    class FakeLib:
+        def glb_ellipticity(self, mode, sigma_eta, normals, n, seed, call, pos, out, st):
+            calls.append((mode, sigma_eta, n, pos.value))
+            e = c128(normals, n) * sigma_eta
+            r = np.hypot(e.real, e.imag)
+            e = e * np.where(r > 0, np.divide(np.tanh(r / 2), np.where(r > 0, r, 1.0)), 1.0)
+            c128(out, n)[:] = e
+            return 0
+
+    monkeypatch.setattr(S._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(S.hp, "_device_index", lambda device=None: 0)
+    real_device = torch.device
+    monkeypatch.setattr(S.torch, "device", lambda *a, **k: real_device("cpu"))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    got = S.ellipticity_intnorm(500, 0.256, rng=Deviates(normal=gold["eps_normals"]))
+    assert isinstance(got, np.ndarray) and np.array_equal(got, gold["eps_intnorm"])
+    s = 0.256
+    assert calls == [(0, s * ((8 + 5 * s**2) / (2 - 4 * s**2)) ** 0.5, 500, 0)]
+    # two populations: consecutive runs of the output, each with its own sigma_eta
+    calls.clear()
+    got2 = S.ellipticity_intnorm(np.array([200, 300]), np.array([0.256, 0.1]), rng=Deviates(normal=gold["eps_normals"]))
+    assert got2.shape == (500,) and np.array_equal(got2[:200], gold["eps_intnorm"][:200])
+    assert [(c[2], c[3]) for c in calls] == [(200, 0), (300, 200)]
+    for bad in (-0.1, 0.5**0.5, 1.0):
+        with pytest.raises(ValueError, match="sigma must be between 0 and sqrt"):
+            S.ellipticity_intnorm(10, bad)
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
