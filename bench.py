@@ -114,6 +114,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm (oracle port): the reference path for one lognormal shell on the host cores
 # ------------------------------------------------------------------------------------------
+_CPU_EARLIER: dict = {}
+
+
 def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> tuple[float, float]:
     """One shell of the reference path on the CPU, as (seconds of the NumPy part, seconds of the
     transform): NumPy normals + banded combine + l-major->m-major (glass/fields.py:404-425) and
@@ -124,9 +127,12 @@ def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> tuple[float, floa
     from oracle import sht_c
 
     gls = synthetic_gls(NCORR + 1, lmax, NCORR)
-    rng = np.random.default_rng(42)
+    rng = np.random.default_rng(42 + len(_CPU_EARLIER))
     n = (lmax + 1) * (lmax + 2) // 2
-    zs = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR)]
+    if lmax not in _CPU_EARLIER:  # the NCORR earlier shells' normals: drawn once per size, outside the timed part
+        _CPU_EARLIER.clear()
+        _CPU_EARLIER[lmax] = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR)]
+    zs = list(_CPU_EARLIER[lmax])
     t0 = time.perf_counter()
     # the (ncorr+1)-th shell has the full set of correlated terms, like every later shell
     zs.append(rng.standard_normal((n, 2)) @ np.array([1, 1j]))
@@ -280,7 +286,7 @@ def run_reference(args) -> None:
     from oracle import sht_c
 
     cores = sht_c.max_threads()
-    ns, _, _ = cpu_sample(12.0, cores)  # timed seconds of CPU work per step (drawing the earlier shells' normals adds about as much untimed)
+    ns, _, _ = cpu_sample(8.0, cores)  # timed seconds of CPU work per step; the other shells of the combine add about as much untimed
     for _ in range(args.warmup):
         cpu_shell_seconds(ns, 2 * ns - 1, cores)
     t_np = t_sht = 0.0
