@@ -443,7 +443,7 @@ def solve_gaussian_spectra(fields, spectra):
                     warnings.warn(f"Gaussian spectrum for fields ({i}, {j}) did not converge", stacklevel=2)
                 out[k] = gl
             continue
-        cols = torch.stack([A_to_dev(spectra[k], device) for k in members], dim=1)
+        cols = torch.stack([_as_device_f64(spectra[k], device) for k in members], dim=1)
         mono = torch.where(cols[0] == 0, torch.zeros_like(cols[0]), torch.full_like(cols[0], float("nan")))
         gl, _rl, info = grf.solve_columns(cols, t1, t2, pad=2 * length, fix_monopole=mono)
         info = info.cpu().numpy()
@@ -456,7 +456,7 @@ def solve_gaussian_spectra(fields, spectra):
     return out
 
 
-def A_to_dev(x, device) -> torch.Tensor:
+def _as_device_f64(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.float64)
     return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device)
