@@ -694,6 +694,56 @@ def test_ellipticity_host_flow_golden(monkeypatch):
             S.ellipticity_intnorm(10, bad)
 
 
+def test_gaussian_phz_host_flow_golden(monkeypatch):
+    """gaussian_phz (glass/galaxies.py:350-455) with the kernel replaced by its definition (normal
+    draw z + (1+z) sigma_0 n; later rounds replace only the out-of-bounds entries; count of those
+    left): bounds handling, validation and the rejection rounds of the product's host side against
+    the reference's own source on the same normals (golden phz_*)."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.galaxies as gal
+    from glass_b200.rng import Deviates
+
+    def f64(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    rounds_run = []
+
+    class FakeLib:
+        def glb_gaussian_phz(self, z, s_arr, s_val, lo_arr, lo_val, hi_arr, hi_val, normals, redraw_only, n, seed, call, out, nbad, st):
+            zz = f64(z, n)
+            sig = (1 + zz) * (f64(s_arr, n) if s_arr else s_val)
+            lo = f64(lo_arr, n) if lo_arr else lo_val
+            hi = f64(hi_arr, n) if hi_arr else hi_val
+            o = f64(out, n)
+            draw = zz + sig * f64(normals, n)  # Generator.normal(loc, scale) = loc + scale * standard_normal
+            if redraw_only:
+                bad = (o < lo) | (o > hi)
+                o[bad] = draw[bad]
+            else:
+                o[:] = draw
+            np.ctypeslib.as_array((C.c_int64 * 1).from_address(nbad))[0] = np.count_nonzero((o < lo) | (o > hi))
+            rounds_run.append(int(redraw_only))
+            return 0
+
+    monkeypatch.setattr(gal._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(gal.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    got = gal.gaussian_phz(gold["phz_z"], 0.2, lower=0.1, upper=1.2, rng=Deviates(normal=list(gold["phz_normals"])))
+    assert got.shape == gold["phz_z"].shape and np.array_equal(got, gold["phz_out"])
+    assert rounds_run[0] == 0 and len(rounds_run) > 2 and all(r == 1 for r in rounds_run[1:])
+    with pytest.raises(ValueError, match="requires lower < upper"):
+        gal.gaussian_phz(gold["phz_z"], 0.2, lower=1.0, upper=0.5)
+    with pytest.raises(ValueError, match="lower and upper must best scalars or have the same shape as z"):
+        gal.gaussian_phz(gold["phz_z"], 0.2, lower=np.zeros(3), upper=np.ones(3))
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
