@@ -744,6 +744,51 @@ def test_gaussian_phz_host_flow_golden(monkeypatch):
         gal.gaussian_phz(gold["phz_z"], 0.2, lower=np.zeros(3), upper=np.ones(3))
 
 
+def test_uniform_positions_host_flow_golden(monkeypatch):
+    """uniform_positions (glass/points.py:543-607) with the kernel replaced by its definition
+    (lon = -180 + 360 u1, lat = degrees(asin(-1 + 2 u2))): Poisson totals, population order, the
+    count arrays, against the reference's own source replayed from the same stream (golden up_*)."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.points as P
+    from glass_b200.rng import Deviates
+
+    def f64(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    class FakeLib:
+        def glb_uniform_positions(self, n, u1, u2, seed, stream, lon, lat, st):
+            f64(lon, n)[:] = -180.0 + 360.0 * f64(u1, n)
+            f64(lat, n)[:] = np.degrees(np.arcsin(-1.0 + 2.0 * f64(u2, n)))
+            return 0
+
+    monkeypatch.setattr(P._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(P.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    pos = {"i": 0}
+
+    def uniforms(n):
+        i = pos["i"]
+        pos["i"] += n
+        return g["up_u_lon"][i : i + n], g["up_u_lat"][i : i + n]
+
+    res = list(P.uniform_positions(g["up_ngal"], rng=Deviates(poisson=[g["up_totals"]], uniform=uniforms)))
+    assert len(res) == 2
+    assert np.array_equal(np.concatenate([r[0] for r in res]), g["up_lon"])
+    assert np.array_equal(np.concatenate([r[1] for r in res]), g["up_lat"])
+    assert np.array_equal(np.stack([r[2] for r in res]), g["up_count"])
+    # scalar density: the count is a plain int
+    pos["i"] = 0
+    (lon, lat, cnt), = list(P.uniform_positions(float(g["up_ngal"][0]), rng=Deviates(poisson=[g["up_totals"][:1]], uniform=uniforms)))
+    assert isinstance(cnt, int) and cnt == int(g["up_totals"][0]) and lon.shape == (cnt,)
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
