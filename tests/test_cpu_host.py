@@ -789,6 +789,56 @@ def test_uniform_positions_host_flow_golden(monkeypatch):
     assert isinstance(cnt, int) and cnt == int(g["up_totals"][0]) and lon.shape == (cnt,)
 
 
+def test_galaxy_shear_host_flow_golden(monkeypatch):
+    """galaxy_shear (glass/galaxies.py:271-347) with the kernel replaced by its definition (pixel lookup,
+    three gathers, reduced-shear formula from the oracle): argument plumbing, broadcasting of scalar
+    maps / ellipticities, the ipix shortcut -- against the reference's own source (golden gs_*)."""
+    import contextlib
+    import ctypes as C
+    import types
+
+    import torch
+
+    import glass_b200.galaxies as gal
+    from oracle import glass_ref as G
+    from oracle import healpix_ref as H
+
+    def f64(ptr, n):
+        return np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+
+    def c128(ptr, n):
+        return f64(ptr, 2 * n).view(np.complex128)
+
+    used_ipix = []
+
+    class FakeLib:
+        def glb_galaxy_shear(self, nside, lon, lat, ipix, eps, n, kappa, g1, g2, reduced, out, st):
+            npix = 12 * nside * nside
+            used_ipix.append(ipix is not None)
+            if ipix is None:
+                lo, la = f64(lon, n), f64(lat, n)
+            else:  # pixel centres stand for the positions: the same pixels are looked up
+                p = np.ctypeslib.as_array((C.c_int64 * n).from_address(ipix))
+                lo, la = H.ring2ang_uv(nside, p, np.full(n, 0.5), np.full(n, 0.5), lonlat=True)
+            c128(out, n)[:] = G.galaxy_shear(lo, la, c128(eps, n), f64(kappa, npix), f64(g1, npix), f64(g2, npix), reduced_shear=bool(reduced))
+            return 0
+
+    monkeypatch.setattr(gal._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(gal.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    args = (g["gs_lon"], g["gs_lat"], g["gs_eps"], g["gs_kappa"], g["gs_g1"], g["gs_g2"])
+    assert np.array_equal(gal.galaxy_shear(*args, reduced_shear=True), g["gs_reduced"])
+    assert np.array_equal(gal.galaxy_shear(*args, reduced_shear=False), g["gs_plain"])
+    ipix = H.ang2pix(4, g["gs_lon"], g["gs_lat"], lonlat=True)
+    assert np.array_equal(gal.galaxy_shear(*args, ipix=ipix), g["gs_reduced"]) and used_ipix == [False, False, True]
+    # one intrinsic ellipticity for all galaxies broadcasts like in the reference
+    one = gal.galaxy_shear(g["gs_lon"], g["gs_lat"], np.complex128(0.1 + 0.2j), g["gs_kappa"], g["gs_g1"], g["gs_g2"])
+    assert one.shape == g["gs_lon"].shape
+    assert np.array_equal(one, G.galaxy_shear(g["gs_lon"], g["gs_lat"], np.full(g["gs_lon"].shape, 0.1 + 0.2j), g["gs_kappa"], g["gs_g1"], g["gs_g2"]))
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
