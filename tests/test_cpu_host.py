@@ -839,6 +839,62 @@ def test_galaxy_shear_host_flow_golden(monkeypatch):
     assert np.array_equal(one, G.galaxy_shear(g["gs_lon"], g["gs_lat"], np.full(g["gs_lon"].shape, 0.1 + 0.2j), g["gs_kappa"], g["gs_g1"], g["gs_g2"]))
 
 
+def test_displace_host_flow_golden(monkeypatch):
+    """displace / displacement (glass/points.py:654-772) with the kernels replaced by the reference's
+    formulas: the complex and the (2, n) form of alpha, broadcasting of a scalar displacement, array
+    kinds -- against the reference's own source (golden displace file), bit for bit."""
+    import contextlib
+    import ctypes as C
+    import math
+    import types
+
+    import torch
+
+    import glass_b200.points as P
+
+    def f64(ptr, n, stride=1):
+        return np.ctypeslib.as_array((C.c_double * (n * stride)).from_address(ptr))[::stride]
+
+    class FakeLib:
+        def glb_displace(self, lon, lat, a1, a2, stride, deflect, n, out_lon, out_lat, st):
+            assert not deflect
+            alpha1, alpha2 = f64(a1, n, stride), f64(a2, n, stride)
+            t = f64(lat, n) / 180 * math.pi
+            ct, st_ = np.sin(t), np.cos(t)
+            a, g = np.hypot(alpha1, alpha2), np.arctan2(alpha2, alpha1)
+            ca, sa, cg, sg = np.cos(a), np.sin(a), np.cos(g), np.sin(g)
+            tp = np.arctan2(ct * ca + st_ * sa * cg, np.hypot(ct * sa - st_ * ca * cg, st_ * sg))
+            d = np.arctan2(sa * sg, st_ * ca - ct * sa * cg)
+            f64(out_lon, n)[:] = f64(lon, n) + d / math.pi * 180
+            f64(out_lat, n)[:] = tp / math.pi * 180
+            return 0
+
+        def glb_displacement(self, from_lon, from_lat, to_lon, to_lat, n, out, st):
+            a, b = np.radians(f64(from_lat, n)), np.radians(f64(to_lat, n))
+            g = np.radians(f64(to_lon, n) - f64(from_lon, n))
+            sa, ca, sb, cb, sg, cg = np.sin(a), np.cos(a), np.sin(b), np.cos(b), np.sin(g), np.cos(g)
+            r = np.arctan2(np.hypot(cb * sg, ca * sb - sa * cb * cg), sa * sb + ca * cb * cg)
+            x = np.arctan2(cb * sg, ca * sb - sa * cb * cg)
+            f64(out, 2 * n).view(np.complex128)[:] = r * np.exp(1j * x)
+            return 0
+
+    monkeypatch.setattr(P._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(P.A, "pick_device", lambda *a: (torch.device("cpu"), False))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_displace.npz"))
+    for alpha in (g["alpha"], np.stack([g["alpha"].real, g["alpha"].imag])):
+        lon, lat = P.displace(g["lon"], g["lat"], alpha)
+        assert isinstance(lon, np.ndarray)
+        assert np.array_equal(lon, g["displace_lon"]) and np.array_equal(lat, g["displace_lat"])
+    lon1, lat1 = P.displace(g["lon"][:5], g["lat"][:5], np.complex128(0.01 + 0.02j))  # scalar alpha broadcasts
+    lon2, lat2 = P.displace(g["lon"][:5], g["lat"][:5], np.full(5, 0.01 + 0.02j))
+    assert np.array_equal(lon1, lon2) and np.array_equal(lat1, lat2)
+    with pytest.raises(ValueError, match="leading axis of size 2"):
+        P.displace(g["lon"][:3], g["lat"][:3], np.zeros((3, 3)))
+    assert np.array_equal(P.displacement(g["lon"], g["lat"], g["to_lon"], g["to_lat"]), g["displacement"])
+
+
 def test_positions_from_delta_host_flow_golden(monkeypatch):
     """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
     their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
