@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "healpix_geom.cuh"
+#include "points_cuts.cuh"
 #include "rng.cuh"
 
 namespace glb {
@@ -520,6 +521,15 @@ __global__ void __launch_bounds__(256) ang2pix_kernel(int64_t nside, const doubl
   ipix[i] = zphi2pix_ring(nside, c, s, phi);
 }
 
+// The chain of batch cuts is sequential (every cut starts where the previous one stopped) but tiny:
+// two binary searches over the offsets per cut.  One thread walks it, so the host fetches the cuts
+// of a population with one copy instead of synchronising several times per batch.
+__global__ void points_cuts_kernel(const int64_t* __restrict__ off, int64_t npix, int64_t batch, int64_t start,
+                                   int64_t remaining, int max_cuts, int64_t* __restrict__ cuts,
+                                   int64_t* __restrict__ state) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) cuts_chain(off, npix, batch, start, remaining, max_cuts, cuts, state);
+}
+
 }  // namespace glb
 
 using namespace glb;
@@ -590,6 +600,16 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
 #undef GLB_COUNT_LAUNCH
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch(1);
+  return GLB_OK;
+}
+
+int glb_points_cuts(const int64_t* d_off, int64_t npix, int64_t batch, int64_t start, int64_t remaining, int max_cuts,
+                    int64_t* d_cuts, int64_t* d_state, void* stream) {
+  GLB_REQUIRE(d_off && d_cuts && d_state, "null pointer");
+  GLB_REQUIRE(npix >= 1 && batch >= 1 && start >= 0 && start <= npix && remaining >= 0 && max_cuts >= 1, "bad size");
+  points_cuts_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_off, npix, batch, start, remaining, max_cuts, d_cuts, d_state);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return GLB_OK;
 }
 

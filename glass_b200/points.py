@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import itertools
 import math
+import os
 from typing import Callable
 
 import numpy as np
@@ -143,12 +144,18 @@ class _Population:
 
     def cuts(self, batch: int):
         """Pixel ranges (start, stop, npoints) of glass/points.py:409-437."""
-        # Closed form of the reference's 1000-pixel stepping loop: a batch is the longest
-        # run of pixels from ``start`` whose total is <= batch (so it may be EMPTY when
-        # zero-count pixels precede a pixel that alone exceeds ``batch`` -- the reference
-        # yields that empty batch too); a pixel that alone exceeds ``batch`` is taken by
-        # itself; and on an exact fit the reference stops at the end of the 1000-pixel
-        # group (counted from ``start``) in which the fit completes.
+        # Closed form of the reference's 1000-pixel stepping loop.  The loop advances in groups of
+        # 1000 pixels (counted from ``start``) until the group in which the running total reaches
+        # min(batch, remaining) -- at pixel q* -- and cuts inside that group with
+        # searchsorted(side="right"): after the last pixel whose running total is still <= batch,
+        # but not beyond the end of the group.  Hence stop = min(p, end of the group of q*) with p the
+        # largest index whose offset is <= off[start] + batch.  Consequences the reference shares: a
+        # batch may be EMPTY when zero-count pixels precede a pixel that alone exceeds ``batch``; a
+        # first pixel that alone exceeds ``batch`` is taken by itself; on an exact fit, and for the
+        # last batch, trailing empty pixels are included up to the end of the group.
+        if os.environ.get("GLB_POINTS_CUTS_DEVICE") == "1":
+            yield from self._cuts_device(batch)
+            return
         start, remaining = 0, self.total
         off = self.off
 
@@ -158,19 +165,33 @@ class _Population:
 
         while remaining > 0:
             base = int(off[start].item())
-            target = base + batch
-            p = min(search(target, True) - 1, self.npix)  # largest p with off[p] <= target
+            p = min(search(base + batch, True) - 1, self.npix)  # largest p with off[p] <= base + batch
             if p <= start:
                 stop = start + 1  # the first pixel alone is too much: use it anyway
             else:
-                stop = p
-                if int(off[p].item()) == target and p < self.npix:
-                    qstar = search(target, False) - 1  # pixel that completes the exact fit
-                    stop = min(start + 1000 * ((qstar - start) // 1000 + 1), p)
+                qstar = search(base + min(batch, remaining), False) - 1  # pixel completing min(batch, remaining)
+                stop = min(p, start + 1000 * ((qstar - start) // 1000 + 1))
             n = int(off[stop].item()) - base
             yield start, stop, n
             start = stop
             remaining -= n
+
+    def _cuts_device(self, batch: int, chunk: int = 4096):
+        """The same cuts walked by ``glb_points_cuts`` on the device (csrc/points_cuts.cuh, host-tested
+        against the reference's loop): one device->host copy per ``chunk`` cuts instead of four
+        synchronisations per batch.  Opt-in (GLB_POINTS_CUTS_DEVICE=1) until it has run on a GPU."""
+        start, remaining = 0, self.total
+        cuts = torch.empty((chunk, 3), dtype=torch.int64, device=self.device)
+        state = torch.empty(3, dtype=torch.int64, device=self.device)
+        while remaining > 0:
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(
+                self.lib.glb_points_cuts(self.off.data_ptr(), self.npix, int(batch), start, remaining, chunk, cuts.data_ptr(), state.data_ptr(), st),
+                "glb_points_cuts",
+            )
+            k, start, remaining = (int(v) for v in state.cpu().numpy())
+            for a, b, n in cuts[:k].cpu().numpy():
+                yield int(a), int(b), int(n)
 
     def fill(self, start: int, stop: int, n: int, uv=None, want_ipix=False):
         lon = torch.empty(n, dtype=torch.float64, device=self.device)

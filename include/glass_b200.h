@@ -129,6 +129,13 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
                       double scale, int remove_monopole, const int64_t* d_counts_in, uint64_t seed,
                       uint32_t stream_id, double* d_nbar_out, int64_t* d_counts, int64_t* d_off,
                       void* d_workspace, void* stream);
+/* The pixel ranges of the batches of _sample_galaxies_per_pixel (points.py:409-437: 1000-pixel
+ * stepping, searchsorted(side="right"), "first pixel alone" rule) from the exclusive scan d_off,
+ * walked on the device: up to max_cuts cuts from pixel `start` with `remaining` galaxies to hand out.
+ * d_cuts [max_cuts][3] = {start, stop, galaxies}; d_state [3] = {cuts written, next start, galaxies
+ * remaining} -- call again from there while galaxies remain. */
+int glb_points_cuts(const int64_t* d_off, int64_t npix, int64_t batch, int64_t start, int64_t remaining,
+                    int max_cuts, int64_t* d_cuts, int64_t* d_state, void* stream);
 /* Positions of every galaxy in ring pixels [pix0, pix1): ipix = repeat(arange, n) (points.py:426)
  * and healpix.randang(nside, ipix, lonlat=True) (points.py:427 -> glass/healpix.py:426-431),
  * written at index d_off[p] - d_off[pix0] + i.  (u, v) in-pixel offsets: Philox keyed by

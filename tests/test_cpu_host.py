@@ -1239,12 +1239,83 @@ def test_batch_cut_rule_closed_form_on_cpu():
     cases.append((np.random.default_rng(1).poisson(2.0, npix), 1000))
     cases.append((np.random.default_rng(2).poisson(0.5, npix), 1))
     cases.append((np.random.default_rng(3).poisson(0.3, 5 * npix), 977))
+    rng = np.random.default_rng(0)
+    for it in range(120):  # random maps incl. exact fits and batch = 1 (ranges of the LAST batch end with its group too)
+        n = int(rng.integers(1, 4000))
+        c = rng.poisson(10 ** rng.uniform(-3, 0.7), n)
+        if c.sum() == 0:
+            continue
+        batch = 1 if it % 5 == 0 else 1 + int(rng.random() ** 2 * 2 * c.sum())
+        if it % 7 == 0:
+            batch = max(1, int(c[: rng.integers(1, n + 1)].sum()))
+        if c.sum() / batch <= 300:
+            cases.append((c, batch))
     for counts, batch in cases:
         ref = G.batch_cuts(counts, batch)
         sizes, ranges = cuts_of(counts, batch)
         assert sizes == [r[2] for r in ref], batch
         assert ranges == [(r[0], r[1]) for r in ref], batch
         assert sum(sizes) == counts.sum()
+
+
+def test_points_cuts_core_host_build_and_run(tmp_path, monkeypatch):
+    """csrc/points_cuts.cuh (the batch-cut rule the device walks for glb_points_cuts) on the host:
+    (a) the native fuzz against the reference's 1000-pixel stepping loop restated in C++
+    (tests/native/points_cuts_host.cpp, ~3000 maps incl. exact fits, oversize pixels, batch = 1);
+    (b) the product's opt-in device path _Population._cuts_device driven through a host build of the
+    same header standing in for the kernel, in chunks of 3 cuts, against the default path."""
+    import ctypes as C
+    import shutil
+    import subprocess
+
+    import torch
+
+    from glass_b200.points import _Population
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "points_cuts_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), os.path.join(root, "tests", "native", "points_cuts_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "points_cuts ok" in r.stdout, r.stdout + r.stderr
+    # (b) a shared library with the header's chain as an extern "C" function
+    src = tmp_path / "chain.cpp"
+    src.write_text(
+        '#include "%s"\nextern "C" void chain(const int64_t* off, int64_t npix, int64_t batch, int64_t start, int64_t remaining,'
+        " int max_cuts, int64_t* cuts, int64_t* state) { glb::cuts_chain(off, npix, batch, start, remaining, max_cuts, cuts, state); }\n"
+        % os.path.join(root, "glass_b200", "csrc", "points_cuts.cuh")
+    )
+    so = tmp_path / "chain.so"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True, capture_output=True, timeout=300)
+    host = C.CDLL(str(so))
+    host.chain.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+
+    class FakeLib:
+        def glb_points_cuts(self, off, npix, batch, start, remaining, max_cuts, cuts, state, st):
+            host.chain(off, npix, batch, start, remaining, max_cuts, cuts, state)
+            return 0
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: __import__("types").SimpleNamespace(cuda_stream=0))
+    rng = np.random.default_rng(4)
+    for it in range(40):
+        npix = int(rng.integers(1, 5000))
+        counts = rng.poisson(10 ** rng.uniform(-2.5, 0.5), npix)
+        if counts.sum() == 0:
+            continue
+        batch = 1 + int(rng.random() ** 2 * 2 * counts.sum())
+        if counts.sum() / batch > 500:
+            continue
+        pop = object.__new__(_Population)
+        pop.npix, pop.lib, pop.device = npix, FakeLib(), torch.device("cpu")
+        pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64))
+        pop.total = int(counts.sum())
+        assert list(pop._cuts_device(batch, chunk=3)) == list(pop.cuts(batch))
+        monkeypatch.setenv("GLB_POINTS_CUTS_DEVICE", "1")
+        assert list(pop.cuts(batch)) == list(pop._cuts_device(batch))
+        monkeypatch.delenv("GLB_POINTS_CUTS_DEVICE")
 
 
 def test_fft_core_host_build_and_run(tmp_path):

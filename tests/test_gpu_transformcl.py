@@ -73,3 +73,23 @@ def test_regularized_spectra_on_device():
     reg = glass.regularized_spectra([torch.as_tensor(b, device="cuda") for b in bad], method="nearest")
     assert all(r.is_cuda for r in reg)
     assert close(torch.stack(reg).cpu().numpy(), g["reg_spectra_nearest"])
+
+
+def test_points_cuts_on_device():
+    """glb_points_cuts (one thread walking csrc/points_cuts.cuh, host-tested against the reference's
+    loop) against the default host-driven cut rule, in chunks of 5 cuts."""
+    import torch
+
+    from glass_b200 import _lib
+    from glass_b200.points import _Population
+
+    rng = np.random.default_rng(9)
+    dev = torch.device("cuda", 0)
+    for npix, dens, batch in [(3072, 0.01, 2), (3072, 2.0, 1000), (12 * 64**2, 0.08, 157), (5000, 0.5, 1)]:
+        counts = rng.poisson(dens, npix)
+        counts[npix // 3] += 40  # an oversize pixel
+        pop = object.__new__(_Population)
+        pop.npix, pop.lib, pop.device = npix, _lib.load(), dev
+        pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), device=dev)
+        pop.total = int(counts.sum())
+        assert list(pop._cuts_device(batch, chunk=5)) == list(pop.cuts(batch))

@@ -12,3 +12,5 @@ python tools/probe_solver.py 60 8191 59 | tee gpurun_out/r02_solver_full.json
 # K12 with 64-byte (default) and 32-byte L2 fetches
 python tools/probe_sampling.py 2>&1 | tail -4 | tee gpurun_out/r02_sampling_default.log
 GLB_L2_FETCH_BYTES=32 python tools/probe_sampling.py 2>&1 | tail -4 | tee gpurun_out/r02_sampling_fetch32.log
+# device-walked batch cuts (opt-in): the points suite with the knob on
+GLB_POINTS_CUTS_DEVICE=1 python -m pytest tests/test_gpu_points.py -x -q 2>&1 | tail -3 | tee gpurun_out/r02_points_cuts_device.log
