@@ -2,8 +2,9 @@
 glass_b200 -- B200-native (sm_100a) implementation of the GLASS per-shell field-generation
 hot path behind GLASS's own API for that path (flat re-export like ``glass/__init__.py``).
 
-Only the hot path of SURVEY.md section 8 lives here; everything else (shells, n(z) models,
-spectra solvers, I/O) stays with upstream GLASS.  There is no CPU fallback: the kernels
+The hot path of SURVEY.md section 8 and its "next" rows (Gaussian-spectra pre-step, catalogue
+sink, per-galaxy post-processing) live here; everything else (shell construction, n(z) models,
+cosmology) stays with upstream GLASS.  There is no CPU fallback: the kernels
 are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if it is
 missing.
 """
