@@ -186,6 +186,16 @@ def compute(cl, t1, t2=None):
     return tcl._wrap(lambda c: tcl.corrtocl_dev(icorr(t1, t2, tcl.cltocorr_dev(c))), cl)
 
 
+def _take(t, idx):
+    """The transformation ``t`` restricted to the columns ``idx``: stacked transformations
+    (``fields._stack_transformations``) carry their parameters as per-column tensors [S],
+    which must be subset together with the data columns; scalar parameters pass through."""
+    pars = {k: v for k, v in vars(t).items() if isinstance(v, torch.Tensor) and v.ndim == 1}
+    if not pars:
+        return t
+    return type(t)(**{**vars(t), **{k: v[idx] for k, v in pars.items()}})
+
+
 def _relerr_cols(dx: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """max |dx / x| per column, entries with dx == 0 ignored (glass/grf/_solver.py:21-24)."""
     q = torch.where(dx != 0, dx / x, torch.zeros_like(dx))
@@ -235,15 +245,19 @@ def solve_columns(cl: torch.Tensor, t1, t2, *, pad: int, initial=None, cltol=1e-
     info = torch.zeros(S, dtype=torch.int32, device=cl.device)
 
     for _ in range(maxiter):
-        info = torch.where((info == 0) & (clerr <= cltol), info | 1, info)
-        act = torch.nonzero(info == 0).flatten()  # columns still iterating
+        # the reference tests clerr at the top of every iteration, also for a column whose step
+        # already converged (info can end as 3); frozen columns keep their clerr
+        running = info == 0
+        info = torch.where(clerr <= cltol, info | 1, info)
+        act = torch.nonzero(running & (info == 0)).flatten()  # columns still iterating
         if act.numel() == 0:
             break
         sub = (lambda x: x) if act.numel() == S else (lambda x: x[:, act])
         cl_a, gl_a, gt_a, fl_a, err_a = sub(cl), sub(gl), sub(gt), sub(fl), clerr[act]
         fixed_a = None if fixed is None else fixed[act]
+        t1_a, t2_a = (t1, t2) if act.numel() == S else (_take(t1, act), _take(t2, act))
         ft = tcl.cltocorr_dev(padded(fl_a))
-        xl = -tcl.corrtocl_dev(ft / dcorr(t1, t2, gt_a))[:n]
+        xl = -tcl.corrtocl_dev(ft / dcorr(t1_a, t2_a, gt_a))[:n]
         if fixed_a is not None and n:
             xl[0] = torch.where(fixed_a, torch.zeros_like(xl[0]), xl[0])
         # halve the step of every column whose residual did not improve, until all did
@@ -252,7 +266,8 @@ def solve_columns(cl: torch.Tensor, t1, t2, *, pad: int, initial=None, cltol=1e-
         while todo.numel():
             g_ = gl_a[:, todo] + xl[:, todo]
             gt_ = tcl.cltocorr_dev(padded(g_))
-            rl_ = tcl.corrtocl_dev(corr(t1, t2, gt_))
+            whole = todo.numel() == act.numel()
+            rl_ = tcl.corrtocl_dev(corr(t1_a if whole else _take(t1_a, todo), t2_a if whole else _take(t2_a, todo), gt_))
             fl_ = rl_[:n] - cl_a[:, todo]
             if fixed_a is not None and n:
                 fl_[0] = torch.where(fixed_a[todo], torch.zeros_like(fl_[0]), fl_[0])

@@ -1142,6 +1142,51 @@ def test_solve_gaussian_spectra_batched_equals_single(transforms_on_cpu):
         assert len(glass.lognormal_gls(spectra[:3])) == 3
 
 
+def test_solve_columns_stop_at_different_iterations(transforms_on_cpu):
+    """Round-1 advisor finding: columns of one batch that stop at different Gauss-Newton iterations
+    (amplitudes differing by orders of magnitude; near-zero cross-spectra converge at once) or take
+    different step halvings must each follow the solve the reference runs on that spectrum alone
+    (glass/grf/_solver.py:114-146), incl. the per-column transformation parameters and the ``info``
+    flags (bit 0 is tested at the top of every iteration, so a column can end with info == 3)."""
+    import torch
+
+    import glass_b200 as glass
+    from glass_b200 import grf
+
+    lmax = 48
+    ell = np.arange(lmax + 1)
+    base = 1.0 / (2 * ell + 1) ** 2
+    fields = [grf.Lognormal(1.0)] * 3
+    amps = {(0, 0): 3e-1, (1, 1): 1e-3, (1, 0): 1e-9, (2, 2): 5e-2, (2, 1): 2e-6, (2, 0): 1e-2}
+    spectra = [amps[(i, j)] * base for i in range(3) for j in range(i, -1, -1)]
+    gls = glass.solve_gaussian_spectra(fields, spectra)
+    infos = []
+    for k, (i, j, cl) in enumerate(glass.enumerate_spectra(spectra)):
+        g, _, info = grf.solve(cl, fields[i], fields[j], pad=2 * cl.shape[0])
+        infos.append(info)
+        assert np.abs(g - gls[k]).max() <= 1e-12 * np.abs(g).max()
+    # mixed lamdas (per-column parameters) and SquaredNormal columns with halvings
+    for mk in (lambda r: grf.Lognormal(0.3 + r), lambda r: grf.SquaredNormal(0.2 + r, 0.5 + r)):
+        rng = np.random.default_rng(7)
+        fs = [mk(rng.random()) for _ in range(3)]
+        sp = [10.0 ** rng.uniform(-6, -1) * base * 0.3 ** (i - j) for i in range(3) for j in range(i, -1, -1)]
+        got = glass.solve_gaussian_spectra(fs, sp)
+        for k, (i, j, cl) in enumerate(glass.enumerate_spectra(sp)):
+            g, _, info = grf.solve(cl, fs[i], fs[j], pad=2 * cl.shape[0])
+            assert np.abs(g - got[k]).max() <= 1e-11 * np.abs(g).max(), (k, info)
+    # the flags of the batched run are the flags of the single runs, column by column
+    cols = torch.as_tensor(np.stack(spectra, 1))
+    t = grf.Lognormal(torch.ones(cols.shape[1], dtype=torch.float64))
+    _, _, info_b = grf.solve_columns(cols, t, t, pad=2 * (lmax + 1))
+    assert info_b.tolist() == infos
+    assert len(set(infos)) > 1 or len({tuple(np.round(g, 3)) for g in gls}) > 1
+    # info == 3: the step converges (bit 1) in the same iteration that brings clerr under cltol
+    _gl, _rl, info3 = grf.solve_columns(cols[:, :1], grf.Lognormal(1.0), grf.Lognormal(1.0), pad=2 * (lmax + 1), cltol=1e-3, gltol=0.1)
+    assert int(info3[0]) == 3
+    _gl, _rl, info2 = grf.solve_columns(cols[:, :1], grf.Lognormal(1.0), grf.Lognormal(1.0), pad=2 * (lmax + 1), cltol=1e-8, gltol=0.1)
+    assert int(info2[0]) == 2
+
+
 def test_regularized_spectra_golden(transforms_on_cpu):
     """cov_clip / nearcorr / cov_nearest (glass/algorithm.py:111-277) and regularized_spectra
     (glass/fields.py:1055-1112) against vectors from executing the reference's source; the batched
