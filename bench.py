@@ -114,59 +114,52 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm (oracle port): the reference path for one lognormal shell on the host cores
 # ------------------------------------------------------------------------------------------
-_CPU_EARLIER: dict = {}
+def host_threads() -> int:
+    """The cores this process may run on.  NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which is a launcher default and not the box."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
-def cpu_shell_seconds(nside: int, lmax: int, nthreads: int) -> tuple[float, float]:
-    """One shell of the reference path on the CPU, as (seconds of the NumPy part, seconds of the
-    transform): NumPy normals + banded combine + l-major->m-major (glass/fields.py:404-425) and
-    NumPy expm1 (grf/_transformations.py:83-89) on one thread, exactly as GLASS runs them; the
-    SIMD/OpenMP synthesis of oracle/sht_fast.cpp standing in for healpy.alm2map
-    (glass/healpix.py:71) on ``nthreads`` threads."""
-    from oracle import glass_ref as G
-    from oracle import sht_c
+class CpuShells:
+    """The reference path shell by shell on the CPU at one size: what glass.generate does per
+    shell (glass/fields.py:404-425, grf/_transformations.py:83-89) with healpy.alm2map
+    (glass/healpix.py:71) replaced by oracle/sht_fast.cpp.  The spectra, the iternorm weights
+    (a (lmax+1) x (ncorr+1) array) and the normals of the NCORR earlier shells are prepared once;
+    ``step`` then does ALL the work of one further shell and nothing else."""
 
-    gls = synthetic_gls(NCORR + 1, lmax, NCORR)
-    rng = np.random.default_rng(42)
-    n = (lmax + 1) * (lmax + 2) // 2
-    if lmax not in _CPU_EARLIER:  # the NCORR earlier shells' normals: drawn once per size, outside the timed part
-        _CPU_EARLIER.clear()
-        _CPU_EARLIER[lmax] = [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(NCORR)]
-    zs = list(_CPU_EARLIER[lmax])
-    t0 = time.perf_counter()
-    # the (ncorr+1)-th shell has the full set of correlated terms, like every later shell
-    zs.append(rng.standard_normal((n, 2)) @ np.array([1, 1j]))
-    t1 = time.perf_counter()
-    alm = G.generate_alms(gls, NCORR, zs)[-1]
-    # only the last shell's combine+reorder is "this shell's" work; generate_alms did
-    # NCORR+1 of them, so charge 1/(NCORR+1) of that part
-    t2 = time.perf_counter()
-    del zs
-    m = sht_c.alm2map_fast(alm, nside, lmax, nthreads=nthreads)
-    t3 = time.perf_counter()
-    var = G.cltovar(gls[0])
-    m = G.lognormal(m, var, 1.0)
-    t4 = time.perf_counter()
-    return (t1 - t0) + (t2 - t1) / (NCORR + 1) + (t4 - t3), t3 - t2
+    def __init__(self, nside: int, lmax: int, nthreads: int):
+        from oracle import glass_ref as G
 
+        self.nside, self.lmax, self.nthreads = nside, lmax, nthreads
+        self.gls = synthetic_gls(NCORR + 1, lmax, NCORR)
+        self.w = G.iternorm(G.cls2cov_rows(self.gls, lmax + 1, NCORR + 1, NCORR))[-1]  # every later shell has this row
+        self.var = G.cltovar(self.gls[0])
+        self.rng = np.random.default_rng(42)
+        self.n = (lmax + 1) * (lmax + 2) // 2
+        self.y = [self.rng.standard_normal((self.n, 2)) @ np.array([1, 1j]) for _ in range(NCORR)]
 
-def cpu_sample(budget_s: float, nthreads: int):
-    """(nside, numpy seconds, transform seconds) of the largest sample whose predicted time fits
-    ``budget_s``: the NumPy part scales with nside^2, the Legendre transform with nside^3."""
-    cpu_shell_seconds(256, 511, nthreads)  # thread pool start-up, first-touch of the libraries
-    p_np, p_sht = cpu_shell_seconds(512, 1023, nthreads)
-    ns = NSIDE
-    while ns > 512 and p_np * (ns / 512) ** 2 + p_sht * (ns / 512) ** 3 > budget_s:
-        ns //= 2
-    return ns, p_np, p_sht
+    def step(self) -> tuple[float, float]:
+        """One shell; returns (seconds in GLASS's NumPy code, seconds in alm2map); their sum is
+        the wall time of the shell."""
+        from oracle import glass_ref as G
+        from oracle import sht_c
 
-
-def cpu_extrapolate(ns: int, t_np: float, t_sht: float) -> tuple[float, str]:
-    """Seconds per shell at NSIDE from a sample at ``ns`` and the words that say how."""
-    if ns == NSIDE:
-        return t_np + t_sht, ""
-    r = NSIDE / ns
-    return t_np * r**2 + t_sht * r**3, f"; extrapolated to nside={NSIDE}: NumPy part x{r**2:.0f} (~nside^2), transform x{r**3:.0f} (~nside^3)"
+        t0 = time.perf_counter()
+        self.y.append(self.rng.standard_normal((self.n, 2)) @ np.array([1, 1j]))  # fields.py:407
+        self.y = self.y[-(NCORR + 1):]  # fields.py:410-414
+        alm = sum(G.multalm(z, self.w[:, i]) for i, z in enumerate(self.y))  # fields.py:420
+        alm = G.glass_to_healpix_alm(alm)  # fields.py:422
+        alm[: self.lmax + 1] = alm[: self.lmax + 1].real + alm[: self.lmax + 1].imag + 0j  # fields.py:425
+        t1 = time.perf_counter()
+        m = sht_c.alm2map_fast(alm, self.nside, self.lmax, nthreads=self.nthreads)
+        t2 = time.perf_counter()
+        m = G.lognormal(m, self.var, 1.0)
+        t3 = time.perf_counter()
+        self.checksum = float(m[0])
+        return (t1 - t0) + (t3 - t2), t2 - t1
 
 
 CPU_NOTE = (
@@ -176,19 +169,30 @@ CPU_NOTE = (
 )
 
 
-def cpu_baseline(budget_s: float = 25.0) -> dict:
-    from oracle import sht_c
+def workload_config(nside: int, lmax: int, world: int) -> dict:
+    """The ``config`` object of BOTH arms (the driver compares them)."""
+    return {
+        "workload": f"correlated lognormal matter shells through generate(), nside={nside} lmax={lmax} ncorr={NCORR}, "
+        f"synthetic power-law C_l (BASELINE.json configs[3] shape; {SHELLS_PER_STEP} shells per GPU per step, shell-sharded over {world} rank(s))",
+        "shells_per_step_per_rank": SHELLS_PER_STEP,
+        "l2": "inputs larger than L2 (a_lm 0.54 GB, phases 2.1 GB, map 1.6 GB per shell)",
+        "parallelism": f"shell-sharded x{world}, no data-path collective",
+    }
 
-    cores = sht_c.max_threads()
-    ns, t_np, t_sht = cpu_sample(budget_s, cores)
-    if ns != 512:
-        t_np, t_sht = cpu_shell_seconds(ns, 2 * ns - 1, cores)
-    t, how = cpu_extrapolate(ns, t_np, t_sht)
+
+def cpu_baseline(nside: int, lmax: int, nshells: int = 3) -> dict:
+    """cpu_baseline leg of the B200 line (N = 1): ``nshells`` shells at the bench size itself
+    (about 5 s each on 16 cores) after one untimed shell."""
+    cores = host_threads()
+    cpu = CpuShells(nside, lmax, cores)
+    cpu.step()
+    t = [cpu.step() for _ in range(nshells)]
+    t_np, t_sht = (sum(x[i] for x in t) / nshells for i in (0, 1))
     sample = (
-        f"1 lognormal shell (alm draw+combine, alm2map, expm1) at nside={ns} lmax={2*ns-1}: "
-        f"{t_np:.2f} s NumPy (1 thread) + {t_sht:.2f} s alm2map on {cores} threads" + how
+        f"{nshells} lognormal shells (alm draw + combine + re-order, alm2map, expm1) at nside={nside} lmax={lmax} after one untimed "
+        f"shell; per shell {t_np:.2f} s NumPy (1 thread) + {t_sht:.2f} s alm2map on {cores} threads; nothing extrapolated"
     )
-    return {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE}
+    return {"value": 1.0 / (t_np + t_sht), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE}
 
 
 def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
@@ -280,25 +284,28 @@ def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
 
 
 def run_reference(args) -> None:
+    """The reference arm: the CPU port of the SAME workload (nside, lmax, ncorr of the B200 arm)
+    on all host cores of the box, one shell per step, every step measured at full size -- nothing
+    extrapolated.  Under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import sht_c
-
-    cores = sht_c.max_threads()
-    ns, _, _ = cpu_sample(8.0, cores)  # timed seconds of CPU work per step; the other shells of the combine add about as much untimed
-    for _ in range(args.warmup):
-        cpu_shell_seconds(ns, 2 * ns - 1, cores)
-    t_np = t_sht = 0.0
-    for _ in range(args.steps):
-        a, b = cpu_shell_seconds(ns, 2 * ns - 1, cores)
-        t_np += a / args.steps
-        t_sht += b / args.steps
-    dt, how = cpu_extrapolate(ns, t_np, t_sht)
+    nside, lmax = args.nside, args.lmax
+    cores = host_threads()
+    cpu = CpuShells(nside, lmax, cores)
+    budget_s = 200.0  # of timed CPU work; the run must end within a few minutes
+    t_first = sum(cpu.step())  # first warm-up step (thread pool start-up, first touch)
+    for _ in range(max(0, min(args.warmup - 1, int(20.0 // t_first)))):
+        cpu.step()
+    steps = max(1, min(args.steps, int(budget_s // t_first)))
+    t = [cpu.step() for _ in range(steps)]
+    t_np, t_sht = (sum(x[i] for x in t) / steps for i in (0, 1))
+    dt = t_np + t_sht
     value = 1.0 / dt
     sample = (
-        f"each step = 1 lognormal shell at nside={ns} lmax={2*ns-1} "
-        f"({t_np:.2f} s NumPy on 1 thread + {t_sht:.2f} s alm2map on {cores} threads)" + how
+        f"each step = 1 lognormal shell at nside={nside} lmax={lmax} measured at full size "
+        f"({t_np:.2f} s NumPy on 1 thread + {t_sht:.2f} s alm2map on {cores} threads per shell); {steps} timed steps"
+        + ("" if steps == args.steps else f" (of the {args.steps} asked for: {budget_s:.0f} s budget)")
     )
     line = {
         "impl": "reference",
@@ -306,7 +313,7 @@ def run_reference(args) -> None:
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
-        "steps": args.steps,
+        "steps": steps,
         "warmup": args.warmup,
         "ms_per_step": dt * 1e3,
         "higher_is_better": True,
@@ -314,7 +321,7 @@ def run_reference(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"lognormal shells nside={NSIDE} lmax={LMAX} ncorr={NCORR} (CPU arm: oracle port on host cores)"},
+        "config": workload_config(nside, lmax, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -521,14 +528,8 @@ def run_b200(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": f"{S} correlated lognormal shells per rank per step, nside={nside} lmax={lmax} ncorr={NCORR}, "
-            f"synthetic power-law C_l (BASELINE.json configs[3] shape, shell-sharded over {world} rank(s))",
-            "shells_per_step_per_rank": S,
-            "l2": "inputs larger than L2 (a_lm 0.54 GB, phases 2.1 GB, map 1.6 GB per shell)",
-            "parallelism": f"shell-sharded x{world}, no data-path collective",
-            "host_binding": (f"rank 0 bound to {len(local_cpus)} GPU-local cores (NVML affinity)" if local_cpus else "none"),
-        },
+        "config": workload_config(nside, lmax, world),
+        "host_binding": (f"rank 0 bound to {len(local_cpus)} GPU-local cores (NVML affinity)" if local_cpus else "none"),
         "clocks": clk,
         "e2e": {
             "value": e2e_value,
@@ -579,7 +580,7 @@ def run_b200(args) -> None:
             line["other_stages"] = {"failed": str(e)}
     if world == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(nside, lmax)
         except Exception as e:  # the CPU arm must not take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)

@@ -13,6 +13,7 @@
 // separately rounded products and sums, so that with *supplied* z it is bit-exact.
 #include "common.cuh"
 #include "rng.cuh"
+#include "iternorm_core.cuh"
 
 namespace glb {
 
@@ -47,15 +48,23 @@ struct CombineArgs {
 };
 
 // alm[l,m] = ((z0*w[l,0]) + z1*w[l,1]) + ... ; m = 0: alm = Re + Im
+// More than MAX_TERMS terms: consecutive launches over chunks of the terms, the running sum kept
+// in alm (resume != 0) and the m = 0 fold applied by the last one (fold != 0) -- the same
+// left-to-right order of separately rounded operations as one pass.
 __global__ void __launch_bounds__(256) alm_combine_kernel(int lmax, int nterms, const CombineArgs a,
                                                           const double* __restrict__ w, int w_stride,
-                                                          double2* __restrict__ alm) {
+                                                          double2* __restrict__ alm, int resume, int fold) {
   const int m = blockIdx.y;
   const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
   if (l > lmax) return;
   const int64_t idx = (int64_t)m * (2 * lmax + 1 - m) / 2 + l;
   const double* wl = w + (int64_t)l * w_stride;
   double re = 0.0, im = 0.0;
+  if (resume) {
+    const double2 v = alm[idx];
+    re = v.x;
+    im = v.y;
+  }
   for (int i = 0; i < nterms; ++i) {
     const double2 zi = a.z[i][idx];
     const double wi = wl[i];
@@ -63,7 +72,7 @@ __global__ void __launch_bounds__(256) alm_combine_kernel(int lmax, int nterms, 
     re = __dadd_rn(re, __dmul_rn(zi.x, wi));
     im = __dadd_rn(im, __dmul_rn(zi.y, wi));
   }
-  if (m == 0) {
+  if (m == 0 && fold) {
     re = __dadd_rn(re, im);
     im = 0.0;
   }
@@ -99,38 +108,9 @@ __global__ void __launch_bounds__(128) iternorm_step_kernel(int n, int k, int fi
                                                             double* __restrict__ w, int* __restrict__ flag) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n) return;
-  const int64_t N = n;
-  const double* rw = row + (int64_t)l * (k + 1);
-  if (!first && k > 0) {
-    const double sv = s[l];
-    const double u = sv > 0.0 ? 1.0 : 0.0;
-    const double sd = sv > 0.0 ? sv : 1.0;
-    for (int c = 0; c < k; ++c) {
-      double acc = 0.0;
-      for (int r = 0; r < k; ++r) acc += a[r * N + l] * m[((int64_t)r * k + c) * N + l];
-      tmp[c * N + l] = acc;
-    }
-    for (int r = 0; r + 1 < k; ++r) {
-      for (int c = 0; c + 1 < k; ++c) m[((int64_t)r * k + c) * N + l] = m[((int64_t)(r + 1) * k + c + 1) * N + l];
-      m[((int64_t)r * k + k - 1) * N + l] = 0.0;
-    }
-    for (int c = 0; c + 1 < k; ++c) m[((int64_t)(k - 1) * k + c) * N + l] = -tmp[(c + 1) * N + l] / sd;
-    m[((int64_t)(k - 1) * k + k - 1) * N + l] = u / sd;
-  }
-  double ss = 0.0;
-  double* wl = w + (int64_t)l * (k + 1);
-  for (int r = 0; r < k; ++r) {
-    double acc = 0.0;
-    for (int c = 0; c < k; ++c) acc += m[((int64_t)r * k + c) * N + l] * rw[k - c];
-    a[r * N + l] = acc;
-    wl[r] = acc;
-    ss += acc * acc;
-  }
-  const double s2 = rw[0] - ss;
-  if (s2 < 0.0) atomicOr(flag, 1);
-  const double sv = sqrt(s2);
-  s[l] = sv;
-  wl[k] = sv;
+  const bool bad = iternorm_step_one(n, k, first != 0, row + (int64_t)l * (k + 1), m + l, a + l, s + l, tmp + l,
+                                     w + (int64_t)l * (k + 1));
+  if (bad) atomicOr(flag, 1);
 }
 
 static inline dim3 lm_grid(int lmax) { return dim3((unsigned)((lmax + 1 + 255) / 256), (unsigned)(lmax + 1)); }
@@ -164,15 +144,19 @@ int glb_alm_glass_to_healpix(int lmax, const double* d_in, double* d_out, void* 
 int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const double* d_w, int w_stride,
                     double* d_alm, void* stream) {
   GLB_REQUIRE(lmax >= 0 && lmax < 65535, "lmax out of range");
-  GLB_REQUIRE(nterms >= 1 && nterms <= MAX_TERMS, "nterms must be in [1, 64]");
+  GLB_REQUIRE(nterms >= 1, "nterms must be positive");
   GLB_REQUIRE(h_zptrs && d_w && d_alm, "null pointer");
   GLB_REQUIRE(w_stride >= nterms, "w_stride smaller than nterms");
-  CombineArgs a;
-  for (int i = 0; i < MAX_TERMS; ++i) a.z[i] = (i < nterms) ? reinterpret_cast<const double2*>(h_zptrs[i]) : nullptr;
-  alm_combine_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(lmax, nterms, a, d_w, w_stride,
-                                                                      reinterpret_cast<double2*>(d_alm));
-  GLB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
+  for (int t0 = 0; t0 < nterms; t0 += MAX_TERMS) {
+    const int nt = nterms - t0 < MAX_TERMS ? nterms - t0 : MAX_TERMS;
+    CombineArgs a;
+    for (int i = 0; i < MAX_TERMS; ++i) a.z[i] = (i < nt) ? reinterpret_cast<const double2*>(h_zptrs[t0 + i]) : nullptr;
+    alm_combine_kernel<<<lm_grid(lmax), 256, 0, (cudaStream_t)stream>>>(lmax, nt, a, d_w + t0, w_stride,
+                                                                        reinterpret_cast<double2*>(d_alm), t0 > 0,
+                                                                        t0 + nt == nterms);
+    GLB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   return GLB_OK;
 }
 

@@ -136,62 +136,56 @@ def _gls_to_host(gls):
     return out
 
 
-def iternorm(cov: Iterable) -> Iterator[np.ndarray]:
+def iternorm(cov: Iterable) -> Iterator:
     """
-    Scaling vectors for iterative normal sampling (glass/fields.py:101-188).
+    Scaling vectors for iterative normal sampling (glass/fields.py:101-188): for every row of
+    shape (..., k+1) of ``cov`` yield ``[a_1..a_k, s]`` of the same shape, so that
+    ``x_i = sum_j a_j z_{i-j} + s z_i`` has the prescribed covariance with the k previous items.
 
-    Host-side (NumPy float64): O(n k^2) per shell on tiny arrays.  Yields, per input
-    row of shape (..., k+1), the row ``[a, s]`` of the banded Cholesky factor.
+    The recursion runs on the GPU (K1, ``glb_iternorm_step``: one thread per leading-dimension
+    element, state resident in HBM); rows come back as NumPy arrays for NumPy rows and as CUDA
+    tensors for CUDA rows.  Errors and their order as in the reference.
     """
-    for i, row in enumerate(cov):
-        row = _np(row)
-        k = row.shape[-1] - 1
-        if k < 0:
+    state = None
+    lead = None
+    for row in cov:
+        on_device = isinstance(row, torch.Tensor) and row.is_cuda
+        shape = tuple(row.shape)
+        if shape[-1] == 0:
             raise ValueError("empty covariance matrix")
-        if i == 0:
-            n = row.shape[:-1]
-            m = np.zeros((*n, k, k))
-            a = np.zeros((*n, k))
-            s = np.ones(n)
-        else:
-            if row.shape[:-1] != n:
-                raise ValueError("shape mismatch in covariance")
-            atm = a[..., None, :] @ m
-            m = np.concatenate([m, np.zeros((*n, m.shape[-2], 1), dtype=m.dtype)], axis=-1)
-            u = np.where(s > 0, np.ones(n, dtype=atm.dtype), np.zeros(n, dtype=atm.dtype))
-            r = np.concatenate([-atm, u[..., None, None]], axis=-1)
-            s = np.where(s > 0, s, np.ones(n, dtype=s.dtype))
-            r /= s[..., None, None]
-            m = np.concatenate([m, r], axis=-2)
-        m = m[..., m.shape[-2] - k :, m.shape[-1] - k :]
-        c = row[..., :0:-1]
-        a = (m @ c[..., None])[..., 0]
-        s = row[..., 0] - np.vecdot(a, a)
-        if np.any(s < 0):
+        if state is None:
+            lead = shape[:-1]
+            device = row.device if on_device else torch.device("cuda", hp._device_index())
+            state = _DeviceIterNorm(int(np.prod(lead, dtype=np.int64)), shape[-1] - 1, 1, device)
+        elif shape[:-1] != lead or shape[-1] - 1 != state.k:
+            raise ValueError("shape mismatch in covariance")
+        w = state.step(row.reshape(state.n, state.k + 1) if on_device else np.reshape(_np(row), (state.n, state.k + 1)), flag_slot=0)
+        if state.failed(0):
             raise ValueError("covariance matrix is not positive definite")
-        s = np.sqrt(s)
-        yield np.concatenate([a, s[..., None]], axis=-1)
+        w = w.reshape(shape)
+        yield w if on_device else w.cpu().numpy()
 
 
 def cls2cov(cls, nl: int, nf: int, nc: int):
     """
-    Cls as rows of a banded covariance for iterative sampling (glass/fields.py:191-236).
-    Like the reference (NumPy backend) the SAME buffer is mutated and re-yielded.
+    Rows of the banded covariance for iterative sampling (glass/fields.py:191-236): for shell j
+    an (nl, nc+1) array whose column i holds half the spectrum of shells (j, j-i), zero-padded;
+    columns beyond the shell's own history keep zeros.  ONE array is filled again for every shell
+    and yielded each time, as the reference does with the NumPy backend -- copy it to keep it.
     """
-    cov = np.zeros((nl, nc + 1))
-    end = 0
+    half = np.zeros((nl, nc + 1))
+    first = 0
     for j in range(nf):
-        begin, end = end, end + j + 1
-        for i, cl in enumerate(cls[begin:end][: nc + 1]):
-            cl = _np(cl)
-            if i == 0 and np.any(np.less(cl, 0)):
-                msg = "negative values in cl"
-                raise ValueError(msg)
-            n = cl.shape[0]
-            cov[:n, i] = cl
-            cov[n:, i] = 0.0
-        cov /= 2
-        yield cov
+        spectra = [_np(c) for c in cls[first : first + min(j, nc) + 1]]
+        first += j + 1
+        if spectra and (spectra[0] < 0).any():
+            msg = "negative values in cl"
+            raise ValueError(msg)
+        for col, c in enumerate(spectra):
+            n = c.shape[0]
+            np.multiply(c, 0.5, out=half[:n, col])
+            half[n:, col] = 0.0
+        yield half
 
 
 def getcl(cls, i: int, j: int, lmax: int | None = None):
@@ -493,54 +487,71 @@ def _glass_to_healpix_alm(alm):
 # --------------------------------------------------------------------------------------
 
 
-#: from this many correlated shells on, the iterative-normal recursion runs on the device (K1,
-#: ``glb_iternorm_step``): the NumPy recursion costs O(n k^2) host time per shell -- 19 ms at
-#: k = 19, 180 ms at k = 59 for lmax 8191 -- which passes the shell's 39 ms of GPU time near
-#: k = 25.  Below it the host recursion is kept: its weights are bit-identical to the
-#: reference's NumPy arithmetic, which the bit-exact a_lm parity tests rely on.
-ITERNORM_DEVICE_MIN_NCORR = 8
-
-
 class _DeviceIterNorm:
-    """glass/fields.py:101-188 with the state (m, a, s) resident on the GPU; ``step`` consumes
-    one row of ``cls2cov`` and returns the weights ``[a, s]`` as a device tensor (n, k+1).
-    "covariance matrix is not positive definite" is recorded per step in ``flags`` and raised
-    by :meth:`check` (one device read per batch of shells instead of one per shell)."""
+    """glass/fields.py:101-188 with the state (m, a, s) resident on the GPU (K1,
+    ``glb_iternorm_step``, one thread per multipole); ``step`` consumes one row of ``cls2cov``
+    and returns the weights ``[a, s]`` as a device tensor (n, k+1).
+
+    The recursion depends on nothing but the spectra, so it runs on its OWN high-priority stream:
+    reading its flags ("covariance matrix is not positive definite", one per step) waits for a
+    few microsecond-sized kernels and never for the transforms queued on the caller's stream.
+    The caller's stream waits for the event recorded after each step before it reads the weights.
+    """
 
     def __init__(self, n: int, k: int, nsteps: int, device):
         self.lib = _lib.load()
         self.n, self.k, self.device = int(n), int(k), device
         kk = max(self.k, 1)
-        self.m = torch.zeros((kk, kk, self.n), dtype=torch.float64, device=device)
-        self.a = torch.zeros((kk, self.n), dtype=torch.float64, device=device)
-        self.s = torch.ones(self.n, dtype=torch.float64, device=device)
-        self.tmp = torch.empty((kk, self.n), dtype=torch.float64, device=device)
-        self.flags = torch.zeros(max(int(nsteps), 1), dtype=torch.int32, device=device)
+        self.stream = torch.cuda.Stream(device, priority=-1)
+        with torch.cuda.stream(self.stream):
+            self.m = torch.zeros((kk, kk, self.n), dtype=torch.float64, device=device)
+            self.a = torch.zeros((kk, self.n), dtype=torch.float64, device=device)
+            self.s = torch.ones(self.n, dtype=torch.float64, device=device)
+            self.tmp = torch.empty((kk, self.n), dtype=torch.float64, device=device)
+            self.flags = torch.zeros(max(int(nsteps), 1), dtype=torch.int32, device=device)
         self.i = 0
         self.checked = 0
 
-    def step(self, row: np.ndarray) -> torch.Tensor:
-        row = np.ascontiguousarray(row, dtype=np.float64)
-        if row.shape[-1] - 1 != self.k or row.shape[0] != self.n:
+    def step(self, row, flag_slot: int | None = None) -> torch.Tensor:
+        """One shell.  ``row``: (n, k+1) NumPy array or CUDA tensor.  The flag of this step goes
+        to ``flags[flag_slot]`` (default: the step index)."""
+        if tuple(row.shape) != (self.n, self.k + 1):
             raise ValueError("shape mismatch in covariance")
         dev = self.device
-        rd = torch.from_numpy(row.copy()).pin_memory().to(dev, non_blocking=True)  # cls2cov re-yields one buffer
-        w = torch.empty((self.n, self.k + 1), dtype=torch.float64, device=dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(
-            self.lib.glb_iternorm_step(self.n, self.k, 1 if self.i == 0 else 0, rd.data_ptr(), self.m.data_ptr(), self.a.data_ptr(),
-                                       self.s.data_ptr(), self.tmp.data_ptr(), w.data_ptr(), self.flags[self.i :].data_ptr(), st),
-            "glb_iternorm_step",
-        )
+        slot = self.i if flag_slot is None else flag_slot
+        caller = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self.stream):
+            if isinstance(row, torch.Tensor):
+                self.stream.wait_stream(caller)
+                rd = row.to(device=dev, dtype=torch.float64).contiguous()
+            else:
+                # pinned copy of the row: cls2cov re-yields one buffer, and a pageable H2D would block
+                rd = torch.from_numpy(np.array(row, dtype=np.float64, order="C")).pin_memory().to(dev, non_blocking=True)
+            if flag_slot is not None:
+                self.flags[slot].zero_()
+            w = torch.empty((self.n, self.k + 1), dtype=torch.float64, device=dev)
+            _lib.check(
+                self.lib.glb_iternorm_step(self.n, self.k, 1 if self.i == 0 else 0, rd.data_ptr(), self.m.data_ptr(), self.a.data_ptr(),
+                                           self.s.data_ptr(), self.tmp.data_ptr(), w.data_ptr(), self.flags[slot:].data_ptr(),
+                                           self.stream.cuda_stream),
+                "glb_iternorm_step",
+            )
+        caller.wait_stream(self.stream)
+        w.record_stream(caller)
         self.i += 1
         return w
 
+    def failed(self, slot: int) -> bool:
+        with torch.cuda.stream(self.stream):
+            return bool(self.flags[slot].item())
+
     def first_failure(self):
         """Index of the first step whose covariance was not positive definite, or None
-        (synchronises with the stream)."""
+        (waits for the recursion's own stream only)."""
         if self.i == self.checked:
             return None
-        f = self.flags[self.checked : self.i].cpu().numpy()
+        with torch.cuda.stream(self.stream):
+            f = self.flags[self.checked : self.i].cpu().numpy()
         bad = np.nonzero(f)[0]
         if bad.size:
             return self.checked + int(bad[0])
@@ -573,12 +584,8 @@ class _ShellSampler:
         self.nalm = self.n * (self.n + 1) // 2
         self.deviates = rng if isinstance(rng, _rng.Deviates) else None
         self.seed = _rng.seed_from(rng)
-        self.dnorm = None
-        if self.ncorr >= ITERNORM_DEVICE_MIN_NCORR:
-            self.dnorm = _DeviceIterNorm(self.n, self.ncorr, ngrf, device)
-            self.witer = cls2cov(gls, self.n, ngrf, self.ncorr)  # rows; the recursion runs on the device
-        else:
-            self.witer = iternorm(cls2cov(gls, self.n, ngrf, self.ncorr))
+        self.dnorm = _DeviceIterNorm(self.n, self.ncorr, ngrf, device)
+        self.witer = cls2cov(gls, self.n, ngrf, self.ncorr)  # rows; the recursion itself is K1
         self.wanted = wanted
         self.zcache: dict[int, torch.Tensor] = {}
         self.shell = 0
@@ -608,9 +615,8 @@ class _ShellSampler:
                 w = next(self.witer)
             except StopIteration:
                 return None
-            if self.dnorm is not None:
-                self.h2d_bytes += w.nbytes
-                w = self.dnorm.step(w)  # device tensor (n, ncorr + 1)
+            self.h2d_bytes += w.nbytes
+            w = self.dnorm.step(w)  # device tensor (n, ncorr + 1)
             j = self.shell
             self.shell += 1
             if self.wanted is None or self.wanted(j):
@@ -622,15 +628,7 @@ class _ShellSampler:
         zs = [self._z(s) for s in range(j - nterms + 1, j + 1)]
         for s in [s for s in self.zcache if s < j - self.ncorr]:
             del self.zcache[s]
-        if self.dnorm is not None:
-            wd, stride = w, w.shape[-1]
-            wptr = wd.data_ptr() + 8 * mis
-        else:
-            wh = np.ascontiguousarray(w[:, mis:], dtype=np.float64)
-            # pinned staging + async copy: a pageable H2D would block the host until the stream drains
-            wd = torch.from_numpy(wh).pin_memory().to(dev, non_blocking=True)
-            self.h2d_bytes += wh.nbytes
-            stride, wptr = nterms, wd.data_ptr()
+        stride, wptr = w.shape[-1], w.data_ptr() + 8 * mis
         zptrs = (C.c_void_p * nterms)(*[t.data_ptr() for t in zs])
         _lib.check(
             lib.glb_alm_combine(self.lmax, nterms, zptrs, wptr, stride, out.data_ptr(), st),
@@ -639,9 +637,9 @@ class _ShellSampler:
         return j
 
     def first_failure(self):
-        """Shell index at which the device recursion found a non positive definite covariance
-        (None if none so far, or when the recursion runs on the host, which raises itself)."""
-        return None if self.dnorm is None else self.dnorm.first_failure()
+        """Shell index at which the recursion found a non positive definite covariance (None if
+        none so far)."""
+        return self.dnorm.first_failure()
 
 
 def _pick_device(gls) -> tuple[torch.device, bool]:

@@ -109,7 +109,9 @@ int glb_iternorm_step(int n, int k, int first, const double* d_row, double* d_m,
 /* alm = sum_i multalm(z_i, w[:, i])   fields.py:420 + harmonics.py:46-47, then the m = 0
  * fix alm = Re + Im (fields.py:425).  h_zptrs: HOST array of nterms DEVICE pointers to
  * m-major z arrays, oldest first; d_w: [lmax+1][w_stride] float64, column i scales z_i.
- * Operation order and rounding match NumPy (no FMA contraction): bit-exact for given z. */
+ * Operation order and rounding match NumPy (no FMA contraction): bit-exact for given z.
+ * Any nterms >= 1 (the reference has no limit, ncorr=None correlates all shells): above 64 terms
+ * the sum continues over further launches in the same left-to-right order. */
 int glb_alm_combine(int lmax, int nterms, const double* const* h_zptrs, const double* d_w, int w_stride,
                     double* d_alm, void* stream);
 

@@ -43,3 +43,49 @@ def synthetic_gls(nshell, lmax, ncorr, ragged=False):
             else:
                 gls.append(np.zeros(0))
     return gls
+
+
+def native_iternorm():
+    """ctypes handle of tests/native/iternorm_host.cpp: the per-multipole body of K1
+    (glass_b200/csrc/iternorm_core.cuh) compiled for the host, with glb_iternorm_step's
+    arguments minus the stream.  CPU test infrastructure (known-answer check of the product's
+    recursion; test double of the C-ABI call in the host-flow tests)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    assert gxx, "g++ needed for the native host tests"
+    out = os.path.join(tempfile.gettempdir(), f"glb_iternorm_host_{os.getpid()}.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(root, "tests", "native", "iternorm_host.cpp")], check=True)
+    lib = C.CDLL(out)
+    dp, ip = C.c_void_p, C.c_void_p
+    lib.iternorm_step_host.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, ip]
+    lib.iternorm_step_host.restype = C.c_int
+    return lib
+
+
+def native_iternorm_rows(rows):
+    """The weights [a, s] of every row through the host build of K1's body; raises like the
+    product where a flag comes back."""
+    lib = native_iternorm()
+    out = []
+    state = None
+    for i, row in enumerate(rows):
+        row = np.array(row, dtype=np.float64)
+        lead, k = row.shape[:-1], row.shape[-1] - 1
+        n = int(np.prod(lead, dtype=np.int64))
+        r = np.ascontiguousarray(row.reshape(n, k + 1))
+        if state is None:
+            kk = max(k, 1)
+            state = [np.zeros((kk, kk, n)), np.zeros((kk, n)), np.ones(n), np.zeros((kk, n))]
+        w = np.empty((n, k + 1))
+        flag = np.zeros(1, dtype=np.int32)
+        lib.iternorm_step_host(n, k, int(i == 0), r.ctypes.data, *(x.ctypes.data for x in state), w.ctypes.data, flag.ctypes.data)
+        if flag[0]:
+            raise ValueError("covariance matrix is not positive definite")
+        out.append(w.reshape(*lead, k + 1))
+    return out

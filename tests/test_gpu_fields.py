@@ -34,15 +34,23 @@ def supplied_z(nshell, lmax, seed=42):
     return [rng.standard_normal((n, 2)) @ np.array([1, 1j]) for _ in range(nshell)]
 
 
-@pytest.mark.parametrize("nshell,lmax,ncorr,ragged", [(4, 16, 2, False), (5, 33, None, False), (6, 20, 1, True), (3, 8, 0, False)])
-def test_alm_bit_exact_with_supplied_z(cuda_device, nshell, lmax, ncorr, ragged):
-    """alm given identical z: bit-exact (products and sums rounded as NumPy does)."""
-    import glass_b200
+@pytest.mark.parametrize("nshell,lmax,ncorr,ragged", [(4, 16, 2, False), (5, 33, None, False), (6, 20, 1, True), (3, 8, 0, False), (70, 6, None, False)])
+def test_alm_with_supplied_z(cuda_device, nshell, lmax, ncorr, ragged):
+    """alm given identical z.  K2 (draw order, combine, re-ordering, m = 0 fix) is BIT-EXACT when it
+    is handed the oracle's weights through the C ABI (products and sums rounded as NumPy does,
+    any number of terms -- the 70-shell case crosses the 64-pointer launch chunk); through
+    ``generate``'s sampler the weights come from K1, whose summation order differs from NumPy's
+    matmul: 1e-13 of the largest alm."""
+    import ctypes as C
+
+    from glass_b200 import _lib
     from glass_b200.fields import _ShellSampler
     from glass_b200.rng import Deviates
 
     nc = nshell - 1 if ncorr is None else ncorr
     gls = synthetic_gls(nshell, lmax, nc, ragged)
+    if nshell > 64:  # 70 fully correlated shells, weakly enough to stay positive definite
+        gls = [gls[0] * (1.0 if i == j else 0.02) for i in range(nshell) for j in range(i, -1, -1)]
     zs = supplied_z(nshell, lmax)
     ref = G.generate_alms(gls, ncorr, zs)
     s = _ShellSampler(gls, 8, ncorr, Deviates(normal_alm=zs), cuda_device)
@@ -50,8 +58,26 @@ def test_alm_bit_exact_with_supplied_z(cuda_device, nshell, lmax, ncorr, ragged)
         out = torch.empty(s.nalm, dtype=torch.complex128, device=cuda_device)
         assert s.next_alm(out) == j
         got = out.cpu().numpy()
-        assert np.array_equal(got, ref[j]), (j, np.abs(got - ref[j]).max())
+        assert np.abs(got - ref[j]).max() <= 1e-13 * np.abs(ref[j]).max(), (j, np.abs(got - ref[j]).max())
     assert s.next_alm(out) is None
+    # K2 alone, on the oracle's weights: bit for bit
+    lib = _lib.load()
+    st = torch.cuda.current_stream(cuda_device).cuda_stream
+    n = lmax + 1
+    ws = G.iternorm(G.cls2cov_rows(gls, n, nshell, nc))
+    zd = []
+    for z in zs:
+        zg = torch.as_tensor(z).to(cuda_device)
+        zm = torch.empty_like(zg)
+        _lib.check(lib.glb_alm_glass_to_healpix(lmax, zg.data_ptr(), zm.data_ptr(), st), "glb_alm_glass_to_healpix")
+        zd.append(zm)
+    for j in range(nshell):
+        nterms = min(j + 1, nc + 1)
+        w = torch.as_tensor(np.ascontiguousarray(ws[j][:, nc + 1 - nterms :])).to(cuda_device)
+        ptrs = (C.c_void_p * nterms)(*[zd[t].data_ptr() for t in range(j - nterms + 1, j + 1)])
+        out = torch.empty(s.nalm, dtype=torch.complex128, device=cuda_device)
+        _lib.check(lib.glb_alm_combine(lmax, nterms, ptrs, w.data_ptr(), nterms, out.data_ptr(), st), "glb_alm_combine")
+        assert np.array_equal(out.cpu().numpy(), ref[j]), j
 
 
 @pytest.mark.parametrize("nside,lmax,nshell,ncorr", [(16, 32, 5, 2), (32, 64, 6, 3), (8, 23, 3, None)])
@@ -116,40 +142,72 @@ def test_generate_errors(cuda_device):
         next(g)
 
 
-@pytest.mark.parametrize("nshell,lmax,ncorr", [(14, 40, 9), (12, 25, 11), (5, 12, 0), (9, 300, 8)])
-def test_device_iternorm_vs_host(cuda_device, nshell, lmax, ncorr):
-    """K1 (glb_iternorm_step) against the host recursion (glass/fields.py:101-188) on the rows
+@pytest.mark.parametrize("nshell,lmax,ncorr", [(14, 40, 9), (12, 25, 11), (5, 12, 0), (9, 300, 8), (6, 64, 3)])
+def test_device_iternorm_vs_oracle(cuda_device, nshell, lmax, ncorr):
+    """K1 (glb_iternorm_step) against the oracle's recursion (glass/fields.py:101-188) on the rows
     of cls2cov, shell by shell.  Tolerance 1e-11 relative: the summation order of NumPy's
     batched matmul is not specified, so this path is not bit-exact by construction."""
-    from glass_b200.fields import _DeviceIterNorm, cls2cov, iternorm
+    from glass_b200.fields import _DeviceIterNorm, cls2cov
 
     gls = synthetic_gls(nshell, lmax, ncorr, ragged=True)
-    host = [w.copy() for w in iternorm(cls2cov(gls, lmax + 1, nshell, ncorr))]
+    want = G.iternorm(G.cls2cov_rows(gls, lmax + 1, nshell, ncorr))
     dn = _DeviceIterNorm(lmax + 1, ncorr, nshell, cuda_device)
     for j, row in enumerate(cls2cov(gls, lmax + 1, nshell, ncorr)):
         w = dn.step(row).cpu().numpy()
-        assert w.shape == host[j].shape
-        assert np.abs(w - host[j]).max() <= 1e-11 * np.abs(host[j]).max(), j
+        assert w.shape == want[j].shape
+        assert np.abs(w - want[j]).max() <= 1e-11 * np.abs(want[j]).max(), j
     assert dn.first_failure() is None
 
 
-def test_generate_device_iternorm_matches_host_path(cuda_device, monkeypatch):
-    """generate() with many correlated shells (device recursion) against the same call forced
-    onto the host recursion, and the reference's error when a covariance is not positive
-    definite: shells before the failing one are still yielded."""
+def test_iternorm_public_function(cuda_device):
+    """glass.iternorm (glass/fields.py:101-188) through the public generator: the reference's
+    known answers (golden vectors from executing its source; tests/core/test_fields.py:96-170:
+    explicit Cholesky, leading dimensions, errors), NumPy in -> NumPy out, CUDA in -> CUDA out."""
+    import os
+
     import glass_b200
-    from glass_b200 import fields as F
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
+    cov = np.array([[1.0, 0.2, 0.1], [0.2, 0.5, 0.2], [0.1, 0.2, 0.3]])
+    for k in (0, 1, 2):
+        rows = [np.pad(cov[i, i::-1][: min(i, k) + 1], (0, k + 1 - min(i + 1, k + 1))) for i in range(3)]
+        got = list(glass_b200.iternorm(rows))
+        assert all(isinstance(g, np.ndarray) for g in got)
+        assert np.abs(np.stack(got) - gold[f"iternorm_k{k}"]).max() <= 1e-14
+    # the factor rebuilt from the weights reproduces the covariance (full band)
+    wts = np.stack(list(glass_b200.iternorm([np.pad(cov[i, i::-1], (0, 2 - i)) for i in range(3)])))
+    lmat = np.zeros((3, 3))
+    for i in range(3):
+        lmat[i, i] = wts[i, 2]
+        for j in range(1, i + 1):
+            lmat[i, i - j] = wts[i, 2 - j]
+    assert np.allclose(lmat @ lmat.T, cov, rtol=0, atol=1e-15)
+    # leading dimensions and device rows
+    rng = np.random.default_rng(3)
+    rows = [np.concatenate([2.0 + rng.random((3, 4, 1)), 0.3 * rng.random((3, 4, 2))], axis=-1) for _ in range(5)]
+    want = G.iternorm(rows)
+    got = list(glass_b200.iternorm(torch.as_tensor(r).to(cuda_device) for r in rows))
+    assert all(g.is_cuda and g.shape == (3, 4, 3) for g in got)
+    assert np.abs(np.stack([g.cpu().numpy() for g in got]) - np.stack(want)).max() <= 1e-13
+    with pytest.raises(ValueError, match="empty covariance"):
+        list(glass_b200.iternorm([np.ones(0)]))
+    with pytest.raises(ValueError, match="shape mismatch"):
+        list(glass_b200.iternorm([np.ones(1), np.ones((5, 2))]))
+    with pytest.raises(ValueError, match="shape mismatch"):
+        list(glass_b200.iternorm([np.ones((1, 1)), np.ones((1, 2))]))
+    with pytest.raises(ValueError, match="not positive definite"):
+        list(glass_b200.iternorm([np.array([1.0, 0.0]), np.array([0.1, 1.0])]))
+
+
+def test_generate_not_positive_definite_is_deferred(cuda_device):
+    """The reference's error when a covariance is not positive definite: shells before the
+    failing one are still yielded (K1 records a flag per shell on its own stream)."""
+    import glass_b200
 
     nshell, lmax, nside, ncorr = 12, 48, 16, 10
     gls = synthetic_gls(nshell, lmax, ncorr)
     flds = [glass_b200.grf.Lognormal()] * nshell
-    dev_maps = [np.array(m) for m in glass_b200.generate(flds, gls, nside, ncorr=ncorr, rng=5)]
-    monkeypatch.setattr(F, "ITERNORM_DEVICE_MIN_NCORR", 10**9)
-    host_maps = [np.array(m) for m in glass_b200.generate(flds, gls, nside, ncorr=ncorr, rng=5)]
-    monkeypatch.undo()
-    assert len(dev_maps) == len(host_maps) == nshell
-    for a, b in zip(dev_maps, host_maps):
-        assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    assert len(list(glass_b200.generate(flds, gls, nside, ncorr=ncorr, rng=5))) == nshell
     # shell 2 is more strongly correlated with shell 1 than a positive definite matrix allows
     bad = [g.copy() for g in gls]
     bad[2 * 3 // 2 + 1] = 3.0 * gls[0]
