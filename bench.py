@@ -236,12 +236,15 @@ def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
     ws = torch.empty(int(lib.glb_points_workspace_bytes(npix)), dtype=torch.uint8, device=dev)
     scale = 0.083  # expected galaxies per pixel (1e9 galaxies over 60 shells at nside 4096)
 
+    tot_d = torch.zeros(1, dtype=torch.int64, device=dev)
+
     def k67():
         _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, 1.2, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
-                                         counts.data_ptr(), off.data_ptr(), ws.data_ptr(), st))
+                                         counts.data_ptr(), off.data_ptr(), None, 0, tot_d.data_ptr(), ws.data_ptr(), st))
 
     t = ev(k67)
-    out["points_counts+offsets (K6+K7)"] = {"ms": t, "GB/s": npix * 32 / t / 1e6, "frac_hbm": npix * 32 / t / 1e6 / hbm_peak, "algorithmic_bytes": npix * 32}
+    out["points_counts+offsets (K6+K7, scan mode)"] = {"ms": t, "GB/s": npix * 32 / t / 1e6, "frac_hbm": npix * 32 / t / 1e6 / hbm_peak, "algorithmic_bytes": npix * 32,
+                                                       "note": "per-pixel counts + exclusive offsets; positions_from_delta uses it above 1 galaxy per pixel"}
     tot = int(off[-1].item())
     lon = torch.empty(tot, dtype=torch.float64, device=dev)
     lat = torch.empty(tot, dtype=torch.float64, device=dev)
@@ -252,7 +255,29 @@ def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
 
     t = ev(k8)
     by = npix * 8 + tot * 16
-    out["points_fill (K8)"] = {"ms": t, "GB/s": by / t / 1e6, "frac_hbm": by / t / 1e6 / hbm_peak, "galaxies": tot, "algorithmic_bytes": by}
+    out["points_fill (K8, scan mode)"] = {"ms": t, "GB/s": by / t / 1e6, "frac_hbm": by / t / 1e6 / hbm_peak, "galaxies": tot, "algorithmic_bytes": by}
+    # LIST mode (the default of positions_from_delta at this density): K6 emits the galaxy -> pixel list
+    # (8 B per galaxy) instead of counts + offsets (16 B per pixel); K8 is one thread per galaxy.  The
+    # algorithmic bytes are SURVEY.md 8(d)'s (32 B/pixel; 8 B/pixel + 16 B/galaxy) -- what a
+    # pixel-array formulation has to move -- so the fractions can exceed 1; "moved" is what this one moves.
+    gpix = torch.empty(tot + 1024, dtype=torch.int64, device=dev)
+
+    def k67l():
+        _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, 1.2, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
+                                         None, None, gpix.data_ptr(), gpix.numel(), tot_d.data_ptr(), ws.data_ptr(), st))
+
+    t = ev(k67l)
+    moved = npix * 8 + tot * 8
+    out["points_counts+offsets (K6+K7)"] = {"ms": t, "GB/s": npix * 32 / t / 1e6, "frac_hbm": npix * 32 / t / 1e6 / hbm_peak, "algorithmic_bytes": npix * 32,
+                                            "moved_bytes": moved, "moved_GB/s": moved / t / 1e6, "frac_hbm_moved": moved / t / 1e6 / hbm_peak, "mode": "list"}
+
+    def k8l():
+        _lib.check(lib.glb_points_fill_list(nside, gpix.data_ptr(), 0, tot, None, None, C.c_uint64(42), C.c_uint32(0), lon.data_ptr(), lat.data_ptr(), st))
+
+    t = ev(k8l)
+    moved = tot * 24
+    out["points_fill (K8)"] = {"ms": t, "GB/s": by / t / 1e6, "frac_hbm": by / t / 1e6 / hbm_peak, "galaxies": tot, "algorithmic_bytes": by,
+                               "moved_bytes": moved, "moved_GB/s": moved / t / 1e6, "frac_hbm_moved": moved / t / 1e6 / hbm_peak, "mode": "list"}
     k3 = torch.zeros(npix, dtype=torch.float64, device=dev)
     k2 = torch.rand(npix, dtype=torch.float64, device=dev, generator=g)
     t = ev(lambda: _lib.check(lib.glb_multiplane_update(k3.data_ptr(), k2.data_ptr(), delta.data_ptr(), 0.0, npix, 0.3, 0.01, st)))
@@ -280,6 +305,108 @@ def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
     out["alm2map_spin s=2 E-only (K11)"] = {"ms": t, "TFLOP/s": 16 * ntri / t / 1e9, "frac_fp64": 16 * ntri / t / 1e9 / fp64_peak, "algorithmic_flop": 16 * ntri}
     hp.clear_plans()
     torch.cuda.empty_cache()
+    return out
+
+
+def bench_msplit(dev, rank: int, world: int, nside: int, lmax: int, single_ms: float | None) -> dict:
+    """SURVEY.md 8(e) axis 2, measured in the same run (N > 1): ONE batch of 4 maps at the bench
+    size with the Legendre stage sharded by m over the N GPUs and the ring FFT by ring band, in
+    both forms of the m -> ring transpose -- an NCCL all-to-all of the phase array, and the fused
+    form in which the Legendre kernel stores F_m(ring) straight into the owner's buffer over
+    NVLink peer mappings.  Times are CUDA events around whole transforms (max over ranks);
+    ``alltoall_ms`` is the collective alone (events around the NCCL calls).  bit_identical: every
+    rank's ring bands equal to the single-GPU transform of the same alm, checked on each rank."""
+    import torch
+    import torch.distributed as dist
+
+    from glass_b200.dist import MSplitTransform
+    from glass_b200.healpix import alm2map_batch
+
+    nb = 4
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)  # the same alm on every rank
+    alm = torch.view_as_complex(torch.randn((nb, nalm, 2), dtype=torch.float64, device=dev, generator=g))
+    ref = alm2map_batch(alm, nside, lmax)
+    out: dict = {"maps": nb, "nside": nside, "lmax": lmax, "n_gpus": world}
+
+    def timed(fn, n=3, warm=2):
+        for _ in range(warm):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    if single_ms is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(2):
+            alm2map_batch(alm, nside, lmax, out=ref)
+        b.record()
+        torch.cuda.synchronize()
+        single_ms = a.elapsed_time(b) / 2
+    out["single_gpu_ms"] = single_ms
+    ok = True
+    for name, p2p in (("nccl_alltoall", False), ("p2p_fused", True)):
+        ms = MSplitTransform(nside, lmax, max_batch=nb, device=dev, p2p=p2p)
+        res = ms.alm2map(alm)
+        torch.cuda.synchronize()
+        same = all(bool(torch.equal(res[:, x:y], ref[:, x:y])) for x, y in ms.pixel_ranges)
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok &= bool(int(flag[0]))
+        t = timed(lambda: ms.alm2map(alm, out=res))
+        # phases this rank hands to the others per transform: its m columns of every foreign ring
+        sent = nb * sum(r for k, r in enumerate(ms.rows) if k != ms.rank) * ms.W * 16
+        ent = {"ms": t, "speedup_vs_1gpu": single_ms / t, "nvlink_bytes_sent_per_rank": sent}
+        if not p2p:
+            send = torch.empty((nb, ms.nring, ms.W), dtype=torch.complex128, device=dev)
+            recv = torch.empty((nb, world, ms.rows[ms.rank], ms.W), dtype=torch.complex128, device=dev)
+            ins, outs = [r * ms.W for r in ms.rows], [ms.rows[ms.rank] * ms.W] * world
+
+            def a2a():
+                for b_ in range(nb):
+                    dist.all_to_all_single(torch.view_as_real(recv[b_]).reshape(-1, 2), torch.view_as_real(send[b_]).reshape(-1, 2),
+                                           output_split_sizes=outs, input_split_sizes=ins)
+
+            ta = timed(a2a)
+            ent.update({"alltoall_ms": ta, "alltoall_GB/s_per_rank": sent / ta / 1e6, "alltoall_share": ta / t})
+            del send, recv
+        out[name] = ent
+        del ms, res
+        torch.cuda.empty_cache()
+    out["bit_identical"] = ok
+    return out
+
+
+def bench_chain(dev, rank: int, world: int) -> dict:
+    """The whole user loop the north star names (examples/2-advanced/stage_4_galaxies.ipynb cell 13,
+    SURVEY.md 3.5) on BASELINE.json configs[3]+[4]: 60 correlated lognormal shells at nside 4096,
+    lmax 8191 -> multi-plane convergence -> shear_from_convergence (niter 3) -> 1.0e9 galaxy
+    positions, redshifts, ellipticities, reduced shear; through the public API, strong scaling
+    over the N GPUs (contiguous shell blocks, multi-plane recurrence pipelined over the ranks).
+    ``wall_s``: maps and catalogues stay in HBM; ``e2e``: the same with every galaxy column copied
+    to host memory inside the timed region (the maps never leave the device)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from run_config import run_chain
+
+    out = {}
+    for key, host in (("device", False), ("e2e", True)):
+        r = run_chain(4, dev=dev, rank=rank, world=world, lensing=True, niter=3, host_catalog=host)
+        out[key] = {k: r[k] for k in ("wall_s", "galaxies", "galaxies_per_s", "shells_per_s", "catalog_d2h_bytes", "stage_ms_total")}
+        if key == "device":
+            out["workload"] = (f"{r['shells']} shells nside={r['nside']} lmax={r['lmax']} ncorr={r['ncorr']} + MultiPlaneConvergence + "
+                               f"shear_from_convergence(niter={r['niter']}) + {r['galaxies']:.3g} galaxies (positions, redshifts, ellipticities, "
+                               f"reduced shear) on {world} GPU(s), strong scaling")
     return out
 
 
@@ -479,6 +606,28 @@ def run_b200(args) -> None:
     h2d = (lmax + 1) * (NCORR + 1) * 8 * S  # iternorm weights of S shells (the only per-step input)
     d2h = npix * 8 * S
 
+    # ---- the m <-> ring split of one transform (N > 1) and the whole north-star chain ----
+    from glass_b200.healpix import clear_plans
+
+    msplit = chain = None
+    del gls_dev, plan
+    clear_plans()
+    torch.cuda.empty_cache()
+    if world > 1 and not args.no_msplit:
+        try:
+            msplit = bench_msplit(dev, rank, world, nside, lmax, dev_s * 1e3 / K if S == 4 else None)
+        except Exception as e:  # never take the headline down
+            msplit = {"failed": f"{type(e).__name__}: {e}"}
+        clear_plans()
+        torch.cuda.empty_cache()
+    if not args.no_chain and nside == NSIDE:
+        try:
+            chain = bench_chain(dev, rank, world)
+        except Exception as e:
+            chain = {"failed": f"{type(e).__name__}: {e}"}
+        clear_plans()
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -573,6 +722,10 @@ def run_b200(args) -> None:
             "traffic": traffic_of("sht_ringfft_synth_kernel"),
         },
     }
+    if msplit is not None:
+        line["msplit"] = msplit
+    if chain is not None:
+        line["chain"] = chain
     if world == 1 and not args.no_extra:
         try:
             line["other_stages"] = extra_stage_rooflines(dev, hbm_peak, peak_tf.value)
@@ -598,6 +751,8 @@ def main():
     ap.add_argument("--lmax", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary per-stage measurements")
+    ap.add_argument("--no-msplit", action="store_true", help="skip the m-split transform measurement (N > 1)")
+    ap.add_argument("--no-chain", action="store_true", help="skip the full-chain (config 4 + lensing + 1e9 galaxies) measurement")
     args = ap.parse_args()
     if args.lmax is None:
         args.lmax = 2 * args.nside - 1

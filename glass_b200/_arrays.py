@@ -62,3 +62,21 @@ def take_leading(a, lead_shape, dims, k):
     off = len(dims) - len(lead_shape)
     idx = tuple(0 if lead_shape[i] == 1 else k[off + i] for i in range(len(lead_shape)))
     return a[idx]
+
+
+def host_slices(batches):
+    """NumPy views for ``(lon, lat, n)`` device batches with ONE device->host copy per underlying
+    allocation: consecutive batches that are slices of the same device arrays (the position
+    sampler writes a whole population at once) are copied together into fresh host arrays and
+    handed out as views of them, instead of one blocking pageable copy per array and batch."""
+    base = None  # (lon storage ptr, lat storage ptr) -> host copies
+    for lon, lat, n in batches:
+        key = (lon.untyped_storage().data_ptr(), lat.untyped_storage().data_ptr())
+        if base is None or base[0] != key:
+            def whole(t):
+                full = torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage())
+                return full.cpu().numpy()
+
+            base = (key, whole(lon), whole(lat))
+        o1, o2 = lon.storage_offset(), lat.storage_offset()
+        yield base[1][o1 : o1 + n], base[2][o2 : o2 + n], n

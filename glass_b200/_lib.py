@@ -45,8 +45,10 @@ SIGNATURES = {
     "glb_alm_combine": (_i, [_i, _i, _vp, _dp, _i, _dp, _vp]),
     "glb_iternorm_step": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp]),
     "glb_points_workspace_bytes": (C.c_size_t, [_i64]),
-    "glb_points_counts": (_i, [_i64, _dp, _dp, _i, C.c_double, C.c_double, _i, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp, _vp]),
+    "glb_points_counts": (_i, [_i64, _dp, _dp, _i, C.c_double, C.c_double, _i, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _dp, _i64, _dp, _vp, _vp]),
     "glb_points_cuts": (_i, [_dp, _i64, _i64, _i64, _i64, _i, _dp, _dp, _vp]),
+    "glb_points_cuts_list": (_i, [_dp, _i64, _i64, _i64, _i64, _i64, _i, _dp, _dp, _vp]),
+    "glb_points_fill_list": (_i, [_i64, _dp, _i64, _i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),
     "glb_points_fill": (_i, [_i64, _dp, _dp, _i64, _i64, _dp, _dp, C.c_uint64, C.c_uint32, _dp, _dp, _dp, _vp]),
     "glb_ring2ang_uv": (_i, [_i64, _dp, _dp, _dp, _i64, _i, _dp, _dp, _vp]),
     "glb_randang": (_i, [_i64, _dp, _i64, C.c_uint64, C.c_uint32, _i, _dp, _dp, _vp]),

@@ -118,8 +118,11 @@ struct CountParams {
   const double* mean;       // may be null (device scalar to subtract: remove_monopole)
   const int64_t* counts_in; // parity mode: supplied counts (may be null)
   double* nbar_out;         // may be null
-  int64_t* counts;          // out [npix]
-  int64_t* off;             // out [npix+1]
+  int64_t* counts;          // out [npix]; may be null (list mode)
+  int64_t* off;             // out [npix+1]; may be null (list mode)
+  int64_t* gpix;            // out: ring pixel of every galaxy, galaxies in pixel order (may be null)
+  int64_t gpix_cap;         // entries of gpix that may be written (the total is exact either way)
+  int64_t* total;           // out [1]: number of galaxies (may be null)
   unsigned long long* status;  // [ntiles] decoupled look-back words, zeroed before the launch
   unsigned int* ticket;        // tile ticket counter, zeroed before the launch
   int64_t npix;
@@ -220,7 +223,10 @@ __global__ void __launch_bounds__(PT_THREADS + 32, 4) points_count_scan_kernel(c
       for (int w = 0; w < PT_WARPS; ++w) agg += s_wtot[w];
       // max: never replace an inclusive word by the aggregate the workers publish
       atomicMax(p.status + tile, ST_INCL | (unsigned long long)(excl + agg));
-      if ((int)tile == p.ntiles - 1) p.off[p.npix] = excl + agg;
+      if ((int)tile == p.ntiles - 1) {
+        if (p.off) p.off[p.npix] = excl + agg;
+        if (p.total) p.total[0] = excl + agg;
+      }
     }
     named_arrive(2, NALL);
     return;
@@ -335,23 +341,46 @@ __global__ void __launch_bounds__(PT_THREADS + 32, 4) points_count_scan_kernel(c
   }
   if (tid == 0 && tile > 0) atomicMax(p.status + tile, ST_AGG | (unsigned long long)agg);
   // the counts do not depend on the prefix: store them while the look-back finishes
+  if (p.counts) {
 #pragma unroll
-  for (int i = 0; i < PT_QUADS; ++i) {
+    for (int i = 0; i < PT_QUADS; ++i) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t pix = wbase + i * 128 + 4 * lane + 2 * h;
-      if (pix < p.npix) *reinterpret_cast<longlong2*>(p.counts + pix) = c[i][h];
+      for (int h = 0; h < 2; ++h) {
+        const int64_t pix = wbase + i * 128 + 4 * lane + 2 * h;
+        if (pix < p.npix) *reinterpret_cast<longlong2*>(p.counts + pix) = c[i][h];
+      }
     }
   }
   named_sync(2, NALL);
   wpre += s_excl;
+  if (p.off) {
 #pragma unroll
-  for (int i = 0; i < PT_QUADS; ++i) {
-    const int64_t pix = wbase + i * 128 + 4 * lane;
-    const int64_t o0 = wpre + ex[i];
-    const int64_t o1 = o0 + c[i][0].x, o2 = o1 + c[i][0].y, o3 = o2 + c[i][1].x;
-    if (pix < p.npix) *reinterpret_cast<longlong2*>(p.off + pix) = make_longlong2(o0, o1);
-    if (pix + 2 < p.npix) *reinterpret_cast<longlong2*>(p.off + pix + 2) = make_longlong2(o2, o3);
+    for (int i = 0; i < PT_QUADS; ++i) {
+      const int64_t pix = wbase + i * 128 + 4 * lane;
+      const int64_t o0 = wpre + ex[i];
+      const int64_t o1 = o0 + c[i][0].x, o2 = o1 + c[i][0].y, o3 = o2 + c[i][1].x;
+      if (pix < p.npix) *reinterpret_cast<longlong2*>(p.off + pix) = make_longlong2(o0, o1);
+      if (pix + 2 < p.npix) *reinterpret_cast<longlong2*>(p.off + pix + 2) = make_longlong2(o2, o3);
+    }
+  }
+  if (p.gpix) {
+    // LIST mode: the galaxy -> pixel map itself (ipix = repeat(arange, n), points.py:426), written at
+    // the galaxies' global positions: a sparse map (0.08 galaxies per pixel at the north-star density)
+    // costs 8 B per GALAXY here instead of 16 B per PIXEL of counts + offsets, the cut rule and the
+    // position kernel then never touch a per-pixel array again.  A tile's galaxies are consecutive,
+    // so its stores fall into a few adjacent lines.
+#pragma unroll
+    for (int i = 0; i < PT_QUADS; ++i) {
+      const int64_t pix = wbase + i * 128 + 4 * lane;
+      int64_t o = wpre + ex[i];
+      const int64_t ce[4] = {c[i][0].x, c[i][0].y, c[i][1].x, c[i][1].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        for (int64_t k = 0; k < ce[e]; ++k)
+          if (o + k < p.gpix_cap) p.gpix[o + k] = pix + e;
+        o += ce[e];
+      }
+    }
   }
 }
 
@@ -521,6 +550,40 @@ __global__ void __launch_bounds__(256) ang2pix_kernel(int64_t nside, const doubl
   ipix[i] = zphi2pix_ring(nside, c, s, phi);
 }
 
+// K8, list mode: one thread per galaxy, its pixel read from the list K6 wrote -- no per-pixel
+// array, no search, no shared memory; consecutive lanes store consecutive galaxies.
+__global__ void __launch_bounds__(256) points_fill_list_kernel(const int64_t* __restrict__ gpix, int64_t g0, int64_t n,
+                                                               const double* __restrict__ us, const double* __restrict__ vs,
+                                                               int64_t nside, uint32_t k0, uint32_t k1, uint32_t stream,
+                                                               double* __restrict__ lon, double* __restrict__ lat) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint64_t gi = (uint64_t)(g0 + g);
+  const int64_t pix = gpix[gi];
+  double u, v;
+  if (us) {
+    u = us[g];
+    v = vs[g];
+  } else {
+    const Philox4 r = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), stream, RNG_TAG_POS, k0, k1);
+    u = u01_closed_open(r.v[0], r.v[1]);
+    v = u01_closed_open(r.v[2], r.v[3]);
+  }
+  int x, y, f;
+  ring2xyf(nside, pix, x, y, f);
+  double z, sth, phi;
+  hpc2loc((double)nside, x, y, f, u, v, z, sth, phi);
+  const double rad2deg = 57.295779513082320877;  // 180/pi, as np.degrees
+  lon[g] = phi * rad2deg;
+  lat[g] = 90.0 - atan2(sth, z) * rad2deg;
+}
+
+__global__ void points_cuts_list_kernel(const int64_t* __restrict__ gpix, int64_t total, int64_t npix, int64_t batch,
+                                        int64_t start, int64_t remaining, int max_cuts, int64_t* __restrict__ cuts,
+                                        int64_t* __restrict__ state) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) cuts_list_chain(gpix, total, npix, batch, start, remaining, max_cuts, cuts, state);
+}
+
 // The chain of batch cuts is sequential (every cut starts where the previous one stopped) but tiny:
 // two binary searches over the offsets per cut.  One thread walks it, so the host fetches the cuts
 // of a population with one copy instead of synchronising several times per batch.
@@ -543,8 +606,11 @@ size_t glb_points_workspace_bytes(int64_t npix) {
 
 int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, int bias_model, double bias,
                       double scale, int remove_monopole, const int64_t* d_counts_in, uint64_t seed, uint32_t stream_id,
-                      double* d_nbar_out, int64_t* d_counts, int64_t* d_off, void* d_workspace, void* stream) {
-  GLB_REQUIRE(npix > 0 && d_delta && d_counts && d_off && d_workspace, "null pointer or empty map");
+                      double* d_nbar_out, int64_t* d_counts, int64_t* d_off, int64_t* d_gpix, int64_t gpix_capacity,
+                      int64_t* d_total, void* d_workspace, void* stream) {
+  GLB_REQUIRE(npix > 0 && d_delta && d_workspace, "null pointer or empty map");
+  GLB_REQUIRE(d_off || d_total, "nowhere to write the total (d_off and d_total both NULL)");
+  GLB_REQUIRE(d_gpix == nullptr || gpix_capacity >= 0, "negative list capacity");
   GLB_REQUIRE(bias_model >= BIAS_NONE && bias_model <= BIAS_LOGLINEAR, "unknown bias model");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblocks = (int)((npix + PT_TILE - 1) / PT_TILE);
@@ -569,6 +635,9 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
   p.nbar_out = d_nbar_out;
   p.counts = d_counts;
   p.off = d_off;
+  p.gpix = d_gpix;
+  p.gpix_cap = gpix_capacity;
+  p.total = d_total;
   p.status = reinterpret_cast<unsigned long long*>(block_sums);
   p.ticket = reinterpret_cast<unsigned int*>(block_sums + nblocks);
   p.npix = npix;
@@ -608,6 +677,33 @@ int glb_points_cuts(const int64_t* d_off, int64_t npix, int64_t batch, int64_t s
   GLB_REQUIRE(d_off && d_cuts && d_state, "null pointer");
   GLB_REQUIRE(npix >= 1 && batch >= 1 && start >= 0 && start <= npix && remaining >= 0 && max_cuts >= 1, "bad size");
   points_cuts_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_off, npix, batch, start, remaining, max_cuts, d_cuts, d_state);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_points_cuts_list(const int64_t* d_gpix, int64_t total, int64_t npix, int64_t batch, int64_t start,
+                         int64_t remaining, int max_cuts, int64_t* d_cuts, int64_t* d_state, void* stream) {
+  GLB_REQUIRE(d_gpix && d_cuts && d_state, "null pointer");
+  GLB_REQUIRE(npix >= 1 && batch >= 1 && start >= 0 && start <= npix && remaining >= 0 && remaining <= total && max_cuts >= 1,
+              "bad size");
+  points_cuts_list_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_gpix, total, npix, batch, start, remaining, max_cuts, d_cuts,
+                                                             d_state);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return GLB_OK;
+}
+
+int glb_points_fill_list(int64_t nside, const int64_t* d_gpix, int64_t g0, int64_t g1, const double* d_u,
+                         const double* d_v, uint64_t seed, uint32_t stream_id, double* d_lon, double* d_lat,
+                         void* stream) {
+  GLB_REQUIRE(nside >= 1 && d_gpix && d_lon && d_lat, "null pointer");
+  GLB_REQUIRE(g0 >= 0 && g1 >= g0, "bad galaxy range");
+  GLB_REQUIRE((d_u == nullptr) == (d_v == nullptr), "u and v must be given together");
+  const int64_t n = g1 - g0;
+  if (n == 0) return GLB_OK;
+  points_fill_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_gpix, g0, n, d_u, d_v, nside, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id, d_lon, d_lat);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;

@@ -76,4 +76,61 @@ GLB_CUTS_HD void cuts_chain(const int64_t* off, int64_t npix, int64_t batch, int
   state[2] = remaining;
 }
 
+// ---- the same rule on the GALAXY LIST ---------------------------------------------------------
+// gpix[g] = ring pixel of galaxy g, non-decreasing, g in [0, total) -- what K6 emits instead of
+// counts and offsets when the map is sparsely populated.  With off[p] = #{g : gpix[g] < p}:
+//   largest p with off[p] <= T     = gpix[T]       (T < total; npix otherwise)
+//   pixel completing V galaxies    = gpix[V - 1]
+//   off[stop]                      = lower bound of `stop` in gpix
+// so the cuts need neither the counts nor the offsets.  `base` = index of the first galaxy not yet
+// handed out (= total - remaining).
+
+// first g in [lo, hi) with gpix[g] >= pix; hi if none
+GLB_CUTS_HD int64_t cuts_list_lower_bound(const int64_t* gpix, int64_t lo, int64_t hi, int64_t pix) {
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (gpix[mid] < pix)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+GLB_CUTS_HD int64_t cuts_list_next(const int64_t* gpix, int64_t total, int64_t npix, int64_t batch, int64_t start,
+                                   int64_t remaining, int64_t* n) {
+  const int64_t base = total - remaining;
+  // base + batch may overflow for absurd batch sizes: compare through the difference
+  const int64_t p = (batch < total - base) ? gpix[base + batch] : npix;
+  int64_t stop;
+  if (p <= start) {
+    stop = start + 1;
+  } else {
+    const int64_t need = batch < remaining ? batch : remaining;
+    const int64_t qstar = gpix[base + need - 1];
+    const int64_t group_end = start + 1000 * ((qstar - start) / 1000 + 1);
+    stop = group_end < p ? group_end : p;
+  }
+  *n = cuts_list_lower_bound(gpix, base, total, stop) - base;
+  return stop;
+}
+
+GLB_CUTS_HD void cuts_list_chain(const int64_t* gpix, int64_t total, int64_t npix, int64_t batch, int64_t start,
+                                 int64_t remaining, int max_cuts, int64_t* cuts, int64_t* state) {
+  int k = 0;
+  while (remaining > 0 && k < max_cuts) {
+    int64_t n;
+    const int64_t stop = cuts_list_next(gpix, total, npix, batch, start, remaining, &n);
+    cuts[3 * k + 0] = start;
+    cuts[3 * k + 1] = stop;
+    cuts[3 * k + 2] = n;
+    ++k;
+    start = stop;
+    remaining -= n;
+  }
+  state[0] = k;
+  state[1] = start;
+  state[2] = remaining;
+}
+
 }  // namespace glb

@@ -9,7 +9,6 @@ by one kernel doing the pixel lookup, the three map gathers and the reduced-shea
 from __future__ import annotations
 
 import ctypes as C
-import itertools
 import warnings
 
 import numpy as np
@@ -20,7 +19,35 @@ from . import _lib
 from . import healpix as hp
 from . import rng as _rng
 
-_CALLS = itertools.count()  # distinct Philox stream per call, in call order
+_CDF_TABLES: dict = {}  # (device, key of z, key of nz) -> (cdf, z) on the device
+
+
+def _array_key(a):
+    """Identity of an array's CONTENT without a device round trip: CUDA tensors by storage and
+    version counter, host arrays by their bytes (n(z) tables are a few hundred numbers)."""
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        return ("cuda", a.data_ptr(), a._version, tuple(a.shape), tuple(a.stride()))
+    h = np.ascontiguousarray(A.to_np(a), dtype=np.float64)
+    return ("host", h.shape, h.tobytes())
+
+
+def _cdf_table(z_k, nz_k, device):
+    """Normalised cumulative trapezoid of n(z) and its grid as device arrays
+    (glass/galaxies.py:77-89), cached: the sampler is called once per batch of galaxies with the
+    same window, and building the table on the host costs a stream synchronisation (CUDA inputs)
+    and two blocking pageable copies each time."""
+    key = (str(device), _array_key(z_k), _array_key(nz_k))
+    hit = _CDF_TABLES.get(key)
+    if hit is None:
+        zh, nzh = np.asarray(A.to_np(z_k), dtype=np.float64), np.asarray(A.to_np(nz_k), dtype=np.float64)
+        zh, nzh = np.broadcast_arrays(zh, nzh)
+        cdf = _cumulative_trapezoid(nzh, zh)
+        cdf /= cdf[-1]
+        if len(_CDF_TABLES) >= 256:
+            _CDF_TABLES.clear()
+        # keep the key's CUDA tensors alive with the entry so that data_ptr cannot be recycled
+        hit = _CDF_TABLES[key] = (A.to_dev(cdf, device), A.to_dev(zh, device), int(cdf.shape[0]), (z_k, nz_k))
+    return hit[:3]
 
 
 def _cumulative_trapezoid(f, x):
@@ -50,15 +77,14 @@ def redshifts_from_nz(count, z, nz, *, rng=None, warn: bool = True):
     device, on_device = A.pick_device(z, nz, count)
     deviates = rng if isinstance(rng, _rng.Deviates) else None
     seed = _rng.seed_from(rng)
-    zh, nzh, ch = A.to_np(z), A.to_np(nz), A.to_np(count)
-    dims = np.broadcast_shapes(ch.shape, zh.shape[:-1], nzh.shape[:-1])
+    ch = A.to_np(count)
+    z, nz = (a if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64) for a in (z, nz))
+    zs, nzs = tuple(z.shape), tuple(nz.shape)
+    dims = np.broadcast_shapes(ch.shape, zs[:-1], nzs[:-1])
     count_out = np.broadcast_to(ch, dims)
-    z_out = np.broadcast_to(zh, dims + zh.shape[-1:])
-    nz_out = np.broadcast_to(nzh, dims + nzh.shape[-1:])
     total = int(np.sum(count_out))
     out = torch.empty(total, dtype=torch.float64, device=device)
     lib = _lib.load()
-    call = next(_CALLS)
     pos = 0
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream
@@ -66,17 +92,14 @@ def redshifts_from_nz(count, z, nz, *, rng=None, warn: bool = True):
             n_k = int(count_out[k])
             if n_k == 0:
                 continue
-            cdf = _cumulative_trapezoid(nz_out[k], z_out[k])
-            cdf /= cdf[-1]
-            d_cdf = A.to_dev(cdf, device)
-            d_z = A.to_dev(z_out[k], device)
+            d_cdf, d_z, ncdf = _cdf_table(A.take_leading(z, zs[:-1], dims, k), A.take_leading(nz, nzs[:-1], dims, k), device)
             u = None
             if deviates is not None and deviates.uniform is not None:
                 u = A.to_dev(deviates.uniform(n_k) if callable(deviates.uniform) else deviates.uniform[pos : pos + n_k], device)
             _lib.check(
                 lib.glb_redshifts_from_cdf(
-                    d_cdf.data_ptr(), d_z.data_ptr(), int(cdf.shape[0]), None if u is None else u.data_ptr(), n_k,
-                    C.c_uint64(seed), C.c_uint32(call & 0xFFFFFFFF), C.c_uint64(pos), out[pos:].data_ptr(), st,
+                    d_cdf.data_ptr(), d_z.data_ptr(), ncdf, None if u is None else u.data_ptr(), n_k,
+                    C.c_uint64(seed), C.c_uint32(_rng.STREAM_REDSHIFTS), C.c_uint64(pos), out[pos:].data_ptr(), st,
                 ),
                 "glb_redshifts_from_cdf",
             )
@@ -198,7 +221,6 @@ def gaussian_phz(z, sigma_0, *, lower=None, upper=None, rng=None, xp=None):
     hi_arr, hi_val = per_galaxy(hi_d)
     out = torch.empty(n, dtype=torch.float64, device=device)
     lib = _lib.load()
-    call = next(_CALLS)
     ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream
@@ -207,7 +229,7 @@ def gaussian_phz(z, sigma_0, *, lower=None, upper=None, rng=None, xp=None):
             _lib.check(
                 lib.glb_gaussian_phz(
                     z_f.data_ptr(), ptr(s_arr), s_val, ptr(lo_arr), lo_val, ptr(hi_arr), hi_val, ptr(normals), redraw_only, n,
-                    C.c_uint64(seed), C.c_uint32(call & 0xFFFFFFFF), out.data_ptr(), ptr(nbad), st,
+                    C.c_uint64(seed), C.c_uint32(_rng.STREAM_PHZ), out.data_ptr(), ptr(nbad), st,
                 ),
                 "glb_gaussian_phz",
             )

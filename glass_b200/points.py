@@ -15,7 +15,6 @@ from __future__ import annotations
 import ctypes as C
 import itertools
 import math
-import os
 from typing import Callable
 
 import numpy as np
@@ -99,10 +98,24 @@ def _bias_code(bias, bias_model):
     return _BIAS_NONE, True
 
 
-class _Population:
-    """Counts, offsets and positions of one population on the device."""
+#: expected galaxies per pixel up to which K6 emits the galaxy -> pixel LIST instead of per-pixel
+#: counts and offsets (8 B per galaxy against 16 B per pixel; the cut rule and the position kernel
+#: then work from the list alone)
+LIST_MODE_MAX_DENSITY = 1.0
 
-    def __init__(self, delta_k, vis_k, ngal_k, bias_k, bias_model, remove_monopole, seed, stream_id, counts_in, device, want_nbar=False):
+
+class _Population:
+    """Counts and positions of one population on the device.
+
+    ``mode``: "scan" -- per-pixel ``counts`` and exclusive offsets ``off`` (K6+K7), positions by
+    walking pixels; "list" -- only the galaxy -> pixel list ``gpix`` (= np.repeat(arange, counts),
+    glass/points.py:426), cuts and positions from it; "auto" -- the list for sparse maps (expected
+    density <= LIST_MODE_MAX_DENSITY galaxies per pixel), the scan otherwise.  Same galaxies
+    either way: counts are a function of (seed, stream, pixel), positions of (seed, stream,
+    galaxy index)."""
+
+    def __init__(self, delta_k, vis_k, ngal_k, bias_k, bias_model, remove_monopole, seed, stream_id, counts_in, device, want_nbar=False,
+                 mode: str = "auto"):
         lib = _lib.load()
         self.lib, self.device = lib, device
         code, prepass = _bias_code(bias_k, bias_model)
@@ -113,97 +126,128 @@ class _Population:
         self.nside = hp.npix2nside(self.npix)
         v = None if vis_k is None else A.to_dev(vis_k, device)
         scale = ARCMIN2_SPHERE / self.npix * float(ngal_k)  # same order as points.py:287
-        self.counts = torch.empty(self.npix, dtype=torch.int64, device=device)
-        self.off = torch.empty(self.npix + 1, dtype=torch.int64, device=device)
+        if mode == "auto":
+            mode = "list" if scale <= LIST_MODE_MAX_DENSITY else "scan"
+        self.mode = mode
+        self.counts = self.off = self.gpix = None
+        cap = 0
+        if mode == "scan":
+            self.counts = torch.empty(self.npix, dtype=torch.int64, device=device)
+            self.off = torch.empty(self.npix + 1, dtype=torch.int64, device=device)
+        else:
+            # first guess of the list length: the mean expected count (delta averages to ~0, vis <= 1)
+            cap = int(1.25 * scale * self.npix) + 65536
+            self.gpix = torch.empty(cap, dtype=torch.int64, device=device)
         self.nbar = torch.empty(self.npix, dtype=torch.float64, device=device) if want_nbar else None
         ws = torch.empty(int(lib.glb_points_workspace_bytes(self.npix)), dtype=torch.uint8, device=device)
         cin = None if counts_in is None else A.to_dev(counts_in, device, torch.int64)
-        st = torch.cuda.current_stream(device).cuda_stream
+        total = torch.zeros(1, dtype=torch.int64, device=device)
         self.seed, self.stream_id = seed, stream_id
-        _lib.check(
-            lib.glb_points_counts(
-                self.npix,
-                d.data_ptr(),
-                None if v is None else v.data_ptr(),
-                code,
-                float(bias_k) if (bias_k is not None and not prepass) else 0.0,
-                scale,
-                int(bool(remove_monopole)),
-                None if cin is None else cin.data_ptr(),
-                C.c_uint64(seed),
-                C.c_uint32(stream_id),
-                None if self.nbar is None else self.nbar.data_ptr(),
-                self.counts.data_ptr(),
-                self.off.data_ptr(),
-                ws.data_ptr(),
-                st,
-            ),
-            "glb_points_counts",
-        )
-        self.total = int(self.off[-1].item())
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
 
-    def cuts(self, batch: int):
-        """Pixel ranges (start, stop, npoints) of glass/points.py:409-437."""
-        # Closed form of the reference's 1000-pixel stepping loop.  The loop advances in groups of
-        # 1000 pixels (counted from ``start``) until the group in which the running total reaches
-        # min(batch, remaining) -- at pixel q* -- and cuts inside that group with
-        # searchsorted(side="right"): after the last pixel whose running total is still <= batch,
-        # but not beyond the end of the group.  Hence stop = min(p, end of the group of q*) with p the
-        # largest index whose offset is <= off[start] + batch.  Consequences the reference shares: a
-        # batch may be EMPTY when zero-count pixels precede a pixel that alone exceeds ``batch``; a
-        # first pixel that alone exceeds ``batch`` is taken by itself; on an exact fit, and for the
-        # last batch, trailing empty pixels are included up to the end of the group.
-        if os.environ.get("GLB_POINTS_CUTS_DEVICE") == "1":
-            yield from self._cuts_device(batch)
-            return
-        start, remaining = 0, self.total
-        off = self.off
+        def launch():
+            _lib.check(
+                lib.glb_points_counts(
+                    self.npix, d.data_ptr(), ptr(v), code, float(bias_k) if (bias_k is not None and not prepass) else 0.0, scale,
+                    int(bool(remove_monopole)), ptr(cin), C.c_uint64(seed), C.c_uint32(stream_id), ptr(self.nbar), ptr(self.counts),
+                    ptr(self.off), ptr(self.gpix), cap, total.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(device).cuda_stream,
+                ),
+                "glb_points_counts",
+            )
+            return int(total.item())
 
-        def search(value, right):
-            v = torch.tensor(value, device=off.device)
-            return int(torch.searchsorted(off, v, right=right).item())
+        self.total = launch()
+        if self.gpix is not None and self.total > cap:  # the guess was too small: same counts again, into a list that fits
+            cap = self.total
+            self.gpix = torch.empty(cap, dtype=torch.int64, device=device)
+            self.total = launch()
 
-        while remaining > 0:
-            base = int(off[start].item())
-            p = min(search(base + batch, True) - 1, self.npix)  # largest p with off[p] <= base + batch
-            if p <= start:
-                stop = start + 1  # the first pixel alone is too much: use it anyway
-            else:
-                qstar = search(base + min(batch, remaining), False) - 1  # pixel completing min(batch, remaining)
-                stop = min(p, start + 1000 * ((qstar - start) // 1000 + 1))
-            n = int(off[stop].item()) - base
-            yield start, stop, n
-            start = stop
-            remaining -= n
+    def cuts(self, batch: int, chunk: int = 4096):
+        """Pixel ranges (start, stop, npoints) of glass/points.py:409-437, walked on the device by
+        ``glb_points_cuts`` (csrc/points_cuts.cuh, host-tested against the reference's loop): one
+        device->host copy per ``chunk`` cuts.
 
-    def _cuts_device(self, batch: int, chunk: int = 4096):
-        """The same cuts walked by ``glb_points_cuts`` on the device (csrc/points_cuts.cuh, host-tested
-        against the reference's loop): one device->host copy per ``chunk`` cuts instead of four
-        synchronisations per batch.  Opt-in (GLB_POINTS_CUTS_DEVICE=1) until it has run on a GPU."""
+        Closed form of the reference's 1000-pixel stepping loop.  The loop advances in groups of
+        1000 pixels (counted from ``start``) until the group in which the running total reaches
+        min(batch, remaining) -- at pixel q* -- and cuts inside that group with
+        searchsorted(side="right"): after the last pixel whose running total is still <= batch,
+        but not beyond the end of the group.  Hence stop = min(p, end of the group of q*) with p the
+        largest index whose offset is <= off[start] + batch.  Consequences the reference shares: a
+        batch may be EMPTY when zero-count pixels precede a pixel that alone exceeds ``batch``; a
+        first pixel that alone exceeds ``batch`` is taken by itself; on an exact fit, and for the
+        last batch, trailing empty pixels are included up to the end of the group."""
         start, remaining = 0, self.total
         cuts = torch.empty((chunk, 3), dtype=torch.int64, device=self.device)
         state = torch.empty(3, dtype=torch.int64, device=self.device)
+        gpix = getattr(self, "gpix", None)
         while remaining > 0:
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(
-                self.lib.glb_points_cuts(self.off.data_ptr(), self.npix, int(batch), start, remaining, chunk, cuts.data_ptr(), state.data_ptr(), st),
-                "glb_points_cuts",
-            )
+            if gpix is not None:
+                _lib.check(
+                    self.lib.glb_points_cuts_list(gpix.data_ptr(), self.total, self.npix, int(batch), start, remaining, chunk, cuts.data_ptr(),
+                                                  state.data_ptr(), st),
+                    "glb_points_cuts_list",
+                )
+            else:
+                _lib.check(
+                    self.lib.glb_points_cuts(self.off.data_ptr(), self.npix, int(batch), start, remaining, chunk, cuts.data_ptr(), state.data_ptr(), st),
+                    "glb_points_cuts",
+                )
             k, start, remaining = (int(v) for v in state.cpu().numpy())
             for a, b, n in cuts[:k].cpu().numpy():
                 yield int(a), int(b), int(n)
 
-    def fill(self, start: int, stop: int, n: int, uv=None, want_ipix=False):
+    def batches(self, batch: int, group: int = 1 << 26):
+        """(lon, lat, npoints) of every batch, as slices of positions written by ONE launch of the
+        fill kernel per ``group`` galaxies (a draw depends on the galaxy's global index only, so
+        the result does not depend on how the launches are cut)."""
+        pending, first_pix, ngal, done = [], None, 0, 0
+
+        def flush():
+            nonlocal pending, first_pix, ngal, done
+            if pending:
+                lon, lat, _ = self.fill(first_pix, pending[-1][0], ngal, first_galaxy=done)
+                pos = 0
+                for _stop, n in pending:
+                    yield lon[pos : pos + n], lat[pos : pos + n], n
+                    pos += n
+                done += ngal
+            pending, first_pix, ngal = [], None, 0
+
+        for start, stop, n in self.cuts(batch):
+            if first_pix is None:
+                first_pix = start
+            pending.append((stop, n))
+            ngal += n
+            if ngal >= group:
+                yield from flush()
+        yield from flush()
+
+    def fill(self, start: int, stop: int, n: int, uv=None, want_ipix=False, first_galaxy: int | None = None):
+        """Positions of the ``n`` galaxies in ring pixels [start, stop).  List mode needs the index of
+        the range's first galaxy: ``first_galaxy`` if the caller tracks it (batches are consecutive),
+        else it is looked up in the list."""
         lon = torch.empty(n, dtype=torch.float64, device=self.device)
         lat = torch.empty(n, dtype=torch.float64, device=self.device)
-        ipix = torch.empty(n, dtype=torch.int64, device=self.device) if want_ipix else None
+        ipix = torch.empty(n, dtype=torch.int64, device=self.device) if (want_ipix and self.gpix is None) else None
         if n == 0:
-            return lon, lat, ipix
+            return lon, lat, (torch.empty(0, dtype=torch.int64, device=self.device) if want_ipix else None)
         u = v = None
         if uv is not None:
             uu, vv = uv(n) if callable(uv) else uv
             u, v = A.to_dev(uu, self.device), A.to_dev(vv, self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
+        if self.gpix is not None:
+            if first_galaxy is None:
+                first_galaxy = int(torch.searchsorted(self.gpix[: self.total], torch.tensor(start, device=self.device)).item())
+            g0 = int(first_galaxy)
+            _lib.check(
+                self.lib.glb_points_fill_list(self.nside, self.gpix.data_ptr(), g0, g0 + n, None if u is None else u.data_ptr(),
+                                              None if v is None else v.data_ptr(), C.c_uint64(self.seed), C.c_uint32(self.stream_id),
+                                              lon.data_ptr(), lat.data_ptr(), st),
+                "glb_points_fill_list",
+            )
+            return lon, lat, (self.gpix[g0 : g0 + n] if want_ipix else None)
         _lib.check(
             self.lib.glb_points_fill(
                 self.nside,
@@ -278,12 +322,22 @@ def positions_from_delta(  # noqa: PLR0913
             else:
                 cmask = 1
             uv = deviates.uv if deviates is not None else None
-            for start, stop, n in pop.cuts(batch):
-                lon, lat, _ = pop.fill(start, stop, n, uv)
-                if on_device:
+            if uv is not None:  # parity mode: the supplied (u, v) are consumed batch by batch
+                def per_cut(pop=pop):
+                    g0 = 0
+                    for start, stop, n in pop.cuts(batch):
+                        lon, lat, _ = pop.fill(start, stop, n, uv, first_galaxy=g0)
+                        g0 += n
+                        yield lon, lat, n
+
+                it = per_cut()
+            else:
+                it = pop.batches(batch)
+            if on_device:
+                for lon, lat, n in it:
                     yield lon, lat, n * cmask
-                else:
-                    yield lon.cpu().numpy(), lat.cpu().numpy(), n * cmask
+            else:
+                yield from ((lo, la, n * cmask) for lo, la, n in A.host_slices(it))
 
 
 def uniform_positions(ngal, *, rng=None, xp=None):

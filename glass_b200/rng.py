@@ -21,6 +21,15 @@ import numpy as np
 
 SEED = 42
 
+# Philox stream ids of the per-galaxy samplers.  A draw is a pure function of (seed, stream,
+# element index): the stream says WHICH sampler, never how many calls were made before, so a
+# given seed gives the same galaxies on any rank, in any order of calls (with ``rng=None`` the
+# reference, too, returns the same draw on every call; pass a ``numpy.random.Generator`` to get
+# a fresh seed per call).
+STREAM_REDSHIFTS = 0x7A5F6E7A  # redshifts_from_nz
+STREAM_PHZ = 0x70687A5F  # gaussian_phz
+STREAM_ELLIPTICITY = 0x65707331  # ellipticity_gaussian / ellipticity_intnorm
+
 
 class Deviates:
     """Explicit deviates for parity tests.

@@ -7,7 +7,6 @@ ellipticity formula in one kernel per population.
 from __future__ import annotations
 
 import ctypes as C
-import itertools
 
 import numpy as np
 import torch
@@ -17,7 +16,6 @@ from . import _lib
 from . import healpix as hp
 from . import rng as _rng
 
-_CALLS = itertools.count()
 
 
 def _run(mode, count, sigma_fn, sigma, rng, xp):
@@ -29,7 +27,6 @@ def _run(mode, count, sigma_fn, sigma, rng, xp):
     total = int(np.sum(cnt))
     out = torch.empty(total, dtype=torch.complex128, device=device)
     lib = _lib.load()
-    call = next(_CALLS)
     pos = 0
     with torch.cuda.device(device):
         st = torch.cuda.current_stream(device).cuda_stream
@@ -44,7 +41,7 @@ def _run(mode, count, sigma_fn, sigma, rng, xp):
             _lib.check(
                 lib.glb_ellipticity(
                     mode, float(sigma_fn(float(sig[k]))), None if normals is None else normals.data_ptr(), n_k,
-                    C.c_uint64(seed), C.c_uint32(call & 0xFFFFFFFF), C.c_uint64(pos), out[pos:].data_ptr(), st,
+                    C.c_uint64(seed), C.c_uint32(_rng.STREAM_ELLIPTICITY), C.c_uint64(pos), out[pos:].data_ptr(), st,
                 ),
                 "glb_ellipticity",
             )

@@ -124,13 +124,19 @@ size_t glb_points_workspace_bytes(int64_t npix);
  * _compute_expected_count (:279-288; scale = ARCMIN2_SPHERE/npix*ngal computed by the caller,
  * remove_monopole subtracts the map mean), _apply_visibility (:314-316; d_vis may be NULL) and
  * _sample_number_galaxies (:340-348; Philox Poisson keyed by (seed, stream_id, pixel), or, in
- * parity mode, d_counts_in supplies the deviates).  Outputs: d_counts [npix] int64,
- * d_off [npix+1] int64 (d_off[p] = galaxies before pixel p, d_off[npix] = total) and,
- * if not NULL, d_nbar_out [npix] = expected counts before clipping. */
+ * parity mode, d_counts_in supplies the deviates).  Outputs, each optional (NULL = not wanted):
+ * d_counts [npix] int64; d_off [npix+1] int64 (d_off[p] = galaxies before pixel p, d_off[npix] =
+ * total); d_nbar_out [npix] = expected counts before clipping; d_total [1] = number of galaxies;
+ * and the GALAXY LIST d_gpix [gpix_capacity] int64: ring pixel of every galaxy, galaxies in pixel
+ * order = np.repeat(np.arange(npix), counts) (points.py:426).  Only the first gpix_capacity galaxies
+ * are listed -- the total is exact regardless, so a caller whose guess was too small calls again
+ * with a larger list (the counts are a function of (seed, stream_id, pixel) and come out the same).
+ * For sparse maps the list replaces counts and offsets altogether (8 B per galaxy instead of 16 B
+ * per pixel): glb_points_cuts_list and glb_points_fill_list work from it alone. */
 int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, int bias_model, double bias,
                       double scale, int remove_monopole, const int64_t* d_counts_in, uint64_t seed,
-                      uint32_t stream_id, double* d_nbar_out, int64_t* d_counts, int64_t* d_off,
-                      void* d_workspace, void* stream);
+                      uint32_t stream_id, double* d_nbar_out, int64_t* d_counts, int64_t* d_off, int64_t* d_gpix,
+                      int64_t gpix_capacity, int64_t* d_total, void* d_workspace, void* stream);
 /* The pixel ranges of the batches of _sample_galaxies_per_pixel (points.py:409-437: 1000-pixel
  * stepping, searchsorted(side="right"), "first pixel alone" rule) from the exclusive scan d_off,
  * walked on the device: up to max_cuts cuts from pixel `start` with `remaining` galaxies to hand out.
@@ -138,6 +144,17 @@ int glb_points_counts(int64_t npix, const double* d_delta, const double* d_vis, 
  * remaining} -- call again from there while galaxies remain. */
 int glb_points_cuts(const int64_t* d_off, int64_t npix, int64_t batch, int64_t start, int64_t remaining,
                     int max_cuts, int64_t* d_cuts, int64_t* d_state, void* stream);
+/* The same cuts from the galaxy list of glb_points_counts (d_gpix [total]); `remaining` of the
+ * `total` galaxies are still to hand out, i.e. the next batch starts at galaxy total - remaining. */
+int glb_points_cuts_list(const int64_t* d_gpix, int64_t total, int64_t npix, int64_t batch, int64_t start,
+                         int64_t remaining, int max_cuts, int64_t* d_cuts, int64_t* d_state, void* stream);
+/* healpix.randang(nside, ipix, lonlat=True) (points.py:427 -> glass/healpix.py:426-431) for the
+ * galaxies [g0, g1) of the list: d_lon/d_lat [g1 - g0]; (u, v) from Philox keyed by (seed,
+ * stream_id, global galaxy index) -- the same draws as glb_points_fill -- or supplied arrays
+ * [g1 - g0] (parity mode).  The galaxies' pixel indices are d_gpix[g0:g1] itself. */
+int glb_points_fill_list(int64_t nside, const int64_t* d_gpix, int64_t g0, int64_t g1, const double* d_u,
+                         const double* d_v, uint64_t seed, uint32_t stream_id, double* d_lon, double* d_lat,
+                         void* stream);
 /* Positions of every galaxy in ring pixels [pix0, pix1): ipix = repeat(arange, n) (points.py:426)
  * and healpix.randang(nside, ipix, lonlat=True) (points.py:427 -> glass/healpix.py:426-431),
  * written at index d_off[p] - d_off[pix0] + i.  (u, v) in-pixel offsets: Philox keyed by

@@ -89,3 +89,46 @@ def native_iternorm_rows(rows):
             raise ValueError("covariance matrix is not positive definite")
         out.append(w.reshape(*lead, k + 1))
     return out
+
+
+def native_points_cuts():
+    """Test double of glb_points_cuts: csrc/points_cuts.cuh (the header the kernel walks) compiled
+    for the host behind the C-ABI call's arguments.  Returns an object with ``glb_points_cuts``."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    assert gxx, "g++ needed for the native host tests"
+    tmp = tempfile.mkdtemp(prefix="glb_cuts_")
+    src = os.path.join(tmp, "chain.cpp")
+    with open(src, "w") as f:
+        f.write(
+            '#include "%s"\nextern "C" void chain(const int64_t* off, int64_t npix, int64_t batch, int64_t start, int64_t remaining,'
+            " int max_cuts, int64_t* cuts, int64_t* state) { glb::cuts_chain(off, npix, batch, start, remaining, max_cuts, cuts, state); }\n"
+            'extern "C" void chain_list(const int64_t* gpix, int64_t total, int64_t npix, int64_t batch, int64_t start, int64_t remaining,'
+            " int max_cuts, int64_t* cuts, int64_t* state) { glb::cuts_list_chain(gpix, total, npix, batch, start, remaining, max_cuts, cuts, state); }\n"
+            % os.path.join(root, "glass_b200", "csrc", "points_cuts.cuh")
+        )
+    so = os.path.join(tmp, "chain.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True, capture_output=True, timeout=300)
+    host = C.CDLL(so)
+    host.chain.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+
+    host.chain_list.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+
+    class FakeLib:
+        @staticmethod
+        def glb_points_cuts(off, npix, batch, start, remaining, max_cuts, cuts, state, st):
+            host.chain(off, npix, batch, start, remaining, max_cuts, cuts, state)
+            return 0
+
+        @staticmethod
+        def glb_points_cuts_list(gpix, total, npix, batch, start, remaining, max_cuts, cuts, state, st):
+            host.chain_list(gpix, total, npix, batch, start, remaining, max_cuts, cuts, state)
+            return 0
+
+    return FakeLib()

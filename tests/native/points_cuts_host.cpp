@@ -60,6 +60,24 @@ static int check(const std::vector<int64_t>& cnt, int64_t batch, int chunk) {
   if (got.size() != ref.size()) return 1;
   for (size_t i = 0; i < ref.size(); ++i)
     if (got[i].start != ref[i].start || got[i].stop != ref[i].stop || got[i].n != ref[i].n) return 1;
+  // the same rule walked on the galaxy list (gpix[g] = pixel of galaxy g), what K6 emits for sparse maps
+  std::vector<int64_t> gpix;
+  for (int64_t i = 0; i < npix; ++i)
+    for (int64_t k = 0; k < cnt[i]; ++k) gpix.push_back(i);
+  const int64_t total = (int64_t)gpix.size();
+  got.clear();
+  start = 0;
+  remaining = total;
+  while (remaining > 0) {
+    glb::cuts_list_chain(gpix.data(), total, npix, batch, start, remaining, chunk, buf.data(), state.data());
+    for (int k = 0; k < state[0]; ++k) got.push_back({buf[3 * k], buf[3 * k + 1], buf[3 * k + 2]});
+    start = state[1];
+    remaining = state[2];
+    if (state[0] == 0) return 4;
+  }
+  if (got.size() != ref.size()) return 3;
+  for (size_t i = 0; i < ref.size(); ++i)
+    if (got[i].start != ref[i].start || got[i].stop != ref[i].stop || got[i].n != ref[i].n) return 3;
   return 0;
 }
 

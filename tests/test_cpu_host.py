@@ -920,18 +920,21 @@ def test_displace_host_flow_golden(monkeypatch):
 
 
 def test_positions_from_delta_host_flow_golden(monkeypatch):
-    """The REAL glass_b200.positions_from_delta on CPU tensors with the three C-ABI calls replaced by
-    their definitions (counts supplied, exclusive scan, np.repeat + pixel -> angle): broadcasting of
+    """The REAL glass_b200.positions_from_delta on CPU tensors with the C-ABI calls replaced by
+    their definitions (counts supplied, exclusive scan or galaxy list, the kernel's own cut-rule
+    header compiled for the host, np.repeat + pixel -> angle): broadcasting of
     the population axes, iteration order, the one-hot batch counts, batch cuts and the concatenated
     positions against the reference's own source run on the same count maps (golden positions file)."""
     import contextlib
     import ctypes as C
+    import itertools
     import types
 
     import torch
 
     import glass_b200.points as P
     from glass_b200.rng import Deviates
+    from helpers import native_points_cuts
     from oracle import healpix_ref as H
 
     def f64(ptr, n):
@@ -941,18 +944,37 @@ def test_positions_from_delta_host_flow_golden(monkeypatch):
         return np.ctypeslib.as_array((C.c_int64 * n).from_address(ptr))
 
     seen = []
+    walker = native_points_cuts()  # csrc/points_cuts.cuh on the host: scan and list walkers
 
     class FakeLib:
+        glb_points_cuts = staticmethod(walker.glb_points_cuts)
+        glb_points_cuts_list = staticmethod(walker.glb_points_cuts_list)
+
         def glb_points_workspace_bytes(self, npix):
             return 64
 
-        def glb_points_counts(self, npix, d, v, code, bias, scale, rm, cin, seed, stream, nbar, counts, off, ws, st):
-            seen.append((code, bias, bool(rm), v is not None, stream.value))
+        def glb_points_counts(self, npix, d, v, code, bias, scale, rm, cin, seed, stream, nbar, counts, off, gpix, cap, total, ws, st):
             c = i64(cin, npix)
-            i64(counts, npix)[:] = c
-            o = i64(off, npix + 1)
-            o[0] = 0
-            o[1:] = np.cumsum(c)
+            if not (gpix and cap < c.sum()):  # a list that was too short is filled again by a second call
+                seen.append((code, bias, bool(rm), v is not None, stream.value))
+            if counts:
+                i64(counts, npix)[:] = c
+            if off:
+                o = i64(off, npix + 1)
+                o[0] = 0
+                o[1:] = np.cumsum(c)
+            if gpix:
+                full = np.repeat(np.arange(npix), c)
+                k = min(cap, full.size)
+                i64(gpix, max(cap, 1))[:k] = full[:k]
+            i64(total, 1)[0] = c.sum()
+            return 0
+
+        def glb_points_fill_list(self, nside, gpix, g0, g1, u, v, seed, stream, lon, lat, st):
+            n = g1 - g0
+            pix = i64(gpix, g1)[g0:g1]
+            lo, la = H.ring2ang_uv(nside, pix, f64(u, n), f64(v, n), lonlat=True)
+            f64(lon, n)[:], f64(lat, n)[:] = lo, la
             return 0
 
         def glb_points_fill(self, nside, counts, off, start, stop, u, v, seed, stream, lon, lat, ipix, st):
@@ -970,7 +992,9 @@ def test_positions_from_delta_host_flow_golden(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=0))
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_positions.npz"))
     centre = lambda n: (np.full(n, 0.5), np.full(n, 0.5))  # noqa: E731
-    for tag, kw in {"lin": {}, "loglin_rm": {"bias_model": P.loglinear_bias, "remove_monopole": True}}.items():
+    # both layouts of the counts: the galaxy list (sparse maps) and the per-pixel scan
+    for (tag, kw), dens in itertools.product({"lin": {}, "loglin_rm": {"bias_model": P.loglinear_bias, "remove_monopole": True}}.items(), (1.0, 0.0)):
+        monkeypatch.setattr(P, "LIST_MODE_MAX_DENSITY", dens)
         seen.clear()
         res = list(P.positions_from_delta(g["ngal"], g["delta"], g["bias"], g["vis"], batch=40,
                                           rng=Deviates(poisson=list(g[f"{tag}_counts"]), uv=centre), **kw))
@@ -1274,23 +1298,30 @@ def test_redshifts_from_bins_order_golden(monkeypatch):
         assert np.array_equal(out[first[label]], np.interp(u, cdf / cdf[-1], g["rb_z"]))
 
 
-def test_batch_cut_rule_closed_form_on_cpu():
+def test_batch_cut_rule_closed_form_on_cpu(monkeypatch):
     """points._Population.cuts -- the closed form of the reference's 1000-pixel stepping loop
-    (glass/points.py:409-437) -- replayed on CPU tensors: against the batch sizes recorded from the
+    (glass/points.py:409-437), walked by glb_points_cuts; here the kernel's header
+    csrc/points_cuts.cuh compiled for the host stands in for the launch -- against the batch sizes recorded from the
     reference's source (golden) and against the oracle's restatement of the loop on corner cases
     (exact fit at a group boundary, empty batches before an oversize pixel, trailing zeros,
     random sparse and dense maps, batch = 1)."""
     import torch
 
     from glass_b200.points import _Population
+    from helpers import native_points_cuts
     from oracle import glass_ref as G
+
+    fake = native_points_cuts()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: __import__("types").SimpleNamespace(cuda_stream=0))
 
     def cuts_of(counts, batch):
         pop = object.__new__(_Population)
-        pop.npix = counts.size
+        pop.npix, pop.lib, pop.device = counts.size, fake, torch.device("cpu")
         pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64))
         pop.total = int(counts.sum())
-        return [n for _a, _b, n in pop.cuts(batch)], [(a, b) for a, b, _n in pop.cuts(batch)]
+        got = list(pop.cuts(batch))
+        assert got == list(pop.cuts(batch, chunk=3))  # the walk resumes correctly between chunks
+        return [n for _a, _b, n in got], [(a, b) for a, b, _n in got]
 
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "glass_reference_vectors.npz"))
     for batch in (1_000_000, 500, 37, 1):
@@ -1327,19 +1358,12 @@ def test_batch_cut_rule_closed_form_on_cpu():
         assert sum(sizes) == counts.sum()
 
 
-def test_points_cuts_core_host_build_and_run(tmp_path, monkeypatch):
+def test_points_cuts_core_host_build_and_run(tmp_path):
     """csrc/points_cuts.cuh (the batch-cut rule the device walks for glb_points_cuts) on the host:
-    (a) the native fuzz against the reference's 1000-pixel stepping loop restated in C++
-    (tests/native/points_cuts_host.cpp, ~3000 maps incl. exact fits, oversize pixels, batch = 1);
-    (b) the product's opt-in device path _Population._cuts_device driven through a host build of the
-    same header standing in for the kernel, in chunks of 3 cuts, against the default path."""
-    import ctypes as C
+    the native fuzz against the reference's 1000-pixel stepping loop restated in C++
+    (tests/native/points_cuts_host.cpp, ~3000 maps incl. exact fits, oversize pixels, batch = 1)."""
     import shutil
     import subprocess
-
-    import torch
-
-    from glass_b200.points import _Population
 
     gxx = shutil.which("g++")
     if gxx is None:
@@ -1350,41 +1374,6 @@ def test_points_cuts_core_host_build_and_run(tmp_path, monkeypatch):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "points_cuts ok" in r.stdout, r.stdout + r.stderr
-    # (b) a shared library with the header's chain as an extern "C" function
-    src = tmp_path / "chain.cpp"
-    src.write_text(
-        '#include "%s"\nextern "C" void chain(const int64_t* off, int64_t npix, int64_t batch, int64_t start, int64_t remaining,'
-        " int max_cuts, int64_t* cuts, int64_t* state) { glb::cuts_chain(off, npix, batch, start, remaining, max_cuts, cuts, state); }\n"
-        % os.path.join(root, "glass_b200", "csrc", "points_cuts.cuh")
-    )
-    so = tmp_path / "chain.so"
-    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)], check=True, capture_output=True, timeout=300)
-    host = C.CDLL(str(so))
-    host.chain.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
-
-    class FakeLib:
-        def glb_points_cuts(self, off, npix, batch, start, remaining, max_cuts, cuts, state, st):
-            host.chain(off, npix, batch, start, remaining, max_cuts, cuts, state)
-            return 0
-
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: __import__("types").SimpleNamespace(cuda_stream=0))
-    rng = np.random.default_rng(4)
-    for it in range(40):
-        npix = int(rng.integers(1, 5000))
-        counts = rng.poisson(10 ** rng.uniform(-2.5, 0.5), npix)
-        if counts.sum() == 0:
-            continue
-        batch = 1 + int(rng.random() ** 2 * 2 * counts.sum())
-        if counts.sum() / batch > 500:
-            continue
-        pop = object.__new__(_Population)
-        pop.npix, pop.lib, pop.device = npix, FakeLib(), torch.device("cpu")
-        pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64))
-        pop.total = int(counts.sum())
-        assert list(pop._cuts_device(batch, chunk=3)) == list(pop.cuts(batch))
-        monkeypatch.setenv("GLB_POINTS_CUTS_DEVICE", "1")
-        assert list(pop.cuts(batch)) == list(pop._cuts_device(batch))
-        monkeypatch.delenv("GLB_POINTS_CUTS_DEVICE")
 
 
 def test_fft_core_host_build_and_run(tmp_path):

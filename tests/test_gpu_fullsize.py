@@ -281,9 +281,11 @@ def test_points_fullsize_properties(cuda_device):
     off = torch.empty(npix + 1, dtype=torch.int64, device=dev)
     ws = torch.empty(int(lib.glb_points_workspace_bytes(npix)), dtype=torch.uint8, device=dev)
     bias, scale = 1.2, 0.083
+    tot_d = torch.zeros(1, dtype=torch.int64, device=dev)
     _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, bias, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
-                                     counts.data_ptr(), off.data_ptr(), ws.data_ptr(), st))
+                                     counts.data_ptr(), off.data_ptr(), None, 0, tot_d.data_ptr(), ws.data_ptr(), st))
     torch.cuda.synchronize()
+    assert int(tot_d) == int(off[-1])
     assert int(counts.min()) >= 0
     assert int(off[0]) == 0
     assert torch.equal(off[1:], torch.cumsum(counts, 0))
@@ -304,6 +306,29 @@ def test_points_fullsize_properties(cuda_device):
     want = torch.repeat_interleave(torch.arange(npix, device=dev), counts)
     assert torch.equal(ipix, want)  # sorted by ring pixel like the reference, every galaxy in its own pixel
     assert float(lon.min()) >= 0.0 and float(lon.max()) < 360.0 and float(lat.abs().max()) <= 90.0
+    # LIST mode (what positions_from_delta uses for sparse maps): the galaxy -> pixel list alone, first
+    # with a capacity that is too small (total still exact, prefix written), then one that fits; the
+    # list is np.repeat(arange, counts) and the positions are bit-identical to the scan path's
+    small = tot // 2
+    gpix = torch.full((tot + 8,), -1, dtype=torch.int64, device=dev)
+    _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, bias, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
+                                     None, None, gpix.data_ptr(), small, tot_d.data_ptr(), ws.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert int(tot_d) == tot and torch.equal(gpix[:small], want[:small]) and bool((gpix[small:] == -1).all())
+    _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, bias, scale, 0, None, C.c_uint64(42), C.c_uint32(0), None,
+                                     None, None, gpix.data_ptr(), tot + 8, tot_d.data_ptr(), ws.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert int(tot_d) == tot and torch.equal(gpix[:tot], want) and bool((gpix[tot:] == -1).all())
+    lon2, lat2 = torch.empty_like(lon), torch.empty_like(lat)
+    _lib.check(lib.glb_points_fill_list(NSIDE, gpix.data_ptr(), 0, tot, None, None, C.c_uint64(42), C.c_uint32(0), lon2.data_ptr(),
+                                        lat2.data_ptr(), st))
+    g0 = tot // 3  # a sub-range: indices are global, outputs relative to g0
+    lon3, lat3 = torch.empty(1000, dtype=torch.float64, device=dev), torch.empty(1000, dtype=torch.float64, device=dev)
+    _lib.check(lib.glb_points_fill_list(NSIDE, gpix.data_ptr(), g0, g0 + 1000, None, None, C.c_uint64(42), C.c_uint32(0),
+                                        lon3.data_ptr(), lat3.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(lon2, lon) and torch.equal(lat2, lat)
+    assert torch.equal(lon3, lon[g0 : g0 + 1000]) and torch.equal(lat3, lat[g0 : g0 + 1000])
 
 
 def test_multiplane_update_fullsize_bit_exact(cuda_device):

@@ -130,8 +130,17 @@ def test_poisson_and_position_statistics(cuda_device):
     npix = 12 * nside**2
     for lam in (0.08, 3.0, 9.5, 25.0, 400.0):
         ngal = lam / (G.ARCMIN2_SPHERE / npix)
-        pop = _Population(np.zeros(npix), None, ngal, None, linear_bias, False, 123, 0, None, cuda_device)
+        pop = _Population(np.zeros(npix), None, ngal, None, linear_bias, False, 123, 0, None, cuda_device, mode="scan")
         c = pop.counts.cpu().numpy()
+        if lam < 10:  # the galaxy list of the same draw (what "auto" picks for sparse maps): np.repeat(arange, counts)
+            lst = _Population(np.zeros(npix), None, ngal, None, linear_bias, False, 123, 0, None, cuda_device, mode="list")
+            assert lst.total == c.sum() and lst.counts is None and lst.off is None
+            assert np.array_equal(lst.gpix[: lst.total].cpu().numpy(), np.repeat(np.arange(npix), c))
+            for batch in (1000, 37):
+                assert list(lst.cuts(batch)) == list(pop.cuts(batch))
+            a, b, n = list(pop.cuts(1000))[3]
+            for x, y in zip(lst.fill(a, b, n, want_ipix=True), pop.fill(a, b, n, want_ipix=True)):
+                assert torch.equal(x, y)
         assert abs(c.mean() - lam) < 6 * np.sqrt(lam / npix)
         assert abs(c.var() - lam) < 6 * lam * np.sqrt(2.0 / npix) + 6 * np.sqrt(lam / npix)
         # chi-square of the histogram against the Poisson pmf
@@ -145,6 +154,7 @@ def test_poisson_and_position_statistics(cuda_device):
         assert pop.off[-1].item() == c.sum() and np.array_equal(pop.off.cpu().numpy()[:-1], np.cumsum(c) - c)
     # in-pixel (u, v) uniformity: invert positions of a single big pixel population
     pop = _Population(np.zeros(npix), None, 200.0 / (G.ARCMIN2_SPHERE / npix), None, linear_bias, False, 5, 0, None, cuda_device)
+    assert pop.mode == "scan"
     lon, lat, ipix = pop.fill(0, npix, pop.total, None, want_ipix=True)
     ip = ipix.cpu().numpy()
     assert np.array_equal(H.ang2pix(nside, lon.cpu().numpy(), lat.cpu().numpy(), lonlat=True), ip)
@@ -233,8 +243,10 @@ def test_poisson_with_visibility_and_bias_variants(cuda_device):
     vis = (np.arange(npix) % 3 != 0).astype(float) * 0.5
     for model, bias, rm in ((linear_bias, 0.9, False), (loglinear_bias, 1.4, False), (linear_bias, 0.9, True)):
         ngal = 6.0 / (G.ARCMIN2_SPHERE / npix)
-        pop = _Population(delta, vis, ngal, bias, model, rm, 77, 3, None, cuda_device, want_nbar=True)
+        pop = _Population(delta, vis, ngal, bias, model, rm, 77, 3, None, cuda_device, want_nbar=True, mode="scan")
         c = pop.counts.cpu().numpy()
+        lst = _Population(delta, vis, ngal, bias, model, rm, 77, 3, None, cuda_device, want_nbar=True, mode="list")
+        assert torch.equal(lst.nbar, pop.nbar) and np.array_equal(lst.gpix[: lst.total].cpu().numpy(), np.repeat(np.arange(npix), c))
         nbar = np.clip(pop.nbar.cpu().numpy(), 0, None)
         name = "linear" if model is linear_bias else "loglinear"
         ref = G.expected_count(delta, ngal, bias, vis, name, rm)

@@ -76,12 +76,13 @@ def test_regularized_spectra_on_device():
 
 
 def test_points_cuts_on_device():
-    """glb_points_cuts (one thread walking csrc/points_cuts.cuh, host-tested against the reference's
-    loop) against the default host-driven cut rule, in chunks of 5 cuts."""
+    """glb_points_cuts (one thread walking csrc/points_cuts.cuh) against the oracle's restatement of
+    the reference's 1000-pixel stepping loop (glass/points.py:409-437), in chunks of 5 cuts."""
     import torch
 
     from glass_b200 import _lib
     from glass_b200.points import _Population
+    from oracle import glass_ref as G
 
     rng = np.random.default_rng(9)
     dev = torch.device("cuda", 0)
@@ -92,4 +93,4 @@ def test_points_cuts_on_device():
         pop.npix, pop.lib, pop.device = npix, _lib.load(), dev
         pop.off = torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), device=dev)
         pop.total = int(counts.sum())
-        assert list(pop._cuts_device(batch, chunk=5)) == list(pop.cuts(batch))
+        assert list(pop.cuts(batch, chunk=5)) == [tuple(int(v) for v in r) for r in G.batch_cuts(counts, batch)]

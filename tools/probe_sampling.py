@@ -43,7 +43,7 @@ ws = torch.empty(int(lib.glb_points_workspace_bytes(npix)), dtype=torch.uint8, d
 for scale, v, label in ((0.083, None, "0.083 gal/pix"), (0.083, vis, "0.083 gal/pix, half-sky vis"), (3.0, None, "3 gal/pix"), (30.0, None, "30 gal/pix (PTRS)")):
     def k67():
         _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), v.data_ptr() if v is not None else None, 1, 1.2, scale, 0, None,
-                                         C.c_uint64(42), C.c_uint32(0), None, counts.data_ptr(), off.data_ptr(), ws.data_ptr(), st))
+                                         C.c_uint64(42), C.c_uint32(0), None, counts.data_ptr(), off.data_ptr(), None, 0, None, ws.data_ptr(), st))
     t = ev(k67)
     by = npix * (32 + (8 if v is not None else 0))
     ref = torch.cumsum(counts, 0)
@@ -53,7 +53,7 @@ for scale, v, label in ((0.083, None, "0.083 gal/pix"), (0.083, vis, "0.083 gal/
           f"mean count {counts.double().mean().item():.5f} vs lambda {lam.mean().item():.5f}; var {counts.double().var().item():.5f}")
 
 _lib.check(lib.glb_points_counts(npix, delta.data_ptr(), None, 1, 1.2, 0.083, 0, None, C.c_uint64(42), C.c_uint32(0), None,
-                                 counts.data_ptr(), off.data_ptr(), ws.data_ptr(), st))
+                                 counts.data_ptr(), off.data_ptr(), None, 0, None, ws.data_ptr(), st))
 tot = int(off[-1].item())
 lon = torch.empty(tot, dtype=torch.float64, device=dev)
 lat = torch.empty(tot, dtype=torch.float64, device=dev)

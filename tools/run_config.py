@@ -45,34 +45,51 @@ class MockCosmology:  # reference tests/fixtures/domain.py:36-97
         return self.hubble_distance * (np.asarray(z2) - np.asarray(z)) * 1_000
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("config", type=int, choices=[1, 2, 3, 4])
-    ap.add_argument("--shells", type=int, default=None)
-    ap.add_argument("--niter", type=int, default=3)
-    ap.add_argument("--ngal", type=float, default=None, help="galaxies per arcmin^2 per shell")
-    ap.add_argument("--lensing", action="store_true")
-    ap.add_argument("--ncorr", type=int, default=3, help="correlated shells (59 = all 60 shells of config 4 fully correlated)")
-    ap.add_argument("--no-galaxies", action="store_true")
-    args = ap.parse_args()
-    S, nside, lmax, lensing = CONFIGS[args.config]
-    S = args.shells or S
-    lensing = lensing or args.lensing
-    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+class HostCatalogSink(glass_b200.user._FitsWriter):
+    """The catalogue columns of every batch copied to HOST memory through the product's
+    double-buffered pinned staging on a side stream (glass_b200.user: the copy of batch i overlaps
+    the kernels of batch i+1); the rows are handed to ``consume`` (default: counted and dropped --
+    what happens to a catalogue on the host is the user's business, the maps never leave HBM)."""
+
+    def __init__(self, consume=None):
+        super().__init__(fh=None)
+        self.bytes = 0
+        self.consume = consume
+
+    def _append_host(self, host_cols: dict) -> None:
+        n = len(next(iter(host_cols.values())))
+        self.nrows += n
+        self.bytes += sum(a.nbytes for a in host_cols.values())
+        if self.consume is not None:
+            self.consume(host_cols)
+
+    def close(self) -> None:
+        self._drain()
+
+
+def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | None = None, niter: int = 3, ngal: float | None = None,
+              lensing: bool = False, ncorr: int = 3, galaxies: bool = True, host_catalog: bool = False, batch: int = 1_000_000) -> dict:
+    """One pass of the user loop of the module docstring over a BASELINE.json configuration,
+    device-resident (maps stay in HBM); with ``host_catalog`` the galaxy columns (lon, lat, z and,
+    with lensing, the sheared ellipticity) are copied to host memory inside the timed region.
+    ``world`` > 1: the caller has initialised torch.distributed (NCCL); contiguous blocks of shells
+    per rank, multi-plane recurrence pipelined over the ranks.  Returns the result dict (identical
+    on every rank: wall = max over ranks, galaxies = sum)."""
+    S, nside, lmax, cfg_lensing = CONFIGS[config]
+    S = shells or S
+    lensing = lensing or cfg_lensing
+    args = argparse.Namespace(config=config, niter=niter, ncorr=ncorr, no_galaxies=not galaxies)
     if world > 1:
         import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
     mine = list(glass_b200.sharding.shard_shells(S, rank, world))
     npix = 12 * nside * nside
     dz = 1.0 / (S + 1)
     shells = [glass_b200.RadialWindow(np.array([i, i + 1.0, i + 2.0]) * dz, np.array([0.0, 1.0, 0.0]), (i + 1.0) * dz) for i in range(S)]
+    shells_dev = [glass_b200.RadialWindow(torch.as_tensor(w.za, device=dev), torch.as_tensor(w.wa, device=dev), w.zeff) for w in shells]
     gls = [torch.as_tensor(g).to(dev) for g in synthetic_gls(S, lmax, args.ncorr)]
-    ngal = args.ngal if args.ngal is not None else 0.083 * npix / glass_b200.points.ARCMIN2_SPHERE * (4096 / nside) ** 2 * 0 + 6.7335 / 60
+    ngal = ngal if ngal is not None else 6.7335 / 60  # per arcmin^2 per shell: 1.0e9 galaxies over 60 shells
     stages = {k: 0.0 for k in ("generate", "multiplane", "shear_from_convergence", "positions", "redshifts", "ellipticity", "galaxy_shear")}
+    sink = HostCatalogSink() if host_catalog else None
 
     def timed(name, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -87,7 +104,6 @@ def main():
     matter = glass_b200.generate(glass_b200.lognormal_fields(shells), gls, nside, ncorr=args.ncorr, rng=42, shells=mine if world > 1 else None)
     ngal_tot = 0
     if world > 1:
-        import torch.distributed as dist
         from glass_b200.dist import multi_plane_block
 
         # the hand-off below is the first NCCL point-to-point of each pair: open the channels
@@ -104,21 +120,26 @@ def main():
     def per_shell(i, delta, kappa, shear=None):
         nonlocal ngal_tot
         g1 = g2 = None
+        rng_i = np.random.default_rng([42, i])  # the shell's own generator: the same galaxies on any number of ranks
         if lensing and shear is not None:
             g1, g2 = shear
         elif lensing:
             g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
-        it = iter(()) if args.no_galaxies else glass_b200.positions_from_delta(ngal, delta, 1.2, rng=42 + i)
+        it = iter(()) if args.no_galaxies else glass_b200.positions_from_delta(ngal, delta, 1.2, rng=rng_i, batch=batch)
         while True:
             try:
                 lon, lat, cnt = timed("positions", lambda: next(it))
             except StopIteration:
                 break
             ngal_tot += cnt
-            z = timed("redshifts", lambda: glass_b200.redshifts(torch.as_tensor(cnt), glass_b200.RadialWindow(torch.as_tensor(shells[i].za, device=dev), torch.as_tensor(shells[i].wa, device=dev), shells[i].zeff), rng=i))
+            z = timed("redshifts", lambda: glass_b200.redshifts(torch.as_tensor(cnt), shells_dev[i], rng=rng_i))
+            cols = {"RA": lon, "DEC": lat, "Z": z}
             if lensing:
-                eps = timed("ellipticity", lambda: glass_b200.ellipticity_intnorm(cnt, 0.27, rng=i, xp=torch))
+                eps = timed("ellipticity", lambda: glass_b200.ellipticity_intnorm(cnt, 0.27, rng=rng_i, xp=torch))
                 she = timed("galaxy_shear", lambda: glass_b200.galaxy_shear(lon, lat, eps, kappa, g1, g2))
+                cols["E1"], cols["E2"] = she.real, she.imag
+            if sink is not None and cnt:
+                sink.write(**cols)
 
     if world == 1:
         for i in range(S):
@@ -136,20 +157,24 @@ def main():
         if lensing:
             conv._like = torch.empty(npix, dtype=torch.float64, device=dev)
             kappas = timed("multiplane", lambda: multi_plane_block(conv, deltas, [shells[i] for i in mine]))
-        shears = {}
-        if lensing:
-            # kappa -> shear for up to four planes of the block at once (batched refinement syntheses)
-            for a in range(0, len(mine), 4):
+        for a in range(0, len(mine), 4):
+            shears = {}
+            if lensing:
+                # kappa -> shear for up to four planes of the block at once (batched refinement syntheses)
                 grp = kappas[a : a + 4]
                 g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(torch.stack(grp), lmax, discretized=False, niter=args.niter))
                 for b in range(len(grp)):
                     shears[mine[a + b]] = (g1[b], g2[b])
-        for i, delta, kappa in zip(mine, deltas, kappas):
-            per_shell(i, delta, kappa, shears.get(i))
+            for b in range(a, min(a + 4, len(mine))):
+                per_shell(mine[b], deltas[b], kappas[b], shears.get(mine[b]))
+                deltas[b] = kappas[b] = None  # this shell is finished: its maps go back to the allocator
+    if sink is not None:
+        sink.close()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     for name, a, b in pend:
         stages[name] += a.elapsed_time(b)
+    host_bytes = sink.bytes if sink is not None else 0
     if world > 1:
         # whole-job numbers: wall = max over ranks, galaxies = sum, stage times = max over ranks
         t = torch.tensor([wall] + [stages[k] for k in stages], dtype=torch.float64, device=dev)
@@ -157,14 +182,38 @@ def main():
         wall = float(t[0])
         for k, v in zip(stages, t[1:].tolist()):
             stages[k] = v
-        g = torch.tensor([int(ngal_tot)], dtype=torch.int64, device=dev)
+        g = torch.tensor([int(ngal_tot), int(host_bytes)], dtype=torch.int64, device=dev)
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        ngal_tot = int(g[0])
-    out = {
+        ngal_tot, host_bytes = int(g[0]), int(g[1])
+    return {
         "config": args.config, "n_gpus": world, "shells": S, "ncorr": args.ncorr, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
         "galaxies": int(ngal_tot), "wall_s": wall, "shells_per_s": S / wall, "galaxies_per_s": ngal_tot / wall,
+        "catalog_d2h_bytes": host_bytes,
         "stage_ms_total": {k: round(v, 2) for k, v in stages.items()},
     }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", type=int, choices=[1, 2, 3, 4])
+    ap.add_argument("--shells", type=int, default=None)
+    ap.add_argument("--niter", type=int, default=3)
+    ap.add_argument("--ngal", type=float, default=None, help="galaxies per arcmin^2 per shell")
+    ap.add_argument("--lensing", action="store_true")
+    ap.add_argument("--ncorr", type=int, default=3, help="correlated shells (59 = all 60 shells of config 4 fully correlated)")
+    ap.add_argument("--no-galaxies", action="store_true")
+    ap.add_argument("--host-catalog", action="store_true", help="copy the galaxy columns to host memory inside the timed region")
+    args = ap.parse_args()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    out = run_chain(args.config, dev=dev, rank=rank, world=world, shells=args.shells, niter=args.niter, ngal=args.ngal, lensing=args.lensing,
+                    ncorr=args.ncorr, galaxies=not args.no_galaxies, host_catalog=args.host_catalog)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
