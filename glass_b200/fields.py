@@ -298,9 +298,9 @@ def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, n
     Apply discretisation effects to angular power spectra (glass/fields.py:239-300): truncate
     to ``lmax``, keep ``ncorr`` correlations, multiply by the squared HEALPix pixel window.
 
-    The reference reads the window from healpy's data files (glass/healpix.py:313-356), which
-    do not exist offline; here ``nside`` needs ``pixwin=`` (array w_l, e.g. ``healpy.pixwin``
-    output) -- everything else is identical.  Host-side: the spectra are tiny.
+    The window is ``hp.pixwin(nside, lmax=lmax)`` -- generated numerically here
+    (glass_b200.pixwin), read from healpy's data files in the reference (glass/healpix.py:313-356)
+    -- or the caller's own table ``pixwin=`` (extension).  Host-side: the spectra are tiny.
     """
     if len(cls) == 0:
         return []
@@ -311,10 +311,7 @@ def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, n
     pw = None
     if nside is not None:
         if pixwin is None:
-            raise NotImplementedError(
-                "discretized_cls(nside=...) needs the HEALPix pixel window: pass pixwin=w_l "
-                "(healpy's data files, glass/healpix.py:313-356, are not available offline)"
-            )
+            pixwin = hp.pixwin(nside, lmax=lmax)
         pw = pixwin[: lmax + 1] if lmax is not None else pixwin
     gls = []
     for cl in cls:

@@ -154,9 +154,13 @@ def alm2map(
     Scalar transforms only: a single alm array, or a sequence of alm arrays with
     ``pol=False`` (each transformed independently, as healpy does).
     """
-    if pixwin:
-        raise NotImplementedError("pixwin=True needs healpy's pixel-window data files (glass/healpix.py:351)")
     single = not isinstance(alms, (list, tuple)) and getattr(alms, "ndim", 1) == 1
+    if pixwin:  # healpy smooths the alm with the pixel window of nside before the synthesis
+        size = (alms if single else alms[0]).shape[-1]
+        lm = alm_getlmax(size) if lmax is None else lmax
+        pw = globals()["pixwin"](nside, lmax=min(lm, 4 * nside))
+        pw = np.concatenate([pw, np.zeros(lm + 1 - pw.size)])
+        alms = almxfl(alms, pw) if single else [almxfl(a, pw) for a in alms]
     if not single and pol:
         raise NotImplementedError("polarised (TEB) alm2map is outside the GLASS hot path; pass pol=False")
     host = not isinstance(alms if single else alms[0], torch.Tensor)
@@ -190,6 +194,24 @@ def _to(x, device, dtype):
 
 def _out(t, on_device):
     return t if on_device else t.cpu().numpy()
+
+
+def pixwin(nside: int, *, lmax: int | None = None, pol: bool = False, xp=None):
+    """
+    Return the pixel window function for the given nside (glass/healpix.py:313-356).
+
+    healpy reads it from data files; here it is generated from its definition on the device
+    (:mod:`glass_b200.pixwin`, cached per nside).  ``pol=True`` returns ``(w^T, w^P)``.  NumPy
+    arrays, or CUDA tensors with ``xp=torch``.
+    """
+    from . import pixwin as _pw
+
+    out = _pw.pixwin(nside, lmax=lmax, pol=pol)
+    if xp is torch:
+        dev = torch.device("cuda", _device_index())
+        conv = lambda a: torch.as_tensor(a, device=dev)  # noqa: E731
+        return tuple(conv(a) for a in out) if pol else conv(out)
+    return out
 
 
 def ring2ang_uv(nside: int, ipix, u, v, *, lonlat: bool = False):

@@ -166,16 +166,14 @@ def _kappa_alm(kappa, lmax, niter, ring_weights):
 
 
 def _pixwin_ratio(nside, lmax, pixwin):
-    """pw2/pw0 of glass/lensing.py:361-362,421-422.  healpy.pixwin reads data files shipped
-    with healpy (glass/healpix.py:351) that are not available offline: the two window
-    functions are therefore an input here (``pixwin=(pw0, pw2)``)."""
+    """pw2/pw0 of glass/lensing.py:361-362,421-422: ``hp.pixwin(nside, lmax=lmax, pol=True)``,
+    generated numerically (glass_b200.pixwin; healpy reads data files that are not available
+    offline), or the caller's own tables ``pixwin=(pw0, pw2)``, e.g. healpy's.  w^P vanishes below
+    l = 2, where the shear factor is zero anyway: the ratio is taken as 0 there."""
     if pixwin is None:
-        raise NotImplementedError(
-            "discretized=True needs the HEALPix pixel window functions (healpy data files, "
-            "glass/healpix.py:313-356): pass pixwin=(pw0, pw2) or use discretized=False"
-        )
+        pixwin = hp.pixwin(nside, lmax=lmax, pol=True)
     pw0, pw2 = (A.to_np(p)[: lmax + 1] for p in pixwin)
-    return pw2 / pw0
+    return np.divide(pw2, pw0, out=np.zeros_like(pw2), where=pw0 != 0)
 
 
 def _convergence_factors(nside, lmax, discretized, pixwin):

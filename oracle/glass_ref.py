@@ -376,14 +376,19 @@ def from_convergence(kappa, lmax=None, potential=False, deflection=False, shear=
     return res
 
 
-def shear_from_convergence(kappa, lmax=None, niter=3, ring_w=None):
-    """glass/lensing.py:403-428 with discretized=False."""
+def shear_from_convergence(kappa, lmax=None, niter=3, ring_w=None, pixwin=None):
+    """glass/lensing.py:403-428; ``pixwin=(pw0, pw2)``: the discretized=True branch, lensing.py:420-422
+    (``fl *= pw2 / pw0`` with the tables hp.pixwin would return), None: discretized=False."""
     nside = H.npix2nside(np.asarray(kappa).shape[-1])
     if lmax is None:
         lmax = 3 * nside - 1
     alm = H.map2alm(kappa, lmax=lmax, niter=niter, ring_w=ring_w)
     blm = np.zeros_like(alm)
-    alm = H.almxfl(alm, kappa_to_shear_fl(lmax))
+    fl = kappa_to_shear_fl(lmax)
+    if pixwin is not None:
+        pw0, pw2 = (np.asarray(p, dtype=np.float64)[: lmax + 1] for p in pixwin)
+        fl = fl * (pw2 / pw0)
+    alm = H.almxfl(alm, fl)
     return list(H.alm2map_spin(alm, blm, nside, 2, lmax))
 
 

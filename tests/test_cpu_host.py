@@ -1108,8 +1108,13 @@ def test_lensing_factor_chain_golden(monkeypatch):
     for k in rec:
         rec[k].clear()
     assert len(L.from_convergence(kappa, lmax, potential=True)) == 1 and len(rec["fl"]) == 1
-    with pytest.raises(NotImplementedError, match="pixel window"):
-        L.from_convergence(kappa, lmax, shear=True)
+    # the reference's default (discretized=True, no tables given) asks hp.pixwin for both windows
+    asked = []
+    monkeypatch.setattr(L.hp, "pixwin", lambda ns, lmax=None, pol=False: asked.append((ns, lmax, pol)) or (g["pw0"], g["pw2"]))
+    for k in rec:
+        rec[k].clear()
+    L.from_convergence(kappa, lmax, shear=True)
+    assert asked == [(nside, lmax, True)] and np.array_equal(np.stack(rec["fl"]), g["fc_disc_fl"])
 
 
 def test_solver_against_reference_source_golden(transforms_on_cpu):
@@ -1614,3 +1619,70 @@ def test_spin_recurrence_host_replay(tmp_path):
                    check=True, capture_output=True, timeout=300)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "spin recurrence ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_pixwin_generator_against_definition(monkeypatch):
+    """glass_b200.pixwin (hp.pixwin, glass/healpix.py:313-356, generated instead of read from healpy's
+    data files): the pair-moment series against the DEFINITION evaluated by brute force -- per pixel
+    the quadrature average of every Y_lm (scipy) and spin-2 harmonic (oracle, Goldberg form), summed
+    over m, averaged over pixels -- at nside 1 and 2; the closed forms of l = 1, 2; convergence of
+    the triangle-split quadrature; nside > EXACT_NSIDE_MAX scaled in (l + 1/2)/nside; defaults and
+    errors.  The device kernel behind the geometry is replaced by the oracle's pixel -> angle."""
+    import torch
+    from scipy.special import sph_harm_y
+
+    import glass_b200.pixwin as PW
+    from oracle import healpix_ref as H
+
+    def positions(nside, ipix, u, v):
+        th, ph = H.ring2ang_uv(nside, ipix.numpy().ravel(), u.numpy().ravel(), v.numpy().ravel())
+        return torch.as_tensor(th).reshape(ipix.shape), torch.as_tensor(ph).reshape(ipix.shape)
+
+    monkeypatch.setattr(PW, "_compute_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(PW, "_positions", positions)
+    monkeypatch.setattr(PW, "_Q", 7)
+    PW._pair_moments.cache_clear()
+
+    def brute(nside, lmax, q=7):
+        uu, vv, ww = PW._pixel_rule(q)  # the same nodes: the comparison isolates the pair-moment algebra
+        npix = 12 * nside * nside
+        wt, wp = np.zeros(lmax + 1), np.zeros(lmax + 1)
+        for p in range(npix):
+            th, ph = H.ring2ang_uv(nside, np.full(ww.size, p), uu, vv)
+            for l in range(lmax + 1):
+                for m in range(-l, l + 1):
+                    wt[l] += 4 * np.pi / (2 * l + 1) * abs((ww * sph_harm_y(l, m, th, ph)).sum()) ** 2
+                    if l >= 2:
+                        wp[l] += 4 * np.pi / (2 * l + 1) * abs((ww * H.sYlm_goldberg(2, l, m, th, ph)).sum()) ** 2
+        return np.sqrt(wt / npix), np.sqrt(wp / npix)
+
+    for nside, lmax in ((1, 4), (2, 6)):
+        wt, wp = PW.pixwin(nside, lmax=lmax, pol=True)
+        bt, bp = brute(nside, lmax)
+        assert np.abs(wt - bt).max() < 1e-13 and np.abs(wp - bp).max() < 1e-13
+        assert wt[0] == 1.0 and wp[0] == wp[1] == 0.0
+    # the quadrature itself: spectral convergence of the triangle-split rule (12 against 16 nodes per
+    # axis), and the converged values at nside 2 that the GPU test checks on the device
+    PW._pair_moments.cache_clear()
+    monkeypatch.setattr(PW, "_Q", 16)
+    w16q = PW.pixwin(2, lmax=8, pol=True)
+    PW._pair_moments.cache_clear()
+    monkeypatch.setattr(PW, "_Q", None)
+    wt, wp = PW.pixwin(2, lmax=8, pol=True)
+    assert np.abs(wt - w16q[0]).max() < 1e-14 and np.abs(wp - w16q[1]).max() < 1e-14
+    assert np.abs(wt - [1.0, 0.977303, 0.93310702, 0.86971852, 0.79038278, 0.69905215, 0.60011811, 0.49813949, 0.39760902]).max() < 1e-8
+    assert PW.pixwin(4).shape == (12,)
+    # lowest multipoles in closed form: P_1 = 1 - 2x, P_2 = 1 - 6x + 6x^2 in x = sin^2(gamma/2)
+    x0, mt, _mp = PW._pair_moments(8)
+    w8 = PW.pixwin(8, lmax=2)
+    assert abs(w8[1] ** 2 - (1 - 2 * x0 * mt[1])) < 1e-15 and abs(w8[2] ** 2 - (1 - 6 * x0 * mt[1] + 6 * x0**2 * mt[2])) < 1e-15
+    # scaling above the exact range: nside 16 from the nside-8 moments against nside 16 itself
+    w16 = PW.pixwin(16, lmax=40, pol=True)
+    monkeypatch.setattr(PW, "EXACT_NSIDE_MAX", 8)
+    s16 = PW.pixwin(16, lmax=40, pol=True)
+    assert np.abs(s16[0] - w16[0]).max() < 2e-3 and np.abs(s16[1] - w16[1])[2:].max() < 5e-3 and s16[1][0] == s16[1][1] == 0.0
+    with pytest.raises(ValueError, match="tabulated up to"):
+        PW.pixwin(4, lmax=17)
+    with pytest.raises(ValueError, match="power of two"):
+        PW.pixwin(12)
+    PW._pair_moments.cache_clear()

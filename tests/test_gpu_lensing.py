@@ -153,11 +153,53 @@ def test_from_convergence_vs_oracle(cuda_device, nside, lmax):
     r1, r2 = G.shear_from_convergence(kappa, lmax)
     assert np.abs(g1 - r1).max() < 1e-10 * np.abs(r1).max() and np.abs(g2 - r2).max() < 1e-10 * np.abs(r1).max()
     np.testing.assert_allclose(g1 + 1j * g2, got[2], rtol=0, atol=1e-12 * np.abs(got[2]).max())
-    with pytest.raises(NotImplementedError, match="pixel window"):
-        glass_b200.shear_from_convergence(kappa, lmax)
+    # the reference's canonical call: discretized=True by default, pixel windows from hp.pixwin
+    # (glass/lensing.py:414-422) -- generated here (glass_b200.pixwin) instead of read from healpy's files
+    lm = 3 * nside - 1 if lmax is None else lmax
+    pw0, pw2 = glass_b200.healpix.pixwin(nside, lmax=lm, pol=True)
+    gd = glass_b200.shear_from_convergence(kappa, lmax)
+    rd = G.shear_from_convergence(kappa, lmax, pixwin=(pw0, pw2))
+    assert np.abs(gd[0] - rd[0]).max() < 1e-10 * np.abs(rd[0]).max() and np.abs(gd[1] - rd[1]).max() < 1e-10 * np.abs(rd[0]).max()
+    assert np.abs(gd[0] - g1).max() > 1e-6 * np.abs(g1).max()  # the window ratio does something
+    fc = glass_b200.from_convergence(kappa, lmax, shear=True)  # discretized=True default (glass/lensing.py:353-363)
+    np.testing.assert_allclose(fc[0], gd[0] + 1j * gd[1], rtol=0, atol=1e-12 * np.abs(rd[0]).max())
+    # caller-supplied tables (e.g. healpy's own) still take precedence
     pw = (np.ones(3 * nside), np.linspace(1.0, 0.9, 3 * nside))
-    gd = glass_b200.shear_from_convergence(kappa, lmax, discretized=True, pixwin=pw)
-    assert gd[0].shape == kappa.shape
+    gu = glass_b200.shear_from_convergence(kappa, lmax, discretized=True, pixwin=pw)
+    ru = G.shear_from_convergence(kappa, lmax, pixwin=pw)
+    assert np.abs(gu[0] - ru[0]).max() < 1e-10 * np.abs(ru[0]).max()
+
+
+def test_pixwin_on_device(cuda_device):
+    """hp.pixwin (glass/healpix.py:313-356) generated on the device: the brute-force definition at
+    nside 2 (sum over m of pixel-averaged harmonics, oracle geometry), the values of the CPU suite,
+    shapes / defaults / errors, the scaled range above nside 128, alm2map(pixwin=True)."""
+    import glass_b200
+    from glass_b200 import healpix as hp
+
+    wt, wp = hp.pixwin(2, lmax=8, pol=True)
+    want_t = [1.0, 0.977303, 0.93310702, 0.86971852, 0.79038278, 0.69905215, 0.60011811, 0.49813949, 0.39760902]
+    assert np.abs(wt - want_t).max() < 1e-8 and wp[0] == wp[1] == 0.0 and np.abs(wp[2:] / wt[2:] - 1).max() < 0.09
+    w = hp.pixwin(64)
+    assert w.shape == (3 * 64,) and w[0] == 1.0 and np.all(np.diff(w) < 0)
+    wt, wp = hp.pixwin(256, lmax=1024, pol=True)  # scaled from the nside-128 moments
+    w128 = hp.pixwin(128, lmax=512)
+    assert np.abs(wt[1::2][:256] - 0.5 * (w128[:256] + w128[1:257])).max() < 2e-4 and abs(wt[1024] - w128[512]) < 1e-3
+    assert wp[0] == wp[1] == 0.0 and np.abs(wp[2:] / wt[2:] - 1).max() < 1e-3
+    t = hp.pixwin(8, lmax=5, xp=torch)
+    assert t.is_cuda and t.shape == (6,)
+    with pytest.raises(ValueError, match="tabulated up to"):
+        hp.pixwin(8, lmax=33)
+    rng = np.random.default_rng(1)
+    alm = rng.standard_normal(45) + 1j * rng.standard_normal(45)
+    alm[:9] = alm[:9].real
+    a = hp.alm2map(alm, 4, pixwin=True, pol=False)
+    b = hp.alm2map(hp.almxfl(alm, hp.pixwin(4, lmax=8)), 4, pol=False)
+    assert np.array_equal(a, b)
+    # discretized_cls picks the generated window up (glass/fields.py:288-299)
+    cl = np.ones(10)
+    got = glass_b200.discretized_cls([cl], nside=4, lmax=8)[0]
+    assert np.allclose(got, hp.pixwin(4, lmax=8) ** 2, rtol=1e-15)
 
 
 def test_gaussian_phz(cuda_device):
