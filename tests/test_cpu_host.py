@@ -376,8 +376,17 @@ def test_discretized_and_effective_cls_golden():
         assert np.array_equal(np.array([r.shape[0] for r in res]), gold[f"dcl_{tag}_len"])
         assert np.array_equal(np.concatenate(res), gold[f"dcl_{tag}"])
     assert glass_b200.discretized_cls([]) == []
-    with pytest.raises(NotImplementedError):
-        glass_b200.discretized_cls(gls, nside=4)
+    # without a table the window comes from hp.pixwin(nside, lmax=lmax) (glass/fields.py:288-289)
+    import glass_b200.fields as F
+
+    asked = []
+    saved = F.hp.pixwin
+    F.hp.pixwin = lambda ns, lmax=None, pol=False: asked.append((ns, lmax)) or gold["dcl_pw"]
+    try:
+        res = glass_b200.discretized_cls(gls, lmax=9, ncorr=2, nside=4)
+    finally:
+        F.hp.pixwin = saved
+    assert asked == [(4, 9)] and np.array_equal(np.concatenate(res), gold["dcl_all"])
     assert np.array_equal(glass_b200.effective_cls(gls, gold["ecl_w1"]), gold["ecl_auto"])
     assert np.array_equal(glass_b200.effective_cls(gls, gold["ecl_w1"], gold["ecl_w2"], lmax=7), gold["ecl_cross"])
     with pytest.raises(ValueError, match="shape mismatch between fields and weights1"):
