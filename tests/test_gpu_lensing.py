@@ -184,7 +184,9 @@ def test_pixwin_on_device(cuda_device):
     assert w.shape == (3 * 64,) and w[0] == 1.0 and np.all(np.diff(w) < 0)
     wt, wp = hp.pixwin(256, lmax=1024, pol=True)  # scaled from the nside-128 moments
     w128 = hp.pixwin(128, lmax=512)
-    assert np.abs(wt[1::2][:256] - 0.5 * (w128[:256] + w128[1:257])).max() < 2e-4 and abs(wt[1024] - w128[512]) < 1e-3
+    # (l + 1/2) / nside is the scaling variable: l = 2j + 1 at nside 256 sits at l' = j + 1/4 of nside 128
+    assert np.abs(wt[1::2][:256] - (0.75 * w128[:256] + 0.25 * w128[1:257])).max() < 1e-4
+    assert abs(wt[1024] - (0.25 * w128[511] + 0.75 * w128[512])) < 1e-4
     assert wp[0] == wp[1] == 0.0 and np.abs(wp[2:] / wt[2:] - 1).max() < 1e-3
     t = hp.pixwin(8, lmax=5, xp=torch)
     assert t.is_cuda and t.shape == (6,)

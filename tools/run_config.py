@@ -68,13 +68,16 @@ class HostCatalogSink(glass_b200.user._FitsWriter):
 
 
 def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | None = None, niter: int = 3, ngal: float | None = None,
-              lensing: bool = False, ncorr: int = 3, galaxies: bool = True, host_catalog: bool = False, batch: int = 1_000_000) -> dict:
+              lensing: bool = False, ncorr: int = 3, galaxies: bool = True, host_catalog: bool = False, batch: int = 1_000_000,
+              group: int = 4, discretized: bool = True) -> dict:
     """One pass of the user loop of the module docstring over a BASELINE.json configuration,
     device-resident (maps stay in HBM); with ``host_catalog`` the galaxy columns (lon, lat, z and,
     with lensing, the sheared ellipticity) are copied to host memory inside the timed region.
     ``world`` > 1: the caller has initialised torch.distributed (NCCL); contiguous blocks of shells
     per rank, multi-plane recurrence pipelined over the ranks.  Returns the result dict (identical
-    on every rank: wall = max over ranks, galaxies = sum)."""
+    on every rank: wall = max over ranks, galaxies = sum).  ``group``: convergence planes lensed per
+    call of shear_from_convergence (a stack of planes shares the Legendre recurrences of the refinement
+    syntheses); ``discretized``: the reference's default, pixel windows from hp.pixwin."""
     S, nside, lmax, cfg_lensing = CONFIGS[config]
     S = shells or S
     lensing = lensing or cfg_lensing
@@ -114,6 +117,8 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
         if rank + 1 < world:
             dist.send(tok, rank + 1)
         dist.barrier()
+    if lensing and discretized:
+        glass_b200.healpix.pixwin(nside, lmax=lmax, pol=True)  # table set-up (cached per nside), like the transform plans
     torch.cuda.synchronize()
     t0 = time.perf_counter()
 
@@ -121,10 +126,8 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
         nonlocal ngal_tot
         g1 = g2 = None
         rng_i = np.random.default_rng([42, i])  # the shell's own generator: the same galaxies on any number of ranks
-        if lensing and shear is not None:
+        if lensing:
             g1, g2 = shear
-        elif lensing:
-            g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappa, lmax, discretized=False, niter=args.niter))
         it = iter(()) if args.no_galaxies else glass_b200.positions_from_delta(ngal, delta, 1.2, rng=rng_i, batch=batch)
         while True:
             try:
@@ -141,14 +144,29 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
             if sink is not None and cnt:
                 sink.write(**cols)
 
+    def shear_group(kappas_g):
+        """kappa -> shear for up to four planes at once (the refinement syntheses of the planes share
+        one Legendre recurrence); one plane: the plain call of the reference's loop."""
+        if len(kappas_g) == 1:
+            return [timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(kappas_g[0], lmax, discretized=discretized, niter=args.niter))]
+        g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(torch.stack(kappas_g), lmax, discretized=discretized, niter=args.niter))
+        return [(g1[b], g2[b]) for b in range(len(kappas_g))]
+
+    group = max(1, int(group))
     if world == 1:
-        for i in range(S):
-            delta = timed("generate", lambda: next(matter))
-            kappa = None
+        # the user loop in groups of `group` shells: the recurrence of the convergence is local, so a
+        # group's planes are made, lensed together and populated before the next group is generated
+        for a in range(0, S, group):
+            idx = list(range(a, min(a + group, S)))
+            deltas = [timed("generate", lambda: next(matter)) for _ in idx]
+            kappas = [None] * len(idx)
             if lensing:
-                timed("multiplane", lambda: conv.add_window(delta, shells[i]))
-                kappa = conv.kappa
-            per_shell(i, delta, kappa)
+                for b, i in enumerate(idx):
+                    timed("multiplane", lambda: conv.add_window(deltas[b], shells[i]))
+                    kappas[b] = conv.kappa.clone() if len(idx) > 1 else conv.kappa  # the recurrence recycles its buffers
+            shears = shear_group(kappas) if lensing else [None] * len(idx)
+            for b, i in enumerate(idx):
+                per_shell(i, deltas[b], kappas[b], shears[b])
     else:
         # 1. matter planes of the block (no communication)  2. multi-plane recurrence, pipelined
         # over the ranks (dist.multi_plane_block)  3. transforms and galaxies (no communication)
@@ -157,16 +175,11 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
         if lensing:
             conv._like = torch.empty(npix, dtype=torch.float64, device=dev)
             kappas = timed("multiplane", lambda: multi_plane_block(conv, deltas, [shells[i] for i in mine]))
-        for a in range(0, len(mine), 4):
-            shears = {}
-            if lensing:
-                # kappa -> shear for up to four planes of the block at once (batched refinement syntheses)
-                grp = kappas[a : a + 4]
-                g1, g2 = timed("shear_from_convergence", lambda: glass_b200.shear_from_convergence(torch.stack(grp), lmax, discretized=False, niter=args.niter))
-                for b in range(len(grp)):
-                    shears[mine[a + b]] = (g1[b], g2[b])
-            for b in range(a, min(a + 4, len(mine))):
-                per_shell(mine[b], deltas[b], kappas[b], shears.get(mine[b]))
+        for a in range(0, len(mine), group):
+            hi = min(a + group, len(mine))
+            shears = shear_group(kappas[a:hi]) if lensing else [None] * (hi - a)
+            for b in range(a, hi):
+                per_shell(mine[b], deltas[b], kappas[b], shears[b - a])
                 deltas[b] = kappas[b] = None  # this shell is finished: its maps go back to the allocator
     if sink is not None:
         sink.close()
@@ -186,7 +199,7 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
         ngal_tot, host_bytes = int(g[0]), int(g[1])
     return {
-        "config": args.config, "n_gpus": world, "shells": S, "ncorr": args.ncorr, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
+        "config": args.config, "n_gpus": world, "group": group, "discretized": discretized, "shells": S, "ncorr": args.ncorr, "nside": nside, "lmax": lmax, "lensing": lensing, "niter": args.niter,
         "galaxies": int(ngal_tot), "wall_s": wall, "shells_per_s": S / wall, "galaxies_per_s": ngal_tot / wall,
         "catalog_d2h_bytes": host_bytes,
         "stage_ms_total": {k: round(v, 2) for k, v in stages.items()},
@@ -203,6 +216,7 @@ def main():
     ap.add_argument("--ncorr", type=int, default=3, help="correlated shells (59 = all 60 shells of config 4 fully correlated)")
     ap.add_argument("--no-galaxies", action="store_true")
     ap.add_argument("--host-catalog", action="store_true", help="copy the galaxy columns to host memory inside the timed region")
+    ap.add_argument("--group", type=int, default=4, help="convergence planes per shear_from_convergence call")
     args = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,7 +227,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     out = run_chain(args.config, dev=dev, rank=rank, world=world, shells=args.shells, niter=args.niter, ngal=args.ngal, lensing=args.lensing,
-                    ncorr=args.ncorr, galaxies=not args.no_galaxies, host_catalog=args.host_catalog)
+                    ncorr=args.ncorr, galaxies=not args.no_galaxies, host_catalog=args.host_catalog, group=args.group)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
