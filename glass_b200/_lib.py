@@ -37,6 +37,7 @@ SIGNATURES = {
     "glb_plan_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i), C.POINTER(_i64)]),
     "glb_alm2map": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_alm2map_spin": (_i, [_vp, _dp, _dp, _i, _dp, _dp, _vp]),
+    "glb_alm2map_spin_batch": (_i, [_vp, _dp, _i, _i, _dp, _dp, _vp]),
     "glb_map2alm": (_i, [_vp, _dp, _dp, _i, _dp, _vp]),
     "glb_map2alm_batch": (_i, [_vp, _dp, _i, _dp, _i, _dp, _vp]),
     "glb_almxfl": (_i, [_i, _dp, _dp, _i, _vp]),

@@ -33,6 +33,8 @@ static int timing_collect(glb_plan* pl) {
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
                         const double* tparams, const int* d_mlim, cudaStream_t st, bool dist = false);
 int plan_dist_setup(glb_plan* pl, int world, int rank, const int* h_rowmap, const int* h_my_rings, int n_my);
+int sht_spin_alm2phase_multi(glb_plan* pl, const double2* const* d_alms, int nb, int spin, double2* d_phase,
+                             cudaStream_t st);
 int sht_spin_alm2phase(glb_plan* pl, const double2* d_alm1, const double2* d_alm2, int spin, double2* d_phase,
                        cudaStream_t st);
 int plan_ensure_spin(glb_plan* pl, int spin);
@@ -158,6 +160,59 @@ int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2,
   if (rc != GLB_OK) return rc;
   double* outs[4] = {d_map1, d_map2, nullptr, nullptr};
   return sht_phase2map_group(plan, plan->d_phase, 2, outs, nullptr, nullptr, plan->d_mlim_spin, st);
+}
+
+// E-only spin synthesis of nb map pairs at once: the two Wigner-d recurrences are shared by the
+// nb coefficient sets (10 DFMA per (l, ring pair) for one map, 7 per map for two, 5.5 for four).
+// Four maps need eight phase maps: allocated on first use (17 GB at nside 4096); if that fails the
+// batch runs as two pairs in the plan's own phase buffer.
+int glb_alm2map_spin_batch(glb_plan* plan, const double* d_alms, int nb, int spin, double* d_maps1, double* d_maps2,
+                           void* stream) {
+  GLB_REQUIRE(plan && d_alms && d_maps1 && d_maps2, "null pointer");
+  GLB_REQUIRE(nb >= 1 && nb <= 4, "nb must be in [1, 4]");
+  GLB_REQUIRE(spin >= 1 && spin <= 3, "spin must be 1, 2 or 3");
+  GLB_REQUIRE(spin <= plan->lmax, "spin exceeds lmax");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  int rc = plan_ensure_spin(plan, spin);
+  if (rc != GLB_OK) return rc;
+  const double2* alm = reinterpret_cast<const double2*>(d_alms);
+  const int64_t phase_map = (int64_t)plan->nring * (plan->mmax + 1);
+  int done = 0;
+  while (done < nb) {
+    int g = nb - done >= 4 ? 4 : (nb - done >= 2 ? 2 : 1);
+    if (g > 1 && plan->max_batch < 4) g = 1;  // the plan's phase buffer holds two maps only
+    double2* phase = plan->d_phase;
+    if (g == 4) {
+      if (!plan->d_phase_spin && cudaMalloc((void**)&plan->d_phase_spin, (size_t)8 * phase_map * sizeof(double2)) != cudaSuccess) {
+        cudaGetLastError();  // not enough memory for eight phase maps: pairs instead
+        plan->d_phase_spin = nullptr;
+        g = 2;
+      } else {
+        phase = plan->d_phase_spin;
+      }
+    }
+    if (g == 1) {
+      rc = sht_spin_alm2phase(plan, alm + (int64_t)done * plan->nalm, nullptr, spin, phase, st);
+    } else {
+      const double2* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+      for (int b = 0; b < g; ++b) ptrs[b] = alm + (int64_t)(done + b) * plan->nalm;
+      rc = sht_spin_alm2phase_multi(plan, ptrs, g, spin, phase, st);
+    }
+    if (rc != GLB_OK) return rc;
+    for (int h = 0; h < 2 * g; h += 4) {  // ring FFTs, four maps per launch group
+      double* outs[4] = {nullptr, nullptr, nullptr, nullptr};
+      const int n = std::min(4, 2 * g - h);
+      for (int q = 0; q < n; ++q) {
+        const int b = done + (h + q) / 2;
+        outs[q] = (((h + q) & 1) ? d_maps2 : d_maps1) + (int64_t)b * plan->npix;
+      }
+      rc = sht_phase2map_group(plan, phase + (int64_t)h * phase_map, n, outs, nullptr, nullptr, plan->d_mlim_spin, st);
+      if (rc != GLB_OK) return rc;
+    }
+    done += g;
+  }
+  return GLB_OK;
 }
 
 // nb maps at once (nb = 1, 2 or 4 <= max_batch): the analyses run map by map, the synthesis of

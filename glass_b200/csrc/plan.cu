@@ -244,8 +244,9 @@ int plan_build(glb_plan* pl) {
   // ---- workspace ----
   const int gb = std::min(pl->max_batch, 4);
   const int gmax = gb >= 4 ? 4 : (gb >= 2 ? 2 : 1);
-  // records: scalar synthesis needs nrec*(4+4B) doubles, the spin transform (E and B) 12 per (l,m)
-  pl->rec_capacity = std::max<int64_t>(pl->nrec * (4 + 4 * gmax), pl->nalm * 12);
+  // records: scalar synthesis needs nrec*(4+4B) doubles, the spin transform 8 + 2 per coefficient
+  // set and (l,m): 12 for E and B of one map, 16 for the E modes of four maps
+  pl->rec_capacity = std::max<int64_t>(pl->nrec * (4 + 4 * gmax), pl->nalm * (gmax >= 4 ? 16 : 12));
   const size_t rec_bytes = (size_t)pl->rec_capacity * sizeof(double);
   const size_t phase_bytes = (size_t)std::max(gmax, 2) * pl->nring * (pl->mmax + 1) * sizeof(double2);
   GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_rec, rec_bytes));
@@ -347,7 +348,8 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_sn_mant);
   cudaFree(pl->d_sn_exp);
   cudaFree(pl->d_soff);
-  cudaFree(pl->d_items_spin);
+  for (auto& kv : pl->spin_item_lists) cudaFree(kv.second.first);
+  cudaFree(pl->d_phase_spin);
   cudaFree(pl->d_spin_tab);
   cudaFree(pl->d_dist_rowmap);
   cudaFree(pl->d_dist_rowidx);

@@ -78,8 +78,8 @@ struct glb_plan {
   int64_t* d_soff = nullptr;         // [mmax+2] spin record offsets (one record per l >= max(m,s))
   int64_t nrec_spin = 0;
   double* d_spin_tab = nullptr;      // [nrec_spin][3] {A'_l, B'_l, sigma_l}
-  glb::LegItem* d_items_spin = nullptr;
-  int nitems_spin = 0;
+  std::map<int, std::pair<glb::LegItem*, int>> spin_item_lists;  // work lists keyed by tile size, built on demand
+  double2* d_phase_spin = nullptr;   // [8][nring][mmax+1] phases of a 4-plane batched spin synthesis, allocated on first use
   int64_t rec_capacity = 0;          // doubles available in d_rec
 
   // analysis (map2alm): per-tile partial sums and a scratch map pair, built lazily

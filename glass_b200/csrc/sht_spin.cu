@@ -75,12 +75,16 @@ __global__ void __launch_bounds__(128) spin_tables_kernel(int lmax, int mmax, in
   }
 }
 
-// ---- prep (per call, fully parallel): records {A', B', -B', 0, -A', A'+B', A'-B', 0, E_l sigma_l [, B_l sigma_l]} ----
+// ---- prep (per call, fully parallel): records {A', B', -B', 0, -A', A'+B', A'-B', 0, (a_l sigma_l) x NB} ----
+// NB coefficient sets share the recurrence: E and B of one map, or the E modes of NB maps.
 // grid: (ceil((lmax+1)/256), mmax+1): blockIdx.y = m, threads over l
+struct SpinAlms {
+  const double2* a[4];
+};
 template <int NB>
-__global__ void __launch_bounds__(256) spin_prep_kernel(const double2* __restrict__ alm1, const double2* __restrict__ alm2,
-                                                         int lmax, int spin, const int64_t* __restrict__ soff,
-                                                         const double* __restrict__ tab, double* __restrict__ rec) {
+__global__ void __launch_bounds__(256) spin_prep_kernel(const SpinAlms alms, int lmax, int spin,
+                                                         const int64_t* __restrict__ soff, const double* __restrict__ tab,
+                                                         double* __restrict__ rec) {
   constexpr int REC = 8 + 2 * NB;
   const int m = blockIdx.y;
   const int l0 = max(m, spin);
@@ -100,15 +104,12 @@ __global__ void __launch_bounds__(256) spin_prep_kernel(const double2* __restric
   rk[5] = A + B;
   rk[6] = A - B;
   rk[7] = 0.0;
-  double2 e = alm1[base + l];
-  if (m == 0) e.y = 0.0;
-  rk[8] = e.x * sig;
-  rk[9] = e.y * sig;
-  if (NB == 2) {
-    double2 b = alm2[base + l];
-    if (m == 0) b.y = 0.0;
-    rk[10] = b.x * sig;
-    rk[11] = b.y * sig;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    double2 e = alms.a[b][base + l];
+    if (m == 0) e.y = 0.0;
+    rk[8 + 2 * b] = e.x * sig;
+    rk[9 + 2 * b] = e.y * sig;
   }
 }
 
@@ -155,7 +156,11 @@ struct SpinParams {
   int lmax, mmax, npair, nring, spin;
 };
 
-template <int R, int NB, int THREADS>
+// EB: the NB = 2 coefficient sets are the E and B modes of ONE map pair; otherwise they are the E
+// modes of NB independent map pairs (several convergence planes sheared at once), written to the
+// phase maps 2b, 2b + 1.  Per l and ring pair the loop executes 6 DFMA for the two recurrences and
+// 4 NB for the sums: 10 for one E-only map, 7 per map for two, 5.5 per map for four.
+template <int R, int NB, bool EB, int THREADS>
 __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256) ? 512 / THREADS : 1) spin_legendre_synth_kernel(const SpinParams p) {
   constexpr int REC = 8 + 2 * NB;
   constexpr int CHUNK_DOUBLES = SP_KT * REC;
@@ -405,6 +410,8 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
     if (!live[j]) continue;
     const int r = pair0 + j;
     double2 An = make_double2(0, 0), Bn = An, As = An, Bs = An;
+    const int64_t in = (int64_t)r * (p.mmax + 1) + m;
+    const int64_t is = (int64_t)(p.nring - 1 - r) * (p.mmax + 1) + m;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       // even / odd (l+m+s) sums of W and X
@@ -422,7 +429,16 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
       const double2 xs = make_double2(X[0].x - X[1].x, X[0].y - X[1].y);
       const double2 b_n = make_double2(-xn.y, xn.x);   // i * xn
       const double2 b_s = make_double2(xs.y, -xs.x);   // -i * xs
-      if (b == 0) {
+      if (!EB && NB > 1) {  // an E-only map pair of its own
+        double2* ph1 = p.phase + (int64_t)(2 * b) * p.phase_map_stride;
+        double2* ph2 = ph1 + p.phase_map_stride;
+        ph1[in] = a_n;
+        ph2[in] = b_n;
+        if (r != p.npair - 1) {
+          ph1[is] = a_s;
+          ph2[is] = b_s;
+        }
+      } else if (b == 0) {
         An = a_n; Bn = b_n; As = a_s; Bs = b_s;
       } else {
         // B-mode input: map1 -= map2(B as E), map2 += map1(B as E)
@@ -430,15 +446,15 @@ __global__ void __launch_bounds__(THREADS, (R * (NB + 1) <= 8 && THREADS <= 256)
         As.x -= b_s.x; As.y -= b_s.y; Bs.x += a_s.x; Bs.y += a_s.y;
       }
     }
-    double2* ph1 = p.phase;
-    double2* ph2 = p.phase + p.phase_map_stride;
-    const int64_t in = (int64_t)r * (p.mmax + 1) + m;
-    ph1[in] = An;
-    ph2[in] = Bn;
-    if (r != p.npair - 1) {
-      const int64_t is = (int64_t)(p.nring - 1 - r) * (p.mmax + 1) + m;
-      ph1[is] = As;
-      ph2[is] = Bs;
+    if (EB || NB == 1) {
+      double2* ph1 = p.phase;
+      double2* ph2 = p.phase + p.phase_map_stride;
+      ph1[in] = An;
+      ph2[in] = Bn;
+      if (r != p.npair - 1) {
+        ph1[is] = As;
+        ph2[is] = Bs;
+      }
     }
   }
 }
@@ -538,13 +554,33 @@ int plan_ensure_spin(glb_plan* pl, int spin) {
       set_last_error("internal: record workspace too small for the spin transform");
       return GLB_ERR_NOMEM;
     }
+    // work lists are built per tile size on demand (spin_items); drop those of another spin
+    for (auto& kv : pl->spin_item_lists) cudaFree(kv.second.first);
+    pl->spin_item_lists.clear();
+  }
+  // static recurrence tables for this spin
+  cudaFree(pl->d_spin_tab);
+  pl->d_spin_tab = nullptr;
+  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_spin_tab, std::max<int64_t>(pl->nrec_spin, 1) * 3 * sizeof(double)));
+  spin_tables_kernel<<<(pl->mmax + 128) / 128, 128>>>(lmax, pl->mmax, spin, pl->d_soff, pl->d_spin_tab);
+  GLB_CUDA_CHECK(cudaGetLastError());
+  GLB_CUDA_CHECK(cudaDeviceSynchronize());
+  count_launch();
+  pl->spin_ready = spin;
+  return GLB_OK;
+}
+
+// (m, ring tile) work list of the spin transform for tiles of T ring pairs, most expensive first
+static int spin_items(glb_plan* pl, int spin, int T, LegItem** d_items, int* nitems) {
+  auto it = pl->spin_item_lists.find(T);
+  if (it == pl->spin_item_lists.end()) {
+    const int lmax = pl->lmax;
     std::vector<int> rmin(pl->mmax + 1, pl->npair);
     int r = 0;
     for (int m = 0; m <= pl->mmax; ++m) {
       while (r < pl->npair && pl->h_mlim_spin[r] < m) ++r;
       rmin[m] = r;
     }
-    const int T = pl->leg_threads * pl->leg_R;
     const int ntile = (pl->npair + T - 1) / T;
     struct Tmp {
       LegItem it;
@@ -563,32 +599,36 @@ int plan_ensure_spin(glb_plan* pl, int spin) {
     std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& b) { return a.cost > b.cost; });
     std::vector<LegItem> items(tmp.size());
     for (size_t i = 0; i < tmp.size(); ++i) items[i] = tmp[i].it;
-    pl->nitems_spin = (int)items.size();
-    if ((rc = upload_vec(&pl->d_items_spin, items)) != GLB_OK) return rc;
+    LegItem* d = nullptr;
+    int rc;
+    if ((rc = upload_vec(&d, items)) != GLB_OK) return rc;
+    it = pl->spin_item_lists.emplace(T, std::make_pair(d, (int)items.size())).first;
   }
-  // static recurrence tables for this spin
-  cudaFree(pl->d_spin_tab);
-  pl->d_spin_tab = nullptr;
-  GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_spin_tab, std::max<int64_t>(pl->nrec_spin, 1) * 3 * sizeof(double)));
-  spin_tables_kernel<<<(pl->mmax + 128) / 128, 128>>>(lmax, pl->mmax, spin, pl->d_soff, pl->d_spin_tab);
-  GLB_CUDA_CHECK(cudaGetLastError());
-  GLB_CUDA_CHECK(cudaDeviceSynchronize());
-  count_launch();
-  pl->spin_ready = spin;
+  *d_items = it->second.first;
+  *nitems = it->second.second;
   return GLB_OK;
 }
 
-template <int NB>
-static int launch_spin(glb_plan* pl, const double2* a1, const double2* a2, int spin, double2* d_phase, cudaStream_t st) {
+template <int R, int NB, bool EB, int THREADS>
+static int launch_spin_cfg(glb_plan* pl, const SpinAlms& alms, int spin, double2* d_phase, cudaStream_t st) {
   dim3 pgrid((unsigned)((pl->lmax + 1 + 255) / 256), (unsigned)(pl->mmax + 1));
-  spin_prep_kernel<NB><<<pgrid, 256, 0, st>>>(a1, a2, pl->lmax, spin, pl->d_soff, pl->d_spin_tab, pl->d_rec);
+  if ((int64_t)pl->nrec_spin * (8 + 2 * NB) > pl->rec_capacity) {
+    set_last_error("internal: record workspace too small for the batched spin transform");
+    return GLB_ERR_NOMEM;
+  }
+  spin_prep_kernel<NB><<<pgrid, 256, 0, st>>>(alms, pl->lmax, spin, pl->d_soff, pl->d_spin_tab, pl->d_rec);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   // phases of rings beyond mlim are never written nor read; zero the rest for m < spin rows etc.
-  GLB_CUDA_CHECK(cudaMemsetAsync(d_phase, 0, (size_t)2 * pl->nring * (pl->mmax + 1) * sizeof(double2), st));
-  if (pl->nitems_spin == 0) return GLB_OK;
+  const int nphase = EB ? 2 : 2 * NB;
+  GLB_CUDA_CHECK(cudaMemsetAsync(d_phase, 0, (size_t)nphase * pl->nring * (pl->mmax + 1) * sizeof(double2), st));
+  LegItem* items = nullptr;
+  int nitems = 0;
+  int rc = spin_items(pl, spin, R * THREADS, &items, &nitems);
+  if (rc != GLB_OK) return rc;
+  if (nitems == 0) return GLB_OK;
   SpinParams p;
-  p.items = pl->d_items_spin;
+  p.items = items;
   p.rec = pl->d_rec;
   p.soff = pl->d_soff;
   p.z = pl->d_z;
@@ -604,32 +644,40 @@ static int launch_spin(glb_plan* pl, const double2* a1, const double2* a2, int s
   p.npair = pl->npair;
   p.nring = pl->nring;
   p.spin = spin;
-  // E-only: 4 ring pairs per thread (fewer shared-memory wavefronts per DFMA, 2 CTAs per SM);
-  // E+B: 2 ring pairs per thread (twice the accumulators)
-  constexpr int R = (NB == 1) ? 4 : 2;
-  const int th = pl->leg_threads * pl->leg_R / R;  // same ring tile as the scalar work list
-  if (th == 64)
-    spin_legendre_synth_kernel<R, NB, 64><<<pl->nitems_spin, 64, 0, st>>>(p);
-  else if (th == 128)
-    spin_legendre_synth_kernel<R, NB, 128><<<pl->nitems_spin, 128, 0, st>>>(p);
-  else if (th == 256)
-    spin_legendre_synth_kernel<R, NB, 256><<<pl->nitems_spin, 256, 0, st>>>(p);
-  else if (th == 512)
-    spin_legendre_synth_kernel<R, NB, 512><<<pl->nitems_spin, 512, 0, st>>>(p);
-  else {
-    set_last_error("internal: spin thread configuration");
-    return GLB_ERR_INVALID_ARG;
-  }
+  spin_legendre_synth_kernel<R, NB, EB, THREADS><<<nitems, THREADS, 0, st>>>(p);
   GLB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return GLB_OK;
 }
 
 // alm1 (E-like), alm2 (B-like, may be null) -> phases [2][nring][mmax+1]
+// E-only: 4 ring pairs per thread (fewer shared-memory wavefronts per DFMA, 2 CTAs per SM);
+// E+B: 2 ring pairs per thread (twice the accumulators); tiles of 1024 ring pairs either way.
 int sht_spin_alm2phase(glb_plan* pl, const double2* d_alm1, const double2* d_alm2, int spin, double2* d_phase,
                        cudaStream_t st) {
-  if (d_alm2) return launch_spin<2>(pl, d_alm1, d_alm2, spin, d_phase, st);
-  return launch_spin<1>(pl, d_alm1, nullptr, spin, d_phase, st);
+  SpinAlms a = {{d_alm1, d_alm2, nullptr, nullptr}};
+  if (d_alm2) return launch_spin_cfg<2, 2, true, 512>(pl, a, spin, d_phase, st);
+  return launch_spin_cfg<4, 1, false, 256>(pl, a, spin, d_phase, st);
+}
+
+// E modes of nb = 2 or 4 map pairs on ONE pair of recurrences -> phases [2 nb][nring][mmax+1]
+// (map pair b in phase maps 2b, 2b + 1).  Variant (tuning knob GLB_SPIN4_R, nb = 4 only): ring pairs
+// per thread, 2 (256 threads, 8 warps per SM) or 1 (512 threads, 16 warps per SM); tiles of 512.
+int sht_spin_alm2phase_multi(glb_plan* pl, const double2* const* d_alms, int nb, int spin, double2* d_phase,
+                             cudaStream_t st) {
+  SpinAlms a = {{nullptr, nullptr, nullptr, nullptr}};
+  for (int b = 0; b < nb; ++b) a.a[b] = d_alms[b];
+  if (nb == 2) return launch_spin_cfg<2, 2, false, 512>(pl, a, spin, d_phase, st);
+  if (nb == 4) {
+    static const int r4 = [] {
+      const char* e = getenv("GLB_SPIN4_R");
+      return e ? atoi(e) : 2;
+    }();
+    if (r4 == 1) return launch_spin_cfg<1, 4, false, 512>(pl, a, spin, d_phase, st);
+    return launch_spin_cfg<2, 4, false, 256>(pl, a, spin, d_phase, st);
+  }
+  set_last_error("internal: batched spin transform takes 2 or 4 maps");
+  return GLB_ERR_INVALID_ARG;
 }
 
 }  // namespace glb

@@ -287,6 +287,25 @@ def almxfl(alm, fl, *, inplace: bool = False):
     return res
 
 
+def alm2map_spin_batch(alms: torch.Tensor, nside: int, spin: int, lmax: int, out=None):
+    """E-only spin synthesis of several map pairs at once (extension; the reference shears one
+    convergence plane per ``hp.alm2map_spin([alm, 0], nside, 2, lmax)`` call, glass/lensing.py:428).
+    ``alms``: CUDA complex128 [nb, nalm], nb <= 4 per launch group (more are done in turn); returns
+    ``(maps1, maps2)`` of shape [nb, npix].  The planes share the two Wigner-d recurrences."""
+    alms = alms.contiguous()
+    nb, dev = alms.shape[0], alms.device
+    if (lmax + 1) * (lmax + 2) // 2 != alms.shape[1]:
+        raise ValueError("alm size does not match lmax (mmax == lmax is required)")
+    pl = get_plan(nside, lmax, max_batch=4 if nb >= 4 else (2 if nb >= 2 else 1), device=dev)
+    m1, m2 = out if out is not None else (torch.empty((nb, pl.npix), dtype=torch.float64, device=dev), torch.empty((nb, pl.npix), dtype=torch.float64, device=dev))
+    with torch.cuda.device(dev):
+        for a in range(0, nb, 4):
+            n = min(4, nb - a)
+            rc = pl.lib.glb_alm2map_spin_batch(pl.handle, alms[a:].data_ptr(), n, int(spin), m1[a:].data_ptr(), m2[a:].data_ptr(), pl.stream_ptr())
+            _lib.check(rc, "glb_alm2map_spin_batch")
+    return m1, m2
+
+
 def alm2map_spin(alms: Sequence, nside: int, spin: int, lmax: int):
     """
     Computes maps from a set of 2 spinned alm (glass/healpix.py:81-108):

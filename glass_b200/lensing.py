@@ -274,7 +274,8 @@ def _shear_from_convergence_stack(kappa, lmax, discretized, pixwin, niter, ring_
     """Extension: ``kappa`` of shape (n, npix) -- several convergence planes at once (the planes
     of a rank's block of shells, ``glass_b200.dist.multi_plane_block``).  The map2alm refinement
     syntheses of up to four planes share one Legendre recurrence (34 ms per map at nside 4096
-    against 50 ms alone); returns ``[gamma1, gamma2]`` of shape (n, npix)."""
+    against 50 ms alone), and so do their spin-2 syntheses (``hp.alm2map_spin_batch``); returns
+    ``[gamma1, gamma2]`` of shape (n, npix)."""
     device, on_device = A.pick_device(kappa)
     k = A.to_dev(kappa, device)
     nside = hp.get_nside(k[0])
@@ -282,12 +283,8 @@ def _shear_from_convergence_stack(kappa, lmax, discretized, pixwin, niter, ring_
         lmax = 3 * nside - 1
     alms = hp.map2alm(list(k), lmax=lmax, pol=False, use_pixel_weights=True, niter=niter, ring_weights=ring_weights)
     fl = _shear_factor(nside, lmax, discretized, pixwin)
-    g1 = torch.empty_like(k)
-    g2 = torch.empty_like(k)
-    for b, alm in enumerate(alms):
-        alm = hp.almxfl(alm, fl, inplace=True)
-        a, c = hp.alm2map_spin([alm, None], nside, 2, lmax)
-        g1[b], g2[b] = a, c
+    stack = torch.stack([hp.almxfl(alm, fl, inplace=True) for alm in alms])
+    g1, g2 = hp.alm2map_spin_batch(stack, nside, 2, lmax)
     return [g1, g2] if on_device else [g1.cpu().numpy(), g2.cpu().numpy()]
 
 

@@ -76,6 +76,11 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map,
  * is what GLASS always passes). */
 int glb_alm2map_spin(glb_plan* plan, const double* d_alm1, const double* d_alm2, int spin,
                      double* d_map1, double* d_map2, void* stream);
+/* The same for the E modes of nb = 1..4 map pairs at once (several convergence planes sheared
+ * together, glass/lensing.py:428 once per plane in the reference): d_alms [nb][nalm] complex128,
+ * d_maps1 / d_maps2 [nb][npix].  The planes share the Wigner-d recurrences. */
+int glb_alm2map_spin_batch(glb_plan* plan, const double* d_alms, int nb, int spin, double* d_maps1, double* d_maps2,
+                           void* stream);
 
 /* healpy.map2alm(map, lmax, pol=False, use_pixel_weights=True)   glass/healpix.py:270
  * (called from glass/lensing.py:306,408).  d_ring_weights: per-ring quadrature weights

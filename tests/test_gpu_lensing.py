@@ -261,3 +261,28 @@ def test_batched_map2alm_and_shear_match_single(cuda_device):
     kd = torch.as_tensor(maps[:2]).to(cuda_device)
     d1, d2 = glass_b200.shear_from_convergence(kd, lmax, discretized=False, niter=1)
     assert d1.is_cuda and np.abs(d1.cpu().numpy() - g1[:2]).max() <= 1e-12 * np.abs(g1).max()
+
+
+@pytest.mark.parametrize("nside,lmax,spin", [(16, 40, 2), (64, 128, 2), (32, 64, 1), (256, 511, 2)])
+def test_batched_spin_synthesis(cuda_device, nside, lmax, spin, monkeypatch):
+    """glb_alm2map_spin_batch: the E modes of 1..7 map pairs on shared Wigner-d recurrences (launch
+    groups of 4, 2, 1 and both ring-pairs-per-thread variants of the four-map kernel) against the
+    one-pair-at-a-time transform and, at small sizes, the oracle (glass/healpix.py:81-108)."""
+    from glass_b200 import healpix as hp
+
+    rng = np.random.default_rng(nside + spin)
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    alms = rng.standard_normal((7, nalm)) + 1j * rng.standard_normal((7, nalm))
+    alms[:, : lmax + 1] = alms[:, : lmax + 1].real
+    ad = torch.as_tensor(alms).to(cuda_device)
+    singles = [hp.alm2map_spin([ad[b], None], nside, spin, lmax) for b in range(7)]
+    scale = max(float(s[0].abs().max()) for s in singles)
+    for nb in (1, 2, 3, 4, 7):
+        m1, m2 = hp.alm2map_spin_batch(ad[:nb], nside, spin, lmax)
+        assert m1.shape == m2.shape == (nb, 12 * nside**2)
+        for b in range(nb):
+            assert float((m1[b] - singles[b][0]).abs().max()) <= 1e-12 * scale, (nb, b)
+            assert float((m2[b] - singles[b][1]).abs().max()) <= 1e-12 * scale, (nb, b)
+    if nside <= 32:
+        r1, r2 = H.alm2map_spin(alms[3], np.zeros(nalm, dtype=complex), nside, spin, lmax)
+        assert np.abs(m1[3].cpu().numpy() - r1).max() <= 1e-10 * np.abs(r1).max() and np.abs(m2[3].cpu().numpy() - r2).max() <= 1e-10 * np.abs(r1).max()
