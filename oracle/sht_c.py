@@ -39,6 +39,10 @@ def _lib(long_double: bool) -> C.CDLL:
             fn.restype = C.c_int
             fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ref_max_threads.restype = C.c_int
+        lib.ref_map2alm_pass.restype = C.c_int
+        lib.ref_map2alm_pass.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.ref_alm2map_spin.restype = C.c_int
+        lib.ref_alm2map_spin.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIBS[long_double] = lib
     return _LIBS[long_double]
 
@@ -93,3 +97,39 @@ def alm2phase(alm, nside: int, lmax: int, *, long_double: bool = False, use_mlim
     out = np.empty((4 * nside - 1, lmax + 1), dtype=np.complex128)
     _lib(long_double).ref_alm2phase(nside, lmax, alm.ctypes.data, out.ctypes.data, int(use_mlim), nthreads)
     return out
+
+
+def map2alm(mp, lmax: int, *, niter: int = 3, ring_w=None, long_double: bool = False, nthreads: int = 0):
+    """Scalar analysis, healpy.map2alm(pol=False) semantics (glass/healpix.py:270): one analysis pass
+    and ``niter`` Jacobi refinements alm += A(map - S(alm)) (healpy's ``iter``); ``ring_w`` stands in
+    for healpy's pixel weights (default uniform).  Same definition as oracle/healpix_ref.py::map2alm."""
+    mp = np.ascontiguousarray(mp, dtype=np.float64)
+    nside = int(round((mp.size / 12) ** 0.5))
+    nalm = (lmax + 1) * (lmax + 2) // 2
+    w = None if ring_w is None else np.ascontiguousarray(ring_w, dtype=np.float64)
+    lib = _lib(long_double)
+
+    def analysis(m):
+        out = np.zeros(nalm, dtype=np.complex128)
+        rc = lib.ref_map2alm_pass(nside, lmax, m.ctypes.data, None if w is None else w.ctypes.data, out.ctypes.data, nthreads)
+        if rc != 0:
+            raise MemoryError("ref_map2alm_pass")
+        return out
+
+    alm = analysis(mp)
+    for _ in range(niter):
+        res = np.ascontiguousarray(mp - alm2map(alm, nside, lmax, long_double=long_double, nthreads=nthreads))
+        alm = alm + analysis(res)
+    return alm
+
+
+def alm2map_spin(alm1, alm2, nside: int, spin: int, lmax: int, *, long_double: bool = False, nthreads: int = 0):
+    """healpy.alm2map_spin semantics (glass/healpix.py:107); ``alm2`` may be None (E-only)."""
+    a1 = np.ascontiguousarray(alm1, dtype=np.complex128)
+    a2 = None if alm2 is None else np.ascontiguousarray(alm2, dtype=np.complex128)
+    assert a1.size == (lmax + 1) * (lmax + 2) // 2
+    m1, m2 = np.empty(12 * nside * nside), np.empty(12 * nside * nside)
+    rc = _lib(long_double).ref_alm2map_spin(nside, lmax, spin, a1.ctypes.data, None if a2 is None else a2.ctypes.data, m1.ctypes.data, m2.ctypes.data, nthreads)
+    if rc != 0:
+        raise MemoryError("ref_alm2map_spin")
+    return m1, m2

@@ -162,3 +162,48 @@ def test_roundtrip_band_limited(cuda_device, nside, lmax):
     assert (a2 - alm[0]).abs().max().item() < 1e-6 * alm.abs().max().item()
     m2 = alm2map_batch(a2[None], nside, lmax)[0]
     assert (m2 - m1).abs().max().item() < 1e-6 * m1.abs().max().item()
+
+
+@pytest.mark.parametrize("nside,lmax", [(1024, 2047), (2048, 4095)])
+def test_alm2map_random_alm_at_configured_sizes(cuda_device, nside, lmax):
+    """BASELINE.json configs[1] and [2] (nside 1024 / lmax 2047, nside 2048 / lmax 4095): random alm
+    through glb_alm2map against the CPU arm's transform (oracle/sht_fast.cpp: standard recurrence in
+    cos(theta), AVX-512 across rings -- an implementation that shares nothing with the kernels and is
+    itself pinned to the scalar and the 80-bit oracle in the CPU suite).  Both are plain FP64, whose
+    recurrences carry ~1e-12..1e-11 at these lmax; the bar is the north star's 1e-10."""
+    from glass_b200.healpix import alm2map_batch
+    from oracle import sht_c
+
+    alm = random_alm(lmax, 31 * nside, 2)
+    got = alm2map_batch(torch.as_tensor(alm).to(cuda_device), nside, lmax).cpu().numpy()
+    for b in range(2):
+        ref = sht_c.alm2map_fast(alm[b], nside, lmax)
+        assert relerr(got[b], ref) < RTOL, (b, relerr(got[b], ref))
+    # one column of the larger case against the 80-bit checker as well (m-subset: zero all other m)
+    if nside == 1024:
+        ref = sht_c.alm2map(alm[0], nside, lmax, long_double=True, use_mlim=True)
+        assert relerr(got[0], ref) < 2e-11, relerr(got[0], ref)
+
+
+@pytest.mark.parametrize("nside,lmax,long_double", [(512, 1023, True), (1024, 2047, False)])
+def test_spin2_and_analysis_at_larger_sizes(cuda_device, nside, lmax, long_double):
+    """K11 (spin-2 synthesis, E-only as GLASS calls it) and K10 (map2alm with Jacobi refinement and
+    ring weights) against the C oracle's standard recurrences (oracle/sht_ref.c: Wigner-d in l with
+    log-space seeds; 80-bit at nside 512, double at nside 1024), i.e. at sizes where range scaling,
+    pole skipping and the t = 1 - cos(theta) variable of the kernels are all active."""
+    from glass_b200 import healpix as hp
+    from oracle import sht_c
+
+    e = _spin_alm(lmax, 2, nside)
+    got = hp.alm2map_spin([e, None], nside, 2, lmax)
+    ref = sht_c.alm2map_spin(e, None, nside, 2, lmax, long_double=long_double)
+    scale = max(np.abs(ref[0]).max(), np.abs(ref[1]).max())
+    for g, r in zip(got, ref):
+        assert np.abs(g - r).max() < RTOL * scale, np.abs(g - r).max() / scale
+    rng = np.random.default_rng(nside)
+    mp = ref[0] / scale + 1e-3 * rng.standard_normal(ref[0].size)  # band-limited signal plus pixel noise
+    w = 1.0 + 0.05 * rng.random(4 * nside - 1)
+    for niter, rw in ((0, w), (2, None)):
+        got = hp.map2alm(mp, lmax=lmax, pol=False, niter=niter, ring_weights=rw)
+        ref_a = sht_c.map2alm(mp, lmax, niter=niter, ring_w=rw, long_double=long_double)
+        assert np.abs(got - ref_a).max() < RTOL * np.abs(ref_a).max(), (niter, np.abs(got - ref_a).max() / np.abs(ref_a).max())
