@@ -252,6 +252,48 @@ int glb_map2alm(glb_plan* plan, const double* d_map, const double* d_ring_weight
   return glb_map2alm_batch(plan, d_map, 1, d_ring_weights, niter, d_alm, stream);
 }
 
+// Host-buffer entry (the one INTEGRATION.md's stub binds): pageable NumPy memory in and out.
+// A cudaMemcpy from pageable memory is staged by the driver through a small bounce buffer and
+// blocks the stream; here both directions go through two page-locked chunks of the plan
+// (allocated once), so the host memcpy of chunk i overlaps the DMA of chunk i+1 and the
+// transfers run at the link rate.  Everything is on `stream`; the call returns when h_map is filled.
+static constexpr size_t HOST_CHUNK = (size_t)64 << 20;
+
+static int staged_h2d(glb_plan* plan, void* d_dst, const void* h_src, size_t bytes, cudaEvent_t* ev, cudaStream_t st) {
+  char* pin[2] = {reinterpret_cast<char*>(plan->h_pin_in), reinterpret_cast<char*>(plan->h_pin_in) + HOST_CHUNK};
+  size_t off = 0;
+  for (int c = 0; off < bytes; ++c, off += HOST_CHUNK) {
+    const size_t n = std::min(HOST_CHUNK, bytes - off);
+    if (c >= 2) GLB_CUDA_CHECK(cudaEventSynchronize(ev[c & 1]));  // the DMA that last read this chunk has finished
+    memcpy(pin[c & 1], static_cast<const char*>(h_src) + off, n);
+    GLB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, pin[c & 1], n, cudaMemcpyHostToDevice, st));
+    GLB_CUDA_CHECK(cudaEventRecord(ev[c & 1], st));
+  }
+  return GLB_OK;
+}
+
+static int staged_d2h(glb_plan* plan, void* h_dst, const void* d_src, size_t bytes, cudaEvent_t* ev, cudaStream_t st) {
+  char* pin[2] = {reinterpret_cast<char*>(plan->h_pin_out), reinterpret_cast<char*>(plan->h_pin_out) + HOST_CHUNK};
+  size_t off = 0, prev_off = 0, prev_n = 0;
+  int c = 0;
+  for (; off < bytes; ++c, off += HOST_CHUNK) {
+    const size_t n = std::min(HOST_CHUNK, bytes - off);
+    GLB_CUDA_CHECK(cudaMemcpyAsync(pin[c & 1], static_cast<const char*>(d_src) + off, n, cudaMemcpyDeviceToHost, st));
+    GLB_CUDA_CHECK(cudaEventRecord(ev[c & 1], st));
+    if (c >= 1) {  // hand the previous chunk to the caller while this one is in flight
+      GLB_CUDA_CHECK(cudaEventSynchronize(ev[(c - 1) & 1]));
+      memcpy(static_cast<char*>(h_dst) + prev_off, pin[(c - 1) & 1], prev_n);
+    }
+    prev_off = off;
+    prev_n = n;
+  }
+  if (c >= 1) {
+    GLB_CUDA_CHECK(cudaEventSynchronize(ev[(c - 1) & 1]));
+    memcpy(static_cast<char*>(h_dst) + prev_off, pin[(c - 1) & 1], prev_n);
+  }
+  return GLB_OK;
+}
+
 int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_map, const int* h_transform,
                      const double* h_tparams, void* stream) {
   GLB_REQUIRE(plan && h_alm && h_map, "null pointer");
@@ -262,13 +304,19 @@ int glb_alm2map_host(glb_plan* plan, const double* h_alm, int nmaps, double* h_m
   const size_t map_bytes = (size_t)plan->npix * sizeof(double) * plan->max_batch;
   if (!plan->d_stage_alm) GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_stage_alm, alm_bytes));
   if (!plan->d_stage_map) GLB_CUDA_CHECK(cudaMalloc((void**)&plan->d_stage_map, map_bytes));
+  if (!plan->h_pin_in) GLB_CUDA_CHECK(cudaHostAlloc((void**)&plan->h_pin_in, 2 * HOST_CHUNK, cudaHostAllocDefault));
+  if (!plan->h_pin_out) GLB_CUDA_CHECK(cudaHostAlloc((void**)&plan->h_pin_out, 2 * HOST_CHUNK, cudaHostAllocDefault));
+  cudaEvent_t ev[2];
+  for (auto& e : ev) GLB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t a_bytes = (size_t)plan->nalm * 2 * sizeof(double) * nmaps;
   const size_t m_bytes = (size_t)plan->npix * sizeof(double) * nmaps;
-  GLB_CUDA_CHECK(cudaMemcpyAsync(plan->d_stage_alm, h_alm, a_bytes, cudaMemcpyHostToDevice, st));
-  const int rc = glb_alm2map(plan, plan->d_stage_alm, nmaps, plan->d_stage_map, h_transform, h_tparams, stream);
+  int rc = staged_h2d(plan, plan->d_stage_alm, h_alm, a_bytes, ev, st);
+  if (rc == GLB_OK) rc = glb_alm2map(plan, plan->d_stage_alm, nmaps, plan->d_stage_map, h_transform, h_tparams, stream);
+  if (rc == GLB_OK) rc = staged_d2h(plan, h_map, plan->d_stage_map, m_bytes, ev, st);
+  const cudaError_t sync = cudaStreamSynchronize(st);
+  for (auto& e : ev) cudaEventDestroy(e);
   if (rc != GLB_OK) return rc;
-  GLB_CUDA_CHECK(cudaMemcpyAsync(h_map, plan->d_stage_map, m_bytes, cudaMemcpyDeviceToHost, st));
-  GLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  GLB_CUDA_CHECK(sync);
   return GLB_OK;
 }
 
