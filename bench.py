@@ -606,6 +606,17 @@ def run_b200(args) -> None:
     h2d = (lmax + 1) * (NCORR + 1) * 8 * S  # iternorm weights of S shells (the only per-step input)
     d2h = npix * 8 * S
 
+    # ---- what the box can copy: all ranks device -> pinned host at once (the ceiling of e2e) ----
+    d2h_ceiling = None
+    if world > 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from probe_d2h import d2h_ceiling as _ceiling
+
+            d2h_ceiling = _ceiling(dev, world, reps=2)
+        except Exception as e:
+            d2h_ceiling = {"failed": f"{type(e).__name__}: {e}"}
+
     # ---- the m <-> ring split of one transform (N > 1) and the whole north-star chain ----
     from glass_b200.healpix import clear_plans
 
@@ -686,6 +697,8 @@ def run_b200(args) -> None:
             "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h,
             "note": "glass_b200.generate with NumPy gls -> NumPy maps; wall clock incl. device->host copies, max over ranks",
+            "d2h_GB/s": e2e_value * npix * 8 / 1e9,
+            "d2h_ceiling": d2h_ceiling,
         },
         "gpu_launches": launches,
         "roofline": {
