@@ -25,7 +25,13 @@
 namespace glb {
 
 constexpr int PT_THREADS = 256;
-constexpr int PT_ITEMS = 8;
+#ifndef GLB_PT_ITEMS
+#define GLB_PT_ITEMS 8
+#endif
+#ifndef GLB_PT_MINBLOCKS
+#define GLB_PT_MINBLOCKS 4
+#endif
+constexpr int PT_ITEMS = GLB_PT_ITEMS;  // pixels per thread and tile (4 or 8): tile = 1024 or 2048 pixels
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
 
 enum { BIAS_NONE = 0, BIAS_LINEAR = 1, BIAS_LOGLINEAR = 2 };
@@ -175,7 +181,7 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
 //  persistent variant that defers the offsets of a tile by one tile 1.99 ms; 128-wide
 //  look-back windows 2.51 ms.)
 template <bool VIS, bool SAMPLE, bool LOGLIN>
-__global__ void __launch_bounds__(PT_THREADS + 32, 4) points_count_scan_kernel(const CountParams p) {
+__global__ void __launch_bounds__(PT_THREADS + 32, GLB_PT_MINBLOCKS) points_count_scan_kernel(const CountParams p) {
   // SAMPLE only: per-pixel counts of the tile and the per-warp queue of pixels that need the slow draw
   __shared__ __align__(16) int s_cnt[SAMPLE ? PT_TILE : 4];
   __shared__ double s_qlam[SAMPLE ? PT_WARPS : 1][SAMPLE ? PT_QCAP : 1];
