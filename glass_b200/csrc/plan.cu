@@ -18,6 +18,7 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ringfft_class_of(int lbuf);
+size_t ringfft_long_scratch_bytes(int device);
 int sht_build_prep_tables(glb_plan* pl, cudaStream_t st);
 int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::vector<int>& Ms,
                           const std::vector<int64_t>& offs, cudaStream_t st);
@@ -202,14 +203,14 @@ int plan_build(glb_plan* pl) {
     }
     max_fft = std::max(max_fft, d.M);
     if (ringfft_class_of(d.M) < 0) {
-      set_last_error("nside too large for the shared-memory ring FFT (FFT length " + std::to_string(d.M) + " > 8192)");
+      set_last_error("nside too large for the ring FFT (FFT length " + std::to_string(d.M) + " > 16384, i.e. nside > 8192)");
       return GLB_ERR_UNSUPPORTED;
     }
     pl->h_rings[r] = d;
   }
   if ((rc = upload(&pl->d_rings, pl->h_rings)) != GLB_OK) return rc;
   {
-    std::vector<int> order[3];
+    std::vector<int> order[4];
     // pairs adjacent (north ring, its southern mirror), largest first
     std::vector<int> pairs(pl->npair);
     for (int r = 0; r < pl->npair; ++r) pairs[r] = r;
@@ -220,10 +221,11 @@ int plan_build(glb_plan* pl) {
       order[c].push_back(r);
       if (r != pl->npair - 1) order[c].push_back(pl->nring - 1 - r);
     }
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 4; ++c) {
       pl->n_ring_class[c] = (int)order[c].size();
       if ((rc = upload(&pl->d_ring_order[c], order[c])) != GLB_OK) return rc;
     }
+    if (pl->n_ring_class[3] > 0) GLB_CUDA_CHECK(cudaMalloc((void**)&pl->d_long_scratch, ringfft_long_scratch_bytes(pl->device)));
   }
   // ---- twiddles e^{-2 pi i t / tw_n}, t < tw_n/2 (long double on host) ----
   {
@@ -313,9 +315,9 @@ int plan_dist_setup(glb_plan* pl, int world, int rank, const int* h_rowmap, cons
   // ring lists per FFT size class, largest first (same order as the single-GPU lists)
   std::vector<int> mine(h_my_rings, h_my_rings + n_my);
   std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) { return pl->h_rings[a].M > pl->h_rings[b].M; });
-  std::vector<int> order[3];
+  std::vector<int> order[4];
   for (int r : mine) order[ringfft_class_of(pl->h_rings[r].M)].push_back(r);
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 4; ++c) {
     cudaFree(pl->d_dist_ring_order[c]);
     pl->d_dist_ring_order[c] = nullptr;
     pl->n_dist_ring_class[c] = (int)order[c].size();
@@ -337,7 +339,8 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_prep_tab);
   cudaFree(pl->d_items);
   cudaFree(pl->d_rings);
-  for (int c = 0; c < 3; ++c) cudaFree(pl->d_ring_order[c]);
+  for (int c = 0; c < 4; ++c) cudaFree(pl->d_ring_order[c]);
+  cudaFree(pl->d_long_scratch);
   cudaFree(pl->d_tw);
   cudaFree(pl->d_bf);
   cudaFree(pl->d_rec);
@@ -353,7 +356,7 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_spin_tab);
   cudaFree(pl->d_dist_rowmap);
   cudaFree(pl->d_dist_rowidx);
-  for (int c = 0; c < 3; ++c) cudaFree(pl->d_dist_ring_order[c]);
+  for (int c = 0; c < 4; ++c) cudaFree(pl->d_dist_ring_order[c]);
   // peer mappings first (the owners free the memory itself), then this rank's receive buffers
   for (int d = 0; d < P2P_MAX_WORLD; ++d)
     if (pl->p2p_peer[d]) cudaIpcCloseMemHandle(pl->p2p_peer[d]);

@@ -96,8 +96,8 @@ struct glb_plan {
   int dist_rows_local = 0;           // rings owned by this rank
   int* d_dist_rowmap = nullptr;      // [nring] row of each ring in the permuted send layout
   int* d_dist_rowidx = nullptr;      // [nring] local row of each owned ring (-1 otherwise)
-  int* d_dist_ring_order[3] = {nullptr, nullptr, nullptr};
-  int n_dist_ring_class[3] = {0, 0, 0};
+  int* d_dist_ring_order[4] = {nullptr, nullptr, nullptr, nullptr};
+  int n_dist_ring_class[4] = {0, 0, 0, 0};
   // fused Legendre + transpose (glb_dist_p2p_*): receive buffers allocated here with cudaMalloc
   // (CUDA IPC needs that), the peers' buffers opened through their IPC handles
   int p2p_nb = 0;                                                // maps a receive buffer holds
@@ -107,8 +107,9 @@ struct glb_plan {
 
   // ring FFT
   glb::RingDesc* d_rings = nullptr;  // [nring]
-  int* d_ring_order[3] = {nullptr, nullptr, nullptr};  // ring index lists per size class
-  int n_ring_class[3] = {0, 0, 0};
+  int* d_ring_order[4] = {nullptr, nullptr, nullptr, nullptr};  // ring index lists per size class (3: long rings)
+  int n_ring_class[4] = {0, 0, 0, 0};
+  double2* d_long_scratch = nullptr; // work buffers of the long-ring FFT kernels (plans with FFT lengths above 8192)
   double2* d_tw = nullptr;           // twiddles e^{-2 pi i t / TW_N}, t < TW_N/2
   int tw_n = 0;
   double2* d_bf = nullptr;           // concatenated chirp spectra (bit-reversed order, scaled 1/M)

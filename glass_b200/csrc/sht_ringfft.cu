@@ -23,6 +23,9 @@
 //             live in registers so shared memory only ever holds one M-length buffer.
 //   4. store  coalesced 16-byte stores of (x[2j], x[2j+1]) with the transform applied --
 //             for the direct path straight from the registers of the last FFT pass.
+#include <algorithm>
+#include <vector>
+
 #include "expm1_fast.cuh"
 #include "fft_core.cuh"
 #include "plan.h"
@@ -46,6 +49,9 @@ struct FftParams {
   int mmax;
   int tw_n;
   int stash_off;     // offset (double2) of the Bluestein stash behind the FFT buffer
+  double2* scratch;  // long rings only: [gridDim.x][3][LONG_LB + 8] work buffers in global memory
+  int nitems;        // long rings only: rings x maps handed out to the resident CTAs
+  int nrings;
   int kind[4];
   double p0[4];
   double p1[4];
@@ -280,6 +286,9 @@ struct FftAnaParams {
   int mmax;
   int tw_n;
   int stash_off;
+  double2* scratch;       // long rings only, as in FftParams
+  int nitems;
+  int nrings;
 };
 
 template <int THREADS, int NREG>
@@ -378,6 +387,198 @@ __global__ void __launch_bounds__(THREADS) sht_ringfft_analysis_kernel(const Fft
   }
 }
 
+// -------------------------------------------------------------------------------------
+// LONG rings: FFT length above 8192 complex points (ring length above 16384 pixels, i.e. nside
+// above 4096).  A 16384-point complex FP64 buffer is 256 KB and no longer fits one SM's shared
+// memory, so these rings run the SAME algorithm (fold / pack / power-of-two or two-sequence
+// Bluestein with the fft_core passes) on three work buffers in GLOBAL memory -- one set per
+// resident CTA, a few hundred KB each, so that they live in the 126 MB L2 -- with a persistent
+// grid handing out (ring, map) items.  Every pass is then an L2 round trip instead of a
+// shared-memory one: slower per ring than the shared-memory kernels, but the Fourier stage is a
+// few per cent of a transform whose Legendre stage grows with nside^3.  Covers FFT lengths up to
+// 16384 (nside <= 8192).
+// -------------------------------------------------------------------------------------
+constexpr int LONG_LB = 16384;
+constexpr int LONG_THREADS = 512;
+constexpr int LONG_TRIG_HI = 2 * 4 * 8192 / 64;  // 2 nphi / 64 for nphi = 4 * 8192
+
+__global__ void __launch_bounds__(LONG_THREADS) sht_ringfft_synth_long_kernel(const FftParams p) {
+  constexpr int THREADS = LONG_THREADS;
+  __shared__ double2 s_thi[LONG_TRIG_HI], s_tlo[64];
+  double2* bufG = p.scratch + (int64_t)blockIdx.x * 3 * (LONG_LB + 8);
+  double2* bufA = bufG + (LONG_LB + 8);
+  double2* bufB = bufA + (LONG_LB + 8);
+  const int tid = threadIdx.x;
+  for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    const int ring = p.order[item % p.nrings];
+    const int b = item / p.nrings;
+    const RingDesc d = p.rings[ring];
+    const int n = d.nphi, h = n >> 1;
+    const int mlim = min(p.mlim[d.pair], p.mmax);
+    const int row = p.rowidx ? p.rowidx[ring] : ring;
+    const double2* __restrict__ Fb = p.phase + b * p.phase_map_stride + (int64_t)row * p.W;
+    const bool one_gpu = (p.G == 1);
+    auto F = [&](int m) -> double2 { return one_gpu ? Fb[m] : Fb[(int64_t)(m % p.G) * p.blk + m / p.G]; };
+    double* __restrict__ out = p.maps[b] + d.start;
+    const int kind = p.kind[b];
+    const double tp0 = p.p0[b], tp1 = p.p1[b];
+    __syncthreads();  // the previous item's readers of the tables and buffers are done
+    const RingTrig tr = ring_trig_setup<THREADS>(s_thi, s_tlo, n);
+    // 1. fold with phase shift -> G[0..h]
+    for (int k = tid; k <= h; k += THREADS) {
+      double2 g = make_double2(0.0, 0.0);
+      int j = k;
+      for (int m = k; m <= mlim; m += n) {
+        double2 t = F(m);
+        if (m == 0) t.y = 0.0;
+        if (d.shifted) t = cmul(t, tr.T(j));
+        g = cadd(g, t);
+        j += n;
+        if (j >= 2 * n) j -= 2 * n;
+      }
+      j = n - k;
+      for (int m = n - k; m <= mlim; m += n) {
+        double2 t = F(m);
+        if (d.shifted) t = cmul(t, tr.T(j));
+        g = cadd(g, cconj(t));
+        j += n;
+        if (j >= 2 * n) j -= 2 * n;
+      }
+      bufG[k] = g;
+    }
+    __syncthreads();
+    const int nfft = 31 - __clz(d.M);
+    if (d.L == 0) {
+      for (int k = tid; k < h; k += THREADS) bufA[fft::sw(k, nfft)] = pack_z(tr, bufG, k, h);
+      __syncthreads();
+      fft::dev_fft_dif_emit<THREADS>(bufA, nfft, p.tw, p.tw_n, true, [&](int j, double2 zv) {
+        double2 o;
+        o.x = apply_transform(zv.x, kind, tp0, tp1);
+        o.y = apply_transform(zv.y, kind, tp0, tp1);
+        *reinterpret_cast<double2*>(out + 2 * j) = o;
+      });
+      continue;
+    }
+    const int L = d.L;
+    for (int q = tid; q < L; q += THREADS) {
+      const double2 c = chirp(tr, q, L);
+      bufA[fft::sw(q, nfft)] = cmul(pack_z(tr, bufG, 2 * q, h), c);
+      bufB[fft::sw(q, nfft)] = cmul(pack_z(tr, bufG, 2 * q + 1, h), c);
+    }
+    __syncthreads();
+    const double2* __restrict__ bf = p.bf + d.bf_off;
+    fft::dev_bluestein_conv<THREADS>(bufA, nfft, p.tw, p.tw_n, bf, L);
+    fft::dev_bluestein_conv<THREADS>(bufB, nfft, p.tw, p.tw_n, bf, L);
+    for (int q = tid; q < L; q += THREADS) {
+      const double2 c = chirp(tr, q, L);
+      const double2 E = cmul(bufA[fft::sw(q, nfft)], c);
+      const double2 O = cmul(cmul(bufB[fft::sw(q, nfft)], c), tr.T(4 * q));  // e^{2 pi i q/h}
+      const double2 z0 = cadd(E, O), z1 = csub(E, O);
+      double2 o;
+      o.x = apply_transform(z0.x, kind, tp0, tp1);
+      o.y = apply_transform(z0.y, kind, tp0, tp1);
+      *reinterpret_cast<double2*>(out + 2 * q) = o;
+      o.x = apply_transform(z1.x, kind, tp0, tp1);
+      o.y = apply_transform(z1.y, kind, tp0, tp1);
+      *reinterpret_cast<double2*>(out + 2 * (q + L)) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LONG_THREADS) sht_ringfft_analysis_long_kernel(const FftAnaParams p) {
+  constexpr int THREADS = LONG_THREADS;
+  __shared__ double2 s_thi[LONG_TRIG_HI], s_tlo[64];
+  double2* bufG = p.scratch + (int64_t)blockIdx.x * 3 * (LONG_LB + 8);
+  double2* bufA = bufG + (LONG_LB + 8);
+  double2* bufB = bufA + (LONG_LB + 8);
+  const int tid = threadIdx.x;
+  for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    const int ring = p.order[item % p.nrings];
+    const int b = item / p.nrings;
+    const RingDesc d = p.rings[ring];
+    const int n = d.nphi, h = n >> 1;
+    const int mlim = min(p.mlim[d.pair], p.mmax);
+    const double* __restrict__ in = p.maps[b] + d.start;
+    double2* __restrict__ F = p.phase + b * p.phase_map_stride + (int64_t)ring * (p.mmax + 1);
+    const double wscale = p.norm * (p.ring_w ? p.ring_w[ring] : 1.0);
+    const int nfft = 31 - __clz(d.M);
+    __syncthreads();
+    const RingTrig tr = ring_trig_setup<THREADS>(s_thi, s_tlo, n);
+    const double2* Z;   // forward transform of z[j] = x[2j] + i x[2j+1], length h
+    bool bitrev_out;
+    if (d.L == 0) {
+      for (int j = tid; j < h; j += THREADS) bufA[fft::sw(j, nfft)] = *reinterpret_cast<const double2*>(in + 2 * j);
+      __syncthreads();
+      fft::dev_fft_dif<THREADS>(bufA, nfft, p.tw, p.tw_n, false);
+      Z = bufA;
+      bitrev_out = true;
+    } else {
+      const int L = d.L;
+      for (int q = tid; q < L; q += THREADS) {
+        const double2 c = chirp(tr, q, L);
+        const double2 ze = *reinterpret_cast<const double2*>(in + 4 * q);
+        const double2 zo = *reinterpret_cast<const double2*>(in + 4 * q + 2);
+        bufA[fft::sw(q, nfft)] = cmul(cconj(ze), c);  // forward DFT as conj(IDFT(conj .))
+        bufB[fft::sw(q, nfft)] = cmul(cconj(zo), c);
+      }
+      __syncthreads();
+      const double2* __restrict__ bf = p.bf + d.bf_off;
+      fft::dev_bluestein_conv<THREADS>(bufA, nfft, p.tw, p.tw_n, bf, L);
+      fft::dev_bluestein_conv<THREADS>(bufB, nfft, p.tw, p.tw_n, bf, L);
+      for (int q = tid; q < L; q += THREADS) {
+        const double2 c = chirp(tr, q, L);
+        const double2 E = cconj(cmul(bufA[fft::sw(q, nfft)], c));
+        const double2 O = cmul(cconj(cmul(bufB[fft::sw(q, nfft)], c)), cconj(tr.T(4 * q)));  // e^{-2 pi i q/h}
+        bufG[q] = cadd(E, O);
+        bufG[q + L] = csub(E, O);
+      }
+      __syncthreads();
+      Z = bufG;
+      bitrev_out = false;
+    }
+    for (int m = tid; m <= mlim; m += THREADS) {
+      const int k = m % n;
+      const int kk = (k <= h) ? k : n - k;
+      int i0 = kk % h, i1 = (h - kk) % h;
+      if (bitrev_out) {
+        i0 = fft::sw((int)fft::bitrev((unsigned)i0, nfft), nfft);
+        i1 = fft::sw((int)fft::bitrev((unsigned)i1, nfft), nfft);
+      }
+      const double2 zk = Z[i0];
+      const double2 zr = cconj(Z[i1]);
+      const double2 sum = cadd(zk, zr), dif = csub(zk, zr);
+      const double2 wd = cmul(cconj(tr.T(2 * kk)), dif);
+      double2 X = make_double2(0.5 * (sum.x + wd.y), 0.5 * (sum.y - wd.x));
+      if (k > h) X = cconj(X);
+      if (d.shifted) X = cmul(X, cconj(tr.T(m % (2 * n))));
+      F[m] = cscale(X, wscale);
+    }
+  }
+}
+
+// chirp spectrum of a LONG ring's Bluestein length, work buffer in global memory (one CTA each)
+__global__ void __launch_bounds__(LONG_THREADS) bluestein_spectrum_long_kernel(const int* Ls, const int* Ms, const int64_t* offs,
+                                                                               const double2* tw, int tw_n, double2* bf,
+                                                                               double2* scratch) {
+  constexpr int THREADS = LONG_THREADS;
+  double2* buf = scratch + (int64_t)blockIdx.x * (LONG_LB + 8);
+  const int tid = threadIdx.x;
+  const int L = Ls[blockIdx.x], M = Ms[blockIdx.x];
+  const int nfft = 31 - __clz(M);
+  for (int i = tid; i < M + 8; i += THREADS) buf[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int q = tid; q < L; q += THREADS) {
+    const double2 c = cconj(chirp(q, L));
+    buf[fft::sw(q, nfft)] = c;
+    if (q > 0) buf[fft::sw(M - q, nfft)] = c;
+  }
+  __syncthreads();
+  fft::dev_fft_dif<THREADS>(buf, nfft, tw, tw_n, false);
+  const double inv = 1.0 / (double)M;
+  double2* o = bf + offs[blockIdx.x];
+  for (int i = tid; i < M; i += THREADS) o[fft::bf_index(i, nfft)] = cscale(buf[fft::sw(i, nfft)], inv);
+}
+
 // chirp spectrum  Bf = DIF_M( b_wrapped ) / M,  b[d] = conj(c[d]) = e^{-i pi d^2 / L}, stored in the
 // block-transposed order the fused Bluestein middle pass reads (fft::bf_index)
 template <int THREADS>
@@ -405,13 +606,23 @@ __global__ void __launch_bounds__(THREADS) bluestein_spectrum_kernel(const int* 
 // -------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------
-static const int kClassLB[3] = {512, 2048, 8192};
+// classes 0..2: shared-memory kernels; class 3: LONG rings (buffers in global memory)
+static const int kClassLB[4] = {512, 2048, 8192, LONG_LB};
 
 int ringfft_class_of(int lbuf) {
-  for (int c = 0; c < 3; ++c)
+  for (int c = 0; c < 4; ++c)
     if (lbuf <= kClassLB[c]) return c;
   return -1;
 }
+
+// resident CTAs of the long-ring kernels and their work buffers (allocated with the plan when it
+// has long rings): two CTAs per SM keep the L2 round trips of the passes overlapped
+int ringfft_long_slots(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return 2 * sms;
+}
+size_t ringfft_long_scratch_bytes(int device) { return (size_t)ringfft_long_slots(device) * 3 * (LONG_LB + 8) * sizeof(double2); }
 
 int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::vector<int>& Ms,
                           const std::vector<int64_t>& offs, cudaStream_t st) {
@@ -425,13 +636,43 @@ int ringfft_build_spectra(glb_plan* pl, const std::vector<int>& Ls, const std::v
   GLB_CUDA_CHECK(cudaMemcpyAsync(dL, Ls.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
   GLB_CUDA_CHECK(cudaMemcpyAsync(dM, Ms.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
   GLB_CUDA_CHECK(cudaMemcpyAsync(dO, offs.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  int maxM = 0;
-  for (int m : Ms) maxM = std::max(maxM, m);
-  const size_t smem = (size_t)(maxM + 8) * sizeof(double2);
-  GLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_spectrum_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-  bluestein_spectrum_kernel<512><<<(unsigned)n, 512, smem, st>>>(dL, dM, dO, pl->d_tw, pl->tw_n, pl->d_bf);
-  GLB_CUDA_CHECK(cudaGetLastError());
+  // the lists are ordered by ring, i.e. not by length: split into the shared-memory kernel's
+  // share (M <= 8192) and the long one's, each launched on its own sub-list
+  std::vector<int> idx_s, idx_l;
+  for (size_t i = 0; i < n; ++i) (Ms[i] <= kClassLB[2] ? idx_s : idx_l).push_back((int)i);
+  auto gather = [&](const std::vector<int>& idx, std::vector<int>& l, std::vector<int>& m, std::vector<int64_t>& o) {
+    for (int i : idx) {
+      l.push_back(Ls[i]);
+      m.push_back(Ms[i]);
+      o.push_back(offs[i]);
+    }
+  };
+  std::vector<int> l2, m2;
+  std::vector<int64_t> o2;
+  gather(idx_s, l2, m2, o2);
+  const size_t ns = l2.size();
+  gather(idx_l, l2, m2, o2);
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dL, l2.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dM, m2.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  GLB_CUDA_CHECK(cudaMemcpyAsync(dO, o2.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (ns) {
+    int maxM = 0;
+    for (size_t i = 0; i < ns; ++i) maxM = std::max(maxM, m2[i]);
+    const size_t smem = (size_t)(maxM + 8) * sizeof(double2);
+    GLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_spectrum_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    bluestein_spectrum_kernel<512><<<(unsigned)ns, 512, smem, st>>>(dL, dM, dO, pl->d_tw, pl->tw_n, pl->d_bf);
+    GLB_CUDA_CHECK(cudaGetLastError());
+  }
+  if (n > ns) {  // long lengths: one global work buffer per CTA, in chunks of the scratch's slots
+    const int slots = 3 * ringfft_long_slots(pl->device);
+    for (size_t a = ns; a < n; a += slots) {
+      const unsigned cnt = (unsigned)std::min<size_t>(slots, n - a);
+      bluestein_spectrum_long_kernel<<<cnt, LONG_THREADS, 0, st>>>(dL + a, dM + a, dO + a, pl->d_tw, pl->tw_n, pl->d_bf,
+                                                                   pl->d_long_scratch);
+      GLB_CUDA_CHECK(cudaGetLastError());
+    }
+  }
   GLB_CUDA_CHECK(cudaStreamSynchronize(st));
   cudaFree(dL);
   cudaFree(dM);
@@ -491,6 +732,15 @@ int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* co
   int rc;
   int* const* order = dist ? pl->d_dist_ring_order : pl->d_ring_order;
   const int* count = dist ? pl->n_dist_ring_class : pl->n_ring_class;
+  if (count[3] > 0) {  // long rings: persistent grid on global work buffers
+    p.order = order[3];
+    p.scratch = pl->d_long_scratch;
+    p.nrings = count[3];
+    p.nitems = count[3] * nb;
+    sht_ringfft_synth_long_kernel<<<std::min(ringfft_long_slots(pl->device), p.nitems), LONG_THREADS, 0, st>>>(p);
+    GLB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   // largest rings first (they take longest)
   p.order = order[2];
   if ((rc = launch_class<512, 16>(p, count[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
@@ -535,6 +785,15 @@ int sht_map2phase_group(glb_plan* pl, const double* const* d_maps, int nb, const
   p.mmax = pl->mmax;
   p.tw_n = pl->tw_n;
   int rc;
+  if (pl->n_ring_class[3] > 0) {
+    p.order = pl->d_ring_order[3];
+    p.scratch = pl->d_long_scratch;
+    p.nrings = pl->n_ring_class[3];
+    p.nitems = pl->n_ring_class[3] * nb;
+    sht_ringfft_analysis_long_kernel<<<std::min(ringfft_long_slots(pl->device), p.nitems), LONG_THREADS, 0, st>>>(p);
+    GLB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   p.order = pl->d_ring_order[2];
   if ((rc = launch_class_ana<512, 16>(p, pl->n_ring_class[2], nb, kClassLB[2], st)) != GLB_OK) return rc;
   p.order = pl->d_ring_order[1];

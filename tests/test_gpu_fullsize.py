@@ -68,37 +68,33 @@ def lam_single(l, m, z, sth):
     return np.ldexp(p, np.clip(e, -2000, 2000).astype(np.int32)).astype(np.float64)
 
 
-def test_single_harmonics_fullsize(cuda_device):
-    """Measured on B200: every mode within 9e-12 of the 80-bit exact-geometry value (2e-9 for the
-    zonal modes before the recurrence variable was chosen per warp and the coefficient tables
-    were computed in double-double, see csrc/sht_tables.cuh)."""
+def _single_harmonics_error(dev, nside, lmax, modes):
+    """Synthesis of a few single harmonics at (nside, lmax) against lambda_lm evaluated ring by ring in
+    80-bit arithmetic on exact ring geometry; returns the largest error relative to the map maximum."""
     from glass_b200 import _lib
     from glass_b200.healpix import alm2map_batch, get_plan
 
-    dev = cuda_device
-    ri = H.ring_info(NSIDE)
-    zx, sx = exact_ring_geometry(NSIDE)
-    modes = [(0, 0, 1.0 + 0j), (1, 0, -0.7 + 0j), (8000, 0, 0.9 + 0j), (8191, 0, 0.4 + 0j), (8191, 8191, 1.1 + 0.5j),
-             (5000, 3000, -0.6 + 0.8j), (8191, 4000, 0.5 + 0.1j), (7000, 6999, 0.2 - 0.9j), (6001, 17, 0.3 + 0.3j)]
-    alm = np.zeros((1, H.alm_size(LMAX)), dtype=np.complex128)
+    ri = H.ring_info(nside)
+    zx, sx = exact_ring_geometry(nside)
+    alm = np.zeros((1, H.alm_size(lmax)), dtype=np.complex128)
     for l, m, a in modes:
-        alm[0, H.alm_index(LMAX, l, m)] = a
-    got = alm2map_batch(torch.as_tensor(alm).to(dev), NSIDE, LMAX)[0]
+        alm[0, H.alm_index(lmax, l, m)] = a
+    got = alm2map_batch(torch.as_tensor(alm).to(dev), nside, lmax)[0]
     # like libsharp2 (sharp_get_mlim) the transform skips m > mlim(ring) = lmax sin(theta) + max(100,
     # lmax / 100): apply the same rule to the reference and bound what it removes
-    pl = get_plan(NSIDE, LMAX, 1, dev)
-    mlim = (C.c_int * (2 * NSIDE))()
+    pl = get_plan(nside, lmax, 1, dev)
+    mlim = (C.c_int * (2 * nside))()
     _lib.check(pl.lib.glb_debug_mlim(pl.handle, mlim), "mlim")
     mlim = np.array(mlim[:])
-    nring = 4 * NSIDE - 1
-    mlim_ring = np.array([mlim[r if r < 2 * NSIDE else nring - 1 - r] for r in range(nring)])
+    nring = 4 * nside - 1
+    mlim_ring = np.array([mlim[r if r < 2 * nside else nring - 1 - r] for r in range(nring)])
     # expected map, assembled on the device from per-ring factors
     nphi = torch.as_tensor(ri["nphi"], device=dev)
     ring = torch.repeat_interleave(torch.arange(nphi.numel(), device=dev), nphi)
-    j = torch.arange(12 * NSIDE * NSIDE, device=dev) - torch.as_tensor(ri["start"], device=dev)[ring]
+    j = torch.arange(12 * nside * nside, device=dev) - torch.as_tensor(ri["start"], device=dev)[ring]
     nphi_p = nphi[ring]
     shifted = torch.as_tensor(ri["shifted"].astype(np.int64), device=dev)[ring]
-    want = torch.zeros(12 * NSIDE * NSIDE, dtype=torch.float64, device=dev)
+    want = torch.zeros(12 * nside * nside, dtype=torch.float64, device=dev)
     for l, m, a in modes:
         lam_np = lam_single(l, m, zx, sx)
         cut = mlim_ring < m
@@ -113,7 +109,16 @@ def test_single_harmonics_fullsize(cuda_device):
         num = (2 * m * j + m * shifted) % (2 * nphi_p)
         ang = math.pi * num.to(torch.float64) / nphi_p.to(torch.float64)
         want += 2.0 * lam * (a.real * torch.cos(ang) - a.imag * torch.sin(ang))
-    err = (got - want).abs().max().item() / want.abs().max().item()
+    return (got - want).abs().max().item() / want.abs().max().item()
+
+
+def test_single_harmonics_fullsize(cuda_device):
+    """Measured on B200: every mode within 9e-12 of the 80-bit exact-geometry value (2e-9 for the
+    zonal modes before the recurrence variable was chosen per warp and the coefficient tables
+    were computed in double-double, see csrc/sht_tables.cuh)."""
+    modes = [(0, 0, 1.0 + 0j), (1, 0, -0.7 + 0j), (8000, 0, 0.9 + 0j), (8191, 0, 0.4 + 0j), (8191, 8191, 1.1 + 0.5j),
+             (5000, 3000, -0.6 + 0.8j), (8191, 4000, 0.5 + 0.1j), (7000, 6999, 0.2 - 0.9j), (6001, 17, 0.3 + 0.3j)]
+    err = _single_harmonics_error(cuda_device, NSIDE, LMAX, modes)
     assert err < 1e-10, err  # BASELINE.json north_star: maps from identical alm within 1e-10 relative
 
 
@@ -372,3 +377,51 @@ def test_generate_two_lognormal_shells_fullsize(cuda_device):
         assert abs(float(m.var()) / math.expm1(var) - 1.0) < 0.05
     cov = float((maps[0] * maps[1]).mean() - maps[0].mean() * maps[1].mean())
     assert abs(cov / math.expm1(0.5 * var) - 1.0) < 0.08
+
+
+def test_long_rings_nside_8192(cuda_device):
+    """nside 8192: rings of up to 32768 pixels, whose FFT (16384 complex points) does not fit one SM's
+    shared memory and runs on global work buffers (sht_ringfft_*_long_kernel).  With a small lmax the
+    Legendre stage is cheap and the C oracle (independent FFT: radix-2 / plain Bluestein per ring) can
+    check EVERY ring: synthesis with alias folding on the polar rings, the fused lognormal store, and
+    the analysis direction with ring weights."""
+    from glass_b200 import _lib
+    from glass_b200 import healpix as hp
+    from oracle import sht_c
+
+    nside, lmax = 8192, 150
+    rng = np.random.default_rng(8192)
+    n = (lmax + 1) * (lmax + 2) // 2
+    alm = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    alm[: lmax + 1] = alm[: lmax + 1].real
+    ref = sht_c.alm2map(alm, nside, lmax)
+    d_alm = torch.as_tensor(alm[None]).to(cuda_device)
+    got = hp.alm2map_batch(d_alm, nside, lmax)[0]
+    err = float((got - torch.as_tensor(ref, device=cuda_device)).abs().max()) / np.abs(ref).max()
+    assert err < 1e-11, err
+    logn = hp.alm2map_batch(0.01 * d_alm, nside, lmax, transforms=[(_lib.T_LOGNORMAL, 0.05, 0.7)])[0]
+    want = 0.7 * np.expm1(0.01 * ref - 0.05)
+    assert float((logn - torch.as_tensor(want, device=cuda_device)).abs().max()) < 1e-12 * np.abs(want).max() + 1e-14
+    del logn
+    # analysis of the synthesised map plus pixel noise, with ring weights
+    mp = ref / np.abs(ref).max() + 1e-3 * rng.standard_normal(ref.size)
+    w = 1.0 + 0.05 * rng.random(4 * nside - 1)
+    ga = hp.map2alm(torch.as_tensor(mp, device=cuda_device), lmax=lmax, pol=False, niter=1, ring_weights=w).cpu().numpy()
+    ra = sht_c.map2alm(mp, lmax, niter=1, ring_w=w)
+    assert np.abs(ga - ra).max() < 1e-10 * np.abs(ra).max(), np.abs(ga - ra).max() / np.abs(ra).max()
+    hp.clear_plans()
+    torch.cuda.empty_cache()
+
+
+def test_single_harmonics_nside_8192(cuda_device):
+    """The whole transform at nside 8192, lmax 16383 -- the size the m-split axis exists for (range
+    scaling down to lambda_mm ~ 1e-60000, pole skipping, long-ring FFTs): single harmonics against the
+    80-bit ring-by-ring evaluation, as test_single_harmonics_fullsize does at nside 4096."""
+    from glass_b200.healpix import clear_plans
+
+    modes = [(0, 0, 1.0 + 0j), (16383, 0, 0.4 + 0j), (16383, 16383, 1.1 + 0.5j), (12001, 7000, -0.6 + 0.8j), (9000, 1, 0.3 + 0.3j),
+             (16383, 8000, 0.5 + 0.1j)]
+    err = _single_harmonics_error(cuda_device, 8192, 16383, modes)
+    assert err < 1e-10, err
+    clear_plans()
+    torch.cuda.empty_cache()
