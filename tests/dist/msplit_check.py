@@ -28,7 +28,7 @@ def main():
     for nside in sizes:
         lmax = 2 * nside - 1 if nside > 8 else 3 * nside - 1
         nalm = (lmax + 1) * (lmax + 2) // 2
-        for nb in (1, 4) if nside <= 1024 else (4,):
+        for nb in (1, 4) if nside <= 1024 else ((4,) if nside <= 4096 else (1,)):  # nside 8192: one map (memory of the single-GPU reference)
             g = torch.Generator(device=dev)
             g.manual_seed(1234 + nside)  # same alm on every rank
             alm = torch.view_as_complex(torch.randn((nb, nalm, 2), dtype=torch.float64, device=dev, generator=g))
