@@ -303,6 +303,12 @@ def extra_stage_rooflines(dev, hbm_peak: float, fp64_peak: float) -> dict:
     alm = hp.map2alm(kap, lmax=lmax, pol=False, niter=0)
     t = ev(lambda: hp.alm2map_spin([alm, None], nside, 2, lmax), n=3, warm=1)
     out["alm2map_spin s=2 E-only (K11)"] = {"ms": t, "TFLOP/s": 16 * ntri / t / 1e9, "frac_fp64": 16 * ntri / t / 1e9 / fp64_peak, "algorithmic_flop": 16 * ntri}
+    # the same for FOUR convergence planes on shared Wigner-d recurrences (what shear_from_convergence does with a stack)
+    alm4 = torch.stack([alm, 0.5 * alm, -alm, 2.0 * alm])
+    t = ev(lambda: hp.alm2map_spin_batch(alm4, nside, 2, lmax), n=3, warm=1)
+    out["alm2map_spin s=2, 4 planes per recurrence (K11 batched)"] = {"ms_per_plane": t / 4, "TFLOP/s": 64 * ntri / t / 1e9, "frac_fp64": 64 * ntri / t / 1e9 / fp64_peak,
+                                                                      "algorithmic_flop": 64 * ntri, "note": "includes the ring FFTs of the eight maps"}
+    del alm4
     hp.clear_plans()
     torch.cuda.empty_cache()
     return out
