@@ -9,7 +9,7 @@ are in ``libglassb200.so`` (``python -m glass_b200.build``) and calls raise if i
 missing.
 """
 
-from . import algorithm, fields, galaxies, grf, harmonics, healpix, lensing, points, rng, shapes, sharding, shells, transformcl, user  # noqa: F401
+from . import algorithm, fields, galaxies, grf, harmonics, healpix, lensing, observations, points, rng, shapes, sharding, shells, transformcl, user  # noqa: F401
 from .fields import (  # noqa: F401
     check_posdef_spectra,
     cls2cov,
@@ -45,6 +45,7 @@ from .lensing import (  # noqa: F401
     multi_plane_weights,
     shear_from_convergence,
 )
+from .observations import vmap_galactic_ecliptic  # noqa: F401
 from .points import (  # noqa: F401
     displace,
     displacement,

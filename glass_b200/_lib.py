@@ -62,6 +62,10 @@ SIGNATURES = {
     "glb_ellipticity": (_i, [_i, C.c_double, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
     "glb_gaussian_phz": (_i, [_dp, _dp, C.c_double, _dp, C.c_double, _dp, C.c_double, _dp, _i, _i64, C.c_uint64, C.c_uint32, _dp, _dp, _vp]),
     "glb_redshifts_from_cdf": (_i, [_dp, _dp, _i, _dp, _i64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _vp]),
+    "glb_query_strip": (_i, [_i64, C.c_double, C.c_double, _dp, _vp]),
+    "glb_rotate_map_pixel": (_i, [_i64, C.POINTER(C.c_double), _dp, _dp, _vp]),
+    "glb_cls_window": (_i, [_i, _i, _i64, _i64, _dp, _dp, _dp, _vp]),
+    "glb_effective_cls": (_i, [_i, _i, _i, _i, _i64, _i, _dp, _dp, _dp, _dp, _vp]),
     "glb_alm2map_host": (_i, [_vp, _dp, _i, _dp, _ip, _dp, _vp]),
     "glb_dist_setup": (_i, [_vp, _i, _i, _ip, _ip, _i]),
     "glb_dist_alm2phase": (_i, [_vp, _dp, _i, _dp, _vp]),

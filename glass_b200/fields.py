@@ -293,6 +293,18 @@ def cltovar(cl) -> float:
     return float(np.sum((2 * ell + 1) / (4 * np.pi) * cl))
 
 
+def _pack_spectra(cls, lmax, device):
+    """Spectra as zero-padded rows [nspec][ld] on the device (one copy each; empty spectra are zero
+    rows) plus their lengths after truncation to lmax."""
+    lens = [min(cl.shape[0], lmax + 1) if lmax is not None else cl.shape[0] for cl in cls]
+    ld = max(max(lens, default=0), 1)
+    rows = torch.zeros((len(cls), ld), dtype=torch.float64, device=device)
+    for s, (cl, n) in enumerate(zip(cls, lens)):
+        if n > 0:
+            rows[s, :n] = torch.as_tensor(cl[:n]).to(device=device, dtype=torch.float64)
+    return rows, lens
+
+
 def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, nside: int | None = None, pixwin=None):
     """
     Apply discretisation effects to angular power spectra (glass/fields.py:239-300): truncate
@@ -300,7 +312,9 @@ def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, n
 
     The window is ``hp.pixwin(nside, lmax=lmax)`` -- generated numerically here
     (glass_b200.pixwin), read from healpy's data files in the reference (glass/healpix.py:313-356)
-    -- or the caller's own table ``pixwin=`` (extension).  Host-side: the spectra are tiny.
+    -- or the caller's own table ``pixwin=`` (extension).  Spectra given as CUDA tensors stay on the
+    device: they are packed as rows and windowed by ONE launch (``glb_cls_window``; a real shell set
+    has S(S+1)/2 = 1830 spectra), the results are row views.  NumPy spectra are handled on the host.
     """
     if len(cls) == 0:
         return []
@@ -313,6 +327,17 @@ def discretized_cls(cls, *, lmax: int | None = None, ncorr: int | None = None, n
         if pixwin is None:
             pixwin = hp.pixwin(nside, lmax=lmax)
         pw = pixwin[: lmax + 1] if lmax is not None else pixwin
+    dev = next((cl.device for cl in cls if isinstance(cl, torch.Tensor) and cl.is_cuda), None)
+    if dev is not None and pw is not None:
+        rows, lens = _pack_spectra(cls, lmax, dev)
+        w = torch.as_tensor(np.asarray(pw) if not isinstance(pw, torch.Tensor) else pw).to(device=dev, dtype=torch.float64).contiguous()
+        n = min(rows.shape[1], w.shape[0])
+        out = torch.empty_like(rows)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.glb_cls_window(rows.shape[0], n, rows.shape[1], out.shape[1], rows.data_ptr(), w.data_ptr(), out.data_ptr(), st), "glb_cls_window")
+        return [out[s, : min(k, n)] if k > 0 else cl for s, (cl, k) in enumerate(zip(cls, lens))]
     gls = []
     for cl in cls:
         if cl.shape[0] > 0:
@@ -332,12 +357,47 @@ def effective_cls(cls, weights1, weights2=None, *, lmax: int | None = None):
     """
     Effective angular power spectra from weights (glass/fields.py:607-694):
     ``out[j1 + j2] = sum_{i1, i2} w1[i1, j1] w2[i2, j2] C_l^{i1 i2}``, accumulated in the
-    reference's order (i1 outer, i2 inner) so that the result is bit-identical.
+    reference's order (i1 outer, i2 inner, transposed elements copied when ``weights2`` is not
+    given) so that the result is bit-identical.  With CUDA tensors (spectra or weights) all output
+    spectra come from ONE launch of ``glb_effective_cls`` and stay on the device; NumPy inputs -- a
+    handful of short arrays -- are summed on the host.
     """
     n = nfields_from_nspectra(len(cls))
-    cls = _gls_to_host(cls)
     if lmax is None:
         lmax = max((cl.shape[0] for cl in cls), default=0) - 1
+    same = weights2 is None
+    dev = next((a.device for a in (*cls, weights1, weights2) if isinstance(a, torch.Tensor) and a.is_cuda), None)
+    if dev is None:
+        return _effective_cls_host(cls, n, weights1, weights2, lmax)
+    w1 = torch.as_tensor(weights1).to(device=dev, dtype=torch.float64)
+    w2 = w1 if same else torch.as_tensor(weights2).to(device=dev, dtype=torch.float64)
+    shape1, shape2 = tuple(w1.shape), tuple(w2.shape)
+    for i, shape in enumerate((shape1, shape2)):
+        if not shape or shape[0] != n:
+            msg = f"shape mismatch between fields and weights{i + 1}"
+            raise ValueError(msg)
+    w1 = w1.reshape(n, -1).contiguous()
+    w2 = w1 if same else w2.reshape(n, -1).contiguous()
+    J1, J2, L = w1.shape[1], w2.shape[1], lmax + 1
+    rows, _ = _pack_spectra(cls, lmax, dev)
+    if rows.shape[1] < L:
+        rows = torch.nn.functional.pad(rows, (0, L - rows.shape[1]))
+    out = torch.empty((J1, J2, L), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(
+            lib.glb_effective_cls(n, J1, J2, L, rows.shape[1], int(same), rows.data_ptr(), w1.data_ptr(), w2.data_ptr(), out.data_ptr(), st),
+            "glb_effective_cls",
+        )
+    return out.reshape(shape1[1:] + shape2[1:] + (L,))
+
+
+def _effective_cls_host(cls, n, weights1, weights2, lmax):
+    """NumPy spectra and weights (a handful of short arrays): the same sums on the host."""
+    import itertools
+
+    cls = [_np(cl) for cl in cls]
     weights1 = _np(weights1)
     same = weights2 is None
     weights2 = weights1 if same else _np(weights2)
@@ -346,8 +406,6 @@ def effective_cls(cls, weights1, weights2=None, *, lmax: int | None = None):
         if not shape or shape[0] != n:
             msg = f"shape mismatch between fields and weights{i + 1}"
             raise ValueError(msg)
-    import itertools
-
     if same:
         pairs = itertools.combinations_with_replacement(np.ndindex(shape1[1:]), 2)
     else:

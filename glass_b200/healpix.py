@@ -266,6 +266,90 @@ def ang2pix(nside: int, theta, phi, *, lonlat: bool = False):
     return _out(out.reshape(shape), on_device)
 
 
+def query_strip(nside: int, thetas, *, dtype=None, xp=None):
+    """
+    Mask of the pixels whose centres lie within the colatitude range ``thetas`` (radians)
+    (glass/healpix.py:359-396 -> healpy.query_strip, RING, not inclusive).  ``thetas[0] >= thetas[1]``
+    selects the complement, as in HEALPix.  int64 unless ``dtype`` says otherwise; NumPy array, or a
+    CUDA tensor with ``xp=torch``.
+    """
+    theta1, theta2 = (float(t) for t in thetas)
+    dev = torch.device("cuda", _device_index())
+    out = torch.empty(nside2npix(nside), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.glb_query_strip(int(nside), theta1, theta2, out.data_ptr(), st), "glb_query_strip")
+    if xp is torch:
+        tdt = dtype if isinstance(dtype, torch.dtype) else (torch.int64 if dtype is None else getattr(torch, np.dtype(dtype).name))
+        return out.to(tdt)
+    return out.cpu().numpy().astype(np.int64 if dtype is None else dtype)
+
+
+_OBLIQUITY_J2000 = (23.452294 - 0.0130125 - 1.63889e-6 + 5.02778e-7) * np.pi / 180.0
+# ecliptic -> galactic, the constant matrix of HEALPix / healpy.rotator.get_coordconv_matrix
+_E2G = np.array(
+    [
+        [-0.054882486, -0.993821033, -0.096476249],
+        [0.494116468, -0.110993846, 0.862281440],
+        [-0.867661702, -0.000346354, 0.497154957],
+    ]
+)
+
+
+def _coordconv_matrix(coord) -> np.ndarray:
+    """Matrix taking directions from system coord[0] to coord[1]; G galactic, E ecliptic,
+    C (or Q) equatorial J2000 -- healpy.rotator.get_coordconv_matrix."""
+    if coord is None:
+        return np.identity(3)
+    if isinstance(coord, str):
+        coord = tuple(coord)
+    names = [str(c).upper()[:1].replace("Q", "C") for c in coord]
+    if len(names) == 1:
+        names = names * 2
+    if len(names) != 2 or any(c not in "GEC" for c in names):
+        msg = "Wrong coord: must be a sequence of one or two of 'G', 'E', 'C'"
+        raise TypeError(msg)
+    a, b = names
+    if a == b:
+        return np.identity(3)
+    ce, se = np.cos(_OBLIQUITY_J2000), np.sin(_OBLIQUITY_J2000)
+    e2q = np.array([[1.0, 0.0, 0.0], [0.0, ce, -se], [0.0, se, ce]])
+    g2e, q2e = np.linalg.inv(_E2G), np.linalg.inv(e2q)
+    return {"EG": _E2G, "GE": g2e, "EC": e2q, "CE": q2e, "GC": e2q @ g2e, "CG": _E2G @ q2e}[a + b]
+
+
+class Rotator:
+    """Rotation operator between astronomical coordinate systems (glass/healpix.py:435-471)."""
+
+    def __init__(self, *, coord=None) -> None:
+        self.coord = coord
+        self._matrix = _coordconv_matrix(coord)
+
+    def rotate_map_pixel(self, m):
+        """
+        Rotate a HEALPix map to the new reference frame in pixel space (glass/healpix.py:457-471 ->
+        healpy.Rotator.rotate_map_pixel): every pixel centre of the output is rotated BACK into the
+        input frame, where the input map is interpolated bilinearly between the four nearest pixels
+        of the two neighbouring rings.  One scalar map (what GLASS passes); NumPy in -> NumPy out,
+        CUDA tensor in -> CUDA tensor out.
+        """
+        dev, on_device = _dev_and_kind(m)
+        src = _to(m, dev, torch.float64)
+        if src.ndim != 1:
+            msg = "rotate_map_pixel takes one scalar map here (polarised triplets are not on the GLASS path)"
+            raise NotImplementedError(msg)
+        nside = npix2nside(src.numel())
+        out = torch.empty_like(src)
+        inv = np.ascontiguousarray(np.linalg.inv(self._matrix), dtype=np.float64)
+        rot9 = (C.c_double * 9)(*inv.reshape(-1))
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.glb_rotate_map_pixel(int(nside), rot9, src.data_ptr(), out.data_ptr(), st), "glb_rotate_map_pixel")
+        return _out(out, on_device)
+
+
 def almxfl(alm, fl, *, inplace: bool = False):
     """Multiply alm by a function of l, zero where not defined (glass/healpix.py:111-140)."""
     dev, on_device = _dev_and_kind(alm)

@@ -225,6 +225,28 @@ int glb_ellipticity(int mode, double sigma, const double* d_normals, int64_t n, 
 int glb_redshifts_from_cdf(const double* d_cdf, const double* d_z, int nz, const double* d_u, int64_t n,
                            uint64_t seed, uint32_t stream_id, uint64_t index0, double* d_out, void* stream);
 
+/* ---- visibility masks and spectra helpers --------------------- */
+/* hp.query_strip(nside, thetas, dtype=float64) (glass/healpix.py:359-396 -> healpy.query_strip,
+ * RING, inclusive = False): d_mask[p] = 1.0 for pixels whose centre ring lies in the colatitude
+ * strip, 0.0 elsewhere; theta1 >= theta2 selects the complement [0, theta2] + [theta1, pi]. */
+int glb_query_strip(int64_t nside, double theta1, double theta2, double* d_mask, void* stream);
+/* hp.Rotator(coord=).rotate_map_pixel(m) (glass/healpix.py:457-471 -> healpy): d_out[p] = HEALPix
+ * bilinear interpolation (get_interp_val, four pixels on the two neighbouring rings) of d_in at
+ * rot9 * (centre of pixel p); rot9 = row-major 3x3 matrix of the BACK rotation (healpy's
+ * Rotator.I), host memory.  Not in place. */
+int glb_rotate_map_pixel(int64_t nside, const double* rot9, const double* d_in, double* d_out, void* stream);
+/* glass.discretized_cls (glass/fields.py:290-299), the window step on spectra packed as rows:
+ * d_out[s * ld_out + l] = d_cl[s * ld_in + l] * (d_pw[l] * d_pw[l]) for s < nspec, l < n. */
+int glb_cls_window(int nspec, int n, int64_t ld_in, int64_t ld_out, const double* d_cl, const double* d_pw,
+                   double* d_out, void* stream);
+/* glass.effective_cls (glass/fields.py:682-691): d_out[(j1 * J2 + j2) * L + l] =
+ * sum_{i1, i2 < nf} (d_w1[i1 * J1 + j1] * d_w2[i2 * J2 + j2]) * C_l^{i1 i2}, accumulated in the
+ * reference's order; C^{ij} (i >= j) is row i (i + 1) / 2 + i - j of d_cls[nspec][ld] (zero padded).
+ * symmetric = 1 (weights2 is weights1, d_w2 == d_w1): elements with j1 > j2 are the transposed element's
+ * sum, as the reference copies them (fields.py:689-690). */
+int glb_effective_cls(int nf, int J1, int J2, int L, int64_t ld, int symmetric, const double* d_cls,
+                      const double* d_w1, const double* d_w2, double* d_out, void* stream);
+
 /* host-buffer forms of the two transforms GLASS calls per shell: H2D, kernels, D2H on
  * `stream`, synchronous on return.  These are what a ctypes binding inside
  * glass/healpix.py would call with NumPy buffers. */

@@ -620,3 +620,188 @@ def almxfl(alm, fl, mmax: int | None = None):
     for m in range(lmax + 1):
         alm[alm_index(lmax, m, m) : alm_index(lmax, lmax, m) + 1] *= f[m:]
     return alm
+
+
+# --------------------------------------------------------------------------
+# visibility-mask helpers behind glass.vmap_galactic_ecliptic (glass/observations.py:96-100):
+# healpy.query_strip (glass/healpix.py:389), healpy.Rotator(coord=).rotate_map_pixel
+# (glass/healpix.py:471).  Third-party (healpy >= 1.15.0 / healpix_cxx, absent from the tree):
+# restated from the published HEALPix C++ algorithms -- T_Healpix_Base::ring_above,
+# query_strip_internal, get_ring_info2, get_interpol (bilinear weights of the four pixels on the two
+# neighbouring rings) -- and healpy's rotator conventions (rotator.py: get_coordconv_matrix with the
+# HEALPix ecliptic->galactic matrix and the J2000 obliquity, Rotator.I = inverse rotation,
+# rotate_map_pixel = interpolate the input map at the back-rotated pixel centres).
+# **Parity with the healpy binaries is unpinned.**
+# --------------------------------------------------------------------------
+
+
+def ring_above(nside: int, z):
+    """Index of the ring just north of cos(theta) = z (0 = above the first ring)."""
+    z = np.asarray(z, dtype=np.float64)
+    az = np.abs(z)
+    eq = (nside * (2.0 - 1.5 * z)).astype(np.int64)
+    ir = (nside * np.sqrt(3.0 * (1.0 - az))).astype(np.int64)
+    return np.where(az <= 2.0 / 3.0, eq, np.where(z > 0, ir, 4 * nside - ir - 1))
+
+
+def _ring_small(nside: int, ring: int):
+    """(first pixel, pixels) of ring 0..4 nside-1 (ring 0 is the empty 'ring' above the pole)."""
+    n = nside
+    if ring < n:
+        return 2 * ring * (ring - 1), 4 * ring
+    if ring < 3 * n:
+        return 2 * n * (n - 1) + (ring - n) * 4 * n, 4 * n
+    nr = 4 * n - ring
+    return 12 * n * n - 2 * nr * (nr + 1), 4 * nr
+
+
+def _strip_internal(nside: int, theta1: float, theta2: float, out):
+    ring1 = max(1, 1 + int(ring_above(nside, math.cos(theta1))))
+    ring2 = min(4 * nside - 1, int(ring_above(nside, math.cos(theta2))))
+    sp1, _ = _ring_small(nside, ring1)
+    sp2, rp2 = _ring_small(nside, ring2)
+    if sp1 <= sp2 + rp2:
+        out[sp1 : sp2 + rp2] = 1
+
+
+def query_strip(nside: int, theta1: float, theta2: float):
+    """0/1 mask of the pixels whose centres lie in the colatitude strip (healpy.query_strip,
+    inclusive=False, RING): theta1 < theta2 the strip between them, otherwise its complement."""
+    out = np.zeros(nside2npix(nside))
+    if theta1 < theta2:
+        _strip_internal(nside, theta1, theta2, out)
+    else:
+        _strip_internal(nside, 0.0, theta2, out)
+        _strip_internal(nside, theta1, math.pi, out)
+    return out
+
+
+def _ring_info2(nside: int, ring):
+    """(first pixel, pixels, theta, shifted) of rings 1..4 nside-1, vectorised."""
+    n = nside
+    ring = np.asarray(ring, dtype=np.int64)
+    north = np.where(ring > 2 * n, 4 * n - ring, ring)
+    cap = north < n
+    tmp = north * north / (3.0 * n * n)
+    th_cap = np.arctan2(np.sqrt(tmp * (2.0 - tmp)), 1.0 - tmp)
+    th_eq = np.arccos(np.clip((2 * n - north) * (2.0 / (3.0 * n)), -1.0, 1.0))
+    theta = np.where(cap, th_cap, th_eq)
+    nr = np.where(cap, 4 * north, 4 * n)
+    shifted = np.where(cap, True, ((north - n) & 1) == 0)
+    sp = np.where(cap, 2 * north * (north - 1), 2 * n * (n - 1) + (north - n) * 4 * n)
+    south = north != ring
+    theta = np.where(south, np.pi - theta, theta)
+    sp = np.where(south, 12 * n * n - sp - nr, sp)
+    return sp, nr, theta, shifted
+
+
+def get_interpol(nside: int, theta, phi):
+    """Pixels (4, N) and weights (4, N) of HEALPix's bilinear interpolation (RING)."""
+    n = nside
+    npix = 12 * n * n
+    theta = np.asarray(theta, dtype=np.float64)
+    phi = np.mod(np.asarray(phi, dtype=np.float64), 2.0 * np.pi)
+    ir1 = ring_above(n, np.cos(theta))
+    ir2 = ir1 + 1
+    pix = np.zeros((4,) + theta.shape, dtype=np.int64)
+    wgt = np.zeros((4,) + theta.shape)
+    th = [None, None]
+    for k, ir in enumerate((ir1, ir2)):
+        valid = (ir > 0) & (ir < 4 * n)
+        sp, nr, th[k], shift = _ring_info2(n, np.clip(ir, 1, 4 * n - 1))
+        dphi = 2.0 * np.pi / nr
+        tmp = phi / dphi - 0.5 * shift
+        i1 = np.where(tmp < 0, tmp.astype(np.int64) - 1, tmp.astype(np.int64))
+        w1 = (phi - (i1 + 0.5 * shift) * dphi) / dphi
+        i2 = i1 + 1
+        i1 = np.where(i1 < 0, i1 + nr, i1)
+        i2 = np.where(i2 >= nr, i2 - nr, i2)
+        pix[2 * k] = np.where(valid, sp + i1, 0)
+        pix[2 * k + 1] = np.where(valid, sp + i2, 0)
+        wgt[2 * k] = np.where(valid, 1.0 - w1, 0.0)
+        wgt[2 * k + 1] = np.where(valid, w1, 0.0)
+    theta1, theta2 = th
+    top, bot = ir1 == 0, ir2 == 4 * n
+    mid = ~(top | bot)
+    # north of the first ring: the four pixels of ring 1, the opposite pair weighted by the rest
+    wt = theta / theta2
+    fac = (1.0 - wt) * 0.25
+    w = wgt.copy()
+    p = pix.copy()
+    w[0] = np.where(top, fac, w[0])
+    w[1] = np.where(top, fac, w[1])
+    w[2] = np.where(top, wgt[2] * wt + fac, w[2])
+    w[3] = np.where(top, wgt[3] * wt + fac, w[3])
+    p[0] = np.where(top, (pix[2] + 2) & 3, p[0])
+    p[1] = np.where(top, (pix[3] + 2) & 3, p[1])
+    # south of the last ring
+    wb = (theta - theta1) / (np.pi - theta1)
+    facb = wb * 0.25
+    w[0] = np.where(bot, wgt[0] * (1.0 - wb) + facb, w[0])
+    w[1] = np.where(bot, wgt[1] * (1.0 - wb) + facb, w[1])
+    w[2] = np.where(bot, facb, w[2])
+    w[3] = np.where(bot, facb, w[3])
+    p[2] = np.where(bot, ((pix[0] + 2) & 3) + npix - 4, p[2])
+    p[3] = np.where(bot, ((pix[1] + 2) & 3) + npix - 4, p[3])
+    # between two rings
+    with np.errstate(invalid="ignore", divide="ignore"):
+        wm = (theta - theta1) / (theta2 - theta1)
+        w[0] = np.where(mid, wgt[0] * (1.0 - wm), w[0])
+        w[1] = np.where(mid, wgt[1] * (1.0 - wm), w[1])
+        w[2] = np.where(mid, wgt[2] * wm, w[2])
+        w[3] = np.where(mid, wgt[3] * wm, w[3])
+    return p, w
+
+
+def get_interp_val(m, theta, phi):
+    """healpy.get_interp_val (RING): sum over the four pixels of m[p] w, rows added in order."""
+    m = np.asarray(m, dtype=np.float64)
+    p, w = get_interpol(npix2nside(m.size), theta, phi)
+    return np.sum(m[p] * w, 0)
+
+
+def coordconv_matrix(coord: str):
+    """healpy.rotator.get_coordconv_matrix for coord = two letters of G, E, C (C = Q, equatorial)."""
+    a, b = (c.upper().replace("Q", "C") for c in coord)
+    eps = (23.452294 - 0.0130125 - 1.63889e-6 + 5.02778e-7) * np.pi / 180.0
+    e2g = np.array(
+        [
+            [-0.054882486, -0.993821033, -0.096476249],
+            [0.494116468, -0.110993846, 0.862281440],
+            [-0.867661702, -0.000346354, 0.497154957],
+        ]
+    )
+    e2q = np.array([[1.0, 0.0, 0.0], [0.0, np.cos(eps), -np.sin(eps)], [0.0, np.sin(eps), np.cos(eps)]])
+    g2e = np.linalg.inv(e2g)
+    q2e = np.linalg.inv(e2q)
+    table = {
+        "EG": e2g,
+        "GE": g2e,
+        "EC": e2q,
+        "CE": q2e,
+        "GC": e2q @ g2e,
+        "CG": e2g @ q2e,
+    }
+    return np.identity(3) if a == b else table[a + b]
+
+
+def rotate_map_pixel(m, coord: str):
+    """healpy.Rotator(coord=coord).rotate_map_pixel(m) for one scalar map."""
+    m = np.asarray(m, dtype=np.float64)
+    nside = npix2nside(m.size)
+    theta, phi = pix2ang_centers(nside)
+    mat = np.linalg.inv(coordconv_matrix(coord))  # Rotator.I: back to the original frame
+    st = np.sin(theta)
+    v = mat @ np.stack([st * np.cos(phi), st * np.sin(phi), np.cos(theta)])
+    th = np.arctan2(np.hypot(v[0], v[1]), v[2])
+    ph = np.arctan2(v[1], v[0])
+    return get_interp_val(m, th, ph)
+
+
+def vmap_galactic_ecliptic(nside: int, galactic=(30, 90), ecliptic=(20, 80)):
+    """glass.vmap_galactic_ecliptic (glass/observations.py:51-101) on the functions above."""
+    m = np.ones(nside2npix(nside))
+    m *= 1 - query_strip(nside, *galactic)
+    m = rotate_map_pixel(m, "GC")
+    m *= 1 - query_strip(nside, *ecliptic)
+    return rotate_map_pixel(m, "CE")

@@ -271,3 +271,49 @@ def test_c_oracle_spin_and_analysis_match_numpy_oracle(nside, lmax, spin):
         a = sht_c.map2alm(mp, lmax, niter=niter, ring_w=rw)
         r = H.map2alm(mp, lmax, niter=niter, ring_w=rw)
         assert np.abs(a - r).max() <= 1e-12 * np.abs(r).max()
+
+
+def test_visibility_mask_oracle_properties():
+    """oracle.healpix_ref.query_strip / get_interpol / rotate_map_pixel (restated from the published
+    HEALPix C++ algorithms; healpy itself is absent): the reference's own known answers
+    (tests/core/test_observations.py:20-52) and the defining properties of the interpolation."""
+    from oracle import healpix_ref as H
+
+    for nside in (1, 2, 4, 16):
+        v = H.vmap_galactic_ecliptic(nside)
+        assert v.shape == (12 * nside**2,) and v.min() >= 0 and v.max() <= 1 + 1e-15
+        z = H.vmap_galactic_ecliptic(nside, galactic=(0, 0), ecliptic=(0, 0))
+        assert np.array_equal(z, np.zeros_like(z))  # "no rotation" case of the reference's test
+    nside = 8
+    theta, phi = H.pix2ang_centers(nside)
+    # strip = pixels whose centre colatitude lies between the bounds; reversed bounds = complement
+    s = H.query_strip(nside, 0.7, 2.1)
+    assert np.array_equal(s == 1, (theta > 0.7) & (theta < 2.1))
+    c = H.query_strip(nside, 2.1, 0.7)
+    assert np.array_equal(c == 1, (theta < 0.7) | (theta > 2.1))
+    assert np.all(H.query_strip(nside, 0.0, np.pi) == 1)
+    assert np.all(H.query_strip(nside, 0.0, 0.0) == 1)  # equal bounds: the complement branch, everything
+    # interpolation: weights are a partition of unity, pixels valid, exact at pixel centres
+    rng = np.random.default_rng(5)
+    th, ph = rng.uniform(0, np.pi, 5000), rng.uniform(-7, 7, 5000)
+    p, w = H.get_interpol(nside, th, ph)
+    assert np.abs(w.sum(0) - 1).max() < 1e-15 and w.min() > -1e-15 and p.min() >= 0 and p.max() < 12 * nside**2
+    m = rng.random(12 * nside**2)
+    np.testing.assert_allclose(H.get_interp_val(m, theta, phi), m, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(H.rotate_map_pixel(m, "CC"), m, rtol=0, atol=1e-13)
+    # second-order accurate for a smooth function away from the poles
+    f = lambda t, q: np.cos(t) + 0.3 * np.sin(t) * np.cos(q)  # noqa: E731
+    errs = []
+    away = (th > 0.3) & (th < np.pi - 0.3)
+    for n in (16, 32, 64):
+        t, q = H.pix2ang_centers(n)
+        errs.append(np.abs(H.get_interp_val(f(t, q), th, ph) - f(th, ph))[away].max())
+    assert errs[1] < errs[0] / 3 and errs[2] < errs[1] / 3
+    # coordinate systems: rotations, the poles where the almanac puts them
+    for cpair in ("GC", "CE", "EG"):
+        M = H.coordconv_matrix(cpair)
+        assert np.abs(M @ M.T - np.eye(3)).max() < 2e-9
+    x, y, z = H.coordconv_matrix("GC") @ np.array([0.0, 0.0, 1.0])
+    assert abs(np.degrees(np.arctan2(y, x)) % 360 - 192.86) < 0.01 and abs(np.degrees(np.arcsin(z)) - 27.13) < 0.01
+    x, y, z = H.coordconv_matrix("EC") @ np.array([0.0, 0.0, 1.0])
+    assert abs(np.degrees(np.arctan2(y, x)) % 360 - 270) < 1e-9 and abs(np.degrees(np.arcsin(z)) - 66.56) < 0.01
