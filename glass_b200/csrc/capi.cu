@@ -11,6 +11,7 @@ int plan_build(glb_plan* pl);
 void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
+int sht_alm2phase_ozaki(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false, int p2p_buffer = -1);
 unsigned long long launch_count();
 int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
@@ -329,6 +330,16 @@ int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* 
                                  (cudaStream_t)stream));
   return sht_alm2phase_group(plan, reinterpret_cast<const double2*>(d_alm), nmaps,
                              reinterpret_cast<double2*>(d_phase), (cudaStream_t)stream);
+}
+
+int glb_debug_alm2phase_int8(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase, void* stream) {
+  GLB_REQUIRE(plan && d_alm && d_phase, "null pointer");
+  GLB_REQUIRE(nmaps == 4 || nmaps == 8, "nmaps must be 4 or 8");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  GLB_CUDA_CHECK(cudaMemsetAsync(d_phase, 0, (size_t)nmaps * plan->nring * (plan->mmax + 1) * sizeof(double2),
+                                 (cudaStream_t)stream));
+  return sht_alm2phase_ozaki(plan, reinterpret_cast<const double2*>(d_alm), nmaps, reinterpret_cast<double2*>(d_phase),
+                             (cudaStream_t)stream);
 }
 
 int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double* d_map, void* stream) {

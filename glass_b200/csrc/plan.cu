@@ -344,6 +344,8 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_tw);
   cudaFree(pl->d_bf);
   cudaFree(pl->d_rec);
+  cudaFree(pl->d_oz);
+  cudaFree(pl->d_oz_toff);
   cudaFree(pl->d_phase);
   cudaFree(pl->d_ch);
   cudaFree(pl->d_sh);

@@ -115,6 +115,11 @@ struct glb_plan {
   double2* d_bf = nullptr;           // concatenated chirp spectra (bit-reversed order, scaled 1/M)
   int64_t bf_total = 0;
 
+  // INT8 tensor-core Legendre path (sht_ozaki.cu), built on first use
+  uint8_t* d_oz = nullptr;           // tile blocks: recurrence coefficients + digit planes of the a_lm coefficients
+  int64_t* d_oz_toff = nullptr;      // [mmax+2] first tile of every m
+  int64_t oz_bytes = 0, oz_tiles = 0;
+
   // workspace
   double* d_rec = nullptr;           // Legendre records  [nrec * (4 + 4*B)]
   double2* d_phase = nullptr;        // [max_batch][nring][mmax+1]

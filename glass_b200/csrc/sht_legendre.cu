@@ -29,6 +29,7 @@
 #include <cstdlib>
 
 #include "plan.h"
+#include "sht_seed.cuh"
 #include "sht_tables.cuh"
 
 namespace glb {
@@ -39,11 +40,6 @@ namespace glb {
 constexpr int LEG_UNROLL = GLB_LEG_UNROLL;  // unroll factor of the FAST loop (development knob)
 constexpr int LEG_KT = 64;      // l-pairs per smem chunk
 constexpr int LEG_STAGES = 4;   // chunks in flight
-constexpr int SCALE_BITS = 512;
-constexpr int BEXP_BIG = 1023 + 256;  // rescale when |p| >= 2^256
-constexpr int BEXP_SIG = 1023 - 70;   // "significant" when scale==0 and |p| >= 2^-70
-
-__device__ __forceinline__ int bexp(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
 
 
 // -------------------------------------------------------------------------------------
@@ -147,47 +143,6 @@ __global__ void __launch_bounds__(PREP_THREADS) sht_prep_kernel(const double2* _
       }
     }
     __syncthreads();
-  }
-}
-
-// -------------------------------------------------------------------------------------
-// lambda_mm(theta) = (-1)^m c_m sin^m(theta) as (value, scale), true = value*2^(512*scale)
-// -------------------------------------------------------------------------------------
-__device__ __forceinline__ void lam_mm_scaled(int m, double sth, double cm_mant, int cm_exp, double& val,
-                                              int& scale) {
-  int e;
-  double bv = frexp(sth, &e);  // sth = bv * 2^e, bv in [0.5, 1)
-  int be = e;
-  double rv = 1.0;
-  int re = 0;
-  int mm = m;
-  while (mm) {
-    if (mm & 1) {
-      rv *= bv;
-      re += be;
-      if (rv < 0.5) {
-        rv *= 2.0;
-        re -= 1;
-      }
-    }
-    bv *= bv;
-    be *= 2;
-    if (bv < 0.5) {
-      bv *= 2.0;
-      be -= 1;
-    }
-    mm >>= 1;
-  }
-  double mant = rv * cm_mant;  // in [0.25, 1)
-  int E = re + cm_exp;
-  if (m & 1) mant = -mant;
-  if (E >= 0) {
-    scale = 0;
-    val = scalbn(mant, E);
-  } else {
-    const int s = (-E) / SCALE_BITS;  // truncation
-    scale = -s;
-    val = scalbn(mant, E + s * SCALE_BITS);  // exponent in (-512, 0]
   }
 }
 

@@ -301,6 +301,9 @@ int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream);
 /* Legendre stage only: alm -> phase array F_m(ring), [nmaps][nring][lmax+1] complex128 */
 int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase,
                         void* stream);
+/* the same stage with the contraction over l on the INT8 tensor cores (tcgen05.mma kind::i8, exact
+ * integer digit products; csrc/sht_ozaki.cu), nmaps = 4 or 8 maps on one recurrence */
+int glb_debug_alm2phase_int8(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase, void* stream);
 /* ring-FFT stage only: phases -> map */
 int glb_debug_phase2map(glb_plan* plan, const double* d_phase, int nmaps, double* d_map,
                         void* stream);
