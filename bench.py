@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NSIDE, LMAX, NCORR = 4096, 8191, 3
-SHELLS_PER_STEP = 4
+SHELLS_PER_STEP = 8  # eight shells share one Legendre recurrence (INT8 tensor-core contraction, csrc/sht_ozaki.cu)
 METRIC = "lognormal HEALPix shells/sec at nside=4096"
 UNIT = "shells/s"
 
@@ -672,6 +672,7 @@ def run_b200(args) -> None:
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic.update(json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))))
     except OSError:
         pass
 
@@ -681,6 +682,44 @@ def run_b200(args) -> None:
             return t["bytes_per_launch"]
         return None
 
+    int8 = int(round(maps_per_launch)) == 8  # groups of eight run the contraction on the INT8 tensor cores
+    roofline = {
+        "kernel": "sht_legendre_ozaki_kernel<32>" if int8 else "sht_legendre_synth_kernel",
+        "bound": "fp64",
+        "achieved": achieved,
+        "peak": peak_tf.value,
+        "unit": "TFLOP/s",
+        "frac": achieved / peak_tf.value,
+        "traffic": traffic_of("sht_legendre_ozaki_kernel" if int8 else "sht_legendre_synth_kernel"),
+        "bound_note": (
+            "SURVEY 8(d) counts this stage in algorithmic FP64 flops against the FP64 vector peak (tcgen05 has no FP64 mode; DMMA "
+            "measured at the same 37 TFLOP/s on the same units, tools/microbench/dmma_mix.cu).  With eight maps per launch only the "
+            "recurrence (2 DFMA per l-pair and ring pair, run twice) stays on that pipe: the contraction over l is an exact Ozaki-type "
+            "integer product on tcgen05.mma kind::i8 with TMEM accumulators (six base-256 digits per operand, 21 digit products), so "
+            "the fraction exceeds 1; what limits the kernel is instruction issue of the digit cutting (ncu: profiles/r02_ncu_int8_legendre.txt), "
+            "neither 'hbm' nor 'tensor'"
+            if int8
+            else "FP64 vector pipe (tcgen05 has no FP64 mode; DMMA measured at the same 37 TFLOP/s on the same units, "
+            "tools/microbench/dmma_mix.cu), so neither 'hbm' nor 'tensor' applies"
+        ),
+        "peak_source": "measured live in this run: register-resident DFMA chains on all SMs "
+        "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
+        "peak_cublas_dgemm_8192": dgemm_tf,
+        "algorithmic_flop_per_launch": alg_flop,
+        "maps_per_launch": maps_per_launch,
+        "ms_per_launch": leg_ms,
+        "share_of_step": ms3[1] / (dev_s * 1e3),
+    }
+    if int8:
+        # executed tensor work: 21 digit products of 128 x (4 B) x 32 MMAs per half tile; N_tri / 2 (ring pair, l-pair) units
+        int8_ops = 2.0 * 21 * 4 * maps_per_launch * (ntri / 2.0)
+        roofline["tensor_int8"] = {
+            "ops_per_launch": int8_ops,
+            "achieved_TOPS": int8_ops / (leg_ms * 1e-3) / 1e12,
+            "dense_int8_TOPS_estimate": 2.0 * peaks.get("bf16_tflops", 2250.0),
+            "estimate_source": "twice the measured dense bf16 rate of MEASURED_PEAKS.json (no INT8 entry there)",
+            "note": "upper bound on the executed INT8 work (tiles of silent rings issue no MMA); the tensor pipe is ~18 % busy (ncu)",
+        }
     line = {
         "metric": METRIC,
         "value": value,
@@ -707,24 +746,7 @@ def run_b200(args) -> None:
             "d2h_ceiling": d2h_ceiling,
         },
         "gpu_launches": launches,
-        "roofline": {
-            "kernel": "sht_legendre_synth_kernel",
-            "bound": "fp64",
-            "achieved": achieved,
-            "peak": peak_tf.value,
-            "unit": "TFLOP/s",
-            "frac": achieved / peak_tf.value,
-            "traffic": traffic_of("sht_legendre_synth_kernel"),
-            "bound_note": "FP64 vector pipe (tcgen05 has no FP64 mode; DMMA measured at the same 37 TFLOP/s on the same units, "
-            "tools/microbench/dmma_mix.cu), so neither 'hbm' nor 'tensor' applies",
-            "peak_source": "measured live in this run: register-resident DFMA chains on all SMs "
-            "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)",
-            "peak_cublas_dgemm_8192": dgemm_tf,
-            "algorithmic_flop_per_launch": alg_flop,
-            "maps_per_launch": maps_per_launch,
-            "ms_per_launch": leg_ms,
-            "share_of_step": ms3[1] / (dev_s * 1e3),
-        },
+        "roofline": roofline,
         "stages_ms_per_step": {
             "prep": ms3[0] / K,
             "legendre": ms3[1] / K,

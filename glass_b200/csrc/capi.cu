@@ -12,6 +12,8 @@ void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
 int sht_alm2phase_ozaki(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
+int sht_ozaki_prep(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
+int sht_ozaki_legendre(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st);
 int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false, int p2p_buffer = -1);
 unsigned long long launch_count();
 int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
@@ -118,24 +120,48 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
   cudaStream_t st = (cudaStream_t)stream;
   GLB_CUDA_CHECK(cudaSetDevice(plan->device));
   int done = 0;
+  const int64_t phase_map = (int64_t)plan->nring * (plan->mmax + 1);
   while (done < nmaps) {
-    const int g = group_size(nmaps - done, plan->max_batch);
+    int g = group_size(nmaps - done, plan->max_batch);
+    // Legendre stage on the INT8 tensor cores (csrc/sht_ozaki.cu): eight maps on one recurrence (auto, nside >= 1024),
+    // or groups of four and eight when the plan says so.  Eight maps need eight phase maps: allocated on first use.
+    bool int8 = false;
+    double2* phase = plan->d_phase;
+    if (plan->legendre_mode != 1 && plan->max_batch >= 4 && g == 4) {
+      if (nmaps - done >= 8 && (plan->legendre_mode == 2 || plan->nside >= 1024)) {
+        if (!plan->d_phase_spin &&
+            cudaMalloc((void**)&plan->d_phase_spin, (size_t)8 * phase_map * sizeof(double2)) != cudaSuccess) {
+          cudaGetLastError();  // not enough memory: stay with groups of four
+          plan->d_phase_spin = nullptr;
+        }
+        if (plan->d_phase_spin) {
+          g = 8;
+          int8 = true;
+          phase = plan->d_phase_spin;
+        }
+      }
+      if (!int8 && plan->legendre_mode == 2) int8 = true;
+    }
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (plan->timing) {
       for (int i = 0; i < 4; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
       GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
     }
-    int rc = sht_prep_group(plan, reinterpret_cast<const double2*>(d_alm) + (int64_t)done * plan->nalm, g, st);
+    const double2* alm = reinterpret_cast<const double2*>(d_alm) + (int64_t)done * plan->nalm;
+    int rc = int8 ? sht_ozaki_prep(plan, alm, g, st) : sht_prep_group(plan, alm, g, st);
     if (rc != GLB_OK) return rc;
     if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
-    rc = sht_legendre_group(plan, g, plan->d_phase, st);
+    rc = int8 ? sht_ozaki_legendre(plan, g, phase, st) : sht_legendre_group(plan, g, phase, st);
     if (rc != GLB_OK) return rc;
     if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[2], st));
-    double* outs[4];
-    for (int b = 0; b < g; ++b) outs[b] = d_map + (int64_t)(done + b) * plan->npix;
-    rc = sht_phase2map_group(plan, plan->d_phase, g, outs, h_transform ? h_transform + done : nullptr,
-                             h_tparams ? h_tparams + 2 * done : nullptr, nullptr, st);
-    if (rc != GLB_OK) return rc;
+    for (int h = 0; h < g; h += 4) {  // ring FFTs in groups of at most four maps
+      const int gh = g - h < 4 ? g - h : 4;
+      double* outs[4];
+      for (int b = 0; b < gh; ++b) outs[b] = d_map + (int64_t)(done + h + b) * plan->npix;
+      rc = sht_phase2map_group(plan, phase + (int64_t)h * phase_map, gh, outs, h_transform ? h_transform + done + h : nullptr,
+                               h_tparams ? h_tparams + 2 * (done + h) : nullptr, nullptr, st);
+      if (rc != GLB_OK) return rc;
+    }
     if (plan->timing) {
       GLB_CUDA_CHECK(cudaEventRecord(ev[3], st));
       for (int i = 0; i < 4; ++i) plan->ev_pool.push_back(ev[i]);
@@ -144,6 +170,13 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
     }
     done += g;
   }
+  return GLB_OK;
+}
+
+int glb_plan_set_legendre_mode(glb_plan* plan, int mode) {
+  GLB_REQUIRE(plan != nullptr, "plan is null");
+  GLB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (FP64) or 2 (INT8)");
+  plan->legendre_mode = mode;
   return GLB_OK;
 }
 

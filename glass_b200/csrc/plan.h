@@ -119,6 +119,7 @@ struct glb_plan {
   uint8_t* d_oz = nullptr;           // tile blocks: recurrence coefficients + digit planes of the a_lm coefficients
   int64_t* d_oz_toff = nullptr;      // [mmax+2] first tile of every m
   int64_t oz_bytes = 0, oz_tiles = 0;
+  int legendre_mode = 0;             // 0 auto (INT8 for groups of eight maps at nside >= 1024), 1 FP64 only, 2 INT8 for groups of four and eight
 
   // workspace
   double* d_rec = nullptr;           // Legendre records  [nrec * (4 + 4*B)]

@@ -34,8 +34,9 @@ from . import _lib, grf
 from . import healpix as hp
 from . import rng as _rng
 
-# how many shells share one Legendre recurrence (1, 2 or 4)
-SHT_BATCH = 4
+# how many shells are synthesised together (up to 8): eight share one recurrence on the INT8 tensor-core
+# Legendre path (nside >= 1024), smaller groups share one on the FP64 pipe in fours, twos or alone
+SHT_BATCH = 8
 
 
 class _PinnedPool:
@@ -718,7 +719,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
         wanted = shells if callable(shells) else (lambda j, _s=frozenset(int(i) for i in shells): j in _s)
     with torch.cuda.device(device):
         sampler = _ShellSampler(gls, nside, ncorr, rng, device, wanted)
-        B = max(1, min(int(SHT_BATCH), 4))
+        B = max(1, min(int(SHT_BATCH), 8))
         npix = hp.nside2npix(nside)
         copy_stream = None if on_device else torch.cuda.Stream(device)
         state = {"error": None}

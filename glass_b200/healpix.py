@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Sequence
 
 import numpy as np
@@ -55,6 +56,9 @@ def _device_index(device=None) -> int:
     return torch.device(device).index or 0
 
 
+LEGENDRE_MODES = {"auto": 0, "fp64": 1, "int8": 2}
+
+
 class Plan:
     """Owner of a ``glb_plan`` (ring tables, twiddles, chirp spectra, workspace)."""
 
@@ -68,6 +72,17 @@ class Plan:
         h = C.c_void_p()
         _lib.check(self.lib.glb_plan_create(C.byref(h), self.nside, self.lmax, self.max_batch, self.device), "glb_plan_create")
         self.handle = h
+        mode = os.environ.get("GLB_LEGENDRE", "auto").lower()
+        if mode not in LEGENDRE_MODES:
+            raise ValueError(f"GLB_LEGENDRE must be one of {sorted(LEGENDRE_MODES)}")
+        self.set_legendre_mode(mode)
+
+    def set_legendre_mode(self, mode: str) -> None:
+        """Where the contraction over l of the scalar synthesis runs: "auto" (groups of eight maps on the
+        INT8 tensor cores at nside >= 1024, the FP64 pipe otherwise), "fp64", or "int8" (groups of four and
+        eight maps at any nside).  See ``glb_plan_set_legendre_mode``."""
+        _lib.check(self.lib.glb_plan_set_legendre_mode(self.handle, LEGENDRE_MODES[mode]), "glb_plan_set_legendre_mode")
+        self.legendre_mode = mode
 
     def __del__(self):
         try:

@@ -297,6 +297,12 @@ uint64_t glb_kernel_launch_count(void);
  * events (MEASURED_PEAKS.json has no FP64 entry). */
 int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream);
 
+/* Where the Legendre stage of glb_alm2map runs its contraction over l (the recurrence itself is always FP64):
+ * 0 = auto: groups of EIGHT maps on the INT8 tensor cores (tcgen05.mma kind::i8, exact integer digit products,
+ * csrc/sht_ozaki.cu) at nside >= 1024, everything else on the FP64 pipe; 1 = FP64 pipe only; 2 = INT8 tensor cores
+ * for groups of four and eight maps at any nside.  Both agree to ~1e-11 of the largest phase. */
+int glb_plan_set_legendre_mode(glb_plan* plan, int mode);
+
 /* ---- debug / test taps (stable, used by tests/ only) --------------------------------- */
 /* Legendre stage only: alm -> phase array F_m(ring), [nmaps][nring][lmax+1] complex128 */
 int glb_debug_alm2phase(glb_plan* plan, const double* d_alm, int nmaps, double* d_phase,

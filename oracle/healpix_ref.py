@@ -701,6 +701,7 @@ def get_interpol(nside: int, theta, phi):
     npix = 12 * n * n
     theta = np.asarray(theta, dtype=np.float64)
     phi = np.mod(np.asarray(phi, dtype=np.float64), 2.0 * np.pi)
+    phi = np.where(phi >= 2.0 * np.pi, 0.0, phi)  # fmodulo: a tiny negative angle must not round to 2 pi
     ir1 = ring_above(n, np.cos(theta))
     ir2 = ir1 + 1
     pix = np.zeros((4,) + theta.shape, dtype=np.int64)

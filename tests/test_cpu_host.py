@@ -652,7 +652,7 @@ def test_generate_host_flow_golden(monkeypatch):
         # the weights come from K1's arithmetic (another summation order than NumPy's matmul): 1e-13
         close = lambda a, b: np.abs(a - b).max() <= 1e-13 * np.abs(b).max()  # noqa: E731
         assert close(np.concatenate([a for a, _t in fed]), gold[f"grf_alm_{name}"])
-        assert [a.shape[0] for a, _t in fed] == ([4] if nshell == 4 else [4, 1])  # batches of SHT_BATCH shells
+        assert [a.shape[0] for a, _t in fed] == [nshell]  # one batch: nshell <= SHT_BATCH = 8 shells
         assert all(t == (L.T_NORMAL, 0.0, 1.0) for _a, tr in fed for t in tr)
         # a rank's shard: only its shells are synthesised, from the same deviates
         fed.clear()
