@@ -74,6 +74,31 @@ __device__ __forceinline__ void oz_scales(int eb, double& s, double& inv) {
   }
 }
 
+// mbarrier wait with a watchdog: a protocol error becomes a launch failure instead of a hung GPU
+template <bool BACKOFF = false>
+__device__ __forceinline__ void oz_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (BACKOFF) __nanosleep(200);  // the issuing thread: do not take issue slots from the producers of its sub-partition
+    if ((spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();  // two seconds in one wait: never in a correct run
+    }
+  }
+}
+
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -101,6 +126,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices, `sbo` bytes
@@ -147,6 +176,7 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
   using T = OzTile<NC>;
   constexpr int REC = 4 + 16;
   __shared__ int s_max[16];
+  __shared__ __align__(16) double s_rec[OZ_KT][REC + 1];     // one tile of records (+1: the rows are read column-wise)
   __shared__ __align__(16) int8_t s_dig[OZ_ND * 16][OZ_KT];  // [digit * 16 + column][k]
   const int m = blockIdx.y, k = threadIdx.x;
   const int K = (lmax - m) / 2 + 1;
@@ -156,43 +186,43 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
   const double* rm = rec + roff[m] * REC;
   const double* am = tab + roff[m] * PREP_TAB + TAB_ALPHA;
   auto tile_field = [&](int t) { return (__double2hiint(am[(int64_t)t * OZ_KT * PREP_TAB]) >> 20) & 0x7ff; };  // exponent field of alpha
+  // coalesced copy of tile t's records (contiguous in global memory) into s_rec, zero rows beyond K
+  auto stage_tile = [&](int t) {
+    const int n = min(OZ_KT, K - t * OZ_KT) * REC;  // doubles
+    const double* src = rm + (int64_t)t * OZ_KT * REC;
+    for (int i = k; i < OZ_KT * REC; i += OZ_KT) s_rec[i / REC][i % REC] = i < n ? src[i] : 0.0;
+  };
   if (k < 16) s_max[k] = 0;
-  __syncthreads();
   // largest |A 2^-sig| per column over the super-tile
-  {
-    int mx[16];
+  int mx[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) mx[c] = 0;
-    for (int t = t0; t < t1; ++t) {
-      const int kk = t * OZ_KT + k;
-      if (kk >= K) break;
-      const double down = __hiloint2double((2046 - tile_field(t)) << 20, 0);  // 2^-sig
-      const double* r = rm + (int64_t)kk * REC;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) mx[c] = max(mx[c], __double2hiint(r[4 + c] * down) & 0x7fffffff);
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) atomicMax(&s_max[c], mx[c]);
-  }
-  __syncthreads();
+  for (int c = 0; c < 16; ++c) mx[c] = 0;
   for (int t = t0; t < t1; ++t) {
-    const int kk = t * OZ_KT + k;
-    const bool valid = kk < K;
-    const double* r = rm + (int64_t)kk * REC;
+    __syncthreads();
+    stage_tile(t);
+    __syncthreads();
+    const double down = __hiloint2double((2046 - tile_field(t)) << 20, 0);  // 2^-sig
+#pragma unroll
+    for (int c = 0; c < 16; ++c) mx[c] = max(mx[c], __double2hiint(s_rec[k][4 + c] * down) & 0x7fffffff);
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) atomicMax(&s_max[c], mx[c]);
+  for (int t = t0; t < t1; ++t) {
+    __syncthreads();
+    if (t1 - t0 > 1 || t == t0) stage_tile(t);  // (a one-tile super-tile is still staged)
+    __syncthreads();
     uint8_t* blk = oz + (toff[m] + t) * (int64_t)T::BYTES;
     const int field = tile_field(t);
     const double down = __hiloint2double((2046 - field) << 20, 0);
     if (col0 == 0) {
-      double4 ab = valid ? *reinterpret_cast<const double4*>(r) : make_double4(0.0, 0.0, 0.0, 0.0);
-      reinterpret_cast<double4*>(blk)[k] = ab;
+      reinterpret_cast<double4*>(blk)[k] = make_double4(s_rec[k][0], s_rec[k][1], s_rec[k][2], s_rec[k][3]);
       if (k == 0) *reinterpret_cast<double*>(blk + T::PSC_OFF) = __hiloint2double(field << 20, 0);  // 2^sig
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       double sc, inv;
       oz_scales(s_max[c] >> 20, sc, inv);
-      const double v = valid ? r[4 + c] * down : 0.0;
-      const double tt = fma(v, sc, OZ_MAGIC);
+      const double tt = fma(s_rec[k][4 + c] * down, sc, OZ_MAGIC);
       const uint32_t lo = (uint32_t)__double2loint(tt), hi = (uint32_t)__double2hiint(tt);
 #pragma unroll
       for (int j = 0; j < OZ_ND; ++j) {
@@ -209,7 +239,6 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
       const uint4 q = *reinterpret_cast<const uint4*>(&s_dig[row][ch * 16]);
       *reinterpret_cast<uint4*>(blk + T::AB_BYTES + ch * T::BOP_LBO + (j * NC + col0 + c) * 16) = q;
     }
-    __syncthreads();
   }
 }
 
@@ -252,12 +281,14 @@ __device__ __forceinline__ double oz_i2d(int x) {
   return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
 }
 
-// pass 2 of one half tile (32 l-pairs from k0): the recurrence, six digit planes of every value to
-// the operand buffer (row `dst`), and the largest |p| that was cut (high word).  FAST: every ring of
-// the warp is at scale 0 (no range tests); FULL: all 32 l-pairs exist.
+// cut of one half tile (32 l-pairs from k0): the recurrence, six digit planes of every value to the
+// operand buffer (row `dst`).  Range check: every FMA result must lie in [2^52, 2^52 + 2^48), i.e.
+// its high word is 0x4330xxxx -- `hor` / `hand` collect the OR and the AND of the high words.
+// FAST: every ring of the warp is at scale 0 (no range tests); FULL: all 32 l-pairs exist.
 template <bool FAST, bool FULL>
-__device__ __forceinline__ void oz_pass2_half(const double* __restrict__ ab, int k0, int kc, double x2, double scale,
-                                              double& p1, double& p2, int& sc, int& maxhi, uint8_t* __restrict__ dst) {
+__device__ __forceinline__ void oz_cut_half(const double* __restrict__ ab, int k0, int kc, double x2, double scale,
+                                            double& p1, double& p2, int& sc, uint32_t& hor, uint32_t& hand,
+                                            uint8_t* __restrict__ dst) {
   const double SMALL = 7.458340731200207e-155;  // 2^-512
 #pragma unroll 1
   for (int ch = 0; ch < 2; ++ch) {
@@ -270,7 +301,6 @@ __device__ __forceinline__ void oz_pass2_half(const double* __restrict__ ab, int
         const int k = k0 + ch * 16 + q * 4 + i;
         const bool in = FULL || k < kc;
         const double v = (in && (FAST || sc == 0)) ? p2 : 0.0;
-        maxhi = max(maxhi, __double2hiint(v) & 0x7fffffff);
         tt[i] = fma(v, scale, OZ_MAGIC);
         if (in) {
           const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * k);
@@ -285,12 +315,19 @@ __device__ __forceinline__ void oz_pass2_half(const double* __restrict__ ab, int
           }
         }
       }
+      const uint32_t h0 = (uint32_t)__double2hiint(tt[0]), h1 = (uint32_t)__double2hiint(tt[1]);
+      const uint32_t h2 = (uint32_t)__double2hiint(tt[2]), h3 = (uint32_t)__double2hiint(tt[3]);
+      hor = (hor | h0 | h1) | (h2 | h3);
+      hand = (hand & h0 & h1) & (h2 & h3);
       oz_planes(tt, w[q]);
     }
 #pragma unroll
     for (int j = 0; j < OZ_ND; ++j)
       *reinterpret_cast<uint4*>(dst + j * OZ_A_SLICE + ch * (OZ_ROWS * 16)) = make_uint4(w[0][j], w[1][j], w[2][j], w[3][j]);
   }
+}
+__device__ __forceinline__ bool oz_in_range(uint32_t hor, uint32_t hand) {
+  return (hor & 0xffff0000u) == 0x43300000u && (hand & 0xfff00000u) == 0x43300000u;
 }
 
 // recurrence alone over l-pairs [k0, k1) of a tile, every ring at scale 0: largest |p| that enters the sum
@@ -311,18 +348,36 @@ __device__ __forceinline__ int oz_scan_fast(const double* __restrict__ ab, int k
 // Ring scales.  |lambda_lm(theta)| <= min(sqrt((2l+1)/4pi), c / sqrt(sin theta)) and p 2^sig is lambda up to a
 // factor below two, so ONE absolute bound per ring serves every tile (2^3 on most rings: 48-bit
 // fixed point with an absolute error of 2^-45 per value, which is what matters for a map whose error
-// is measured against its largest pixel).  Fixed scales mean that the integer sums of consecutive tiles can stay
-// in TMEM (a "run", at most one super-tile = one set of column scales) and D is read and converted
-// once per run ("flush") instead of once per tile.  Every cut checks the bound half tile by half
-// tile, BEFORE the half's MMAs are issued; a ring that exceeds it (never observed) closes the run --
-// everything summed so far is valid -- and the half is cut again with its exact range.
-// A warp whose rings are all still negligible stays silent: it only runs the recurrence (pass 1),
-// and cuts the tile in a second pass once a ring becomes significant; from the first tile cut with
-// every ring at scale 0 on it goes straight to the cut.  The tile's two halves (32 l-pairs, one
-// K = 32 instruction per digit each) are pipelined: the MMAs of a half run while the threads cut
-// the next one.
+// is measured against its largest pixel).  Fixed scales mean that the integer sums of consecutive
+// tiles stay in TMEM and D is read and converted once per super-tile (= one set of column scales,
+// 512 l-pairs) instead of once per tile.
+//
+// Roles.  Four PRODUCER warps own 32 rings each (thread = ring = TMEM lane): they run the recurrence
+// and cut the digits of their rows, half tile by half tile (32 l-pairs = one K = 32 instruction per
+// digit), into the operand buffer.  A fifth warp ISSUES: one thread waits until the four producers
+// have written a half (mbarrier), issues its six MMAs, commits them to the mbarrier that frees the
+// half for the next tile, and keeps the TMA pipeline of tile blocks filled.  There is no CTA-wide
+// barrier in the loop: a warp is only ever held up by the operand half it wants to overwrite.
+//   * A warp whose rings are all still negligible stays silent: its operand rows are zero (its rows
+//     of D therefore stay zero), it only runs the recurrence (pass 1) and cuts the tile in a second
+//     pass once a ring becomes significant; after that it always goes straight to the cut.
+//   * Reading D ("flush") is PRIVATE to a warp: it waits for the MMAs issued so far, loads its 32
+//     lanes, adds them to its FP64 accumulators with its ring scales and the super-tile's column
+//     scales, and clears the lanes (tcgen05.st) -- the MMAs always accumulate.  Every warp flushes
+//     at a super-tile boundary before it cuts the first half of the new super-tile; the issuer
+//     cannot run ahead of that because it needs all four warps' halves.
+//   * Every cut checks the bound (oz_in_range).  A ring that exceeds it (never observed) makes its
+//     warp flush, cut the half again with the exact range of its values, and flush once more when it
+//     returns to the fixed scale.
+constexpr int OZ_THREADS = OZ_ROWS + 32;
+#ifdef GLB_OZ_TIMERS
+constexpr bool OZ_TIMERS = true;  // development: where the producer warps and the issuer spend their cycles (GLB_OZ_DEBUG=1)
+#else
+constexpr bool OZ_TIMERS = false;
+#endif
+
 template <int NC>
-__global__ void __launch_bounds__(OZ_ROWS) sht_legendre_ozaki_kernel(const OzParams p) {
+__global__ void __launch_bounds__(OZ_THREADS) sht_legendre_ozaki_kernel(const OzParams p) {
   using T = OzTile<NC>;
   constexpr int B = NC / 4;
   constexpr int TMEM_COLS = (OZ_ND * NC <= 128) ? 128 : 256;
@@ -331,9 +386,10 @@ __global__ void __launch_bounds__(OZ_ROWS) sht_legendre_ozaki_kernel(const OzPar
   uint8_t* sA = oz_smem;
   uint8_t* sT = oz_smem + OZ_A_BYTES;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(sT + OZ_STAGES * T::BYTES);
-  uint64_t* s_mma = s_full + OZ_STAGES;  // [h]: the MMAs of half h issued so far are done
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mma + 2);
-  int* s_flag = reinterpret_cast<int*>(s_tmem + 1);  // [3] votes of the CTA-wide decisions, rotating
+  uint64_t* s_mma = s_full + OZ_STAGES;   // [h]: the MMAs of half h of a tile are done (or there were none)
+  uint64_t* s_ready = s_mma + 2;          // [h]: the four producer warps have written half h of a tile
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_ready + 2);
+  int* s_emit = reinterpret_cast<int*>(s_tmem + 1);  // [2][2] (tile parity, half): a producer cut this half
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -348,8 +404,10 @@ __global__ void __launch_bounds__(OZ_ROWS) sht_legendre_ozaki_kernel(const OzPar
     for (int s = 0; s < OZ_STAGES; ++s) mbar_init(&s_full[s], 1);
     mbar_init(&s_mma[0], 1);
     mbar_init(&s_mma[1], 1);
+    mbar_init(&s_ready[0], OZ_ROWS / 32);
+    mbar_init(&s_ready[1], OZ_ROWS / 32);
     mbar_fence_init();
-    s_flag[0] = s_flag[1] = s_flag[2] = 0;
+    s_emit[0] = s_emit[1] = s_emit[2] = s_emit[3] = 0;
   }
   if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
   tc_fence_before();
@@ -357,80 +415,130 @@ __global__ void __launch_bounds__(OZ_ROWS) sht_legendre_ozaki_kernel(const OzPar
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  auto issue = [&](int t) {
-    const int s = t % OZ_STAGES;
-    mbar_arrive_expect_tx(&s_full[s], (uint32_t)T::BYTES);
-    bulk_g2s(sT + s * T::BYTES, blk_m + (int64_t)t * T::BYTES, (uint32_t)T::BYTES, &s_full[s]);
-  };
-  if (tid == 0) {
-    for (int t = 0; t < OZ_STAGES - 1 && t < ntiles; ++t) issue(t);
-  }
-
-  // ---- per-thread ring state ----
-  const int r = item.tile * OZ_ROWS + tid;
-  const bool live = (r < p.npair) && (p.mlim[min(r, p.npair - 1)] >= m);
-  const double zw = p.z[min(item.tile * OZ_ROWS + (tid & ~31), p.npair - 1)];
-  const bool use_u = zw * zw >= 0.5;  // the warp's recurrence variable (sht_legendre.cu)
-  const int ab_off = use_u ? 2 : 0;
-  double p1 = 0.0, p2 = 0.0, x2 = 0.0, zz = 0.0;
-  int sc = 0, eg_ring = 1023;
-  if (live) {
-    zz = p.z[r];
-    const double sth = p.sth[r];
-    x2 = use_u ? sth * sth : zz * zz;
-    lam_mm_scaled(m, sth, p.cm_mant[m], p.cm_exp[m], p2, sc);
-    // exponent field bounding |p 2^sig| on this ring: 2^(eg_ring - 1022) > min(bound_pole, bound_c / sqrt(sin theta))
-    eg_ring = ((__double2hiint(fmin(p.bound_pole, p.bound_c * rsqrt(sth))) >> 20) & 0x7ff) + 1;
-  }
-  double acc[NC];
+  if (warp == OZ_ROWS / 32) {
+    // =========================== issuer ===========================
+    if (lane == 0) {
+      auto issue = [&](int t) {
+        const int s = t % OZ_STAGES;
+        mbar_arrive_expect_tx(&s_full[s], (uint32_t)T::BYTES);
+        bulk_g2s(sT + s * T::BYTES, blk_m + (int64_t)t * T::BYTES, (uint32_t)T::BYTES, &s_full[s]);
+      };
+      for (int t = 0; t < OZ_STAGES - 1 && t < ntiles; ++t) issue(t);
+      bool first = true;  // D has not been written yet
+      long long iw = 0, ii = 0, iq = (OZ_TIMERS && p.dbg) ? clock64() : 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int stage = t % OZ_STAGES;
+        const uint8_t* tp = sT + stage * T::BYTES;
+        const uint32_t par = (uint32_t)(t & 1);
+        const int kc = min(OZ_KT, K - t * OZ_KT);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        for (int h = 0; h < 2; ++h) {
+          oz_wait<true>(&s_ready[h], par);
+          if (OZ_TIMERS && p.dbg) {
+            const long long now = clock64();
+            iw += now - iq;
+            iq = now;
+          }
+          if (h == 0 && t + OZ_STAGES - 1 < ntiles) {
+            // stage (t - 1) % OZ_STAGES: its MMAs are done, the producers have moved on to tile t
+            if (t > 0) oz_wait(&s_mma[1], par ^ 1u);
+            issue(t + OZ_STAGES - 1);
+          }
+          int* flag = &s_emit[(t & 1) * 2 + h];
+          const bool any = *reinterpret_cast<volatile int*>(flag) != 0 && (h == 0 || kc > 32);
+          *flag = 0;
+          if (any) {
+            oz_wait(&s_full[stage], (uint32_t)((t / OZ_STAGES) & 1));  // (the producers have seen it already)
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA) + h * HALF, b0 = smem_u32(tp + T::AB_BYTES) + h * 2 * T::BOP_LBO;
+#pragma unroll
+            for (int a = OZ_ND - 1; a >= 0; --a) {
+              const uint64_t ad = umma_desc(a0 + a * OZ_A_SLICE, OZ_ROWS * 16, 128);
+              const uint64_t bd = umma_desc(b0 + NC * (OZ_ND - 1 - a) * 16, T::BOP_LBO, 128);
+              umma_i8(tmem, ad, bd, umma_idesc_i8(NC * (a + 1)), (first && a == OZ_ND - 1) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(&s_mma[h]);
+          } else {
+            mbar_arrive(&s_mma[h]);
+          }
+          if (OZ_TIMERS && p.dbg) {
+            const long long now = clock64();
+            ii += now - iq;
+            iq = now;
+          }
+        }
+      }
+      if (OZ_TIMERS && p.dbg) {
+        atomicAdd(p.dbg + 8, (unsigned long long)iw);
+        atomicAdd(p.dbg + 9, (unsigned long long)ii);
+      }
+    }
+  } else {
+    // =========================== producers ===========================
+    const int r = item.tile * OZ_ROWS + tid;
+    const bool live = (r < p.npair) && (p.mlim[min(r, p.npair - 1)] >= m);
+    const double zw = p.z[min(item.tile * OZ_ROWS + (tid & ~31), p.npair - 1)];
+    const bool use_u = zw * zw >= 0.5;  // the warp's recurrence variable (sht_legendre.cu)
+    const int ab_off = use_u ? 2 : 0;
+    double p1 = 0.0, p2 = 0.0, x2 = 0.0, zz = 0.0;
+    int sc = 0, eg_ring = 1023;
+    double bound = 1.0;
+    if (live) {
+      zz = p.z[r];
+      const double sth = p.sth[r];
+      x2 = use_u ? sth * sth : zz * zz;
+      lam_mm_scaled(m, sth, p.cm_mant[m], p.cm_exp[m], p2, sc);
+      // bound on |p 2^sig| on this ring and its exponent field: 2^(eg_ring - 1022) > bound
+      bound = fmin(p.bound_pole, p.bound_c * rsqrt(sth));
+      eg_ring = (__double2hiint(bound) >> 20) & 0x7ff;
+    }
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    uint8_t* dst = sA + tid * 16;
+    // silent rows are zero digits
+#pragma unroll
+    for (int j = 0; j < OZ_ND; ++j)
+#pragma unroll
+      for (int ch = 0; ch < OZ_KT / 16; ++ch)
+        *reinterpret_cast<uint4*>(dst + j * OZ_A_SLICE + ch * (OZ_ROWS * 16)) = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
 
-  const double SMALL = 7.458340731200207e-155;  // 2^-512
-  int nc0 = 0, nc1 = 0;            // commits so far on s_mma[0], s_mma[1] (CTA-uniform)
-  int nsync = 0;                   // votes so far (CTA-uniform)
-  bool run_open = false;           // CTA-uniform: D holds sums that have not been read
-  bool run_rows = false;           // warp-uniform: this warp has rows in them
-  int run_stage = 0;               // a resident tile block of the run's super-tile (column scales)
-  double run_inv = 0.0;            // inverse ring scale of the run
-  int eg = 0;                      // exponent field bounding this ring's |p 2^sig| in the run
-  double scale = 0.0;
-  bool awake = false;              // warp-uniform: the warp has cut a tile with every ring at scale 0 (no pass 1 any more)
+    const double SMALL = 7.458340731200207e-155;  // 2^-512
+    auto count = [&](int i) {
+      if (p.dbg && lane == 0) atomicAdd(p.dbg + i, 1ull);
+    };
+    long long tm[6] = {0, 0, 0, 0, 0, 0}, tq = 0;  // development: cycles in wait-TMA, pass 1, wait-operand, cut, fence + arrive, flush
+    auto tick = [&](int i) {
+      if (OZ_TIMERS && p.dbg) {
+        const long long now = clock64();
+        tm[i] += now - tq;
+        tq = now;
+      }
+    };
+    if (OZ_TIMERS && p.dbg) tq = clock64();
+    bool awake = false;   // warp-uniform: the warp cuts (its rows of D are in use)
+    bool dirty = false;   // warp-uniform: its lanes of D hold sums that have not been read
+    int eg = 0;           // exponent field bounding this ring's |p 2^sig| at the scale in use
+    double scale = 0.0, run_inv = 0.0;
+    int run_stage = 0;    // a resident tile block of the current super-tile (column scales)
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
 
-  // CTA-wide OR of a few bits (one barrier)
-  auto vote = [&](int bits) -> int {
-    int* f = &s_flag[nsync % 3];
-    bits = __reduce_or_sync(0xffffffffu, bits);
-    if (lane == 0 && bits) atomicOr(f, bits);
-    __syncthreads();
-    const int res = *f;
-    if (tid == 0) s_flag[(nsync + 2) % 3] = 0;
-    ++nsync;
-    return res;
-  };
-  // every MMA issued so far is complete
-  auto mma_wait_all = [&]() {
-    if (nc0) mbar_wait(&s_mma[0], (uint32_t)((nc0 - 1) & 1));
-    if (nc1) mbar_wait(&s_mma[1], (uint32_t)((nc1 - 1) & 1));
-  };
-  // close the run: D -> FP64 accumulators (a barrier follows before the next MMA is issued)
-  auto count = [&](int i) {
-    if (p.dbg && lane == 0) atomicAdd(p.dbg + i, 1ull);
-  };
-  auto flush = [&]() {
-    count(0 + (run_rows ? 1 : 0));  // warp-flushes without / with rows
-    mma_wait_all();
-    tc_fence_after();
-    if (run_rows) {
-      const uint8_t* tp = sT + run_stage * T::BYTES;
-      const double* invA = reinterpret_cast<const double*>(tp + T::INVA_OFF);
-      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // this warp's lanes of D -> FP64 accumulators, lanes cleared.  `t`, `h`: the last half whose MMAs were issued.
+    auto flush = [&](int t, int h) {
+      count(1);
+      oz_wait(&s_mma[h], (uint32_t)(t & 1));  // in order: everything issued before it is complete as well
+      tc_fence_after();
+      const double* invA = reinterpret_cast<const double*>(sT + run_stage * T::BYTES + T::INVA_OFF);
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
         uint32_t d[OZ_ND][8];
 #pragma unroll
         for (int g = 0; g < OZ_ND; ++g) tmem_ld8(lane_base + g * NC + c0, d[g]);
         tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < OZ_ND; ++g) tmem_st8_zero(lane_base + g * NC + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           double val = oz_i2d((int)d[OZ_ND - 1][i]);
@@ -439,218 +547,173 @@ __global__ void __launch_bounds__(OZ_ROWS) sht_legendre_ozaki_kernel(const OzPar
           acc[c0 + i] = fma(val, run_inv * invA[c0 + i], acc[c0 + i]);
         }
       }
-    }
-    tc_fence_before();
-    run_open = false;
-    run_rows = false;
-  };
-  // the six MMAs of one half tile (one thread)
-  auto mma_half = [&](const uint8_t* tp, int h, bool first) {
-    const uint32_t a0 = smem_u32(sA) + h * HALF, b0 = smem_u32(tp + T::AB_BYTES) + h * 2 * T::BOP_LBO;
-#pragma unroll
-    for (int a = OZ_ND - 1; a >= 0; --a) {
-      const uint64_t ad = umma_desc(a0 + a * OZ_A_SLICE, OZ_ROWS * 16, 128);
-      const uint64_t bd = umma_desc(b0 + NC * (OZ_ND - 1 - a) * 16, T::BOP_LBO, 128);
-      umma_i8(tmem, ad, bd, umma_idesc_i8(NC * (a + 1)), (first && a == OZ_ND - 1) ? 0u : 1u);
-    }
-  };
+      tmem_st_wait();
+      tc_fence_before();
+      dirty = false;
+    };
 
-  for (int t = 0; t < ntiles; ++t) {
-    const int stage = t % OZ_STAGES;
-    mbar_wait(&s_full[stage], (uint32_t)((t / OZ_STAGES) & 1));
-    const uint8_t* tp = sT + stage * T::BYTES;
-    const double* ab = reinterpret_cast<const double*>(tp) + ab_off;
-    const int kc = min(OZ_KT, K - t * OZ_KT);
-    const bool full = kc == OZ_KT;
-    uint8_t* dst = sA + tid * 16;
-    const double psc = *reinterpret_cast<const double*>(tp + T::PSC_OFF);  // the tile's 2^sig: p is cut as p 2^sig
-    const int sig = ((__double2hiint(psc) >> 20) & 0x7ff) - 1023;
-    const bool newsup = (t % OZ_SUP) == 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int stage = t % OZ_STAGES;
+      oz_wait(&s_full[stage], (uint32_t)((t / OZ_STAGES) & 1));
+      tick(0);
+      const uint8_t* tp = sT + stage * T::BYTES;
+      const double* ab = reinterpret_cast<const double*>(tp) + ab_off;
+      const int kc = min(OZ_KT, K - t * OZ_KT);
+      const bool full = kc == OZ_KT;
+      const double psc = *reinterpret_cast<const double*>(tp + T::PSC_OFF);  // the tile's 2^sig: p is cut as p 2^sig
+      const int sig = ((__double2hiint(psc) >> 20) & 0x7ff) - 1023;
+      const uint32_t prev = (uint32_t)((t & 1) ^ 1);
 
-    const double s_p1 = p1, s_p2 = p2;
-    const int s_sc = sc;
-    const bool fast = __all_sync(0xffffffffu, sc == 0);
-    const bool has = run_open && run_rows;  // this warp has valid sums in D
-    // ---- this warp's part in the tile: cut (emit) or silent; the ring scale is the fixed absolute one
-    //      (p.eg_fix bounds every |lambda_lm|) unless a value should ever exceed it ----
-    bool one, emit;
-    int need = 0;
-    if (awake && fast && full) {
-      one = true;  // straight to the cut; the range is checked half by half
-      emit = true;
-      count(2);
-    } else {
-      // ---- pass 1: the recurrence alone; largest |p| that enters the sum (scale 0) ----
-      one = false;
-      int maxhi = 0;
-      if (fast) {
-        maxhi = oz_scan_fast(ab, 0, kc, x2, p1, p2);
-      } else {
-        int k = 0;
-        // far below significance: blocks of four steps with one range test (sht_legendre.cu, SKIP phase)
-        while (k + 4 <= kc) {
-          const bool near = (sc == 0) && (bexp(p2) >= BEXP_SIG - 80);
-          if (__any_sync(0xffffffffu, near)) break;
+      // ---- new column scales: read what the old ones produced ----
+      if (dirty && (t % OZ_SUP) == 0) flush(t - 1, 1);  // (column scales of tile t - 1, whose block is still resident)
+      run_stage = stage;
+      tick(5);
+
+      const double s_p1 = p1, s_p2 = p2;
+      const int s_sc = sc;
+      const bool fast = __all_sync(0xffffffffu, sc == 0);
+      bool emit = awake;
+      if (!awake) {
+        // ---- pass 1: the recurrence alone; does any ring become significant in this tile? ----
+        int maxhi = 0;
+        if (fast) {
+          maxhi = oz_scan_fast(ab, 0, kc, x2, p1, p2);
+        } else {
+          int k = 0;
+          // far below significance: blocks of four steps with one range test (sht_legendre.cu, SKIP phase)
+          while (k + 4 <= kc) {
+            const bool near = (sc == 0) && (bexp(p2) >= BEXP_SIG - 80);
+            if (__any_sync(0xffffffffu, near)) break;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * (k + u));
+            for (int u = 0; u < 4; ++u) {
+              const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * (k + u));
+              const double rr = fma(c2.x, x2, c2.y);
+              const double tn = fma(rr, p2, -p1);
+              p1 = p2;
+              p2 = tn;
+            }
+            if (bexp(p2) >= BEXP_BIG) {
+              p1 *= SMALL;
+              p2 *= SMALL;
+              sc += 1;
+            }
+            k += 4;
+          }
+#pragma unroll 2
+          for (; k < kc; ++k) {
+            const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * k);
+            if (sc == 0) maxhi = max(maxhi, __double2hiint(p2) & 0x7fffffff);
             const double rr = fma(c2.x, x2, c2.y);
             const double tn = fma(rr, p2, -p1);
             p1 = p2;
             p2 = tn;
-          }
-          if (bexp(p2) >= BEXP_BIG) {
-            p1 *= SMALL;
-            p2 *= SMALL;
-            sc += 1;
-          }
-          k += 4;
-        }
-#pragma unroll 2
-        for (; k < kc; ++k) {
-          const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * k);
-          if (sc == 0) maxhi = max(maxhi, __double2hiint(p2) & 0x7fffffff);
-          const double rr = fma(c2.x, x2, c2.y);
-          const double tn = fma(rr, p2, -p1);
-          p1 = p2;
-          p2 = tn;
-          if (bexp(p2) >= BEXP_BIG) {
-            p1 *= SMALL;
-            p2 *= SMALL;
-            sc += 1;
+            if (bexp(p2) >= BEXP_BIG) {
+              p1 *= SMALL;
+              p2 *= SMALL;
+              sc += 1;
+            }
           }
         }
+        emit = __any_sync(0xffffffffu, (maxhi >> 20) >= BEXP_SIG);
+        count(emit ? 4 : 6);
+        if (emit) {
+          p1 = s_p1;
+          p2 = s_p2;
+          sc = s_sc;
+          awake = true;
+        }
+      } else {
+        count(2);
       }
-      emit = __any_sync(0xffffffffu, (maxhi >> 20) >= BEXP_SIG);
-      count(emit ? (fast ? 4 : 5) : 6);
-      need = maxhi ? (maxhi >> 20) + sig : 0;
-      if (emit) {
-        p1 = s_p1;
-        p2 = s_p2;
-        sc = s_sc;
-        awake = awake || fast;
+      // the fixed scale of the ring (after an excursion to an exact range: read D first)
+      if (__any_sync(0xffffffffu, emit && eg != eg_ring)) {  // (warp-uniform: the flush is a warp-wide operation)
+        if (dirty) flush(t - 1, 1);
+        eg = eg_ring;
+        scale = (OZ_HEADROOM * 140737488355328.0) / bound;  // 0.99 * 2^47 / bound: the ring's fixed scale
+        run_inv = bound * (1.0 / (OZ_HEADROOM * 140737488355328.0));
       }
-    }
-    int eg_new = max(need, eg_ring);
-    double scale_new = scale, inv_new = run_inv;
-    if (eg_new != eg) oz_scales(eg_new, scale_new, inv_new);
-    // D must be read first if this warp's rows change scale, appear or disappear, or the column scales change
-    const bool brk = emit ? (run_open && !(has && eg_new == eg && !newsup)) : has;
-    double sc_t = scale_new * psc;
+      double sc_t = scale * psc;
+      tick(1);
 
-    // ---- first half (operand half 0 is free once the MMAs issued on it are done) ----
-    int seen = 0;  // largest |p| actually cut
-    if (nc0) mbar_wait(&s_mma[0], (uint32_t)((nc0 - 1) & 1));
-    if (emit) {
-      if (fast && full)
-        oz_pass2_half<true, true>(ab, 0, kc, x2, sc_t, p1, p2, sc, seen, dst);
-      else
-        oz_pass2_half<false, false>(ab, 0, kc, x2, sc_t, p1, p2, sc, seen, dst);
-      fence_async_smem();
-    }
-    bool bad = one && seen != 0 && (seen >> 20) + sig > eg_new;  // a ring outgrew the guessed range
-    const int v = vote((emit ? 1 : 0) | (bad ? 2 : 0) | (brk ? 8 : 0));
-    const bool any = (v & 1) != 0;
-    if (__any_sync(0xffffffffu, bad)) count(7);
-    if (brk) count(8);
-    if (v & 10) {
-      // nothing of this tile has been issued: close the run with the old scales
-      if (run_open) flush();
-      if ((v & 2) && __any_sync(0xffffffffu, bad)) {
-        // exact range of the whole tile for this warp
-        p1 = s_p1;
-        p2 = s_p2;
-        const int mx = oz_scan_fast(ab, 0, kc, x2, p1, p2);
-        eg_new = mx ? (mx >> 20) + sig : 0;
-        oz_scales(eg_new, scale_new, inv_new);
-        sc_t = scale_new * psc;
-        p1 = s_p1;
-        p2 = s_p2;
-        seen = 0;
-        oz_pass2_half<true, true>(ab, 0, kc, x2, sc_t, p1, p2, sc, seen, dst);
-        fence_async_smem();
-        one = false;
-      }
-      __syncthreads();
-    }
-    eg = eg_new;
-    scale = scale_new;
-    run_inv = inv_new;
-    if (any) {
-      if (tid == 0) {
-        tc_fence_after();
-        mma_half(tp, 0, !run_open);
-        umma_commit(&s_mma[0]);
-      }
-      ++nc0;
-      run_open = true;
-      run_stage = stage;
-      run_rows = run_rows || emit;
-    }
-
-    // ---- second half ----
-    const double h_p1 = p1, h_p2 = p2;
-    if (nc1) mbar_wait(&s_mma[1], (uint32_t)((nc1 - 1) & 1));
-    if (emit && kc > 32) {
-      if (fast && full)
-        oz_pass2_half<true, true>(ab, 32, kc, x2, sc_t, p1, p2, sc, seen, dst + HALF);
-      else
-        oz_pass2_half<false, false>(ab, 32, kc, x2, sc_t, p1, p2, sc, seen, dst + HALF);
-      fence_async_smem();
-    }
-    bad = one && seen != 0 && (seen >> 20) + sig > eg;
-    if (__any_sync(0xffffffffu, bad)) count(9);
-    const int redo = __syncthreads_or(bad ? 1 : 0);
-    if (any) {
-      if (redo) {
-        // the first half is in D with the old scales: close the run, then the second half with its exact range
-        flush();
-        if (__any_sync(0xffffffffu, bad)) {
-          p1 = h_p1;
-          p2 = h_p2;
-          const int mx = oz_scan_fast(ab, 32, kc, x2, p1, p2);
-          eg = mx ? (mx >> 20) + sig : 0;
-          oz_scales(eg, scale, run_inv);
-          sc_t = scale * psc;
-          p1 = h_p1;
-          p2 = h_p2;
-          int dummy = 0;
-          oz_pass2_half<true, true>(ab, 32, kc, x2, sc_t, p1, p2, sc, dummy, dst + HALF);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int k0 = 32 * h;
+        if (t > 0) oz_wait(&s_mma[h], prev);  // the operand half is free: the MMAs of the previous tile have read it
+        tick(2);
+        const bool work = emit && k0 < kc;
+        if (work) {
+          const double h_p1 = p1, h_p2 = p2;
+          const int h_sc = sc;
+          uint32_t hor = 0u, hand = 0xffffffffu;
+          if (fast && full)
+            oz_cut_half<true, true>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
+          else
+            oz_cut_half<false, false>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
+          if (__any_sync(0xffffffffu, !oz_in_range(hor, hand))) {
+            // a value beyond the bound: read D at the old scale, then this half with the exact range of its values
+            count(7);
+            if (dirty) flush(h == 0 ? t - 1 : t, h == 0 ? 1 : 0);
+            p1 = h_p1;
+            p2 = h_p2;
+            sc = h_sc;
+            int mx = 0;
+            for (int k = k0; k < min(k0 + 32, kc); ++k) {
+              const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * k);
+              if (sc == 0) mx = max(mx, __double2hiint(p2) & 0x7fffffff);
+              const double rr = fma(c2.x, x2, c2.y);
+              const double tn = fma(rr, p2, -p1);
+              p1 = p2;
+              p2 = tn;
+              if (bexp(p2) >= BEXP_BIG) {
+                p1 *= SMALL;
+                p2 *= SMALL;
+                sc += 1;
+              }
+            }
+            eg = max(mx ? (mx >> 20) + sig : 0, eg);
+            oz_scales(eg, scale, run_inv);
+            sc_t = scale * psc;
+            p1 = h_p1;
+            p2 = h_p2;
+            sc = h_sc;
+            oz_cut_half<false, false>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
+          }
+          tick(3);
           fence_async_smem();
+          dirty = true;
         }
-        __syncthreads();
-      }
-      if (kc > 32) {
-        if (tid == 0) {
-          tc_fence_after();
-          mma_half(tp, 1, !run_open);
-          umma_commit(&s_mma[1]);
+        __syncwarp();
+        if (lane == 0) {
+          if (work) atomicOr(&s_emit[(t & 1) * 2 + h], 1);
+          __threadfence_block();
+          mbar_arrive(&s_ready[h]);
         }
-        ++nc1;
-        run_open = true;
-        run_rows = run_rows || emit;
+        tick(4);
       }
     }
-    if (tid == 0 && t + OZ_STAGES - 1 < ntiles) issue(t + OZ_STAGES - 1);
+    if (dirty) flush(ntiles - 1, (min(OZ_KT, K - (ntiles - 1) * OZ_KT) > 32) ? 1 : 0);
+    tick(5);
+    if (OZ_TIMERS && p.dbg && lane == 0)
+      for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + 10 + i, (unsigned long long)tm[i]);
+
+    // ---- F_m of the north and south ring of the pair ----
+    if (live) {
+      const int slot = m;
+      const int W = p.mmax + 1;
+      const int rs = p.nring - 1 - r;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const double er = acc[4 * b + 0], ei = acc[4 * b + 1];
+        const double orr = acc[4 * b + 2] * zz, oi = acc[4 * b + 3] * zz;
+        double2* ph = p.phase + b * p.phase_map_stride;
+        ph[(int64_t)r * W + slot] = make_double2(er + orr, ei + oi);
+        if (r != p.npair - 1) ph[(int64_t)rs * W + slot] = make_double2(er - orr, ei - oi);
+      }
+    }
   }
-  if (run_open) flush();
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
-
-  // ---- F_m of the north and south ring of the pair ----
-  if (live) {
-    const int slot = m;
-    const int W = p.mmax + 1;
-    const int rs = p.nring - 1 - r;
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-      const double er = acc[4 * b + 0], ei = acc[4 * b + 1];
-      const double orr = acc[4 * b + 2] * zz, oi = acc[4 * b + 3] * zz;
-      double2* ph = p.phase + b * p.phase_map_stride;
-      ph[(int64_t)r * W + slot] = make_double2(er + orr, ei + oi);
-      if (r != p.npair - 1) ph[(int64_t)rs * W + slot] = make_double2(er - orr, ei - oi);
-    }
-  }
 }
 
 // -------------------------------------------------------------------------------------
@@ -723,22 +786,22 @@ static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
   p.nring = pl->nring;
   // |lambda_lm| <= sqrt((2l+1)/4pi) everywhere; away from the poles the Airy peak at the turning point is the
   // largest value: |lambda_lm| sqrt(sin theta) < 0.54 lmax^(1/6) (measured with the oracle up to lmax 2047: 1.69 at
-  // lmax 1023); a quarter on top for the drift of alpha inside a tile.  The kernel checks the bound on every value.
-  p.bound_pole = 1.25 * std::sqrt((2.0 * pl->lmax + 1.0) / (4.0 * 3.14159265358979323846));
-  p.bound_c = 1.25 * 0.6 * std::pow((double)std::max(pl->lmax, 1), 1.0 / 6.0);
+  // lmax 1023); a fifth on top for the drift of alpha inside a tile.  The kernel checks the bound on every value.
+  p.bound_pole = 1.2 * std::sqrt((2.0 * pl->lmax + 1.0) / (4.0 * 3.14159265358979323846));
+  p.bound_c = 1.2 * 0.6 * std::pow((double)std::max(pl->lmax, 1), 1.0 / 6.0);
   static unsigned long long* d_dbg = nullptr;
   const bool debug = getenv("GLB_OZ_DEBUG") != nullptr;
   if (debug && !d_dbg) GLB_CUDA_CHECK(cudaMalloc((void**)&d_dbg, 16 * sizeof(unsigned long long)));
   if (debug) GLB_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0, 16 * sizeof(unsigned long long), st));
   p.dbg = debug ? d_dbg : nullptr;
-  const size_t smem = OZ_A_BYTES + OZ_STAGES * T::BYTES + (OZ_STAGES + 2) * sizeof(uint64_t) + 32;
+  const size_t smem = OZ_A_BYTES + OZ_STAGES * T::BYTES + (OZ_STAGES + 4) * sizeof(uint64_t) + 32;
   static bool attr_set = false;
   if (!attr_set) {
     GLB_CUDA_CHECK(cudaFuncSetAttribute(sht_legendre_ozaki_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (nitems > 0) {
-    sht_legendre_ozaki_kernel<NC><<<nitems, OZ_ROWS, smem, st>>>(p);
+    sht_legendre_ozaki_kernel<NC><<<nitems, OZ_THREADS, smem, st>>>(p);
     GLB_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
@@ -746,7 +809,11 @@ static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
     unsigned long long h[16];
     GLB_CUDA_CHECK(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
     GLB_CUDA_CHECK(cudaStreamSynchronize(st));
-    fprintf(stderr, "[oz NC=%d] warp-tiles: one-pass %llu, two-pass fast %llu / checked %llu, silent %llu | warp flushes %llu (+%llu without rows), bad half0 %llu half1 %llu, brk %llu\n", NC, h[2], h[4], h[5], h[6], h[1], h[0], h[7], h[9], h[8]);
+    fprintf(stderr, "[oz NC=%d] warp-tiles: cut directly %llu, woken up %llu, silent %llu | warp flushes %llu, halves beyond the bound %llu\n", NC, h[2], h[4], h[6], h[1], h[7]);
+    if (OZ_TIMERS) {
+    const double tot = (double)(h[10] + h[11] + h[12] + h[13] + h[14] + h[15]);
+    fprintf(stderr, "[oz NC=%d] producer warp cycles: wait TMA %.1f%%, mode / pass 1 %.1f%%, wait operand half %.1f%%, cut %.1f%%, fence + arrive %.1f%%, flush %.1f%% of %.3g; issuer: waiting %.3g, issuing %.3g cycles\n", NC, 100 * h[10] / tot, 100 * h[11] / tot, 100 * h[12] / tot, 100 * h[13] / tot, 100 * h[14] / tot, 100 * h[15] / tot, tot, (double)h[8], (double)h[9]);
+    }
   }
   return GLB_OK;
 }

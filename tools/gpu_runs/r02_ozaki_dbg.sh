@@ -1,4 +1,4 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-GLB_OZ_DEBUG=1 timeout 120 python tools/probe_ozaki.py 512:1023,2048:4095 8 0 > gpurun_out/oz_dbg.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/oz_dbg.log
+GLB_OZ_DEBUG=1 timeout 60 python tools/probe_ozaki.py 2048:4095 ${1:-8} 0 > gpurun_out/oz_dbg.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/oz_dbg.log
