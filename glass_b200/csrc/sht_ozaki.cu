@@ -37,7 +37,8 @@ constexpr int OZ_KT = 64;      // l-pairs per tile
 constexpr int OZ_ND = 6;       // base-256 digits per operand
 constexpr int OZ_ROWS = 128;   // ring pairs per CTA = threads = TMEM lanes
 constexpr int OZ_STAGES = 3;   // tile blocks in flight (TMA)
-constexpr int OZ_SUP = 8;      // tiles per super-tile: one set of column scales, D may accumulate across them
+constexpr int OZ_SUP = 16;     // tiles per super-tile: one set of column scales, D may accumulate across them
+constexpr int OZ_PERK = 2;     // the first tiles of every m carry one power of two per l-pair (alpha falls fast there)
 constexpr int OZ_A_SLICE = (OZ_KT / 16) * OZ_ROWS * 16;  // bytes of one digit plane of the p operand
 constexpr int OZ_A_BYTES = OZ_ND * OZ_A_SLICE;
 
@@ -49,8 +50,9 @@ struct OzTile {
   static constexpr int BOP_LBO = OZ_ND * NC * 16;           // bytes between the 16-byte k chunks
   static constexpr int BOP_BYTES = BOP_LBO * (OZ_KT / 16);
   static constexpr int INVA_OFF = AB_BYTES + BOP_BYTES;     // double[NC]
-  static constexpr int PSC_OFF = INVA_OFF + NC * 8;         // double: the tile's power of two 2^sig (see oz_prep_kernel)
-  static constexpr int BYTES = PSC_OFF + 32;
+  static constexpr int PSC_OFF = INVA_OFF + NC * 8;         // double: the tile's power of two 2^sig (see oz_prep_kernel), 0: per l-pair
+  static constexpr int SK_OFF = PSC_OFF + 32;               // double[64]: powers of two per l-pair (tiles with PSC = 0)
+  static constexpr int BYTES = SK_OFF + OZ_KT * 8;
   static_assert(BYTES % 32 == 0, "bulk copies move multiples of 16 bytes, the coefficient rows are stored as double4");
 };
 
@@ -163,10 +165,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 //
 // Scales.  The rescaling alpha_k of the recurrence (lambda = alpha_k p_k, sht_tables.cuh) drifts
 // with l, so p_k and the coefficients A_k = alpha_k a_lm drift in opposite directions.  Every tile
-// therefore carries ONE power of two 2^sig (the exponent of alpha at its first l-pair): the
+// therefore carries ONE power of two 2^sig (the exponent of alpha at its first l-pair; the first two
+// tiles of every m, where alpha falls by a factor of ten, carry one per l-pair): the
 // coefficients are cut as A 2^-sig, the kernel cuts p 2^sig -- both then vary like the physical
 // lambda_lm and a_lm -- and the product is unchanged.  On top of that the COLUMN scales are common
-// to the super-tile (largest |A 2^-sig| of its 512 l-pairs), so that the integer sums of its tiles
+// to the super-tile (largest |A 2^-sig| of its 1024 l-pairs), so that the integer sums of its tiles
 // can be added up in TMEM.  col0 = first column of this pass (B = 8: two passes).
 // -------------------------------------------------------------------------------------
 template <int NC>
@@ -185,7 +188,12 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
   const int t1 = min(t0 + OZ_SUP, (K + OZ_KT - 1) / OZ_KT);
   const double* rm = rec + roff[m] * REC;
   const double* am = tab + roff[m] * PREP_TAB + TAB_ALPHA;
-  auto tile_field = [&](int t) { return (__double2hiint(am[(int64_t)t * OZ_KT * PREP_TAB]) >> 20) & 0x7ff; };  // exponent field of alpha
+  // exponent field of alpha: per l-pair in the first OZ_PERK tiles (alpha falls by a factor of ten there), of the
+  // tile's first l-pair afterwards (a few per cent of drift per tile)
+  auto field_of = [&](int t, int kk) {
+    const int kr = t < OZ_PERK ? min(kk, K - 1) : t * OZ_KT;
+    return (__double2hiint(am[(int64_t)kr * PREP_TAB]) >> 20) & 0x7ff;
+  };
   // coalesced copy of tile t's records (contiguous in global memory) into s_rec, zero rows beyond K
   auto stage_tile = [&](int t) {
     const int n = min(OZ_KT, K - t * OZ_KT) * REC;  // doubles
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
     __syncthreads();
     stage_tile(t);
     __syncthreads();
-    const double down = __hiloint2double((2046 - tile_field(t)) << 20, 0);  // 2^-sig
+    const double down = __hiloint2double((2046 - field_of(t, t * OZ_KT + k)) << 20, 0);  // 2^-sig
 #pragma unroll
     for (int c = 0; c < 16; ++c) mx[c] = max(mx[c], __double2hiint(s_rec[k][4 + c] * down) & 0x7fffffff);
   }
@@ -212,11 +220,12 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
     if (t1 - t0 > 1 || t == t0) stage_tile(t);  // (a one-tile super-tile is still staged)
     __syncthreads();
     uint8_t* blk = oz + (toff[m] + t) * (int64_t)T::BYTES;
-    const int field = tile_field(t);
+    const int field = field_of(t, t * OZ_KT + k);
     const double down = __hiloint2double((2046 - field) << 20, 0);
     if (col0 == 0) {
       reinterpret_cast<double4*>(blk)[k] = make_double4(s_rec[k][0], s_rec[k][1], s_rec[k][2], s_rec[k][3]);
-      if (k == 0) *reinterpret_cast<double*>(blk + T::PSC_OFF) = __hiloint2double(field << 20, 0);  // 2^sig
+      reinterpret_cast<double*>(blk + T::SK_OFF)[k] = __hiloint2double(field << 20, 0);  // 2^sig of this l-pair
+      if (k == 0) *reinterpret_cast<double*>(blk + T::PSC_OFF) = t < OZ_PERK ? 0.0 : __hiloint2double(field << 20, 0);
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
@@ -285,10 +294,10 @@ __device__ __forceinline__ double oz_i2d(int x) {
 // operand buffer (row `dst`).  Range check: every FMA result must lie in [2^52, 2^52 + 2^48), i.e.
 // its high word is 0x4330xxxx -- `hor` / `hand` collect the OR and the AND of the high words.
 // FAST: every ring of the warp is at scale 0 (no range tests); FULL: all 32 l-pairs exist.
-template <bool FAST, bool FULL>
+template <bool FAST, bool FULL, bool PERK = false>
 __device__ __forceinline__ void oz_cut_half(const double* __restrict__ ab, int k0, int kc, double x2, double scale,
                                             double& p1, double& p2, int& sc, uint32_t& hor, uint32_t& hand,
-                                            uint8_t* __restrict__ dst) {
+                                            uint8_t* __restrict__ dst, const double* __restrict__ sk = nullptr) {
   const double SMALL = 7.458340731200207e-155;  // 2^-512
 #pragma unroll 1
   for (int ch = 0; ch < 2; ++ch) {
@@ -301,7 +310,7 @@ __device__ __forceinline__ void oz_cut_half(const double* __restrict__ ab, int k
         const int k = k0 + ch * 16 + q * 4 + i;
         const bool in = FULL || k < kc;
         const double v = (in && (FAST || sc == 0)) ? p2 : 0.0;
-        tt[i] = fma(v, scale, OZ_MAGIC);
+        tt[i] = fma(v, PERK ? scale * sk[k] : scale, OZ_MAGIC);
         if (in) {
           const double2 c2 = *reinterpret_cast<const double2*>(ab + 4 * k);
           const double rr = fma(c2.x, x2, c2.y);
@@ -350,7 +359,7 @@ __device__ __forceinline__ int oz_scan_fast(const double* __restrict__ ab, int k
 // fixed point with an absolute error of 2^-45 per value, which is what matters for a map whose error
 // is measured against its largest pixel).  Fixed scales mean that the integer sums of consecutive
 // tiles stay in TMEM and D is read and converted once per super-tile (= one set of column scales,
-// 512 l-pairs) instead of once per tile.
+// 1024 l-pairs) instead of once per tile.
 //
 // Roles.  Four PRODUCER warps own 32 rings each (thread = ring = TMEM lane): they run the recurrence
 // and cut the digits of their rows, half tile by half tile (32 l-pairs = one K = 32 instruction per
@@ -561,7 +570,9 @@ __global__ void __launch_bounds__(OZ_THREADS) sht_legendre_ozaki_kernel(const Oz
       const int kc = min(OZ_KT, K - t * OZ_KT);
       const bool full = kc == OZ_KT;
       const double psc = *reinterpret_cast<const double*>(tp + T::PSC_OFF);  // the tile's 2^sig: p is cut as p 2^sig
-      const int sig = ((__double2hiint(psc) >> 20) & 0x7ff) - 1023;
+      const bool perk = psc == 0.0;                                          // ... or one power of two per l-pair
+      const double* sk = reinterpret_cast<const double*>(tp + T::SK_OFF);
+      const int sig = perk ? 0 : ((__double2hiint(psc) >> 20) & 0x7ff) - 1023;
       const uint32_t prev = (uint32_t)((t & 1) ^ 1);
 
       // ---- new column scales: read what the old ones produced ----
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(OZ_THREADS) sht_legendre_ozaki_kernel(const Oz
         scale = (OZ_HEADROOM * 140737488355328.0) / bound;  // 0.99 * 2^47 / bound: the ring's fixed scale
         run_inv = bound * (1.0 / (OZ_HEADROOM * 140737488355328.0));
       }
-      double sc_t = scale * psc;
+      double sc_t = perk ? scale : scale * psc;
       tick(1);
 
 #pragma unroll 1
@@ -645,7 +656,11 @@ __global__ void __launch_bounds__(OZ_THREADS) sht_legendre_ozaki_kernel(const Oz
           const double h_p1 = p1, h_p2 = p2;
           const int h_sc = sc;
           uint32_t hor = 0u, hand = 0xffffffffu;
-          if (fast && full)
+          if (perk && fast && full)
+            oz_cut_half<true, true, true>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF, sk);
+          else if (perk)
+            oz_cut_half<false, false, true>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF, sk);
+          else if (fast && full)
             oz_cut_half<true, true>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
           else
             oz_cut_half<false, false>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
@@ -672,11 +687,14 @@ __global__ void __launch_bounds__(OZ_THREADS) sht_legendre_ozaki_kernel(const Oz
             }
             eg = max(mx ? (mx >> 20) + sig : 0, eg);
             oz_scales(eg, scale, run_inv);
-            sc_t = scale * psc;
+            sc_t = perk ? scale : scale * psc;
             p1 = h_p1;
             p2 = h_p2;
             sc = h_sc;
-            oz_cut_half<false, false>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
+            if (perk)
+              oz_cut_half<false, false, true>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF, sk);
+            else
+              oz_cut_half<false, false>(ab, k0, kc, x2, sc_t, p1, p2, sc, hor, hand, dst + h * HALF);
           }
           tick(3);
           fence_async_smem();
