@@ -641,7 +641,9 @@ def run_b200(args) -> None:
         try:
             chain = bench_chain(dev, rank, world)
         except Exception as e:
-            chain = {"failed": f"{type(e).__name__}: {e}"}
+            free, total = torch.cuda.mem_get_info(dev)
+            chain = {"failed": f"{type(e).__name__}: {e}", "mem_free_GB": free / 1e9, "torch_allocated_GB": torch.cuda.memory_allocated(dev) / 1e9,
+                     "torch_reserved_GB": torch.cuda.memory_reserved(dev) / 1e9}
         clear_plans()
         torch.cuda.empty_cache()
 

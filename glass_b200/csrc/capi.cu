@@ -173,6 +173,16 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
   return GLB_OK;
 }
 
+int glb_plan_release_scratch(glb_plan* plan) {
+  GLB_REQUIRE(plan != nullptr, "plan is null");
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  GLB_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaFree(plan->d_oz);
+  plan->d_oz = nullptr;
+  plan->oz_bytes = 0;
+  return GLB_OK;
+}
+
 int glb_plan_set_legendre_mode(glb_plan* plan, int mode) {
   GLB_REQUIRE(plan != nullptr, "plan is null");
   GLB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (FP64) or 2 (INT8)");

@@ -115,6 +115,13 @@ def clear_plans() -> None:
     _PLANS.clear()
 
 
+def release_scratch() -> None:
+    """Give back what the cached plans allocate on first use and rebuild on demand (the tile blocks of the
+    INT8 Legendre path): for a caller that is done generating fields and needs the memory for maps."""
+    for pl in _PLANS.values():
+        _lib.check(pl.lib.glb_plan_release_scratch(pl.handle), "glb_plan_release_scratch")
+
+
 def _as_cuda_c128(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.complex128).contiguous()

@@ -302,6 +302,9 @@ int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream);
  * csrc/sht_ozaki.cu) at nside >= 1024, everything else on the FP64 pipe; 1 = FP64 pipe only; 2 = INT8 tensor cores
  * for groups of four and eight maps at any nside.  Both agree to ~1e-11 of the largest phase. */
 int glb_plan_set_legendre_mode(glb_plan* plan, int mode);
+/* Give back the buffers a plan allocates on first use and can rebuild on the next (the tile blocks of the INT8 Legendre
+ * path, 4 GB at nside 4096): for callers that are done generating and need the memory for maps.  Synchronises the device. */
+int glb_plan_release_scratch(glb_plan* plan);
 
 /* ---- debug / test taps (stable, used by tests/ only) --------------------------------- */
 /* Legendre stage only: alm -> phase array F_m(ring), [nmaps][nring][lmax+1] complex128 */

@@ -170,17 +170,51 @@ def run_chain(config: int, *, dev, rank: int = 0, world: int = 1, shells: int | 
     else:
         # 1. matter planes of the block (no communication)  2. multi-plane recurrence, pipelined
         # over the ranks (dist.multi_plane_block)  3. transforms and galaxies (no communication)
-        deltas = [timed("generate", lambda: next(matter)) for _ in mine]
-        kappas = [None] * len(mine)
+        # (copies: the generator yields views of its batches of eight maps, and a batch would stay allocated until the
+        # last of its eight shells is finished)
+        deltas = [timed("generate", lambda: next(matter).clone()) for _ in mine]
+        matter.close()  # the generator's batch buffers and the transform's scratch go back before the planes are lensed
+        glass_b200.healpix.release_scratch()
+        torch.cuda.empty_cache()  # the library allocates its lensing workspace with cudaMalloc: give it what torch has cached
+        conv2 = None
         if lensing:
-            conv._like = torch.empty(npix, dtype=torch.float64, device=dev)
-            kappas = timed("multiplane", lambda: multi_plane_block(conv, deltas, [shells[i] for i in mine]))
+            # the recurrence runs through the block TWICE: once right away, to hand its state to the next rank as early
+            # as possible (1 ms per plane), and again group by group below from a snapshot of the state it started
+            # from -- the block's 30 convergence planes (48 GB at nside 4096) are never held at the same time
+            from glass_b200.dist import _MP_MAPS, _MP_SCALARS, recv_multi_plane_state, send_multi_plane_state
+
+            like = deltas[0] if deltas else torch.empty(npix, dtype=torch.float64, device=dev)
+
+            def advance():
+                if rank > 0:
+                    recv_multi_plane_state(conv, rank - 1, like=like)
+                snap = ({k: getattr(conv, k) for k in _MP_SCALARS},
+                        {k: (getattr(conv, k).clone() if getattr(conv, k) is not None else None) for k in _MP_MAPS})
+                for b, i in enumerate(mine):
+                    conv.add_window(deltas[b], shells[i])
+                if rank + 1 < world:
+                    send_multi_plane_state(conv, rank + 1, like=like)
+                return snap
+
+            snap = timed("multiplane", advance)
+            conv2 = glass_b200.MultiPlaneConvergence(MockCosmology())
+            for k, v in snap[0].items():
+                setattr(conv2, k, v)
+            for k, v in snap[1].items():
+                conv2._set_state_map(k, v)
+        torch.cuda.empty_cache()  # (the transforms' workspace is allocated by the library on first use)
         for a in range(0, len(mine), group):
             hi = min(a + group, len(mine))
-            shears = shear_group(kappas[a:hi]) if lensing else [None] * (hi - a)
+            kappas = [None] * (hi - a)
+            if lensing:
+                for b in range(a, hi):
+                    timed("multiplane", lambda: conv2.add_window(deltas[b], shells[mine[b]]))
+                    kappas[b - a] = conv2.kappa.clone()
+            shears = shear_group(kappas) if lensing else [None] * (hi - a)
             for b in range(a, hi):
-                per_shell(mine[b], deltas[b], kappas[b], shears[b - a])
-                deltas[b] = kappas[b] = None  # this shell is finished: its maps go back to the allocator
+                per_shell(mine[b], deltas[b], kappas[b - a], shears[b - a])
+                deltas[b] = None  # this shell is finished: its map goes back to the allocator
+            kappas = shears = None
     if sink is not None:
         sink.close()
     torch.cuda.synchronize()
