@@ -719,7 +719,8 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
         wanted = shells if callable(shells) else (lambda j, _s=frozenset(int(i) for i in shells): j in _s)
     with torch.cuda.device(device):
         sampler = _ShellSampler(gls, nside, ncorr, rng, device, wanted)
-        B = max(1, min(int(SHT_BATCH), 8))
+        # eight maps at once need eight phase maps and eight output maps in HBM: 30 GB at nside 4096, 120 GB at 8192
+        B = max(1, min(int(SHT_BATCH), 8 if nside <= 4096 else 4))
         npix = hp.nside2npix(nside)
         copy_stream = None if on_device else torch.cuda.Stream(device)
         state = {"error": None}

@@ -1695,3 +1695,24 @@ def test_pixwin_generator_against_definition(monkeypatch):
     with pytest.raises(ValueError, match="power of two"):
         PW.pixwin(12)
     PW._pair_moments.cache_clear()
+
+
+def test_vmap_and_rotator_host_side():
+    """glass/observations.py:88-94 raises before any array work; the coordinate matrices are healpy's constants
+    (rotations to 1e-9, the poles where the almanac puts them); no device is needed for either."""
+    import glass_b200
+    from glass_b200.healpix import _coordconv_matrix
+
+    with pytest.raises(TypeError, match="galactic stripe must be a pair of numbers"):
+        glass_b200.vmap_galactic_ecliptic(4, galactic=(1,))
+    with pytest.raises(TypeError, match="ecliptic stripe must be a pair of numbers"):
+        glass_b200.vmap_galactic_ecliptic(4, ecliptic=(1, 2, 3))
+    for c in ("GC", "CE", "EG", ("G", "C"), "gq"):
+        M = _coordconv_matrix(c)
+        assert np.abs(M @ M.T - np.eye(3)).max() < 2e-9
+    assert np.array_equal(_coordconv_matrix("C"), np.eye(3)) and np.array_equal(_coordconv_matrix(None), np.eye(3))
+    assert np.allclose(_coordconv_matrix("GQ"), _coordconv_matrix("GC"))
+    x, y, z = _coordconv_matrix("GC") @ np.array([0.0, 0.0, 1.0])
+    assert abs(np.degrees(np.arctan2(y, x)) % 360 - 192.86) < 0.01 and abs(np.degrees(np.arcsin(z)) - 27.13) < 0.01
+    with pytest.raises(TypeError):
+        _coordconv_matrix("GX")
