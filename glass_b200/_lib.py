@@ -81,6 +81,8 @@ SIGNATURES = {
     "glb_debug_alm2phase": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_plan_set_legendre_mode": (_i, [_vp, _i]),
     "glb_plan_release_scratch": (_i, [_vp]),
+    "glb_alm2map_prepare": (_i, [_vp, _dp, _i, _i, _vp]),
+    "glb_alm2map_finish": (_i, [_vp, _i, _i, _dp, _ip, _dp, _vp]),
     "glb_debug_alm2phase_int8": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_debug_phase2map": (_i, [_vp, _dp, _i, _dp, _vp]),
     "glb_debug_mlim": (_i, [_vp, _ip]),

@@ -12,8 +12,8 @@ void plan_free(glb_plan* pl);
 int sht_alm2phase_group(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
 int sht_alm2phase_ozaki(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st);
-int sht_ozaki_prep(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
-int sht_ozaki_legendre(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st);
+int sht_ozaki_prep(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st, int slot = 2);
+int sht_ozaki_legendre(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, int slot = 2);
 int sht_legendre_group(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, bool dist = false, int p2p_buffer = -1);
 unsigned long long launch_count();
 int measure_fp64_peak(int device, double* tflops, double* ms, cudaStream_t st);
@@ -31,6 +31,27 @@ static int timing_collect(glb_plan* pl) {
   }
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   pl->ev_pool.clear();
+  // the split form (glb_alm2map_prepare on one stream, glb_alm2map_finish on another)
+  for (size_t i = 0; i + 1 < pl->ev_prep.size(); i += 2) {
+    float ms = 0.f;
+    GLB_CUDA_CHECK(cudaEventSynchronize(pl->ev_prep[i + 1]));
+    GLB_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_prep[i], pl->ev_prep[i + 1]));
+    pl->stage_ms[0] += ms;
+    pl->stage_launches[0] += 1;
+  }
+  for (size_t i = 0; i + 2 < pl->ev_fin.size(); i += 3) {
+    GLB_CUDA_CHECK(cudaEventSynchronize(pl->ev_fin[i + 2]));
+    for (int s = 0; s < 2; ++s) {
+      float ms = 0.f;
+      GLB_CUDA_CHECK(cudaEventElapsedTime(&ms, pl->ev_fin[i + s], pl->ev_fin[i + s + 1]));
+      pl->stage_ms[1 + s] += ms;
+      pl->stage_launches[1 + s] += 1;
+    }
+  }
+  for (cudaEvent_t e : pl->ev_prep) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_fin) cudaEventDestroy(e);
+  pl->ev_prep.clear();
+  pl->ev_fin.clear();
   return GLB_OK;
 }
 int sht_phase2map_group(glb_plan* pl, const double2* d_phase, int nb, double* const* d_maps, const int* kind,
@@ -173,13 +194,83 @@ int glb_alm2map(glb_plan* plan, const double* d_alm, int nmaps, double* d_map, c
   return GLB_OK;
 }
 
+// glb_alm2map in two halves for EIGHT maps on the INT8 path, so that a caller can prepare the next batch (records, digit
+// planes; `slot` = which of the two sets of tile blocks) on a side stream while the Legendre kernel of the current batch runs
+static bool int8_group_of_eight(const glb_plan* plan) {
+  return plan->legendre_mode != 1 && plan->max_batch >= 4 && (plan->legendre_mode == 2 || plan->nside >= 1024);
+}
+
+int glb_alm2map_prepare(glb_plan* plan, const double* d_alm, int nmaps, int slot, void* stream) {
+  GLB_REQUIRE(plan && d_alm, "null pointer");
+  GLB_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  if (nmaps != 8 || !int8_group_of_eight(plan)) {
+    set_last_error("glb_alm2map_prepare: only groups of eight maps on the INT8 Legendre path are split");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const int64_t phase_map = (int64_t)plan->nring * (plan->mmax + 1);
+  if (!plan->d_phase_spin && cudaMalloc((void**)&plan->d_phase_spin, (size_t)8 * phase_map * sizeof(double2)) != cudaSuccess) {
+    cudaGetLastError();
+    plan->d_phase_spin = nullptr;
+    set_last_error("glb_alm2map_prepare: not enough memory for eight phase maps");
+    return GLB_ERR_UNSUPPORTED;
+  }
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (plan->timing) {
+    for (int i = 0; i < 2; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
+    GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+  }
+  const int rc = sht_ozaki_prep(plan, reinterpret_cast<const double2*>(d_alm), 8, st, slot);
+  if (rc != GLB_OK) return rc == GLB_ERR_NOMEM ? GLB_ERR_UNSUPPORTED : rc;
+  if (plan->timing) {
+    GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
+    plan->ev_prep.push_back(ev[0]);
+    plan->ev_prep.push_back(ev[1]);
+  }
+  return GLB_OK;
+}
+
+int glb_alm2map_finish(glb_plan* plan, int nmaps, int slot, double* d_map, const int* h_transform, const double* h_tparams,
+                       void* stream) {
+  GLB_REQUIRE(plan && d_map, "null pointer");
+  GLB_REQUIRE(nmaps == 8 && (slot == 0 || slot == 1) && plan->d_phase_spin, "glb_alm2map_finish follows glb_alm2map_prepare");
+  cudaStream_t st = (cudaStream_t)stream;
+  GLB_CUDA_CHECK(cudaSetDevice(plan->device));
+  const int64_t phase_map = (int64_t)plan->nring * (plan->mmax + 1);
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (plan->timing) {
+    for (int i = 0; i < 3; ++i) GLB_CUDA_CHECK(cudaEventCreate(&ev[i]));
+    GLB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+  }
+  int rc = sht_ozaki_legendre(plan, 8, plan->d_phase_spin, st, slot);
+  if (rc != GLB_OK) return rc;
+  if (plan->timing) GLB_CUDA_CHECK(cudaEventRecord(ev[1], st));
+  for (int h = 0; h < 8; h += 4) {
+    double* outs[4];
+    for (int b = 0; b < 4; ++b) outs[b] = d_map + (int64_t)(h + b) * plan->npix;
+    rc = sht_phase2map_group(plan, plan->d_phase_spin + (int64_t)h * phase_map, 4, outs, h_transform ? h_transform + h : nullptr,
+                             h_tparams ? h_tparams + 2 * h : nullptr, nullptr, st);
+    if (rc != GLB_OK) return rc;
+  }
+  if (plan->timing) {
+    GLB_CUDA_CHECK(cudaEventRecord(ev[2], st));
+    for (int i = 0; i < 3; ++i) plan->ev_fin.push_back(ev[i]);
+    plan->stage_maps += 8;
+    if (plan->ev_fin.size() > 3072) timing_collect(plan);
+  }
+  return GLB_OK;
+}
+
 int glb_plan_release_scratch(glb_plan* plan) {
   GLB_REQUIRE(plan != nullptr, "plan is null");
   GLB_CUDA_CHECK(cudaSetDevice(plan->device));
   GLB_CUDA_CHECK(cudaDeviceSynchronize());
   cudaFree(plan->d_oz);
-  plan->d_oz = nullptr;
-  plan->oz_bytes = 0;
+  cudaFree(plan->d_oz1);
+  cudaFree(plan->d_oz2);
+  plan->d_oz = plan->d_oz1 = plan->d_oz2 = nullptr;
+  plan->oz_bytes = plan->oz_bytes1 = plan->oz_bytes2 = 0;
   return GLB_OK;
 }
 

@@ -345,6 +345,8 @@ void plan_free(glb_plan* pl) {
   cudaFree(pl->d_bf);
   cudaFree(pl->d_rec);
   cudaFree(pl->d_oz);
+  cudaFree(pl->d_oz1);
+  cudaFree(pl->d_oz2);
   cudaFree(pl->d_oz_toff);
   cudaFree(pl->d_phase);
   cudaFree(pl->d_ch);

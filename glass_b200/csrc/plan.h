@@ -119,6 +119,11 @@ struct glb_plan {
   uint8_t* d_oz = nullptr;           // tile blocks: recurrence coefficients + digit planes of the a_lm coefficients
   int64_t* d_oz_toff = nullptr;      // [mmax+2] first tile of every m
   int64_t oz_bytes = 0, oz_tiles = 0;
+  uint8_t* d_oz1 = nullptr;          // sets 0 and 1: glb_alm2map_prepare / _finish (the next batch is prepared on a side stream
+  int64_t oz_bytes1 = 0;             // while the Legendre kernel of the current one reads the other set; a prepared set must
+  uint8_t* d_oz2 = nullptr;          // survive whatever the caller runs in between); set 2: every other call (glb_alm2map,
+  int64_t oz_bytes2 = 0;             // the refinement syntheses of glb_map2alm_batch)
+  std::vector<cudaEvent_t> ev_prep, ev_fin;  // stage timing of the split form: pairs (prep) and triples (Legendre, ring FFT)
   int legendre_mode = 0;             // 0 auto (INT8 for groups of eight maps at nside >= 1024), 1 FP64 only, 2 INT8 for groups of four and eight
 
   // workspace

@@ -741,7 +741,7 @@ int plan_items(glb_plan* pl, int tile, int G, int rank, LegItem** d_items, int* 
 int sht_prep_group(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st);
 
 template <int NC>
-static int ozaki_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
+static int ozaki_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st, int slot) {
   using T = OzTile<NC>;
   constexpr int B = NC / 4;
   // tile offsets per m
@@ -753,16 +753,18 @@ static int ozaki_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
     GLB_CUDA_CHECK(cudaMemcpy(pl->d_oz_toff, toff.data(), toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
   }
   const int64_t need = pl->oz_tiles * (int64_t)T::BYTES;
-  if (pl->oz_bytes < need) {
-    cudaFree(pl->d_oz);
-    pl->d_oz = nullptr;
-    pl->oz_bytes = 0;
-    if (cudaMalloc((void**)&pl->d_oz, (size_t)need) != cudaSuccess) {
+  uint8_t*& d_oz = slot == 0 ? pl->d_oz : (slot == 1 ? pl->d_oz1 : pl->d_oz2);
+  int64_t& oz_bytes = slot == 0 ? pl->oz_bytes : (slot == 1 ? pl->oz_bytes1 : pl->oz_bytes2);
+  if (oz_bytes < need) {
+    cudaFree(d_oz);
+    d_oz = nullptr;
+    oz_bytes = 0;
+    if (cudaMalloc((void**)&d_oz, (size_t)need) != cudaSuccess) {
       cudaGetLastError();
       set_last_error("out of device memory for the INT8 Legendre tile blocks");
       return GLB_ERR_NOMEM;
     }
-    pl->oz_bytes = need;
+    oz_bytes = need;
   }
   if ((int64_t)pl->nrec * (4 + 16) > pl->rec_capacity) {
     set_last_error("the INT8 Legendre path needs a plan with max_batch >= 4");
@@ -773,7 +775,7 @@ static int ozaki_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
     int rc = sht_prep_group(pl, d_alm + (int64_t)g * 4 * pl->nalm, 4, st);
     if (rc != GLB_OK) return rc;
     oz_prep_kernel<NC><<<dim3((ntile_max + OZ_SUP - 1) / OZ_SUP, pl->mmax + 1), OZ_KT, 0, st>>>(pl->d_rec, pl->d_prep_tab, pl->d_roff, pl->d_oz_toff, pl->lmax,
-                                                                       16 * g, pl->d_oz);
+                                                                       16 * g, d_oz);
     GLB_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
@@ -781,7 +783,7 @@ static int ozaki_prep(glb_plan* pl, const double2* d_alm, cudaStream_t st) {
 }
 
 template <int NC>
-static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
+static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st, int slot) {
   using T = OzTile<NC>;
   OzParams p;
   int nitems = 0;
@@ -789,7 +791,7 @@ static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
   int rc = plan_items(pl, OZ_ROWS, 1, 0, &items, &nitems);
   if (rc != GLB_OK) return rc;
   p.items = items;
-  p.oz = pl->d_oz;
+  p.oz = slot == 0 ? pl->d_oz : (slot == 1 ? pl->d_oz1 : pl->d_oz2);
   p.toff = pl->d_oz_toff;
   p.z = pl->d_z;
   p.sth = pl->d_sth;
@@ -838,22 +840,22 @@ static int ozaki_legendre(glb_plan* pl, double2* d_phase, cudaStream_t st) {
 
 // the two halves of the INT8 Legendre stage, nb in {4, 8}: alm [nb][nalm] -> tile blocks (records, digit planes), and
 // tile blocks -> phase [nb][nring][mmax+1]
-int sht_ozaki_prep(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st) {
-  if (nb == 4) return ozaki_prep<16>(pl, d_alm, st);
-  if (nb == 8) return ozaki_prep<32>(pl, d_alm, st);
+int sht_ozaki_prep(glb_plan* pl, const double2* d_alm, int nb, cudaStream_t st, int slot) {
+  if (nb == 4) return ozaki_prep<16>(pl, d_alm, st, slot);
+  if (nb == 8) return ozaki_prep<32>(pl, d_alm, st, slot);
   set_last_error("the INT8 Legendre path takes 4 or 8 maps");
   return GLB_ERR_INVALID_ARG;
 }
-int sht_ozaki_legendre(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st) {
-  if (nb == 4) return ozaki_legendre<16>(pl, d_phase, st);
-  if (nb == 8) return ozaki_legendre<32>(pl, d_phase, st);
+int sht_ozaki_legendre(glb_plan* pl, int nb, double2* d_phase, cudaStream_t st, int slot) {
+  if (nb == 4) return ozaki_legendre<16>(pl, d_phase, st, slot);
+  if (nb == 8) return ozaki_legendre<32>(pl, d_phase, st, slot);
   set_last_error("the INT8 Legendre path takes 4 or 8 maps");
   return GLB_ERR_INVALID_ARG;
 }
 int sht_alm2phase_ozaki(glb_plan* pl, const double2* d_alm, int nb, double2* d_phase, cudaStream_t st) {
-  const int rc = sht_ozaki_prep(pl, d_alm, nb, st);
+  const int rc = sht_ozaki_prep(pl, d_alm, nb, st, 2);
   if (rc != GLB_OK) return rc;
-  return sht_ozaki_legendre(pl, nb, d_phase, st);
+  return sht_ozaki_legendre(pl, nb, d_phase, st, 2);
 }
 
 }  // namespace glb

@@ -725,11 +725,21 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
         copy_stream = None if on_device else torch.cuda.Stream(device)
         state = {"error": None}
 
-        def batches():
-            """Launch one batch (<= B shells) per iteration: alm draw/combine, batched
-            synthesis with fused transforms and, in host mode, the async D2H copies."""
-            exhausted = False
-            while state["error"] is None and not exhausted:
+        main = torch.cuda.current_stream(device)
+        # the next batch's a_lm, records and digit planes are made here (a high-priority stream moves the same few ms from
+        # the ring FFT, which the look-ahead otherwise overlaps with, into the Legendre kernel: no difference in the step)
+        side = torch.cuda.Stream(device)
+        lib = _lib.load()
+        pipe = {"split": B == 8, "slot": 0, "freed": [None, None], "last": False}
+
+        def start():
+            """Draw and combine the next batch (<= B shells) on the side stream and, for a full batch of
+            eight on the INT8 Legendre path, prepare its transform there as well (glb_alm2map_prepare)
+            while the caller's stream is busy with the previous batch.  None when there is nothing left."""
+            if pipe["last"] or state["error"] is not None:
+                return None
+            side.wait_stream(main)  # (order after what the caller queued before the call)
+            with torch.cuda.stream(side):
                 alms = torch.empty((B, sampler.nalm), dtype=torch.complex128, device=device)
                 idx = []
                 while len(idx) < B:
@@ -739,7 +749,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                         state["error"] = e
                         break
                     if j is None:
-                        exhausted = True
+                        pipe["last"] = True
                         break
                     idx.append(j)
                 bad = sampler.first_failure()
@@ -747,16 +757,57 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                     # the reference raises when it reaches shell `bad`: yield the earlier ones first
                     idx = [j for j in idx if j < bad]
                     state["error"] = ValueError("covariance matrix is not positive definite")
-                    exhausted = True
+                    pipe["last"] = True
+                if not idx:
+                    return None
+                rec = {"alms": alms, "idx": idx, "slot": None}
+                if pipe["split"] and len(idx) == 8:
+                    slot = pipe["slot"]
+                    if pipe["freed"][slot] is not None:
+                        side.wait_event(pipe["freed"][slot])  # the Legendre kernel that read this set of tile blocks
+                    pl = hp.get_plan(nside, sampler.lmax, max_batch=4, device=device)
+                    rc = lib.glb_alm2map_prepare(pl.handle, alms.data_ptr(), 8, slot, side.cuda_stream)
+                    if rc == _lib.GLB_ERR_UNSUPPORTED:
+                        pipe["split"] = False  # not a size the INT8 path takes: the plain call below
+                    else:
+                        _lib.check(rc, "glb_alm2map_prepare")
+                        rec["slot"], rec["plan"] = slot, pl
+                        pipe["slot"] = slot ^ 1
+                rec["ready"] = torch.cuda.Event()
+                rec["ready"].record(side)
+            return rec
+
+        def batches():
+            """One batch per iteration: the look-ahead batch is started (side stream) before the current
+            one is synthesised on the caller's stream -- batched transform with fused pixel
+            transformations and, in host mode, the async D2H copies."""
+            cur = start()
+            while cur is not None:
+                nxt = start()
+                alms, idx = cur["alms"], cur["idx"]
                 nb = len(idx)
-                if nb == 0:
-                    break
+                main.wait_event(cur["ready"])
+                alms.record_stream(main)
                 tr = [transforms_for(j) or (_lib.T_NORMAL, 0.0, 1.0) for j in idx]
-                maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
+                if cur["slot"] is not None:
+                    pl = cur["plan"]
+                    maps = torch.empty((nb, npix), dtype=torch.float64, device=device)
+                    kinds, params, _keep = hp._transform_args(tr)
+                    _lib.check(lib.glb_alm2map_finish(pl.handle, 8, cur["slot"], maps.data_ptr(), kinds, params, main.cuda_stream), "glb_alm2map_finish")
+                    done_leg = torch.cuda.Event()
+                    done_leg.record(main)
+                    pipe["freed"][cur["slot"]] = done_leg
+                else:
+                    maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
+                if nxt is not None:
+                    # the look-ahead batch used the plan's record buffer on the side stream: whatever the consumer runs on
+                    # this stream next (other transforms of the same plan) comes after it
+                    main.wait_event(nxt["ready"])
                 if stats is not None:
                     stats["h2d_bytes"] = sampler.h2d_bytes
                 if on_device:
                     yield [(idx[b], maps[b], None) for b in range(nb)]
+                    cur = nxt
                     continue
                 done = torch.cuda.Event()
                 done.record(torch.cuda.current_stream(device))
@@ -771,6 +822,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                         out.append((idx[b], h, ev))
                 maps.record_stream(copy_stream)
                 yield out
+                cur = nxt
 
         def drain(batch):
             for j, m, ev in batch:

@@ -302,6 +302,15 @@ int glb_measure_fp64_peak(int device, double* tflops, double* ms, void* stream);
  * csrc/sht_ozaki.cu) at nside >= 1024, everything else on the FP64 pipe; 1 = FP64 pipe only; 2 = INT8 tensor cores
  * for groups of four and eight maps at any nside.  Both agree to ~1e-11 of the largest phase. */
 int glb_plan_set_legendre_mode(glb_plan* plan, int mode);
+/* glb_alm2map for EIGHT maps in two halves (the INT8 path, same results): `prepare` turns the a_lm into Legendre records and
+ * digit planes (set `slot` = 0 or 1 of the plan's tile blocks), `finish` runs the Legendre kernel on that set and the ring
+ * FFTs with the fused transformations.  A caller that gives them different streams -- prepare of batch i+1 ordered after
+ * finish of batch i-1 (same slot), finish of batch i after its prepare -- overlaps the memory-bound preparation with the
+ * latency-bound Legendre kernel (glass_b200/fields.py does).  GLB_ERR_UNSUPPORTED: not a group the INT8 path takes
+ * (nmaps != 8, FP64-only mode, nside < 1024 in auto mode, no memory): use glb_alm2map. */
+int glb_alm2map_prepare(glb_plan* plan, const double* d_alm, int nmaps, int slot, void* stream);
+int glb_alm2map_finish(glb_plan* plan, int nmaps, int slot, double* d_map, const int* h_transform, const double* h_tparams,
+                       void* stream);
 /* Give back the buffers a plan allocates on first use and can rebuild on the next (the tile blocks of the INT8 Legendre
  * path, 4 GB at nside 4096): for callers that are done generating and need the memory for maps.  Synchronises the device. */
 int glb_plan_release_scratch(glb_plan* plan);

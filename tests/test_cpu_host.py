@@ -614,6 +614,9 @@ def test_generate_host_flow_golden(monkeypatch):
             c128(dst, n)[:] = c128(src, n)[order(lmax)[0]]
             return 0
 
+        def glb_alm2map_prepare(self, plan, alm, nmaps, slot, st):  # the split form is the INT8 path's: not on this fake
+            return L.GLB_ERR_UNSUPPORTED
+
         def glb_alm_combine(self, lmax, nterms, zptrs, w, stride, out, st):
             n = (lmax + 1) * (lmax + 2) // 2
             ls = order(lmax)[1]
@@ -633,9 +636,10 @@ def test_generate_host_flow_golden(monkeypatch):
     monkeypatch.setattr(F, "_pick_device", lambda gls: (torch.device("cpu"), True))
     monkeypatch.setattr(F.hp, "alm2map_batch", alm2map_batch)
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
-    fake_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, wait_stream=lambda s: None)  # noqa: E731
+    fake_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, wait_stream=lambda s: None, wait_event=lambda e: None)  # noqa: E731
     monkeypatch.setattr(torch.cuda, "current_stream", fake_stream)
     monkeypatch.setattr(torch.cuda, "Stream", fake_stream)
+    monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: types.SimpleNamespace(record=lambda s=None: None, synchronize=lambda: None))
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
