@@ -80,3 +80,24 @@ def host_slices(batches):
             base = (key, whole(lon), whole(lat))
         o1, o2 = lon.storage_offset(), lat.storage_offset()
         yield base[1][o1 : o1 + n], base[2][o2 : o2 + n], n
+
+
+def nvtx(name: str):
+    """Decorator: an NVTX range around a public entry point, so that a timeline (nsys, ncu --nvtx) shows the stages of the
+    user loop by their GLASS names.  A few hundred nanoseconds per call; nothing when no tool listens."""
+    import functools
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            if not torch.cuda.is_available():  # (the host-flow tests of the CPU suite)
+                return fn(*a, **k)
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+
+        return inner
+
+    return wrap

@@ -20,6 +20,7 @@ otherwise as NumPy arrays (device->host copies overlap the next shells' compute)
 from __future__ import annotations
 
 import collections
+import contextlib
 import ctypes as C
 import functools
 import math
@@ -698,6 +699,19 @@ class _ShellSampler:
         return self.dnorm.first_failure()
 
 
+@contextlib.contextmanager
+def _nvtx_range(name: str):
+    """NVTX range (timelines show the stages by name); nothing without a device."""
+    on = torch.cuda.is_available()
+    if on:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        if on:
+            torch.cuda.nvtx.range_pop()
+
+
 def _pick_device(gls) -> tuple[torch.device, bool]:
     """(device, on_device): the device of the first CUDA spectrum, else the current CUDA device
     (raises without one); on_device decides the array rule of the module docstring."""
@@ -739,7 +753,7 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
             if pipe["last"] or state["error"] is not None:
                 return None
             side.wait_stream(main)  # (order after what the caller queued before the call)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), _nvtx_range("glass.generate: draw, combine, prepare (look-ahead batch)"):
                 alms = torch.empty((B, sampler.nalm), dtype=torch.complex128, device=device)
                 idx = []
                 while len(idx) < B:
@@ -789,16 +803,17 @@ def _generate_maps(gls, nside, ncorr, rng, transforms_for, shells=None, stats=No
                 main.wait_event(cur["ready"])
                 alms.record_stream(main)
                 tr = [transforms_for(j) or (_lib.T_NORMAL, 0.0, 1.0) for j in idx]
-                if cur["slot"] is not None:
-                    pl = cur["plan"]
-                    maps = torch.empty((nb, npix), dtype=torch.float64, device=device)
-                    kinds, params, _keep = hp._transform_args(tr)
-                    _lib.check(lib.glb_alm2map_finish(pl.handle, 8, cur["slot"], maps.data_ptr(), kinds, params, main.cuda_stream), "glb_alm2map_finish")
-                    done_leg = torch.cuda.Event()
-                    done_leg.record(main)
-                    pipe["freed"][cur["slot"]] = done_leg
-                else:
-                    maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
+                with _nvtx_range("glass.generate: alm2map of a batch"):
+                    if cur["slot"] is not None:
+                        pl = cur["plan"]
+                        maps = torch.empty((nb, npix), dtype=torch.float64, device=device)
+                        kinds, params, _keep = hp._transform_args(tr)
+                        _lib.check(lib.glb_alm2map_finish(pl.handle, 8, cur["slot"], maps.data_ptr(), kinds, params, main.cuda_stream), "glb_alm2map_finish")
+                        done_leg = torch.cuda.Event()
+                        done_leg.record(main)
+                        pipe["freed"][cur["slot"]] = done_leg
+                    else:
+                        maps = hp.alm2map_batch(alms[:nb], nside, sampler.lmax, transforms=tr)
                 if nxt is not None:
                     # the look-ahead batch used the plan's record buffer on the side stream: whatever the consumer runs on
                     # this stream next (other transforms of the same plan) comes after it

@@ -62,6 +62,7 @@ def redshifts(n, w, *, rng=None):
     return redshifts_from_nz(n, w.za, w.wa, rng=rng, warn=False)
 
 
+@A.nvtx("glass.redshifts_from_nz")
 def redshifts_from_nz(count, z, nz, *, rng=None, warn: bool = True):
     """
     Generate galaxy redshifts from a source distribution (glass/galaxies.py:188-268):
@@ -141,6 +142,7 @@ def redshifts_from_bins(bins, z, nz_dict, *, rng=None):
     return out.reshape(tuple(b.shape))
 
 
+@A.nvtx("glass.galaxy_shear")
 def galaxy_shear(lon, lat, eps, kappa, gamma1, gamma2, *, reduced_shear: bool = True, ipix=None):
     """
     Observed galaxy shears from weak lensing (glass/galaxies.py:271-347).

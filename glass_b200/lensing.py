@@ -50,6 +50,7 @@ class MultiPlaneConvergence:
         lens_weight = float(np.trapezoid(wa, za) / np.interp(zsrc, za, wa))
         self.add_plane(delta, zsrc, lens_weight)
 
+    @A.nvtx("glass.MultiPlaneConvergence.add_plane")
     def add_plane(self, delta, zsrc, wlens: float = 1.0) -> None:
         """Add a mass plane at redshift ``zsrc`` (glass/lensing.py:511-586)."""
         if zsrc <= self.z3:
@@ -192,6 +193,7 @@ def _convergence_factors(nside, lmax, discretized, pixwin):
     return f_psi, f_alpha, f_gamma
 
 
+@A.nvtx("glass.from_convergence")
 def from_convergence(  # noqa: PLR0913
     kappa,
     lmax: int | None = None,
@@ -245,6 +247,7 @@ def from_convergence(  # noqa: PLR0913
     return results
 
 
+@A.nvtx("glass.shear_from_convergence")
 def shear_from_convergence(kappa, lmax: int | None = None, *, discretized: bool = True, pixwin=None, niter: int = 3, ring_weights=None):
     r"""
     Weak lensing shear from convergence (glass/lensing.py:374-428; deprecated in the

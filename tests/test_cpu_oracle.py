@@ -317,3 +317,39 @@ def test_visibility_mask_oracle_properties():
     assert abs(np.degrees(np.arctan2(y, x)) % 360 - 192.86) < 0.01 and abs(np.degrees(np.arcsin(z)) - 27.13) < 0.01
     x, y, z = H.coordconv_matrix("EC") @ np.array([0.0, 0.0, 1.0])
     assert abs(np.degrees(np.arctan2(y, x)) % 360 - 270) < 1e-9 and abs(np.degrees(np.arcsin(z)) - 66.56) < 0.01
+
+
+def test_int8_digit_scheme_emulation():
+    """The arithmetic of the INT8 tensor-core Legendre kernel (csrc/sht_ozaki.cu), emulated step by step with exact
+    integers (tests/studies/ozaki_device_scheme.py): magic-constant fixed point, balanced base-256 digits as bytes ^ 0x80,
+    the 21 digit products with i + j >= 5 grouped by significance, the pair-wise int32 combination -- reproduces the FP64
+    contraction F = sum_k lambda_k A_k to 1e-12 of its maximum, with every integer inside its range."""
+    import importlib.util
+    import os
+
+    from oracle import healpix_ref as H
+
+    path = os.path.join(os.path.dirname(__file__), "studies", "ozaki_device_scheme.py")
+    spec = importlib.util.spec_from_file_location("ozaki_device_scheme", path)
+    oz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(oz)
+    # the bytes of V = rint(x s) + BIAS, sign-flipped, ARE the balanced digits
+    x = np.array([0.0, 1.0, -1.0, 0.123456789, -0.987654321, 1.999, -1.999])
+    s_, inv = oz.scales(np.full(x.shape, 1.999))
+    d = oz.digits(x, s_)
+    assert d.min() >= -128 and d.max() <= 127
+    rec = sum(d[j].astype(np.float64) * 256.0**j for j in range(oz.ND)) * inv
+    assert np.abs(rec - x).max() <= 2.0**-46
+    assert np.all(oz.digits(np.zeros(3), s_[:3]) == 0)
+    nside, lmax = 64, 127
+    ri = H.ring_info(nside)
+    z, sth = ri["z"][: 2 * nside], ri["sth"][: 2 * nside]
+    rng = np.random.default_rng(2)
+    for m in (0, 3, 40, 101):
+        lam = H.lam_lm(lmax, m, z, sth).T[:, ::2]
+        l = np.arange(m, lmax + 1, 2)
+        a = rng.standard_normal((l.size, 16)) * np.sqrt(1e-2 * (l + 1.0) ** -1.5)[:, None]
+        ref = lam @ a
+        F, worst = oz.contraction(lam, a, 64)
+        assert np.abs(F - ref).max() <= 1e-12 * np.abs(ref).max(), m
+        assert worst < 6 * 64 * 128 * 128
