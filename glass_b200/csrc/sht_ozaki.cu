@@ -6,23 +6,26 @@
 //     D[ring, c] = sum_k p_k(ring) A_k[c]        c = (Ae_re, Ae_im, Ao_re, Ao_im) x maps
 // is an Ozaki-type exact integer product on tcgen05.mma kind::i8 with int32 accumulators in TMEM:
 //
-//   * per (ring, tile of 64 l-pairs) the values p_k are cut into six base-256 digits relative to the
-//     largest |p_k| of the tile:  V = rint(p s) + BIAS comes out of ONE FMA with the magic constant
-//     2^52 + BIAS (the low 48 mantissa bits are V), and with BIAS = sum_j 128 256^j the BYTES u_j of V
-//     are the balanced digits d_j = u_j - 128 in [-128, 127] -- as an int8 that is u_j ^ 0x80: no
-//     shifts, masks or carries, only byte permutes (a 4 x 4 byte transpose per four l-pairs) and one
-//     XOR per word;
-//   * the coefficients A_k[c] are cut the same way per (column, tile) by a preparation kernel;
+//   * every value p_k is turned into 48-bit fixed point by ONE FMA with a magic constant:
+//     t = fma(p, s, 2^52 + BIAS) has V = rint(p s) + BIAS in its low mantissa bits, and with
+//     BIAS = sum_j 128 256^j the BYTES u_j of V are the balanced base-256 digits d_j = u_j - 128 in
+//     [-128, 127] -- as an int8 that is u_j ^ 0x80: no shifts, masks or carries, only byte permutes (a
+//     4 x 4 byte transpose per four l-pairs) and one XOR per word put the six digit planes into shared
+//     memory in the tensor core's K-major core-matrix layout;
+//   * the coefficients A_k[c] are cut the same way by a preparation kernel (oz_prep_kernel) into tile
+//     blocks of 64 l-pairs that one TMA bulk copy brings in;
 //   * digit products with i + j >= 5 (21 of 36) are accumulated by significance s = i + j into six
 //     column groups of D:  p digit a against the coefficient digits 5-a..5 is ONE MMA of N = NC (a+1)
-//     columns; 12 MMAs (M = 128 rings, K = 32) per tile; |D| <= 6 64 2^14 < 2^23;
-//   * epilogue per tile: D from TMEM (thread = TMEM lane = ring), pairs of groups combined in int32
-//     (< 2^31), three FP64 operations per column, accumulated in FP64 registers with the two scales.
+//     columns; 12 MMAs (M = 128 rings, K = 32) per tile; |D| <= 6 64 2^14 < 2^23 per tile;
+//   * the scales are FIXED -- one absolute bound per ring (|lambda_lm| <= min(sqrt((2l+1)/4pi),
+//     c / sqrt(sin theta))), one power of two per tile that follows the rescaling alpha_k of the
+//     recurrence, column scales per super-tile of 16 tiles -- so the integer sums of consecutive tiles
+//     stay in TMEM and D is read, converted and scaled once per super-tile.
 //
 // Accuracy: exact integer arithmetic on 48-bit operands; the dropped digit products are below 2^-46 of
-// max |p| max |A| per term (emulated step by step in tests/studies/ozaki_device_scheme.py).  One thread owns one ring pair (128 per CTA), walks l in
-// two passes per tile (pass 1: recurrence only, finds the tile's largest |p|; pass 2: the same
-// recurrence again, digits to shared memory in the tensor core's K-major core-matrix layout).
+// max |p| max |A| per term (emulated step by step in tests/studies/ozaki_device_scheme.py); measured
+// 4-8e-12 of the largest phase at nside 4096 against the FP64 kernel.  The comment above the kernel
+// describes the scales, the roles of the warps and the synchronisation; DESIGN.md 3.1b the measurements.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(OZ_KT) oz_prep_kernel(const double* __restrict
   for (int c = 0; c < 16; ++c) atomicMax(&s_max[c], mx[c]);
   for (int t = t0; t < t1; ++t) {
     __syncthreads();
-    if (t1 - t0 > 1 || t == t0) stage_tile(t);  // (a one-tile super-tile is still staged)
+    stage_tile(t);
     __syncthreads();
     uint8_t* blk = oz + (toff[m] + t) * (int64_t)T::BYTES;
     const int field = field_of(t, t * OZ_KT + k);
