@@ -36,12 +36,17 @@ class MultiPlaneConvergence:
         self.kappa2 = None
         self.kappa3 = None
         self._host = False
+        self._host_delta = None  # the caller's own NumPy matter plane (host mode): what `delta` hands back
+        self._host_kappa = None  # host copy of the current convergence plane, made once per plane on first access
+        self._pin = [None, None]  # two page-locked staging buffers, recycled like the planes themselves
+        self._npin = 0
         self._like = None  # map-shaped tensor sizing the hand-off of an empty block (dist.multi_plane_block)
 
     def _set_state_map(self, name: str, value) -> None:
         """Install a received map (delta3, kappa2, kappa3) of the recurrence state
         (glass_b200.dist.recv_multi_plane_state)."""
         setattr(self, name, value)
+        self._host_kappa = None
 
     def add_window(self, delta, w) -> None:
         """Add a mass plane from a window function (glass/lensing.py:489-509)."""
@@ -58,6 +63,8 @@ class MultiPlaneConvergence:
             raise ValueError(msg)
         device, on_device = A.pick_device(delta)
         self._host = not on_device
+        self._host_delta = None if on_device else delta
+        self._host_kappa = None
         delta_d = A.to_dev(delta, device)
 
         # cycle mass plane, redshifts and weights (lensing.py:544-549)
@@ -112,17 +119,35 @@ class MultiPlaneConvergence:
 
     @property
     def kappa(self):
-        """The current convergence plane."""
+        """The current convergence plane.  Host mode (NumPy planes in): ONE device -> host copy per plane,
+        through page-locked staging at the link rate, however often the property is read; the array is
+        recycled two planes later, like the reference's own buffers (glass/lensing.py:580)."""
         if self.kappa3 is None:
             return None
-        return self.kappa3.cpu().numpy() if self._host else self.kappa3
+        if not self._host:
+            return self.kappa3
+        if self._host_kappa is None:
+            k = self.kappa3
+            if not k.is_cuda:
+                self._host_kappa = k.numpy()
+            else:
+                slot = self._npin & 1
+                self._npin += 1
+                if self._pin[slot] is None or self._pin[slot].shape != k.shape:
+                    self._pin[slot] = torch.empty(k.shape, dtype=k.dtype, pin_memory=True)
+                self._pin[slot].copy_(k, non_blocking=True)
+                torch.cuda.current_stream(k.device).synchronize()
+                self._host_kappa = self._pin[slot].numpy()
+        return self._host_kappa
 
     @property
     def delta(self):
-        """The current matter plane."""
+        """The current matter plane (host mode: the array that was added, as in the reference)."""
         if self.delta3 is None:
             return None
-        return self.delta3.cpu().numpy() if self._host else self.delta3
+        if self._host:
+            return self._host_delta if self._host_delta is not None else self.delta3.cpu().numpy()
+        return self.delta3
 
     @property
     def wlens(self) -> float:
