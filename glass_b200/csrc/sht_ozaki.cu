@@ -31,13 +31,13 @@
 #include <cstdlib>
 
 #include "plan.h"
+#include "oz_digits.cuh"
 #include "sht_seed.cuh"
 #include "sht_tables.cuh"
 
 namespace glb {
 
 constexpr int OZ_KT = 64;      // l-pairs per tile
-constexpr int OZ_ND = 6;       // base-256 digits per operand
 constexpr int OZ_ROWS = 128;   // ring pairs per CTA = threads = TMEM lanes
 constexpr int OZ_STAGES = 3;   // tile blocks in flight (TMA)
 constexpr int OZ_SUP = 16;     // tiles per super-tile: one set of column scales, D may accumulate across them
@@ -58,26 +58,6 @@ struct OzTile {
   static constexpr int BYTES = SK_OFF + OZ_KT * 8;
   static_assert(BYTES % 32 == 0, "bulk copies move multiples of 16 bytes, the coefficient rows are stored as double4");
 };
-
-constexpr double OZ_HEADROOM = 0.99;  // |V| <= 0.99 * 2^47 keeps V + BIAS inside 48 bits
-__host__ __device__ constexpr int64_t oz_bias() {
-  int64_t b = 0;
-  for (int j = 0; j < OZ_ND; ++j) b += (int64_t)128 << (8 * j);
-  return b;
-}
-constexpr double OZ_MAGIC = 4503599627370496.0 + (double)oz_bias();  // 2^52 + BIAS
-
-// scale s = 0.99 * 2^(47 - e) and its inverse for |x| < 2^e, from the biased exponent field eb of the
-// largest |x| (e = eb - 1022); tiny maxima (eb < 64) count as zero
-__device__ __forceinline__ void oz_scales(int eb, double& s, double& inv) {
-  if (eb < 64) {
-    s = 0.0;
-    inv = 0.0;
-  } else {
-    s = __hiloint2double((2092 - eb) << 20, 0) * OZ_HEADROOM;
-    inv = __hiloint2double((eb - 46) << 20, 0) * (1.0 / OZ_HEADROOM);
-  }
-}
 
 // mbarrier wait with a watchdog: a protocol error becomes a launch failure instead of a hung GPU
 template <bool BACKOFF = false>
@@ -270,29 +250,6 @@ struct OzParams {
   unsigned long long* dbg;  // event counters (development), or null
 };
 
-// the six digit planes of four consecutive values: a 4 x 4 byte transpose of the low words, a 4 x 2
-// one of the high words (__byte_perm), and the sign flip of the balanced digits
-__device__ __forceinline__ void oz_planes(const double (&tt)[4], uint32_t (&w)[OZ_ND]) {
-  const uint32_t l0 = (uint32_t)__double2loint(tt[0]), l1 = (uint32_t)__double2loint(tt[1]);
-  const uint32_t l2 = (uint32_t)__double2loint(tt[2]), l3 = (uint32_t)__double2loint(tt[3]);
-  const uint32_t h0 = (uint32_t)__double2hiint(tt[0]), h1 = (uint32_t)__double2hiint(tt[1]);
-  const uint32_t h2 = (uint32_t)__double2hiint(tt[2]), h3 = (uint32_t)__double2hiint(tt[3]);
-  const uint32_t t0 = __byte_perm(l0, l1, 0x5140), t1 = __byte_perm(l0, l1, 0x7362);
-  const uint32_t t2 = __byte_perm(l2, l3, 0x5140), t3 = __byte_perm(l2, l3, 0x7362);
-  const uint32_t s0 = __byte_perm(h0, h1, 0x5140), s1 = __byte_perm(h2, h3, 0x5140);
-  w[0] = __byte_perm(t0, t2, 0x5410) ^ 0x80808080u;
-  w[1] = __byte_perm(t0, t2, 0x7632) ^ 0x80808080u;
-  w[2] = __byte_perm(t1, t3, 0x5410) ^ 0x80808080u;
-  w[3] = __byte_perm(t1, t3, 0x7632) ^ 0x80808080u;
-  w[4] = __byte_perm(s0, s1, 0x5410) ^ 0x80808080u;
-  w[5] = __byte_perm(s0, s1, 0x7632) ^ 0x80808080u;
-}
-
-// int32 -> double without a conversion instruction: the mantissa of 2^52 + 2^31 + x
-__device__ __forceinline__ double oz_i2d(int x) {
-  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
-}
-
 // cut of one half tile (32 l-pairs from k0): the recurrence, six digit planes of every value to the
 // operand buffer (row `dst`).  Range check: every FMA result must lie in [2^52, 2^52 + 2^48), i.e.
 // its high word is 0x4330xxxx -- `hor` / `hand` collect the OR and the AND of the high words.
@@ -337,9 +294,6 @@ __device__ __forceinline__ void oz_cut_half(const double* __restrict__ ab, int k
     for (int j = 0; j < OZ_ND; ++j)
       *reinterpret_cast<uint4*>(dst + j * OZ_A_SLICE + ch * (OZ_ROWS * 16)) = make_uint4(w[0][j], w[1][j], w[2][j], w[3][j]);
   }
-}
-__device__ __forceinline__ bool oz_in_range(uint32_t hor, uint32_t hand) {
-  return (hor & 0xffff0000u) == 0x43300000u && (hand & 0xfff00000u) == 0x43300000u;
 }
 
 // recurrence alone over l-pairs [k0, k1) of a tile, every ring at scale 0: largest |p| that enters the sum

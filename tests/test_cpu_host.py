@@ -1720,3 +1720,21 @@ def test_vmap_and_rotator_host_side():
     assert abs(np.degrees(np.arctan2(y, x)) % 360 - 192.86) < 0.01 and abs(np.degrees(np.arcsin(z)) - 27.13) < 0.01
     with pytest.raises(TypeError):
         _coordconv_matrix("GX")
+
+
+def test_int8_digit_arithmetic_host_build_and_run(tmp_path):
+    """csrc/oz_digits.cuh (the digit arithmetic of the INT8 tensor-core Legendre kernel: magic-constant fixed point, the byte
+    transposes that lay the digit planes out for the tensor core, the range check, the int32 -> double trick) built for the
+    host and checked bit for bit -- the device code is the same source with the intrinsics in place of their host shims."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "oz_digits_host"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "native", "oz_digits_host.cpp")],
+                   check=True, capture_output=True, timeout=300)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "oz_digits ok" in r.stdout, r.stdout + r.stderr
