@@ -734,6 +734,8 @@ def run_b200(args) -> None:
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f64",
+        "dtype_note": ("FP64 in and out; for groups of eight shells the contraction over l of the Legendre stage is an exact integer product of 48-bit "
+                       "fixed-point digits on the INT8 tensor cores (phases within 1e-11 of the FP64 kernel, maps within the 1e-10 bar: tests/test_gpu_int8.py)"),
         "data": "synthetic",
         "config": workload_config(nside, lmax, world),
         "host_binding": (f"rank 0 bound to {len(local_cpus)} GPU-local cores (NVML affinity)" if local_cpus else "none"),
